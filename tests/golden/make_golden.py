@@ -1,0 +1,280 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (it needs /root/reference, which does not exist on the
+GPU box):   python tests/golden/make_golden.py
+
+It imports the reference's own modules (matplotlib is absent from the image and is
+stubbed; patch_based_pde_discovery.py creates an output directory at import time, which
+is suppressed because the reference tree is read-only), calls the hot-path functions on
+small seeded inputs and stores inputs + outputs as .npz / .json.  It also runs
+ks2d_stridge_benchmark.main() for configs C1, C2 and C2+rich+sweep and records the
+numbers it prints.  Nothing here is imported by the product or by the GPU tests; the
+tests read only the files it wrote.
+"""
+
+from __future__ import annotations
+
+import contextlib
+import importlib.util
+import io
+import json
+import re
+import sys
+from pathlib import Path
+from unittest import mock
+
+import numpy as np
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+
+
+def _load(name: str, path: Path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_reference():
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, mock.MagicMock())
+    ks = _load("ref_ks2d", REF / "scripts" / "ks2d_stridge_benchmark.py")
+    ba = _load("ref_basic", REF / "examples" / "basic_usage.py")
+    with mock.patch.object(Path, "mkdir", lambda *a, **k: None):
+        pa = _load("ref_patch", REF / "scripts" / "patch_based_pde_discovery.py")
+    return ks, ba, pa
+
+
+# --------------------------------------------------------------------------- ks2d
+def golden_ks2d_small(ks):
+    cfg = ks.SimConfig(Nx=20, Ny=12, n_seconds=0.016, seed=7)
+    U, dx, dy, DT = ks.simulate(cfg)
+    U = U + 0.01 * np.random.default_rng(3).standard_normal(U.shape)  # make it less smooth
+    out = dict(U=U, dx=dx, dy=dy, DT=DT)
+    gx, gy = ks.gradients(U[3], dx, dy)
+    out.update(gx3=gx, gy3=gy, lap3=ks.laplacian(U[3], dx, dy))
+    Uf = U[:-1]
+    Ut = (U[1:] - U[:-1]) / DT
+    names_r, terms_r = ks.build_dictionary(Uf, dx=dx, dy=dy)
+    names_t, terms_t = ks.build_dictionary_true(Uf, dx=dx, dy=dy)
+    names_a, terms_a = ks.build_dictionary_true(Uf, dx=dx, dy=dy, include_advection=True)
+    out["names_rich"] = np.array(names_r)
+    out["names_true"] = np.array(names_t)
+    out["names_adv"] = np.array(names_a)
+    out["rich_terms"] = np.stack([terms_r[n] for n in names_r])
+    out["adv_terms"] = np.stack([terms_a[n] for n in names_a])
+    for tag, (bt, bx, by) in {"388": (3, 8, 8), "453": (4, 5, 3), "111": (1, 1, 1)}.items():
+        X, y = ks.build_blockwise_dataset(Ut, terms_r, names_r, block_t=bt, block_x=bx, block_y=by)
+        out[f"bw{tag}_X_rich"], out[f"bw{tag}_y"] = X, y
+        X, y = ks.build_blockwise_dataset(Ut, terms_t, names_t, block_t=bt, block_x=bx, block_y=by)
+        out[f"bw{tag}_X_true"] = X
+    # STRidge on the rich (3,8,8)... too few rows; use the (4,5,3) rows (8*4*4 = 128 rows)
+    X, y = out["bw453_X_rich"], out["bw453_y"]
+    grid = [(1e-6, 1e-10), (1e-3, 1e-6), (1e-2, 1e-2), (1e-2, 0.2), (1e-1, 5.0)]
+    out["stridge_grid"] = np.array(grid)
+    out["stridge_rich"] = np.stack([ks.stridge(X, y, alpha=a, threshold=t, max_iter=25) for a, t in grid])
+    Xp, yp = out["bw111_X_rich"], out["bw111_y"]
+    out["stridge_rich_pointwise"] = np.stack([ks.stridge(Xp, yp, alpha=a, threshold=t, max_iter=25) for a, t in grid])
+    out["stridge_true_pointwise"] = np.stack(
+        [ks.stridge(out["bw111_X_true"], yp, alpha=a, threshold=t, max_iter=25) for a, t in grid])
+    mean, scale = ks.standardize_fit(Xp)
+    out["std_mean"], out["std_scale"] = mean, scale
+    out["ridge_fit"] = ks.ridge_fit(ks.standardize_transform(Xp, mean, scale), yp, 1e-3)
+    np.savez_compressed(OUT / "ks2d_small.npz", **out)
+
+
+def _run_main(ks, argv):
+    buf = io.StringIO()
+    with mock.patch.object(sys, "argv", ["ks2d_stridge_benchmark.py"] + argv), contextlib.redirect_stdout(buf):
+        ks.main()
+    return buf.getvalue()
+
+
+def _parse_main(text: str):
+    res = {}
+    m = re.search(r"hyperparams:\n(\{.*\})", text)
+    if m:
+        d = eval(m.group(1), {"__builtins__": {}}, {})  # dict literal printed by the script
+        res["hyper"] = {k: v for k, v in d.items() if k != "key"}
+    res["coeffs_printed"] = {n: float(v) for n, v in re.findall(r"^\s+(\S+)\s*: ([+-]\d+\.\d+)$", text, flags=re.M)}
+    m = re.search(r"(?:Sampled|Blockwise) dataset: X=\((\d+), (\d+)\)", text)
+    res["X_shape"] = [int(m.group(1)), int(m.group(2))]
+    m = re.search(r"Train R2=([\d.eE+-]+), RMSE=([\d.eE+-]+)", text)
+    res["train_r2_rmse_printed"] = [float(m.group(1)), float(m.group(2))]
+    return res
+
+
+def golden_ks2d_configs(ks):
+    """C1 / C2 / C2+rich+sweep exactly as main() runs them."""
+    runs = {
+        "c1": [],
+        "c2": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05"],
+        "c2_rich_sweep": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05",
+                          "--dictionary", "rich", "--grid-search"],
+    }
+    out = {}
+    for tag, argv in runs.items():
+        out[tag] = _parse_main(_run_main(ks, argv))
+        out[tag]["argv"] = argv
+    # full-precision replay of the same configs through the reference's own functions
+    U, dx, dy, DT = ks.simulate(ks.SimConfig())
+    full = {}
+    for tag, (noise, method, dictionary, sweep) in {
+        "c1": (0.0, "pointwise", "true", False),
+        "c2": (0.05, "blockwise", "true", False),
+        "c2_rich_sweep": (0.05, "blockwise", "rich", True),
+    }.items():
+        Uo = U.astype(np.float64, copy=True)
+        if noise > 0:
+            rng_obs = np.random.default_rng(999)
+            Uo = Uo + rng_obs.normal(0.0, noise * float(np.std(Uo)), size=Uo.shape)
+        rng = np.random.default_rng(0)
+        Uf, Ut = Uo[:-1], (Uo[1:] - Uo[:-1]) / DT
+        names, terms = (ks.build_dictionary_true(Uf, dx=dx, dy=dy) if dictionary == "true"
+                        else ks.build_dictionary(Uf, dx=dx, dy=dy))
+        if method == "blockwise":
+            X, y = ks.build_blockwise_dataset(Ut, terms, names, block_t=3, block_x=8, block_y=8)
+        else:
+            idx = rng.choice(Ut.size, size=50_000, replace=False)
+            y = Ut.reshape(-1)[idx]
+            X = np.column_stack([terms[n].reshape(-1)[idx] for n in names])
+        perm = rng.permutation(len(y))
+        split = int(0.7 * len(y))
+        tr, te = perm[:split], perm[split:]
+        scale = np.sqrt(np.mean(X[tr] ** 2, axis=0)) + 1e-12
+        for j, n in enumerate(names):
+            if n == "1":
+                scale[j] = 1.0
+        table = []
+        pairs = [(a, t) for a in (1e-6, 1e-5, 1e-4, 1e-3, 1e-2) for t in (1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5)] \
+            if sweep else [(1e-6, 1e-10)]
+        for a, t in pairs:
+            c = ks.stridge(X[tr] / scale, y[tr], alpha=a, threshold=t, max_iter=25) / scale
+            pred = X[te] @ c
+            table.append(dict(alpha=a, threshold=t, coeffs=c.tolist(), r2_test=ks.r2_score(y[te], pred),
+                              rmse_test=ks.rmse(y[te], pred), n_active=int(np.sum(np.abs(c) > 0))))
+        full[tag] = dict(names=names, X_shape=list(X.shape), table=table,
+                         X_head=X[:4].tolist(), y_head=y[:4].tolist(),
+                         X_colsum=X.sum(axis=0).tolist(), y_sum=float(y.sum()),
+                         U_checksum=[float(Uo.sum()), float((Uo ** 2).sum()), float(Uo[-1, 1, 2])])
+    out["full_precision"] = full
+    (OUT / "ks2d_configs.json").write_text(json.dumps(out, indent=1, ensure_ascii=False))
+
+
+# --------------------------------------------------------------------------- basic_usage
+def golden_basic(ba):
+    out = {}
+    u, x, y, t = ba.generate_synthetic_data(n_frames=30, h=60, w=60)
+    dx, dy, dt = x[1] - x[0], y[1] - y[0], t[1] - t[0]
+    ut, uu, ux, uy, lap = ba.compute_derivatives(u, dx, dy, dt)
+    Theta, names = ba.build_library(uu, ux, uy, lap)
+    out["default_spacing"] = np.array([dx, dy, dt])
+    out["default_Theta_shape"] = np.array(Theta.shape)
+    out["default_coef"] = ba.stridge_regression(Theta, ut.flatten(), alpha=0.01, threshold=0.01)
+    out["default_G"] = Theta.T @ Theta
+    out["default_b"] = Theta.T @ ut.flatten()
+    out["default_u_sample"] = u[::7, ::11, ::13]
+    # a small rough field stored in full
+    rng = np.random.default_rng(11)
+    v = rng.standard_normal((6, 9, 11))
+    d = (0.3, 0.7, 0.05)
+    vt, vv, vx, vy, vl = ba.compute_derivatives(v, *d)
+    Th, _ = ba.build_library(vv, vx, vy, vl)
+    out.update(small_u=v, small_d=np.array(d), small_ut=vt, small_ux=vx, small_uy=vy, small_lap=vl, small_Theta=Th)
+    grid = [(0.01, 0.01), (0.01, 0.3), (1e-6, 1e-10), (1.0, 0.05), (0.01, 50.0)]
+    out["small_grid"] = np.array(grid)
+    out["small_coef"] = np.stack([ba.stridge_regression(Th, vt.flatten(), alpha=a, threshold=t) for a, t in grid])
+    out["small_coef_iter0"] = ba.stridge_regression(Th, vt.flatten(), max_iter=0)
+    np.savez_compressed(OUT / "basic.npz", **out)
+
+
+# --------------------------------------------------------------------------- patch
+def synthetic_stack(shape, seed=0):
+    from scipy.ndimage import gaussian_filter
+
+    a = gaussian_filter(np.random.default_rng(seed).standard_normal(shape), sigma=(1, 2, 2))
+    a = (a - a.min()) / (a.max() - a.min())
+    return a.astype(np.float32)
+
+
+def golden_patch(pa):
+    out = {}
+    U = synthetic_stack((14, 30, 34), seed=5)
+    out["U"] = U
+    rt, rs, deg, dt, dx, dy = 2, 3, 3, 1.0, 0.1, 0.1
+    pts = [(2, 3, 3), (11, 26, 30), (5, 10, 17), (7, 20, 4), (9, 3, 30), (4, 15, 15)]
+    out["pts"] = np.array(pts)
+    out["derivs"] = np.array([pa.local_poly_derivatives(U, t0, y0, x0, rt, rs, deg, dt, dx, dy) for t0, y0, x0 in pts])
+    out["derivs_deg2_r1"] = np.array([pa.local_poly_derivatives(U, t0, y0, x0, 1, 2, 2, 0.5, 0.2, 0.3) for t0, y0, x0 in pts])
+    lib8 = pa.Library(names=["1", "u", "u_x", "u_y", "lap(u)", "u^2", "u*u_x", "u*u_y"])
+    lib6 = pa.Library(names=["1", "u", "u_x", "u_y", "lap(u)", "u^2"])
+    X8, y8 = pa.build_dataset(U, pts, rt, rs, deg, dt, dx, dy, lib8)
+    X6, _ = pa.build_dataset(U, pts, rt, rs, deg, dt, dx, dy, lib6)
+    out.update(X8=X8, y8=y8, X6=X6)
+    out["patch_grid_30_34_9_4"] = np.array(pa.patch_grid(30, 34, 9, 4))
+    out["patch_grid_1024"] = np.array([len(pa.patch_grid(1024, 1024, 21, 10))])
+    # the per-patch loop of main() (patch:361-429) on this small stack, via the reference's functions
+    t_len, h, w = U.shape
+    t_valid = np.arange(rt, t_len - rt)
+    split = int(np.floor(0.7 * len(t_valid)))
+    t_train, t_test = t_valid[:split], t_valid[split:]
+    coords = pa.patch_grid(h, w, 11, 5)
+    rng = np.random.default_rng(0)
+    n_s = 40
+    C, tr_all, te_all = [], [], []
+    for (y0, x0) in coords:
+        ys_low, ys_high = max(rs, y0 + rs), min(h - rs, y0 + 11 - rs)
+        xs_low, xs_high = max(rs, x0 + rs), min(w - rs, x0 + 11 - rs)
+        if ys_high <= ys_low or xs_high <= xs_low:
+            continue
+        ys = rng.integers(ys_low, ys_high, size=n_s)
+        xs = rng.integers(xs_low, xs_high, size=n_s)
+        ts = rng.choice(t_train, size=n_s, replace=True)
+        ys2 = rng.integers(ys_low, ys_high, size=max(30, n_s // 3))
+        xs2 = rng.integers(xs_low, xs_high, size=max(30, n_s // 3))
+        ts2 = rng.choice(t_test, size=max(30, n_s // 3), replace=True)
+        tr_pts = list(zip(ts.tolist(), ys.tolist(), xs.tolist()))
+        Xtr, ytr = pa.build_dataset(U, tr_pts, rt=rt, rs=rs, deg=deg, dt=dt, dx=dx, dy=dy, lib=lib8)
+        C.append(pa.stridge(Xtr, ytr, alpha=0.01, threshold=1e-5))
+        tr_all.append(np.array(tr_pts))
+        te_all.append(np.stack([ts2, ys2, xs2], 1))
+    C = np.stack(C)
+    out.update(loop_C=C, loop_train_pts=np.stack(tr_all), loop_test_pts=np.stack(te_all), loop_coords=np.array(coords))
+    nonzero = np.abs(C) > 1e-5
+    med = np.median(C, axis=0)
+    out["loop_freq"] = nonzero.mean(axis=0)
+    out["loop_median"] = med
+    out["loop_q25"] = np.percentile(C, 25, axis=0)
+    out["loop_q75"] = np.percentile(C, 75, axis=0)
+    out["loop_sign_stability"] = np.mean(np.sign(C) == np.sign(med + 1e-12), axis=0)
+    out["loop_agg"] = np.where(out["loop_freq"] >= 0.6, med, 0.0)
+    # sklearn-dialect STRidge on assorted small problems (incl. a constant column)
+    rng2 = np.random.default_rng(21)
+    Xs_, ys_, cs_, grid_ = [], [], [], []
+    for k in range(8):
+        n, p = 60, 8
+        X = rng2.standard_normal((n, p)) * rng2.uniform(0.1, 30, size=p) + rng2.uniform(-3, 3, size=p)
+        X[:, 0] = 1.0
+        w_true = np.where(rng2.random(p) < 0.5, 0.0, rng2.standard_normal(p))
+        y = X @ w_true + 0.05 * rng2.standard_normal(n)
+        a, t = [(0.01, 1e-5), (0.01, 0.05), (1.0, 0.5), (1e-4, 2.0)][k % 4]
+        Xs_.append(X); ys_.append(y); grid_.append((a, t))
+        cs_.append(pa.stridge(X, y, alpha=a, threshold=t))
+    out.update(sk_X=np.stack(Xs_), sk_y=np.stack(ys_), sk_grid=np.array(grid_), sk_coef=np.stack(cs_))
+    np.savez_compressed(OUT / "patch.npz", **out)
+
+
+def main():
+    ks, ba, pa = load_reference()
+    golden_ks2d_small(ks)
+    golden_basic(ba)
+    golden_patch(pa)
+    golden_ks2d_configs(ks)
+    for f in sorted(OUT.glob("*.npz")) + sorted(OUT.glob("*.json")):
+        print(f.name, f.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()
