@@ -1,0 +1,197 @@
+/*
+ * pdegram.h -- C ABI of libpdegram.so: the B200 (sm_100a) implementation of the
+ * FD -> library -> (block average) -> Gram -> STRidge hot path of
+ * anpeata/pde-discovery-laser-matter.
+ *
+ * The reference is pure Python and has no FFI; the boundary it offers is the set of
+ * Python functions named below (paths relative to the reference root: "ks2d" =
+ * scripts/ks2d_stridge_benchmark.py, "basic" = examples/basic_usage.py, "patch" =
+ * scripts/patch_based_pde_discovery.py).  Each entry point cites the reference function
+ * it serves.  The Python package pde_b200 binds these with ctypes and re-exposes the
+ * reference signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns
+ *     all buffers; the library keeps only a private per-device scratch (pg_shutdown frees it)
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default)
+ *   - return 0 on success, a negative PG_E* code otherwise; pg_last_error() gives the
+ *     thread-local message.  No C++ exception crosses this boundary.
+ *   - fields are C-contiguous doubles U[t][a0][a1]; d0/d1 are the grid spacings along
+ *     a0/a1.  ks2d calls a0 "x" (ks2d:70-73); basic calls a1 "x" (basic:58).
+ *
+ * Statistics vector of one fold ("stats"), length PG_STATS_LEN(p) doubles:
+ *   [0] n  [1] sum y  [2] sum y^2  [3..3+p) sum theta_j  [3+p..3+2p) sum theta_j*y
+ *   [3+2p..) upper triangle of Theta^T Theta, row-major (i <= j)
+ */
+#ifndef PDEGRAM_H
+#define PDEGRAM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_VERSION 100
+
+#if defined(__GNUC__)
+#define PG_API __attribute__((visibility("default")))
+#else
+#define PG_API
+#endif
+
+#define PG_MAX_P 16
+#define PG_MAX_FOLDS 8
+#define PG_STATS_LEN(p) (3 + 2 * (p) + ((p) * ((p) + 1)) / 2)
+
+/* error codes */
+#define PG_OK 0
+#define PG_EINVAL (-1)   /* bad argument (shape, enum, null pointer) */
+#define PG_ECUDA (-2)    /* CUDA runtime / driver error */
+#define PG_ENOMEM (-3)   /* scratch allocation failed */
+#define PG_EUNSUPPORTED (-4) /* valid request this build has no kernel for */
+
+/* finite-difference dialect */
+#define PG_FD_KS_PERIODIC 0 /* ks2d:63-73   periodic np.roll stencils, rows = all points of U[:-1] */
+#define PG_FD_BASIC_TRIM 1  /* basic:32-72  interior stencils, rows = U[:-1, 2:-2, 2:-2]           */
+
+/* candidate library (column order is the reference's) */
+#define PG_LIB_KS_TRUE 0       /* p=3  lap, bih, |grad|^2                         ks2d:1095-1099 */
+#define PG_LIB_KS_TRUE_ADV 1   /* p=5  + u_x, u_y                                 ks2d:1100-1102 */
+#define PG_LIB_KS_RICH 2       /* p=9  1,u,u^2,u_x,u_y,lap,bih,|grad|^2,u*lap     ks2d:1048-1059 */
+#define PG_LIB_KS_RICH_NOADV 3 /* p=7  rich without u_x,u_y                       ks2d:1536-1539 */
+#define PG_LIB_BASIC 4         /* p=6  1,u,u_x,u_y,lap,u^2                        basic:89-99    */
+#define PG_LIB_KS_GRAD 5       /* p=2  gx, gy        (pg_fd_terms only)           ks2d:70-73     */
+#define PG_LIB_KS_LAP 6        /* p=1  lap           (pg_fd_terms only)           ks2d:63-67     */
+#define PG_LIB_PATCH_MODEL4 7  /* p=6  1,u,u_x,u_y,lap,u^2      (pg_poly_rows)    patch:160-162  */
+#define PG_LIB_PATCH_FULL 8    /* p=8  + u*u_x, u*u_y           (pg_poly_rows)    patch:163-172  */
+#define PG_LIB_PATCH_DERIVS 9  /* p=6  u,u_t,u_x,u_y,u_xx,u_yy  (pg_poly_rows)    patch:240-246  */
+
+/* STRidge dialect */
+#define PG_STRIDGE_KS 0      /* ks2d:404-428   centre+scale X, LU solve, 1+max_iter fits      */
+#define PG_STRIDGE_SKLEARN 1 /* patch:78-98    StandardScaler + Ridge(intercept), Cholesky     */
+#define PG_STRIDGE_BASIC 2   /* basic:104-143  raw Gram, restart from full solve each iteration */
+/* STRidge flags */
+#define PG_STRIDGE_RMS_PRESCALE 1 /* ks2d:1647-1655: divide columns by sqrt(G_jj/n)+1e-12 first
+                                     ('1' columns keep scale 1) and unscale the coefficients  */
+
+/* kernel variant for pg_fd_lib_gram */
+#define PG_VARIANT_AUTO 0    /* tiled TMA kernel where it applies, generic kernel for the rest */
+#define PG_VARIANT_GENERIC 1 /* force the generic (reference-arithmetic) kernel everywhere    */
+#define PG_VARIANT_TILED 2   /* require the tiled kernel; PG_EUNSUPPORTED if it cannot run     */
+
+PG_API int pg_version(void);
+PG_API const char *pg_last_error(void);
+/* frees the per-device scratch of the current device */
+PG_API int pg_shutdown(void);
+/* number of columns of a library, or PG_EINVAL */
+PG_API int pg_library_width(int library_id);
+
+/*
+ * K1 -- fused finite differences + library row + (block mean) + Gram.  Replaces, without
+ * materialising Theta: gradients/laplacian (ks2d:63-73), build_dictionary(_true)
+ * (ks2d:1017-1104), the forward u_t (ks2d:1511,1555), build_blockwise_dataset
+ * (ks2d:358-401) and X.T@X / X.T@y (ks2d:55-58); or compute_derivatives + build_library +
+ * Theta.T@Theta (basic:32-101,123-124).
+ *
+ *   U             [T][A0][A1]; rows come from frames 0..T-2 (frame T-1 only feeds u_t)
+ *   bt,b0,b1      block sizes along t,a0,a1 (1,1,1 = pointwise); ragged trailing blocks
+ *                 are kept with their own divisor (ks2d:384-389)
+ *   fold_of_row   nullable, one fold id per block row in reference row order (t-block major,
+ *                 then a0-block, then a1-block); takes precedence over fold_of_frame
+ *   fold_of_frame nullable, one fold id per frame 0..T-2; a block takes the fold of its first
+ *                 frame (time-holdout folds); both NULL = a single fold 0
+ *   stats_out     [n_folds][PG_STATS_LEN(p)]
+ *   nonfinite_out nullable, 1 int64: number of block rows skipped because a mean was not
+ *                 finite (ks2d:394-395).  If it is non-zero and fold_of_row was given, the
+ *                 caller's row numbering no longer matches the reference's (which renumbers
+ *                 after dropping) and must use pg_block_means + pg_rows_gram instead.
+ */
+PG_API int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                   int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
+                   const int32_t *fold_of_frame, int n_folds, double *stats_out, int64_t *nonfinite_out,
+                   int variant, void *stream);
+
+/*
+ * Materialised term stacks, bit-identical to the reference's NumPy arithmetic (no FMA
+ * contraction, true division).  PG_FD_KS_PERIODIC: terms_out [p][T][A0][A1] over ALL T
+ * frames given (ks2d:63-73, 1017-1104).  PG_FD_BASIC_TRIM with PG_LIB_BASIC: terms_out is
+ * the 5 arrays (u_t, u, u_x, u_y, lap) of compute_derivatives, each [T-1][A0-4][A1-4]
+ * (basic:32-72; `dt` used only here).
+ */
+PG_API int pg_fd_terms(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                int fd_dialect, int library_id, double *terms_out, void *stream);
+
+/*
+ * K1c -- sampled pointwise rows (ks2d:1625-1636): flat_idx indexes the row space
+ * ((T-1)*A0*A1 for KS, (T-1)*(A0-4)*(A1-4) for BASIC); X_out [n][p], y_out [n].
+ */
+PG_API int pg_fd_gather_rows(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                      int fd_dialect, int library_id, const int64_t *flat_idx, int64_t n, double *X_out,
+                      double *y_out, void *stream);
+
+/*
+ * Block means of k stacked arrays (the literal build_blockwise_dataset(Ut, terms, names)
+ * signature, ks2d:358-401): stack [k][T][A0][A1] -> out [nrows][k], nrows =
+ * ceil(T/bt)*ceil(A0/b0)*ceil(A1/b1), reference row order.  Dropping non-finite rows is
+ * left to the caller.
+ */
+PG_API int pg_block_means(const double *stack, int k, int64_t T, int64_t A0, int64_t A1, int bt, int b0, int b1,
+                   double *out, void *stream);
+
+/*
+ * Rows -> statistics for B independent problems of n rows each: X [B][n][ldx] (first p columns
+ * used), y [B][n], optional fold per row [B][n].  Serves the literal stridge(X, y) signatures
+ * (ks2d:404, patch:78, basic:104) and the per-patch fits (patch:420-423).
+ *   shift         nullable [B][p]: statistics are taken of (X - shift), which removes the
+ *                 cancellation in G - n*mu*mu^T when mean^2 >> variance (use e.g. the first row)
+ *   stats_out     [B][n_folds][PG_STATS_LEN(p)]
+ *   colminmax_out nullable [B][n_folds][2][p] = per-column min / max of the unshifted values; lets
+ *                 the solver detect exactly-constant columns the way np.std()==0 does (ks2d:46-47)
+ */
+PG_API int pg_rows_gram(const double *X, const double *y, int64_t B, int64_t n, int p, int64_t ldx,
+                 const uint8_t *fold_of_row, int n_folds, const double *shift, double *stats_out,
+                 double *colminmax_out, void *stream);
+
+/*
+ * K2 -- local-polynomial derivative rows (patch:193-280).  The lstsq fit of patch:231 has a
+ * constant design matrix, so it is the fixed stencil W6 [6][(2rt+1)(2rs+1)^2] (rows u, u_t,
+ * u_x, u_y, u_xx, u_yy; neighbour order t, y, x with x fastest).  U [T][H][W] is float32
+ * (dtype 0, as the script stores it, patch:116) or float64 (dtype 1); pts [n][3] = (t,y,x).
+ * X_out [n][p], y_out [n] (= u_t).
+ */
+PG_API int pg_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, const int32_t *pts, int64_t n,
+                 const double *W6, int rt, int rs, int library_id, double *X_out, double *y_out, void *stream);
+
+/*
+ * K3 -- batched STRidge on statistics, one warp per (problem, alpha, threshold).
+ *   stats        [B][PG_STATS_LEN(p)] training statistics
+ *   alphas/thrs  [na] / [nt] DEVICE arrays: the sweep grid (ks2d:1720-1722)
+ *   const_mask   nullable [p] uint8: columns known to be constant ('1'), forced to an exact
+ *                zero coefficient as centring does in the reference
+ *   colminmax    nullable [B][2][p] from pg_rows_gram: adds exact constant detection
+ *   shift        nullable [B][p]: the statistics (train and held-out) are of (X - shift)
+ *   eval_stats   nullable [B][PG_STATS_LEN(p)]: held-out statistics -> metrics_out
+ *                [B][na][nt][2] = (r2, rmse) (ks2d:29-40) and best_out [B] = flat index
+ *                a*nt+t maximising (r2, -n_active, -rmse), first maximum wins (ks2d:1731-1741)
+ *   coef_out     [B][na][nt][p] coefficients in the units of the given columns
+ */
+PG_API int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect, int flags, const double *alphas,
+                       int na, const double *thrs, int nt, int max_iter, const uint8_t *const_mask,
+                       const double *colminmax, const double *shift, const double *eval_stats,
+                       double *coef_out, double *metrics_out, int32_t *best_out, void *stream);
+
+/*
+ * Synthetic field generator for the large benchmark stacks: frames
+ * t_offset..t_offset+T-1 of a smooth travelling-wave field plus counter-based noise,
+ * written straight into HBM.  kind 0 = periodic (KS-shaped), 1 = laser-image-shaped [0,1].
+ * Deterministic in (seed, global frame index, a0, a1), so time slabs generated on different
+ * GPUs tile the same global stack.
+ */
+PG_API int pg_synth_field(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total,
+                   uint64_t seed, int kind, double noise, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDEGRAM_H */

@@ -1,0 +1,318 @@
+// extern "C" entry points of libpdegram.so (include/pdegram.h): argument validation, scratch
+// management and kernel dispatch.  No exception crosses this boundary.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace pg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// One scratch buffer per (device, stream): calls on one stream are ordered, so reuse is safe.
+struct Scratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+static std::mutex g_mu;
+static std::map<std::pair<int, void *>, Scratch> g_scratch;
+
+static int scratch_for(cudaStream_t st, size_t bytes, void **ptr) {
+    int dev = 0;
+    PG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    Scratch &s = g_scratch[{dev, (void *)st}];
+    if (s.bytes < bytes) {
+        if (s.ptr) {
+            // earlier work on this stream may still read the old buffer
+            PG_CUDA(cudaStreamSynchronize(st));
+            PG_CUDA(cudaFree(s.ptr));
+            s.ptr = nullptr;
+            s.bytes = 0;
+        }
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        if (cudaMalloc(&s.ptr, want) != cudaSuccess) {
+            cudaGetLastError();
+            s.ptr = nullptr;
+            PG_FAIL(PG_ENOMEM, "cannot allocate %zu bytes of device scratch", want);
+        }
+        s.bytes = want;
+    }
+    *ptr = s.ptr;
+    return PG_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+static bool ks_lib(int lib) {
+    return lib == PG_LIB_KS_TRUE || lib == PG_LIB_KS_TRUE_ADV || lib == PG_LIB_KS_RICH || lib == PG_LIB_KS_RICH_NOADV;
+}
+
+// Validate (dialect, library, shape) and fill the row-space description.
+static int describe(K1Params &P, const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                    int dialect, int lib, bool fused) {
+    if (!U) PG_FAIL(PG_EINVAL, "U is null");
+    if (T < 1 || A0 < 1 || A1 < 1) PG_FAIL(PG_EINVAL, "bad shape T=%lld A0=%lld A1=%lld", (long long)T, (long long)A0, (long long)A1);
+    if (!(d0 > 0) || !(d1 > 0) || !(dt > 0)) PG_FAIL(PG_EINVAL, "grid spacings must be positive");
+    P.U = U; P.T = T; P.A0 = A0; P.A1 = A1;
+    P.c = make_consts(d0, d1, dt);
+    P.dialect = dialect;
+    if (dialect == PG_FD_KS_PERIODIC) {
+        if (fused && !ks_lib(lib)) PG_FAIL(PG_EINVAL, "library %d does not belong to the KS dialect", lib);
+        P.R0 = A0; P.R1 = A1; P.off = 0;
+    } else if (dialect == PG_FD_BASIC_TRIM) {
+        if (lib != PG_LIB_BASIC) PG_FAIL(PG_EINVAL, "the basic_usage dialect only has library PG_LIB_BASIC");
+        if (A0 < 5 || A1 < 5) PG_FAIL(PG_EINVAL, "basic_usage dialect needs A0, A1 >= 5 (interior [2:-2])");
+        P.R0 = A0 - 4; P.R1 = A1 - 4; P.off = 2;
+    } else {
+        PG_FAIL(PG_EINVAL, "unknown finite-difference dialect %d", dialect);
+    }
+    return PG_OK;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+int pg_version(void) { return PG_VERSION; }
+const char *pg_last_error(void) { return g_err; }
+int pg_library_width(int library_id) {
+    const int w = library_width(library_id);
+    if (w < 0) PG_FAIL(PG_EINVAL, "unknown library %d", library_id);
+    return w;
+}
+
+int pg_shutdown(void) {
+    int dev = 0;
+    PG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto it = g_scratch.begin(); it != g_scratch.end();) {
+        if (it->first.first == dev) {
+            if (it->second.ptr) cudaFree(it->second.ptr);
+            it = g_scratch.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    return PG_OK;
+}
+
+int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+                   int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
+                   int n_folds, double *stats_out, int64_t *nonfinite_out, int variant, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    K1Params P{};
+    int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, true);
+    if (rc) return rc;
+    if (bt <= 0 || b0 <= 0 || b1 <= 0) PG_FAIL(PG_EINVAL, "block sizes must be > 0");  // ks2d:378-379
+    if (n_folds < 1 || n_folds > PG_MAX_FOLDS) PG_FAIL(PG_EINVAL, "n_folds must be in 1..%d", PG_MAX_FOLDS);
+    if (!stats_out) PG_FAIL(PG_EINVAL, "stats_out is null");
+    if (variant < PG_VARIANT_AUTO || variant > PG_VARIANT_TILED) PG_FAIL(PG_EINVAL, "unknown variant %d", variant);
+    const int p = library_width(library_id), S = PG_STATS_LEN(p);
+    const int64_t Trows = T - 1;
+    P.bt = bt; P.b0 = b0; P.b1 = b1;
+    P.fold_of_row = fold_of_row; P.fold_of_frame = fold_of_frame; P.n_folds = n_folds;
+    const int64_t len = (int64_t)n_folds * S;
+    if (Trows <= 0) {  // a single frame has no u_t: zero rows
+        PG_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * len, st));
+        if (nonfinite_out) PG_CUDA(cudaMemsetAsync(nonfinite_out, 0, sizeof(int64_t), st));
+        return PG_OK;
+    }
+    const int64_t nBt = (Trows + bt - 1) / bt;
+    P.nB0 = (P.R0 + b0 - 1) / b0; P.nB1 = (P.R1 + b1 - 1) / b1;
+
+    // Tiled TMA kernel over the region it supports; the generic kernel covers what is left.
+    TiledPlan plan{};
+    bool tiled = false;
+    if (variant != PG_VARIANT_GENERIC) {
+        tiled = tiled_plan(P, library_id, nBt, sm_count(), plan);
+        if (!tiled && variant == PG_VARIANT_TILED)
+            PG_FAIL(PG_EUNSUPPORTED, "no tiled kernel for dialect %d library %d block (%d,%d,%d) shape (%lld,%lld,%lld)",
+                    fd_dialect, library_id, bt, b0, b1, (long long)T, (long long)A0, (long long)A1);
+    }
+    // generic launches: up to 3 boxes of block indices (the whole space when not tiled)
+    struct Box { int64_t t0, t1, a0, a1, c0, c1; };
+    Box boxes[3];
+    int nbox = 0;
+    if (!tiled) {
+        boxes[nbox++] = {0, nBt, 0, P.nB0, 0, P.nB1};
+    } else {
+        // plan covers block indices [0,plan.nbt) x [0,plan.nb0) x [0,plan.nb1)
+        if (plan.nbt < nBt) boxes[nbox++] = {plan.nbt, nBt, 0, P.nB0, 0, P.nB1};
+        if (plan.nb0 < P.nB0) boxes[nbox++] = {0, plan.nbt, plan.nb0, P.nB0, 0, P.nB1};
+        if (plan.nb1 < P.nB1) boxes[nbox++] = {0, plan.nbt, 0, plan.nb0, plan.nb1, P.nB1};
+    }
+    const int max_ctas = sm_count() * 8;
+    int box_ctas[3] = {0, 0, 0};
+    int64_t gen_parts = 0;
+    for (int k = 0; k < nbox; ++k) {
+        const int64_t items = (boxes[k].t1 - boxes[k].t0) * (boxes[k].a1 - boxes[k].a0) * (boxes[k].c1 - boxes[k].c0);
+        int64_t g = (items + GW_THREADS - 1) / GW_THREADS;
+        box_ctas[k] = (int)(g < 1 ? 1 : (g > max_ctas ? max_ctas : g));
+        gen_parts += (int64_t)box_ctas[k] * GW_WARPS;
+    }
+    const int64_t tiled_parts = tiled ? plan.n_parts : 0;
+    const size_t bytes = 64 + sizeof(double) * (size_t)((gen_parts + tiled_parts) * len) + (tiled ? plan.extra_scratch : 0);
+    void *scr = nullptr;
+    rc = scratch_for(st, bytes, &scr);
+    if (rc) return rc;
+    unsigned long long *counters = (unsigned long long *)scr;
+    double *partials = (double *)((char *)scr + 64);
+    PG_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+    P.counters = counters;
+    int64_t part_off = 0;
+    if (tiled) {
+        rc = tiled_launch(P, library_id, plan, partials, (char *)(partials + (gen_parts + tiled_parts) * len), st);
+        if (rc) return rc;
+        part_off = tiled_parts;
+    }
+    for (int k = 0; k < nbox; ++k) {
+        K1Params Q = P;
+        Q.tb_lo = boxes[k].t0; Q.tb_hi = boxes[k].t1; Q.i0_lo = boxes[k].a0; Q.i0_hi = boxes[k].a1;
+        Q.i1_lo = boxes[k].c0; Q.i1_hi = boxes[k].c1;
+        Q.partials = partials + part_off * len;
+        rc = launch_k1_generic(library_id, Q, box_ctas[k], st);
+        if (rc) return rc;
+        part_off += (int64_t)box_ctas[k] * GW_WARPS;
+    }
+    rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st);
+    if (rc) return rc;
+    if (nonfinite_out)
+        PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    return PG_OK;
+}
+
+int pg_fd_terms(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+                int library_id, double *terms_out, void *stream) {
+    K1Params P{};
+    int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, false);
+    if (rc) return rc;
+    if (!terms_out) PG_FAIL(PG_EINVAL, "terms_out is null");
+    if (fd_dialect == PG_FD_KS_PERIODIC && !ks_lib(library_id) && library_id != PG_LIB_KS_GRAD && library_id != PG_LIB_KS_LAP)
+        PG_FAIL(PG_EINVAL, "library %d does not belong to the KS dialect", library_id);
+    return launch_fd_terms(fd_dialect, library_id, U, T, A0, A1, P.c, terms_out, (cudaStream_t)stream);
+}
+
+int pg_fd_gather_rows(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                      int fd_dialect, int library_id, const int64_t *flat_idx, int64_t n, double *X_out, double *y_out,
+                      void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    K1Params P{};
+    int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, true);
+    if (rc) return rc;
+    if (n < 0) PG_FAIL(PG_EINVAL, "n < 0");
+    if (n == 0) return PG_OK;
+    if (!flat_idx || !X_out || !y_out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (T < 2) PG_FAIL(PG_EINVAL, "need at least 2 frames for u_t");
+    void *scr = nullptr;
+    rc = scratch_for(st, 64, &scr);
+    if (rc) return rc;
+    PG_CUDA(cudaMemsetAsync(scr, 0, 64, st));
+    P.counters = (unsigned long long *)scr;
+    return launch_fd_gather(library_id, P, flat_idx, n, X_out, y_out, st);
+}
+
+int pg_block_means(const double *stack, int k, int64_t T, int64_t A0, int64_t A1, int bt, int b0, int b1, double *out,
+                   void *stream) {
+    if (!stack || !out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (k < 1 || T < 1 || A0 < 1 || A1 < 1) PG_FAIL(PG_EINVAL, "bad shape");
+    if (bt <= 0 || b0 <= 0 || b1 <= 0) PG_FAIL(PG_EINVAL, "block sizes must be > 0");
+    return launch_block_means(stack, k, T, A0, A1, bt, b0, b1, out, (cudaStream_t)stream);
+}
+
+int pg_rows_gram(const double *X, const double *y, int64_t B, int64_t n, int p, int64_t ldx, const uint8_t *fold_of_row,
+                 int n_folds, const double *shift, double *stats_out, double *colminmax_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p < 1 || p > PG_MAX_P) PG_FAIL(PG_EINVAL, "p must be in 1..%d", PG_MAX_P);
+    if (n_folds < 1 || n_folds > PG_MAX_FOLDS) PG_FAIL(PG_EINVAL, "n_folds must be in 1..%d", PG_MAX_FOLDS);
+    if (B < 0 || n < 0 || ldx < p) PG_FAIL(PG_EINVAL, "bad shape B=%lld n=%lld ldx=%lld", (long long)B, (long long)n, (long long)ldx);
+    if (!stats_out) PG_FAIL(PG_EINVAL, "stats_out is null");
+    if (B == 0) return PG_OK;
+    if (n > 0 && (!X || !y)) PG_FAIL(PG_EINVAL, "null rows");
+    const int S = PG_STATS_LEN(p);
+    RowsParams R{};
+    R.X = X; R.y = y; R.B = B; R.n = n; R.ldx = ldx; R.p = p; R.fold_of_row = fold_of_row; R.n_folds = n_folds;
+    R.shift = shift;
+    int64_t chunks = (n + GW_THREADS * 64 - 1) / (GW_THREADS * 64);  // ~64 rows per thread
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (chunks * B > cap) chunks = cap / B;
+    if (chunks < 1) chunks = 1;
+    R.chunks = (int)chunks;
+    const int64_t parts = B * chunks * GW_WARPS;
+    const size_t b_stats = sizeof(double) * (size_t)(parts * n_folds * S);
+    const size_t b_mm = colminmax_out ? sizeof(double) * (size_t)(parts * n_folds * 2 * p) : 0;
+    void *scr = nullptr;
+    int rc = scratch_for(st, 64 + b_stats + b_mm, &scr);
+    if (rc) return rc;
+    PG_CUDA(cudaMemsetAsync(scr, 0, 64, st));
+    R.counters = (unsigned long long *)scr;
+    R.partials = (double *)((char *)scr + 64);
+    R.mm_partials = colminmax_out ? (double *)((char *)scr + 64 + b_stats) : nullptr;
+    return launch_rows_gram(R, stats_out, colminmax_out, st);
+}
+
+int pg_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, const int32_t *pts, int64_t n,
+                 const double *W6, int rt, int rs, int library_id, double *X_out, double *y_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype != 0 && dtype != 1) PG_FAIL(PG_EINVAL, "dtype must be 0 (float32) or 1 (float64)");
+    if (library_id != PG_LIB_PATCH_MODEL4 && library_id != PG_LIB_PATCH_FULL && library_id != PG_LIB_PATCH_DERIVS) PG_FAIL(PG_EINVAL, "library %d is not a patch library", library_id);
+    if (rt < 0 || rs < 0 || rt > 8 || rs > 8) PG_FAIL(PG_EINVAL, "rt, rs must be in 0..8");
+    if (n < 0) PG_FAIL(PG_EINVAL, "n < 0");
+    if (n == 0) return PG_OK;
+    if (!U || !pts || !W6 || !X_out || !y_out) PG_FAIL(PG_EINVAL, "null buffer");
+    void *scr = nullptr;
+    int rc = scratch_for(st, 64, &scr);
+    if (rc) return rc;
+    PG_CUDA(cudaMemsetAsync(scr, 0, 64, st));
+    return launch_poly_rows(U, dtype, T, H, W, pts, n, W6, rt, rs, library_id == PG_LIB_PATCH_FULL ? 1 : (library_id == PG_LIB_PATCH_DERIVS ? 2 : 0), X_out, y_out,
+                            (unsigned long long *)scr, st);
+}
+
+int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect, int flags, const double *alphas, int na,
+                       const double *thrs, int nt, int max_iter, const uint8_t *const_mask, const double *colminmax,
+                       const double *shift, const double *eval_stats, double *coef_out, double *metrics_out,
+                       int32_t *best_out, void *stream) {
+    if (p < 1 || p > PG_MAX_P) PG_FAIL(PG_EINVAL, "p must be in 1..%d", PG_MAX_P);
+    if (dialect < PG_STRIDGE_KS || dialect > PG_STRIDGE_BASIC) PG_FAIL(PG_EINVAL, "unknown STRidge dialect %d", dialect);
+    if (B < 0 || na < 1 || nt < 1 || max_iter < 0) PG_FAIL(PG_EINVAL, "bad sizes");
+    if (!stats || !alphas || !thrs || !coef_out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (dialect == PG_STRIDGE_BASIC && shift) PG_FAIL(PG_EINVAL, "the basic_usage dialect works on the raw Gram; shift must be null");
+    if ((eval_stats != nullptr) != (metrics_out != nullptr)) PG_FAIL(PG_EINVAL, "eval_stats and metrics_out go together");
+    if (best_out && !metrics_out) PG_FAIL(PG_EINVAL, "best_out needs eval_stats/metrics_out");
+    StridgeParams P{};
+    P.stats = stats; P.B = B; P.p = p; P.dialect = dialect; P.flags = flags; P.alphas = alphas; P.na = na;
+    P.thrs = thrs; P.nt = nt; P.max_iter = max_iter; P.const_mask = const_mask; P.colminmax = colminmax;
+    P.shift = shift; P.eval_stats = eval_stats; P.coef_out = coef_out; P.metrics_out = metrics_out;
+    return launch_stridge(P, best_out, (cudaStream_t)stream);
+}
+
+int pg_synth_field(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total, uint64_t seed,
+                   int kind, double noise, void *stream) {
+    if (!U) PG_FAIL(PG_EINVAL, "U is null");
+    if (T < 0 || A0 < 1 || A1 < 1) PG_FAIL(PG_EINVAL, "bad shape");
+    return launch_synth(U, T, A0, A1, t_offset, T_total, seed, kind, noise, (cudaStream_t)stream);
+}
+
+}  // extern "C"

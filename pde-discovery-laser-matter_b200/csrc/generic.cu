@@ -1,0 +1,405 @@
+// Generic (any shape, reference-arithmetic) kernels of libpdegram:
+//   k1_generic      fused FD + library row + block mean + Gram for any dialect / block / fold layout
+//   fd_terms        materialised term stacks, bit-identical to the reference's NumPy arithmetic
+//   fd_gather       sampled pointwise rows
+//   block_means     build_blockwise_dataset on caller-supplied stacks
+//   rows_gram       rows -> statistics (+ per-column min/max)
+//   reduce_partials fixed-order compensated reduction of per-warp partial statistics
+// The tiled TMA kernels in tiled.cu are the fast path; these cover every other shape, the
+// ragged edge blocks the tiled kernels leave out, and serve as their on-device cross-check.
+#include <math.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace pg {
+
+constexpr int GW = GW_WARPS;
+
+template <int LIB>
+__device__ __forceinline__ void eval_point(const K1Params &P, const double *F, int64_t i, int64_t j, PointVals &v) {
+    if constexpr (LIB == PG_LIB_BASIC) {
+        basic_point(F, P.A1, i + P.off, j + P.off, P.c, v);
+    } else {
+        ks_point<Lib<LIB>::BIH>(F, P.A0, P.A1, i, j, P.c, v);
+    }
+}
+
+__device__ __forceinline__ void fill_pairs(uint8_t *pa, uint8_t *pb, int p, int S) {
+    for (int e = threadIdx.x; e < S; e += blockDim.x) {
+        int a, b;
+        stats_pair(e, p, a, b);
+        pa[e] = (uint8_t)a;
+        pb[e] = (uint8_t)b;
+    }
+}
+
+template <int LIB>
+__global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
+    constexpr int p = Lib<LIB>::P;
+    constexpr int S = PG_STATS_LEN(p);
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wacc_all = sm;                                   // [GW][n_folds][S]
+    double *ext_all = wacc_all + GW * P.n_folds * S;         // [GW][32][p+2]
+    uint8_t *pa = reinterpret_cast<uint8_t *>(ext_all + GW * 32 * (p + 2));
+    uint8_t *pb = pa + S;
+    for (int e = threadIdx.x; e < GW * P.n_folds * S; e += blockDim.x) wacc_all[e] = 0.0;
+    fill_pairs(pa, pb, p, S);
+    __syncthreads();
+    double *wacc = wacc_all + warp * P.n_folds * S;
+    double *ext = ext_all + warp * 32 * (p + 2);
+
+    const int64_t n0 = P.tb_hi - P.tb_lo, n1 = P.i0_hi - P.i0_lo, n2 = P.i1_hi - P.i1_lo;
+    const int64_t total = n0 * n1 * n2;
+    const int64_t stride = (int64_t)gridDim.x * GW * 32;
+    const int64_t frame = P.A0 * P.A1;
+    const int64_t Trows = P.T - 1;
+    unsigned long long bad_rows = 0, bad_fold = 0;
+
+    for (int64_t base = ((int64_t)blockIdx.x * GW + warp) * 32; base < total; base += stride) {
+        const int64_t idx = base + lane;
+        bool valid = idx < total;
+        double th[p], y = 0.0;
+        int fold = 0;
+#pragma unroll
+        for (int k = 0; k < p; ++k) th[k] = 0.0;
+        if (valid) {
+            const int64_t jb = P.i1_lo + idx % n2;
+            const int64_t ib = P.i0_lo + (idx / n2) % n1;
+            const int64_t tb = P.tb_lo + idx / (n2 * n1);
+            const int64_t t0 = tb * P.bt, t1 = min(Trows, t0 + P.bt);
+            const int64_t i0 = ib * P.b0, i1 = min(P.R0, i0 + P.b0);
+            const int64_t j0 = jb * P.b1, j1 = min(P.R1, j0 + P.b1);
+            for (int64_t t = t0; t < t1; ++t) {
+                const double *F = P.U + t * frame;
+                const double *Fn = F + frame;
+                for (int64_t i = i0; i < i1; ++i)
+                    for (int64_t j = j0; j < j1; ++j) {
+                        PointVals v;
+                        eval_point<LIB>(P, F, i, j, v);
+                        double row[p];
+                        lib_row<LIB>(v, row);
+                        const int64_t o = (i + P.off) * P.A1 + (j + P.off);
+                        y = __dadd_rn(y, __ddiv_rn(__dsub_rn(Fn[o], F[o]), P.c.dt));
+#pragma unroll
+                        for (int k = 0; k < p; ++k) th[k] = __dadd_rn(th[k], row[k]);
+                    }
+            }
+            const double cnt = (double)((t1 - t0) * (i1 - i0) * (j1 - j0));
+            y = __ddiv_rn(y, cnt);
+            bool fin = isfinite(y);
+#pragma unroll
+            for (int k = 0; k < p; ++k) {
+                th[k] = __ddiv_rn(th[k], cnt);
+                fin = fin && isfinite(th[k]);
+            }
+            if (P.fold_of_row) fold = P.fold_of_row[(tb * P.nB0 + ib) * P.nB1 + jb];
+            else if (P.fold_of_frame) fold = P.fold_of_frame[t0];
+            if (!fin) { valid = false; ++bad_rows; }
+            else if (fold < 0 || fold >= P.n_folds) { valid = false; ++bad_fold; }
+        }
+        warp_accumulate_rows(wacc, ext, pa, pb, p, S, lane, valid, fold, th, y);
+    }
+    if (bad_rows) atomicAdd(&P.counters[0], bad_rows);
+    if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
+    double *out = P.partials + ((int64_t)blockIdx.x * GW + warp) * P.n_folds * S;
+    for (int e = lane; e < P.n_folds * S; e += 32) out[e] = wacc[e];
+}
+
+// out[e] (+)= sum over parts of partials[part][e], fixed order, Kahan-compensated.
+__global__ void reduce_partials_kernel(const double *__restrict__ partials, int64_t n_parts, int64_t len,
+                                       double *__restrict__ out, int accumulate) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    double s = accumulate ? out[e] : 0.0, comp = 0.0;
+    for (int64_t k = 0; k < n_parts; ++k) {
+        const double x = __dsub_rn(partials[k * len + e], comp);
+        const double t = __dadd_rn(s, x);
+        comp = __dsub_rn(__dsub_rn(t, s), x);
+        s = t;
+    }
+    out[e] = s;
+}
+
+// ----------------------------------------------------------------------------- term stacks
+template <int LIB>
+__global__ void fd_terms_ks_kernel(const double *__restrict__ U, int64_t T, int64_t A0, int64_t A1, FdConsts c,
+                                   double *__restrict__ out) {
+    constexpr int p = Lib<LIB>::P;
+    const int64_t frame = A0 * A1, total = T * frame;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = idx / frame, r = idx % frame;
+        PointVals v;
+        ks_point<Lib<LIB>::BIH>(U + t * frame, A0, A1, r / A1, r % A1, c, v);
+        double row[p];
+        lib_row<LIB>(v, row);
+#pragma unroll
+        for (int k = 0; k < p; ++k) out[k * total + idx] = row[k];
+    }
+}
+
+// compute_derivatives (basic:32-72): out = [u_t, u, u_x, u_y, lap], each [T-1][A0-4][A1-4]
+__global__ void fd_terms_basic_kernel(const double *__restrict__ U, int64_t T, int64_t A0, int64_t A1, FdConsts c,
+                                      double *__restrict__ out) {
+    const int64_t R0 = A0 - 4, R1 = A1 - 4, frame = A0 * A1, total = (T - 1) * R0 * R1;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = idx / (R0 * R1), r = idx % (R0 * R1);
+        const int64_t i = r / R1 + 2, j = r % R1 + 2;
+        const double *F = U + t * frame;
+        PointVals v;
+        basic_point(F, A1, i, j, c, v);
+        out[0 * total + idx] = __ddiv_rn(__dsub_rn(F[frame + i * A1 + j], F[i * A1 + j]), c.dt);
+        out[1 * total + idx] = v.u;
+        out[2 * total + idx] = v.g1;
+        out[3 * total + idx] = v.g0;
+        out[4 * total + idx] = v.lap;
+    }
+}
+
+template <int LIB>
+__global__ void fd_gather_kernel(K1Params P, const int64_t *__restrict__ flat_idx, int64_t n, double *__restrict__ X,
+                                 double *__restrict__ y) {
+    constexpr int p = Lib<LIB>::P;
+    const int64_t frame = P.A0 * P.A1, rs = P.R0 * P.R1, nrows = (P.T - 1) * rs;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t idx = flat_idx[k];
+        if (idx < 0 || idx >= nrows) {  // caller error; poison the row so it cannot pass silently
+            for (int c = 0; c < p; ++c) X[k * p + c] = nan("");
+            y[k] = nan("");
+            atomicAdd(&P.counters[1], 1ull);
+            continue;
+        }
+        const int64_t t = idx / rs, r = idx % rs, i = r / P.R1, j = r % P.R1;
+        const double *F = P.U + t * frame;
+        PointVals v;
+        eval_point<LIB>(P, F, i, j, v);
+        double row[p];
+        lib_row<LIB>(v, row);
+#pragma unroll
+        for (int c = 0; c < p; ++c) X[k * p + c] = row[c];
+        const int64_t o = (i + P.off) * P.A1 + (j + P.off);
+        y[k] = __ddiv_rn(__dsub_rn(F[frame + o], F[o]), P.c.dt);
+    }
+}
+
+// ----------------------------------------------------------------------------- block means of given stacks
+__global__ void block_means_kernel(const double *__restrict__ stack, int k, int64_t T, int64_t A0, int64_t A1, int bt,
+                                   int b0, int b1, int64_t nBt, int64_t nB0, int64_t nB1, double *__restrict__ out) {
+    const int64_t nrows = nBt * nB0 * nB1, total = nrows * k, vol = T * A0 * A1;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / k;
+        const int a = (int)(idx % k);
+        const int64_t jb = row % nB1, ib = (row / nB1) % nB0, tb = row / (nB1 * nB0);
+        const int64_t t0 = tb * bt, t1 = min(T, t0 + bt), i0 = ib * b0, i1 = min(A0, i0 + b0), j0 = jb * b1,
+                      j1 = min(A1, j0 + b1);
+        const double *src = stack + (int64_t)a * vol;
+        double s = 0.0;
+        for (int64_t t = t0; t < t1; ++t)
+            for (int64_t i = i0; i < i1; ++i)
+                for (int64_t j = j0; j < j1; ++j) s = __dadd_rn(s, src[(t * A0 + i) * A1 + j]);
+        out[idx] = __ddiv_rn(s, (double)((t1 - t0) * (i1 - i0) * (j1 - j0)));
+    }
+}
+
+// ----------------------------------------------------------------------------- rows -> statistics
+__global__ void __launch_bounds__(GW * 32) rows_gram_kernel(RowsParams P) {
+    const int p = P.p, S = PG_STATS_LEN(p), W = p + 2;
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wacc_all = sm;                                 // [GW][n_folds][S]
+    double *ext_all = wacc_all + GW * P.n_folds * S;       // [GW][32][p+2]
+    double *mm_all = ext_all + GW * 32 * W;                // [GW][n_folds][2][p]
+    uint8_t *pa = reinterpret_cast<uint8_t *>(mm_all + GW * P.n_folds * 2 * p);
+    uint8_t *pb = pa + S;
+    for (int e = threadIdx.x; e < GW * P.n_folds * S; e += blockDim.x) wacc_all[e] = 0.0;
+    for (int e = threadIdx.x; e < GW * P.n_folds * 2 * p; e += blockDim.x)
+        mm_all[e] = ((e / p) & 1) ? -INFINITY : INFINITY;
+    fill_pairs(pa, pb, p, S);
+    __syncthreads();
+    double *wacc = wacc_all + warp * P.n_folds * S;
+    double *ext = ext_all + warp * 32 * W;
+    double *mm = mm_all + warp * P.n_folds * 2 * p;
+
+    const int64_t b = blockIdx.x / P.chunks;
+    const int chunk = (int)(blockIdx.x % P.chunks);
+    const double *Xb = P.X + b * P.n * P.ldx;
+    const double *yb = P.y + b * P.n;
+    const uint8_t *fb = P.fold_of_row ? P.fold_of_row + b * P.n : nullptr;
+    const double *sh = P.shift ? P.shift + b * p : nullptr;
+    const int64_t stride = (int64_t)P.chunks * GW * 32;
+    unsigned long long bad_fold = 0;
+    for (int64_t base = ((int64_t)chunk * GW + warp) * 32; base < P.n; base += stride) {
+        const int64_t r = base + lane;
+        bool valid = r < P.n;
+        int fold = 0;
+        ext[lane * W] = 1.0;
+        if (valid) {
+            ext[lane * W + 1] = yb[r];
+            for (int j = 0; j < p; ++j) ext[lane * W + 2 + j] = sh ? __dsub_rn(Xb[r * P.ldx + j], sh[j]) : Xb[r * P.ldx + j];
+            if (fb) fold = fb[r];
+            if (fold >= P.n_folds) { valid = false; ++bad_fold; }
+        }
+        __syncwarp();
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        for (int l = 0; l < 32; ++l) {
+            if (!((vmask >> l) & 1u)) continue;
+            const int f = __shfl_sync(0xffffffffu, fold, l);
+            const double *row = ext + l * W;
+            double *acc = wacc + f * S;
+            for (int e = lane; e < S; e += 32) acc[e] = fma(row[pa[e]], row[pb[e]], acc[e]);
+            if (lane < p) {
+                // min/max of the UNSHIFTED column values
+                const double xv = sh ? Xb[(base + l) * P.ldx + lane] : row[2 + lane];
+                double *m = mm + f * 2 * p;
+                m[lane] = fmin(m[lane], xv);
+                m[p + lane] = fmax(m[p + lane], xv);
+            }
+        }
+        __syncwarp();
+    }
+    if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
+    const int64_t part = (b * P.chunks + chunk) * GW + warp;
+    double *out = P.partials + part * P.n_folds * S;
+    for (int e = lane; e < P.n_folds * S; e += 32) out[e] = wacc[e];
+    if (P.mm_partials) {
+        double *mo = P.mm_partials + part * P.n_folds * 2 * p;
+        for (int e = lane; e < P.n_folds * 2 * p; e += 32) mo[e] = mm[e];
+    }
+}
+
+// per problem: stats[b][e] = sum_k partials[b][k][e];  colminmax likewise with min / max
+__global__ void rows_reduce_kernel(const double *__restrict__ partials, const double *__restrict__ mm_partials,
+                                   int64_t B, int parts, int len, int mmlen, int p, double *__restrict__ stats,
+                                   double *__restrict__ colminmax) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < B * len) {
+        const int64_t b = idx / len, e = idx % len;
+        double s = 0.0, comp = 0.0;
+        for (int k = 0; k < parts; ++k) {
+            const double x = __dsub_rn(partials[(b * parts + k) * len + e], comp);
+            const double t = __dadd_rn(s, x);
+            comp = __dsub_rn(__dsub_rn(t, s), x);
+            s = t;
+        }
+        stats[idx] = s;
+    }
+    if (colminmax && idx < B * mmlen) {
+        const int64_t b = idx / mmlen, e = idx % mmlen;
+        const bool is_max = ((e / p) & 1) != 0;
+        double m = is_max ? -INFINITY : INFINITY;
+        for (int k = 0; k < parts; ++k) {
+            const double x = mm_partials[(b * parts + k) * mmlen + e];
+            m = is_max ? fmax(m, x) : fmin(m, x);
+        }
+        colminmax[idx] = m;
+    }
+}
+
+// ----------------------------------------------------------------------------- host launchers
+static int grid_for(int64_t work_items, int per_cta, int max_ctas) {
+    int64_t g = (work_items + per_cta - 1) / per_cta;
+    if (g < 1) g = 1;
+    if (g > max_ctas) g = max_ctas;
+    return (int)g;
+}
+
+template <int LIB> static int launch_k1_generic_t(const K1Params &P, int n_parts_cta, cudaStream_t st) {
+    constexpr int p = Lib<LIB>::P;
+    constexpr int S = PG_STATS_LEN(p);
+    const size_t smem = sizeof(double) * (GW * P.n_folds * S + GW * 32 * (p + 2)) + 2 * S + 16;
+    PG_CUDA(cudaFuncSetAttribute(k1_generic_kernel<LIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_generic_kernel<LIB><<<n_parts_cta, GW * 32, smem, st>>>(P);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st) {
+    switch (lib) {
+        case PG_LIB_KS_TRUE: return launch_k1_generic_t<PG_LIB_KS_TRUE>(P, ctas, st);
+        case PG_LIB_KS_TRUE_ADV: return launch_k1_generic_t<PG_LIB_KS_TRUE_ADV>(P, ctas, st);
+        case PG_LIB_KS_RICH: return launch_k1_generic_t<PG_LIB_KS_RICH>(P, ctas, st);
+        case PG_LIB_KS_RICH_NOADV: return launch_k1_generic_t<PG_LIB_KS_RICH_NOADV>(P, ctas, st);
+        case PG_LIB_BASIC: return launch_k1_generic_t<PG_LIB_BASIC>(P, ctas, st);
+        default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_lib_gram", lib);
+    }
+}
+
+int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate,
+                           cudaStream_t st) {
+    reduce_partials_kernel<<<(unsigned)((len + 127) / 128), 128, 0, st>>>(partials, n_parts, len, out, accumulate);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+int launch_fd_terms(int dialect, int lib, const double *U, int64_t T, int64_t A0, int64_t A1, const FdConsts &c,
+                    double *out, cudaStream_t st) {
+    if (dialect == PG_FD_BASIC_TRIM) {
+        const int64_t total = (T - 1) * (A0 - 4) * (A1 - 4);
+        if (total <= 0) return PG_OK;
+        fd_terms_basic_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, st>>>(U, T, A0, A1, c, out);
+    } else {
+        const int64_t total = T * A0 * A1;
+        if (total <= 0) return PG_OK;
+        const int g = grid_for(total, 256, 148 * 16);
+        switch (lib) {
+#define PG_CASE(L) case L: fd_terms_ks_kernel<L><<<g, 256, 0, st>>>(U, T, A0, A1, c, out); break;
+            PG_CASE(PG_LIB_KS_TRUE) PG_CASE(PG_LIB_KS_TRUE_ADV) PG_CASE(PG_LIB_KS_RICH) PG_CASE(PG_LIB_KS_RICH_NOADV)
+            PG_CASE(PG_LIB_KS_GRAD) PG_CASE(PG_LIB_KS_LAP)
+#undef PG_CASE
+            default: PG_FAIL(PG_EINVAL, "library %d is not a KS-dialect library", lib);
+        }
+    }
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+int launch_fd_gather(int lib, const K1Params &P, const int64_t *flat_idx, int64_t n, double *X, double *y,
+                     cudaStream_t st) {
+    if (n <= 0) return PG_OK;
+    const int g = grid_for(n, 128, 148 * 8);
+    switch (lib) {
+#define PG_CASE(L) case L: fd_gather_kernel<L><<<g, 128, 0, st>>>(P, flat_idx, n, X, y); break;
+        PG_CASE(PG_LIB_KS_TRUE) PG_CASE(PG_LIB_KS_TRUE_ADV) PG_CASE(PG_LIB_KS_RICH) PG_CASE(PG_LIB_KS_RICH_NOADV)
+        PG_CASE(PG_LIB_BASIC)
+#undef PG_CASE
+        default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_gather_rows", lib);
+    }
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+int launch_block_means(const double *stack, int k, int64_t T, int64_t A0, int64_t A1, int bt, int b0, int b1,
+                       double *out, cudaStream_t st) {
+    const int64_t nBt = (T + bt - 1) / bt, nB0 = (A0 + b0 - 1) / b0, nB1 = (A1 + b1 - 1) / b1;
+    const int64_t total = nBt * nB0 * nB1 * k;
+    if (total <= 0) return PG_OK;
+    block_means_kernel<<<grid_for(total, 128, 148 * 16), 128, 0, st>>>(stack, k, T, A0, A1, bt, b0, b1, nBt, nB0, nB1,
+                                                                      out);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+size_t rows_gram_smem(int p, int n_folds) {
+    const int S = PG_STATS_LEN(p);
+    return sizeof(double) * (GW * n_folds * S + GW * 32 * (p + 2) + GW * n_folds * 2 * p) + 2 * S + 16;
+}
+
+int launch_rows_gram(const RowsParams &P, double *stats, double *colminmax, cudaStream_t st) {
+    const int S = PG_STATS_LEN(P.p);
+    const size_t smem = rows_gram_smem(P.p, P.n_folds);
+    PG_CUDA(cudaFuncSetAttribute(rows_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rows_gram_kernel<<<(unsigned)(P.chunks * P.B), GW * 32, smem, st>>>(P);
+    PG_CUDA(cudaGetLastError());
+    const int len = P.n_folds * S, mmlen = P.n_folds * 2 * P.p;
+    const int64_t work = P.B * (int64_t)(len > mmlen ? len : mmlen);
+    rows_reduce_kernel<<<(unsigned)((work + 127) / 128), 128, 0, st>>>(P.partials, P.mm_partials, P.B, P.chunks * GW,
+                                                                       len, mmlen, P.p, stats, colminmax);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+}  // namespace pg

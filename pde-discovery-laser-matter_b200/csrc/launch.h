@@ -1,0 +1,84 @@
+// Parameter blocks and host launchers shared between api.cu and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace pg {
+
+constexpr int GW_WARPS = 4;                 // warps per CTA in the generic kernels
+constexpr int GW_THREADS = GW_WARPS * 32;
+
+struct K1Params {
+    const double *U;
+    int64_t T, A0, A1;
+    FdConsts c;
+    int dialect;
+    int bt, b0, b1;
+    int64_t R0, R1;        // row-space extents along a0/a1 (A0,A1 for KS; A0-4,A1-4 for BASIC)
+    int64_t off;           // index offset of the row space inside a frame (0 for KS, 2 for BASIC)
+    int64_t nB0, nB1;      // number of blocks along a0/a1 (ceil)
+    int64_t tb_lo, tb_hi, i0_lo, i0_hi, i1_lo, i1_hi;  // block-index ranges this launch covers
+    const uint8_t *fold_of_row;
+    const int32_t *fold_of_frame;
+    int n_folds;
+    double *partials;               // [parts][n_folds][S]
+    unsigned long long *counters;   // [0] non-finite rows, [1] rows with an out-of-range fold id / index
+};
+
+struct RowsParams {
+    const double *X, *y;
+    int64_t B, n, ldx;
+    int p;
+    const uint8_t *fold_of_row;  // [B][n] or null
+    int n_folds;
+    const double *shift;         // [B][p] or null: statistics are of (X - shift)
+    int chunks;                  // CTAs per problem
+    double *partials;            // [B][chunks*GW_WARPS][n_folds][S]
+    double *mm_partials;         // [B][chunks*GW_WARPS][n_folds][2][p] or null
+    unsigned long long *counters;
+};
+
+struct StridgeParams {
+    const double *stats;     // [B][S]
+    int64_t B;
+    int p, dialect, flags;
+    const double *alphas; int na;
+    const double *thrs; int nt;
+    int max_iter;
+    const uint8_t *const_mask;   // [p] or null
+    const double *colminmax;     // [B][2][p] or null
+    const double *shift;         // [B][p] or null
+    const double *eval_stats;    // [B][S] or null
+    double *coef_out;            // [B][na][nt][p]
+    double *metrics_out;         // [B][na][nt][2] or null
+};
+
+// What the tiled kernel covers: block indices [0,nbt) x [0,nb0) x [0,nb1) of the row space.
+struct TiledPlan {
+    int64_t nbt, nb0, nb1;
+    int64_t n_parts;        // partial-statistics slots it writes
+    size_t extra_scratch;   // bytes of scratch beyond the partials (tensor maps, work counters)
+    int kernel_id;          // which specialisation
+    int grid;
+    int tile0, tile1, chunk_t;
+    int64_t n_tiles0, n_tiles1, n_chunks;
+};
+
+int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st);
+int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate, cudaStream_t st);
+int launch_fd_terms(int dialect, int lib, const double *U, int64_t T, int64_t A0, int64_t A1, const FdConsts &c, double *out, cudaStream_t st);
+int launch_fd_gather(int lib, const K1Params &P, const int64_t *flat_idx, int64_t n, double *X, double *y, cudaStream_t st);
+int launch_block_means(const double *stack, int k, int64_t T, int64_t A0, int64_t A1, int bt, int b0, int b1, double *out, cudaStream_t st);
+int launch_rows_gram(const RowsParams &P, double *stats, double *colminmax, cudaStream_t st);
+int launch_stridge(const StridgeParams &P, int32_t *best_out, cudaStream_t st);
+int launch_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, const int32_t *pts, int64_t n, const double *W6, int rt, int rs, int mode, double *X, double *y, unsigned long long *counters, cudaStream_t st);
+int launch_synth(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total, uint64_t seed, int kind, double noise, cudaStream_t st);
+
+// tiled.cu
+bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan);
+int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st);
+
+}  // namespace pg

@@ -1,0 +1,121 @@
+// K2 -- local-polynomial derivative rows (patch:193-280) as a fixed (2rt+1)(2rs+1)^2-tap stencil,
+// and the synthetic-field generator used for the large benchmark stacks.
+#include <math.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace pg {
+
+constexpr int PW = 8;  // warps per CTA
+
+template <typename TIn>
+__global__ void __launch_bounds__(PW * 32) poly_rows_kernel(const TIn *__restrict__ U, int64_t T, int64_t H, int64_t W,
+                                                           const int32_t *__restrict__ pts, int64_t n,
+                                                           const double *__restrict__ W6, int rt, int rs, int mode,
+                                                           double *__restrict__ X, double *__restrict__ y,
+                                                           unsigned long long *counters) {
+    extern __shared__ double wsm[];  // [6][nnb]
+    const int side = 2 * rs + 1, nnb = (2 * rt + 1) * side * side;
+    for (int e = threadIdx.x; e < 6 * nnb; e += blockDim.x) wsm[e] = W6[e];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = mode == 1 ? 8 : 6;  // mode 0 = model4, 1 = full, 2 = raw derivatives
+    for (int64_t k = (int64_t)blockIdx.x * PW + warp; k < n; k += (int64_t)gridDim.x * PW) {
+        const int64_t t0 = pts[3 * k], y0 = pts[3 * k + 1], x0 = pts[3 * k + 2];
+        const bool ok = t0 - rt >= 0 && t0 + rt < T && y0 - rs >= 0 && y0 + rs < H && x0 - rs >= 0 && x0 + rs < W;
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        if (ok) {
+            for (int e = lane; e < nnb; e += 32) {
+                const int ox = e % side, oy = (e / side) % side, ot = e / (side * side);
+                const double v = (double)U[((t0 - rt + ot) * H + (y0 - rs + oy)) * W + (x0 - rs + ox)];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) acc[q] = fma(wsm[q * nnb + e], v, acc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) {
+            if (!ok) {  // the reference would raise on an out-of-range neighbourhood; poison the row
+                for (int c = 0; c < p; ++c) X[k * p + c] = nan("");
+                y[k] = nan("");
+                atomicAdd(&counters[1], 1ull);
+            } else {
+                const double u = acc[0], ux = acc[2], uy = acc[3], lap = __dadd_rn(acc[4], acc[5]);
+                double *r = X + k * p;
+                if (mode == 2) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) r[q] = acc[q];
+                } else {
+                    r[0] = 1.0; r[1] = u; r[2] = ux; r[3] = uy; r[4] = lap; r[5] = __dmul_rn(u, u);
+                    if (mode == 1) { r[6] = __dmul_rn(u, ux); r[7] = __dmul_rn(u, uy); }
+                }
+                y[k] = acc[1];
+            }
+        }
+    }
+}
+
+int launch_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, const int32_t *pts, int64_t n,
+                     const double *W6, int rt, int rs, int mode, double *X, double *y, unsigned long long *counters,
+                     cudaStream_t st) {
+    if (n <= 0) return PG_OK;
+    const int side = 2 * rs + 1, nnb = (2 * rt + 1) * side * side;
+    const size_t smem = sizeof(double) * 6 * nnb;
+    int64_t g = (n + PW - 1) / PW;
+    if (g > 148 * 8) g = 148 * 8;
+    if (dtype == 0) {
+        PG_CUDA(cudaFuncSetAttribute(poly_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        poly_rows_kernel<float><<<(unsigned)g, PW * 32, smem, st>>>((const float *)U, T, H, W, pts, n, W6, rt, rs, mode,
+                                                                    X, y, counters);
+    } else {
+        PG_CUDA(cudaFuncSetAttribute(poly_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        poly_rows_kernel<double><<<(unsigned)g, PW * 32, smem, st>>>((const double *)U, T, H, W, pts, n, W6, rt, rs,
+                                                                     mode, X, y, counters);
+    }
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+// ----------------------------------------------------------------------------- synthetic field
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void synth_kernel(double *__restrict__ U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total,
+                             uint64_t seed, int kind, double noise) {
+    const int64_t frame = A0 * A1, total = T * frame;
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tl = idx / frame, r = idx % frame, i = r / A1, j = r % A1;
+        const int64_t t = tl + t_offset;
+        const double a = two_pi * (double)i / (double)A0, b = two_pi * (double)j / (double)A1;
+        const double s = two_pi * (double)t / (double)(T_total > 0 ? T_total : 1);
+        // a few travelling waves with integer wave numbers (periodic in a0, a1)
+        double v = 0.50 * sin(3.0 * a + 2.0 * b - 5.0 * s) + 0.30 * sin(7.0 * a - 4.0 * b + 3.0 * s + 0.7) +
+                   0.15 * sin(13.0 * a + 11.0 * b - 9.0 * s + 1.9) + 0.05 * cos(29.0 * a - 17.0 * b + 2.0 * s);
+        const uint64_t hsh = splitmix64(seed ^ splitmix64((uint64_t)t * 0x100000001B3ull + (uint64_t)r));
+        const double un = (double)(hsh >> 11) * (1.0 / 9007199254740992.0) - 0.5;  // U(-0.5, 0.5)
+        v += noise * un;
+        U[idx] = kind == 1 ? 0.5 + 0.4 * v : v;
+    }
+}
+
+int launch_synth(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total, uint64_t seed,
+                 int kind, double noise, cudaStream_t st) {
+    const int64_t total = T * A0 * A1;
+    if (total <= 0) return PG_OK;
+    int64_t g = (total + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    synth_kernel<<<(unsigned)g, 256, 0, st>>>(U, T, A0, A1, t_offset, T_total, seed, kind, noise);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+}  // namespace pg

@@ -1,0 +1,224 @@
+"""Drop-in for the hot-path functions of scripts/ks2d_stridge_benchmark.py ("ks2d").
+
+Same names, argument meaning and error behaviour as the reference; every function runs on
+the GPU through libpdegram.so and returns NumPy arrays of the reference's shape and dtype.
+``fit_from_field`` is the fused fast path (field -> statistics -> STRidge, Theta never
+materialised) that restates the reference's main() hot path (ks2d:1508-1743).
+
+Layout: ``U[t, x, y]`` with "x" on frame axis 0 (ks2d:70-73, ks2d:1295).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from . import ops
+
+RICH_NAMES = ["1", "u", "u^2", "u_x", "u_y", "∇²u", "∇⁴u", "|∇u|²", "u·∇²u"]  # ks2d:1048-1059
+TRUE_NAMES = ["∇²u", "∇⁴u", "|∇u|²"]                                         # ks2d:1095-1099
+ADV_NAMES = TRUE_NAMES + ["u_x", "u_y"]                                       # ks2d:1100-1102
+RICH_NOADV_NAMES = [n for n in RICH_NAMES if n not in ("u_x", "u_y")]         # ks2d:1536-1539
+GRID_ALPHAS = (1e-6, 1e-5, 1e-4, 1e-3, 1e-2)                                  # ks2d:1721
+GRID_THRESHOLDS = (1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5)                       # ks2d:1722
+
+_LIB_OF = {"true": (L.LIB_KS_TRUE, TRUE_NAMES), "true_adv": (L.LIB_KS_TRUE_ADV, ADV_NAMES),
+           "rich": (L.LIB_KS_RICH, RICH_NAMES), "rich_noadv": (L.LIB_KS_RICH_NOADV, RICH_NOADV_NAMES)}
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _frame(f2d):
+    f = np.asarray(f2d, dtype=np.float64)
+    if f.ndim != 2:
+        raise ValueError("expected a 2-D frame")
+    return f[None]
+
+
+# ------------------------------------------------------------------ stencils (ks2d:63-73)
+def laplacian(f2d, dx: float, dy: float):
+    """ks2d:63-67: periodic 5-point Laplacian of one frame."""
+    return _np(ops.fd_terms(_frame(f2d), dx, dy, 1.0, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_LAP))[0, 0]
+
+
+def gradients(f2d, dx: float, dy: float):
+    """ks2d:70-73: periodic central differences (gx along axis 0, gy along axis 1)."""
+    g = _np(ops.fd_terms(_frame(f2d), dx, dy, 1.0, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_GRAD))
+    return g[0, 0], g[1, 0]
+
+
+# ------------------------------------------------------------------ dictionaries (ks2d:1017-1104)
+def _dictionary(U, dx, dy, deriv, key):
+    if deriv != "finite":
+        raise NotImplementedError("only deriv='finite' is GPU-accelerated; the spectral path has no CPU fallback here")
+    lib, names = _LIB_OF[key]
+    terms = _np(ops.fd_terms(U, dx, dy, 1.0, dialect=L.FD_KS_PERIODIC, library=lib))
+    return list(names), {n: terms[k] for k, n in enumerate(names)}
+
+
+def build_dictionary(U_mid, dx: float, dy: float, *, deriv: str = "finite", spectral_cutoff: float = 1.0):
+    """ks2d:1017-1060: the p=9 rich dictionary; returns (names, {name: (T,Nx,Ny) array})."""
+    return _dictionary(U_mid, dx, dy, deriv, "rich")
+
+
+def build_dictionary_true(U_frames, dx: float, dy: float, *, deriv: str = "finite", spectral_cutoff: float = 1.0,
+                          include_advection: bool = False):
+    """ks2d:1063-1104: [lap, bih, |grad|^2] (+ u_x, u_y)."""
+    return _dictionary(U_frames, dx, dy, deriv, "true_adv" if include_advection else "true")
+
+
+# ------------------------------------------------------------------ blockwise means (ks2d:358-401)
+def build_blockwise_dataset(Ut, terms, names, *, block_t: int, block_x: int, block_y: int):
+    """ks2d:358-401: mean of Ut and of each term over (bt,bx,by) blocks, ragged trailing
+    blocks kept, rows with a non-finite mean dropped."""
+    Ut = np.asarray(Ut)
+    if Ut.ndim != 3:
+        raise ValueError("Ut must be (T, Nx, Ny)")
+    bt, bx, by = int(block_t), int(block_x), int(block_y)
+    if bt <= 0 or bx <= 0 or by <= 0:
+        raise ValueError("block sizes must be > 0")
+    torch = L.torch_cuda()
+    stack = torch.stack([ops._dev(Ut, torch.float64)] + [ops._dev(terms[n], torch.float64) for n in names])
+    rows = _np(ops.block_means(stack, (bt, bx, by)))
+    keep = np.isfinite(rows).all(axis=1)
+    if not keep.any():
+        return np.zeros((0, len(names)), dtype=np.float64), np.zeros((0,), dtype=np.float64)
+    return rows[keep, 1:].copy(), rows[keep, 0].copy()
+
+
+# ------------------------------------------------------------------ STRidge (ks2d:43-60, 404-428)
+def _stats_of_rows(X, y):
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if X.ndim != 2 or y.shape != (X.shape[0],):
+        raise ValueError("X must be (n, p) and y (n,)")
+    if X.shape[1] > L.PG_MAX_P:
+        raise ValueError(f"at most {L.PG_MAX_P} columns are supported")
+    shift = X[:1].copy()
+    stats, mm = ops.rows_gram(X, y, shift=shift, want_minmax=True)
+    return stats[:, 0], mm[:, 0], shift
+
+
+def standardize_fit(X):
+    """ks2d:43-48: (mean, population std with 0 -> 1) per column, from GPU statistics."""
+    X = np.asarray(X, dtype=np.float64)
+    stats, mm, shift = _stats_of_rows(X, np.zeros(X.shape[0]))
+    s, mm = _np(stats)[0], _np(mm)[0]
+    p, n = X.shape[1], s[0]
+    mu = s[3:3 + p] / n
+    diag = np.array([s[3 + 2 * p + i * p - (i * (i - 1)) // 2] for i in range(p)])
+    var = np.maximum(diag / n - mu * mu, 0.0)
+    scale = np.sqrt(var)
+    scale[(mm[0] == mm[1]) | ~(scale > 0)] = 1.0
+    return mu + shift[0], scale
+
+
+def ridge_fit(X, y, alpha: float):
+    """ks2d:55-60: solve (X^T X + alpha I) b = X^T y (LU with partial pivoting on the GPU)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    stats = ops.rows_gram(X, np.asarray(y, dtype=np.float64))[:, 0]
+    out = ops.stridge_batched(stats, X.shape[1], dialect=L.STRIDGE_BASIC, alphas=[alpha], thresholds=[0.0], max_iter=1)
+    return _np(out["coef"])[0, 0, 0]
+
+
+def stridge(X, y, *, alpha: float = 1e-3, threshold: float = 1e-6, max_iter: int = 25):
+    """ks2d:404-428 on the GPU: rows -> statistics (pg_rows_gram) -> K3 (pg_stridge_batched)."""
+    stats, mm, shift = _stats_of_rows(X, y)
+    out = ops.stridge_batched(stats, np.asarray(X).shape[1], dialect=L.STRIDGE_KS, alphas=[alpha],
+                              thresholds=[threshold], max_iter=int(max_iter), colminmax=mm, shift=shift)
+    return _np(out["coef"])[0, 0, 0]
+
+
+# ------------------------------------------------------------------ fused path (ks2d:1508-1743)
+def library_of(dictionary: str, include_advection: bool = False, enforce_no_advection: bool = False):
+    if dictionary == "true":
+        return _LIB_OF["true_adv" if (include_advection and not enforce_no_advection) else "true"]
+    return _LIB_OF["rich_noadv" if enforce_no_advection else "rich"]
+
+
+def split_folds(n_rows: int, rng):
+    """ks2d:1638-1641 as a fold vector: 0 = train (first 70 % of the permutation), 1 = test."""
+    perm = rng.permutation(n_rows)
+    split = int(0.7 * n_rows)
+    fold = np.ones(n_rows, dtype=np.uint8)
+    fold[perm[:split]] = 0
+    return fold, perm
+
+
+def fit_from_stats(stats_train, stats_test, names, *, alpha=1e-6, threshold=1e-10, grid_search=False, max_iter=25):
+    """ks2d:1647-1779 on statistics: train-RMS scale, STRidge (or the 5x6 sweep), held-out
+    r2/rmse and the reference's arg-max, all inside pg_stridge_batched."""
+    p = len(names)
+    const_cols = [j for j, n in enumerate(names) if n == "1"]
+    alphas = GRID_ALPHAS if grid_search else (alpha,)
+    thrs = GRID_THRESHOLDS if grid_search else (threshold,)
+    out = ops.stridge_batched(stats_train, p, dialect=L.STRIDGE_KS, flags=L.STRIDGE_RMS_PRESCALE, alphas=alphas,
+                              thresholds=thrs, max_iter=max_iter, const_cols=const_cols, eval_stats=stats_test)
+    coef, met, best = _np(out["coef"])[0], _np(out["metrics"])[0], int(_np(out["best"])[0])
+    ia, it = divmod(best, len(thrs))
+    c = coef[ia, it]
+    return dict(names=list(names), alpha=alphas[ia], threshold=thrs[it], coeffs=c, r2_test=float(met[ia, it, 0]),
+                rmse_test=float(met[ia, it, 1]), n_active=int(np.sum(np.abs(c) > 0)),
+                table=[(alphas[a], thrs[t], float(met[a, t, 0]), float(met[a, t, 1]),
+                        int(np.sum(np.abs(coef[a, t]) > 0))) for a in range(len(alphas)) for t in range(len(thrs))],
+                coef_grid=coef)
+
+
+def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", include_advection=False,
+                   enforce_no_advection=False, block=(3, 8, 8), n_sample=50_000, alpha=1e-6, threshold=1e-10,
+                   grid_search=False, fold_of_frame=None, seed=0, variant=L.VARIANT_AUTO):
+    """The reference's main() hot path for one config, fused on the GPU.
+
+    method="blockwise": K1 forms block means and both folds' Grams in one pass over U; the
+        70/30 row permutation (ks2d:1638-1641) stays on the host RNG and is passed as one fold
+        byte per block row.
+    method="pointwise": the 50 000-point sample (ks2d:1625-1636) is gathered by K1c, then split.
+    method="full": every grid point is a row and ``fold_of_frame`` gives time-holdout folds
+        (0 = train, 1 = test); this is the large-stack configuration C4/C5.
+    """
+    lib, names = library_of(dictionary, include_advection, enforce_no_advection)
+    torch = L.torch_cuda()
+    Ud = ops.field(U)
+    T, A0, A1 = Ud.shape
+    rng = np.random.default_rng(seed)  # ks2d:1470
+    info = {}
+    if method == "blockwise":
+        bt, b0, b1 = block
+        n_rows = -(-(T - 1) // bt) * -(-A0 // b0) * -(-A1 // b1)
+        fold, _ = split_folds(n_rows, rng)
+        stats, bad = ops.fd_lib_gram(Ud, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib, block=block,
+                                     fold_of_row=fold, n_folds=2, variant=variant, return_nonfinite=True)
+        if int(bad.item()):
+            # non-finite rows renumber the reference's permutation: redo through materialised block rows
+            terms = ops.fd_terms(Ud[:-1], dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib)
+            Ut = ((Ud[1:] - Ud[:-1]) / DT)[None]
+            rows = ops.block_means(torch.cat([Ut, terms]), block)
+            rows = rows[torch.isfinite(rows).all(dim=1)]
+            rng = np.random.default_rng(seed)
+            fold, _ = split_folds(rows.shape[0], rng)
+            stats = ops.rows_gram(rows[:, 1:].contiguous(), rows[:, 0].contiguous(), fold_of_row=fold, n_folds=2)[0]
+            n_rows = rows.shape[0]
+        info["X_shape"] = (n_rows, len(names))
+    elif method == "pointwise":
+        n_total = (T - 1) * A0 * A1
+        flat_idx = rng.choice(n_total, size=int(min(n_sample, n_total)), replace=False)
+        X, y = ops.fd_gather_rows(Ud, dx, dy, DT, flat_idx, dialect=L.FD_KS_PERIODIC, library=lib)
+        ok = torch.isfinite(X).all(dim=1) & torch.isfinite(y)
+        if not bool(ok.all()):
+            X, y = X[ok].contiguous(), y[ok].contiguous()
+        fold, _ = split_folds(X.shape[0], rng)
+        stats = ops.rows_gram(X, y, fold_of_row=fold, n_folds=2)[0]
+        info["X_shape"] = tuple(X.shape)
+    elif method == "full":
+        if fold_of_frame is None:
+            raise ValueError("method='full' needs fold_of_frame (time-holdout folds)")
+        stats = ops.fd_lib_gram(Ud, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib, block=(1, 1, 1),
+                                fold_of_frame=fold_of_frame, n_folds=2, variant=variant)
+        info["X_shape"] = ((T - 1) * A0 * A1, len(names))
+    else:
+        raise ValueError(method)
+    out = fit_from_stats(stats[0], stats[1], names, alpha=alpha, threshold=threshold, grid_search=grid_search)
+    out.update(info, stats=_np(stats))
+    return out

@@ -1,0 +1,194 @@
+"""Device-level operators: one Python function per C-ABI entry point of libpdegram.so.
+
+Inputs may be NumPy arrays (copied to the current CUDA device) or torch CUDA tensors (used
+in place); outputs are torch CUDA tensors.  All calls are asynchronous on torch's current
+stream.  The dialect modules (ks2d, basic_usage, patch) build the reference signatures on
+top of these.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _dev(a, dtype=None):
+    """NumPy array / torch tensor -> contiguous CUDA tensor of `dtype` (torch dtype)."""
+    torch = L.torch_cuda()
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        t = a
+        if not t.is_cuda:
+            t = t.cuda()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def field(U):
+    """A (T, A0, A1) float64 stack on the device."""
+    torch = L.torch_cuda()
+    t = _dev(U, torch.float64)
+    if t.ndim != 3:
+        raise ValueError("field must be (T, A0, A1)")
+    return t
+
+
+def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row=None, fold_of_frame=None,
+                n_folds=1, variant=L.VARIANT_AUTO, return_nonfinite=False):
+    """K1: field -> statistics [n_folds][S(p)] without materialising Theta (pg_fd_lib_gram)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, A0, A1 = U.shape
+    p = L.LIB_WIDTH[library]
+    bt, b0, b1 = (int(b) for b in block)
+    fr = _dev(fold_of_row, torch.uint8)
+    ff = _dev(fold_of_frame, torch.int32)
+    if fr is not None:
+        R0, R1 = (A0, A1) if dialect == L.FD_KS_PERIODIC else (A0 - 4, A1 - 4)
+        nrows = -(-(T - 1) // bt) * -(-R0 // b0) * -(-R1 // b1)
+        if fr.numel() != nrows:
+            raise ValueError(f"fold_of_row has {fr.numel()} entries, the block grid has {nrows} rows")
+    if ff is not None and ff.numel() != T - 1:
+        raise ValueError(f"fold_of_frame must have T-1 = {T - 1} entries")
+    stats = torch.empty((n_folds, L.stats_len(p)), dtype=torch.float64, device=U.device)
+    bad = torch.zeros(1, dtype=torch.int64, device=U.device)
+    L.check(lib.pg_fd_lib_gram(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0, b1,
+                               L.ptr(fr), L.ptr(ff), n_folds, L.ptr(stats), L.ptr(bad), variant, L.stream_ptr()))
+    return (stats, bad) if return_nonfinite else stats
+
+
+def fd_terms(U, d0, d1, dt, *, dialect, library):
+    """Materialised term stacks (pg_fd_terms): KS -> [p][T][A0][A1]; BASIC -> [5][T-1][A0-4][A1-4]."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, A0, A1 = U.shape
+    if dialect == L.FD_BASIC_TRIM:
+        shape = (5, max(T - 1, 0), max(A0 - 4, 0), max(A1 - 4, 0))
+    else:
+        shape = (L.LIB_WIDTH[library], T, A0, A1)
+    out = torch.empty(shape, dtype=torch.float64, device=U.device)
+    L.check(lib.pg_fd_terms(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, L.ptr(out),
+                            L.stream_ptr()))
+    return out
+
+
+def fd_gather_rows(U, d0, d1, dt, flat_idx, *, dialect, library):
+    """K1c: sampled pointwise rows (pg_fd_gather_rows) -> (X [n][p], y [n])."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, A0, A1 = U.shape
+    idx = _dev(flat_idx, torch.int64)
+    n, p = idx.numel(), L.LIB_WIDTH[library]
+    X = torch.empty((n, p), dtype=torch.float64, device=U.device)
+    y = torch.empty((n,), dtype=torch.float64, device=U.device)
+    L.check(lib.pg_fd_gather_rows(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, L.ptr(idx), n,
+                                  L.ptr(X), L.ptr(y), L.stream_ptr()))
+    return X, y
+
+
+def block_means(stack, block):
+    """pg_block_means: [k][T][A0][A1] -> [nrows][k] in reference row order."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    s = _dev(stack, torch.float64)
+    k, T, A0, A1 = s.shape
+    bt, b0, b1 = (int(b) for b in block)
+    if bt <= 0 or b0 <= 0 or b1 <= 0:
+        raise ValueError("block sizes must be > 0")
+    nrows = -(-T // bt) * -(-A0 // b0) * -(-A1 // b1)
+    out = torch.empty((nrows, k), dtype=torch.float64, device=s.device)
+    L.check(lib.pg_block_means(L.ptr(s), k, T, A0, A1, bt, b0, b1, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def rows_gram(X, y, *, fold_of_row=None, n_folds=1, shift=None, want_minmax=False):
+    """pg_rows_gram: X [n][p] or [B][n][p], y [n] or [B][n] -> stats [B][n_folds][S] (+ colminmax)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    X = _dev(X, torch.float64)
+    y = _dev(y, torch.float64)
+    if X.ndim == 2:
+        X, y = X[None], y[None]
+    B, n, p = X.shape
+    if y.shape != (B, n):
+        raise ValueError("y must match the rows of X")
+    fr = _dev(fold_of_row, torch.uint8)
+    sh = _dev(shift, torch.float64)
+    if sh is not None:
+        sh = sh.reshape(B, p).contiguous()
+    stats = torch.empty((B, n_folds, L.stats_len(p)), dtype=torch.float64, device=X.device)
+    mm = torch.empty((B, n_folds, 2, p), dtype=torch.float64, device=X.device) if want_minmax else None
+    L.check(lib.pg_rows_gram(L.ptr(X), L.ptr(y), B, n, p, p, L.ptr(fr), n_folds, L.ptr(sh), L.ptr(stats), L.ptr(mm),
+                             L.stream_ptr()))
+    return (stats, mm) if want_minmax else stats
+
+
+def poly_rows(U, pts, W6, rt, rs, *, library):
+    """K2: pg_poly_rows.  U float32 or float64 (T,H,W); pts [n][3] (t,y,x) -> (X [n][p], y [n])."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    if isinstance(U, np.ndarray):
+        if U.dtype not in (np.float32, np.float64):
+            U = U.astype(np.float64)
+        U = _dev(U)
+    if U.dtype not in (torch.float32, torch.float64):
+        U = U.to(torch.float64)
+    U = U.contiguous()
+    T, H, W = U.shape
+    pts = _dev(pts, torch.int32).reshape(-1, 3).contiguous()
+    W6 = _dev(W6, torch.float64)
+    nnb = (2 * rt + 1) * (2 * rs + 1) ** 2
+    if tuple(W6.shape) != (6, nnb):
+        raise ValueError(f"W6 must be (6, {nnb})")
+    n, p = pts.shape[0], L.LIB_WIDTH[library]
+    X = torch.empty((n, p), dtype=torch.float64, device=U.device)
+    y = torch.empty((n,), dtype=torch.float64, device=U.device)
+    L.check(lib.pg_poly_rows(L.ptr(U), 0 if U.dtype == torch.float32 else 1, T, H, W, L.ptr(pts), n, L.ptr(W6), rt, rs,
+                             library, L.ptr(X), L.ptr(y), L.stream_ptr()))
+    return X, y
+
+
+def stridge_batched(stats, p, *, dialect, alphas, thresholds, max_iter, flags=0, const_cols=(), colminmax=None,
+                    shift=None, eval_stats=None):
+    """K3: pg_stridge_batched.  stats [B][S] -> dict(coef [B][na][nt][p], metrics, best)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    stats = _dev(stats, torch.float64).reshape(-1, L.stats_len(p)).contiguous()
+    B = stats.shape[0]
+    al = _dev(np.atleast_1d(np.asarray(alphas, dtype=np.float64)))
+    th = _dev(np.atleast_1d(np.asarray(thresholds, dtype=np.float64)))
+    na, nt = al.numel(), th.numel()
+    cm = None
+    if len(tuple(const_cols)):
+        m = np.zeros(p, dtype=np.uint8)
+        m[list(const_cols)] = 1
+        cm = _dev(m)
+    mm = None if colminmax is None else _dev(colminmax, torch.float64).reshape(B, 2, p).contiguous()
+    sh = None if shift is None else _dev(shift, torch.float64).reshape(B, p).contiguous()
+    ev = None if eval_stats is None else _dev(eval_stats, torch.float64).reshape(B, L.stats_len(p)).contiguous()
+    coef = torch.empty((B, na, nt, p), dtype=torch.float64, device=stats.device)
+    metrics = torch.empty((B, na, nt, 2), dtype=torch.float64, device=stats.device) if ev is not None else None
+    best = torch.empty((B,), dtype=torch.int32, device=stats.device) if ev is not None else None
+    L.check(lib.pg_stridge_batched(L.ptr(stats), B, p, dialect, flags, L.ptr(al), na, L.ptr(th), nt, int(max_iter),
+                                   L.ptr(cm), L.ptr(mm), L.ptr(sh), L.ptr(ev), L.ptr(coef), L.ptr(metrics), L.ptr(best),
+                                   L.stream_ptr()))
+    return dict(coef=coef, metrics=metrics, best=best)
+
+
+def synth_field(T, A0, A1, *, t_offset=0, T_total=None, seed=0, kind=0, noise=0.0, out=None):
+    """pg_synth_field: synthetic benchmark stack generated in HBM (no host transfer)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    if out is None:
+        out = torch.empty((T, A0, A1), dtype=torch.float64, device="cuda")
+    L.check(lib.pg_synth_field(L.ptr(out), T, A0, A1, int(t_offset), int(T_total if T_total is not None else T),
+                               int(seed), int(kind), float(noise), L.stream_ptr()))
+    return out

@@ -1,0 +1,275 @@
+"""GPU parity, KS-2D dialect: every test calls the CUDA path through the C ABI (pde_b200 ->
+ctypes -> libpdegram.so) and checks it against the golden fixtures / the oracle on the same
+seeded inputs.  Bars: bit-exact for the materialised stencil terms, GRAM_RTOL for statistics,
+COEF_RTOL + identical support for coefficients."""
+
+import numpy as np
+import pytest
+
+from helpers import COEF_RTOL, GRAM_RTOL, assert_coef_close, assert_stats_close, ks_rows
+from oracle import gram, ks2d as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import pde_b200
+    from pde_b200 import ks2d
+
+    pde_b200.load()
+    return ks2d
+
+
+@pytest.fixture(scope="module")
+def L():
+    from pde_b200 import _lib
+
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pde_b200 import ops
+
+    return ops
+
+
+def test_stencils_bitexact(K, golden_ks2d):
+    g = golden_ks2d
+    U, dx, dy = g["U"], float(g["dx"]), float(g["dy"])
+    gx, gy = K.gradients(U[3], dx, dy)
+    assert np.array_equal(gx, g["gx3"]) and np.array_equal(gy, g["gy3"])
+    assert np.array_equal(K.laplacian(U[3], dx, dy), g["lap3"])
+
+
+def test_dictionaries_bitexact(K, golden_ks2d):
+    g = golden_ks2d
+    U, dx, dy = g["U"], float(g["dx"]), float(g["dy"])
+    names, terms = K.build_dictionary(U[:-1], dx, dy)
+    assert names == list(g["names_rich"])
+    for k, n in enumerate(names):
+        assert terms[n].shape == U[:-1].shape and terms[n].dtype == np.float64
+        assert np.array_equal(terms[n], g["rich_terms"][k]), n
+    names, terms = K.build_dictionary_true(U[:-1], dx, dy, include_advection=True)
+    assert names == list(g["names_adv"])
+    for k, n in enumerate(names):
+        assert np.array_equal(terms[n], g["adv_terms"][k]), n
+    assert K.build_dictionary_true(U[:-1], dx, dy)[0] == list(g["names_true"])
+    with pytest.raises(NotImplementedError):
+        K.build_dictionary(U[:-1], dx, dy, deriv="spectral")
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 1), (2, 2, 3), (2, 5, 2), (4, 3, 4)])
+def test_stencils_tiny_periodic_shapes(K, shape):
+    """np.roll wraps any size, including extents 1 and 2 where +-1 / +-2 alias each other."""
+    U = np.random.default_rng(5).standard_normal(shape)
+    names, terms = K.build_dictionary(U, 0.3, 0.7)
+    _, ref = O.build_dictionary(U, 0.3, 0.7)
+    for n in names:
+        assert np.array_equal(terms[n], ref[n]), n
+
+
+@pytest.mark.parametrize("tag,block", [("388", (3, 8, 8)), ("453", (4, 5, 3)), ("111", (1, 1, 1))])
+def test_build_blockwise_dataset(K, golden_ks2d, tag, block):
+    g = golden_ks2d
+    U, dx, dy, DT = g["U"], float(g["dx"]), float(g["dy"]), float(g["DT"])
+    Ut = (U[1:] - U[:-1]) / DT
+    names, terms = O.build_dictionary(U[:-1], dx, dy)
+    X, y = K.build_blockwise_dataset(Ut, terms, names, block_t=block[0], block_x=block[1], block_y=block[2])
+    assert X.shape == g[f"bw{tag}_X_rich"].shape and y.shape == g[f"bw{tag}_y"].shape
+    np.testing.assert_allclose(X, g[f"bw{tag}_X_rich"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(y, g[f"bw{tag}_y"], rtol=1e-11, atol=1e-13)
+
+
+def test_build_blockwise_dataset_errors_and_nonfinite(K):
+    Ut = np.ones((4, 4, 4))
+    with pytest.raises(ValueError, match="Ut must be"):
+        K.build_blockwise_dataset(Ut[0], {"a": Ut}, ["a"], block_t=1, block_x=1, block_y=1)
+    with pytest.raises(ValueError, match="block sizes"):
+        K.build_blockwise_dataset(Ut, {"a": Ut}, ["a"], block_t=0, block_x=1, block_y=1)
+    a = Ut.copy()
+    a[0, 0, 0] = np.nan
+    X, y = K.build_blockwise_dataset(Ut, {"a": a}, ["a"], block_t=2, block_x=2, block_y=2)
+    assert X.shape == (7, 1) and y.shape == (7,)
+    X, y = K.build_blockwise_dataset(Ut * np.nan, {"a": a}, ["a"], block_t=2, block_x=2, block_y=2)
+    assert X.shape == (0, 1) and y.shape == (0,)
+
+
+def test_stridge_golden(K, golden_ks2d):
+    g = golden_ks2d
+    for X, y, key in [(g["bw453_X_rich"], g["bw453_y"], "stridge_rich"),
+                      (g["bw111_X_rich"], g["bw111_y"], "stridge_rich_pointwise"),
+                      (g["bw111_X_true"], g["bw111_y"], "stridge_true_pointwise")]:
+        for (a, t), ref in zip(g["stridge_grid"], g[key]):
+            c = K.stridge(X, y, alpha=a, threshold=t, max_iter=25)
+            assert_coef_close(c, ref, what=f"{key} alpha={a} thr={t}")
+    m, s = K.standardize_fit(g["bw111_X_rich"])
+    np.testing.assert_allclose(m, g["std_mean"], rtol=1e-10, atol=1e-15)
+    np.testing.assert_allclose(s, g["std_scale"], rtol=1e-10)
+    Xs = O.standardize_transform(g["bw111_X_rich"], g["std_mean"], g["std_scale"])
+    np.testing.assert_allclose(K.ridge_fit(Xs, g["bw111_y"], 1e-3), g["ridge_fit"], rtol=COEF_RTOL)
+
+
+def test_stridge_max_iter_edge_cases(K, golden_ks2d):
+    g = golden_ks2d
+    X, y = g["bw453_X_rich"], g["bw453_y"]
+    for mi in (0, 1, 2):
+        for a, t in [(1e-3, 1e-6), (1e-2, 0.2), (1e-1, 5.0)]:
+            assert_coef_close(K.stridge(X, y, alpha=a, threshold=t, max_iter=mi),
+                              O.stridge(X, y, alpha=a, threshold=t, max_iter=mi), what=f"max_iter={mi} {a} {t}")
+
+
+LIBS = [("true", False, "LIB_KS_TRUE"), ("true", True, "LIB_KS_TRUE_ADV"), ("rich", False, "LIB_KS_RICH")]
+
+
+@pytest.mark.parametrize("dictionary,adv,libname", LIBS)
+@pytest.mark.parametrize("block", [(1, 1, 1), (3, 8, 8), (4, 5, 3), (2, 20, 12), (50, 50, 50)])
+def test_fused_gram_generic_vs_oracle(ops, L, golden_ks2d, dictionary, adv, libname, block):
+    """K1 (generic kernel): statistics of the fused path == statistics of the oracle's rows."""
+    g = golden_ks2d
+    U, dx, dy, DT = g["U"], float(g["dx"]), float(g["dy"]), float(g["DT"])
+    names, X, y = ks_rows(U, dx, dy, DT, dictionary, adv, block)
+    stats = ops.fd_lib_gram(U, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=getattr(L, libname), block=block,
+                            variant=L.VARIANT_GENERIC).cpu().numpy()
+    assert_stats_close(stats[0], gram.pack_stats(X, y), len(names))
+
+
+def test_fused_gram_folds(ops, L, golden_ks2d):
+    g = golden_ks2d
+    U, dx, dy, DT = g["U"], float(g["dx"]), float(g["dy"]), float(g["DT"])
+    names, X, y = ks_rows(U, dx, dy, DT, "rich", False, (3, 8, 8))
+    fold = np.random.default_rng(2).integers(0, 3, size=len(y)).astype(np.uint8)
+    stats = ops.fd_lib_gram(U, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_RICH, block=(3, 8, 8),
+                            fold_of_row=fold, n_folds=3, variant=L.VARIANT_GENERIC).cpu().numpy()
+    for f in range(3):
+        assert_stats_close(stats[f], gram.pack_stats(X[fold == f], y[fold == f]), 9)
+    # time-holdout folds: a block takes the fold of its first frame
+    T1 = U.shape[0] - 1
+    fof = (np.arange(T1) >= 9).astype(np.int32)
+    stats = ops.fd_lib_gram(U, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 4, 4),
+                            fold_of_frame=fof, n_folds=2, variant=L.VARIANT_GENERIC).cpu().numpy()
+    names, X, y = ks_rows(U, dx, dy, DT, "true", False, (3, 4, 4))
+    rows_per_tb = len(y) // 5
+    row_fold = np.repeat(fof[::3], rows_per_tb)
+    for f in range(2):
+        assert_stats_close(stats[f], gram.pack_stats(X[row_fold == f], y[row_fold == f]), 3)
+    with pytest.raises(ValueError, match="fold_of_row"):
+        ops.fd_lib_gram(U, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8),
+                        fold_of_row=fold[:-1], n_folds=3)
+
+
+def test_fused_gram_edge_shapes(ops, L):
+    """Single frame (no u_t -> zero rows), 2 frames, extents smaller than the stencil radius."""
+    rng = np.random.default_rng(9)
+    s = ops.fd_lib_gram(rng.standard_normal((1, 6, 6)), 1.0, 1.0, 1.0, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_RICH).cpu().numpy()
+    assert not s.any()
+    for shape in [(2, 1, 1), (2, 2, 2), (3, 1, 7), (3, 4, 1)]:
+        U = rng.standard_normal(shape)
+        names, X, y = ks_rows(U, 0.5, 0.25, 0.1, "rich", False, (1, 1, 1))
+        s = ops.fd_lib_gram(U, 0.5, 0.25, 0.1, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_RICH).cpu().numpy()
+        assert_stats_close(s[0], gram.pack_stats(X, y), 9)
+
+
+def test_fused_gram_nonfinite_rows_are_dropped(ops, L, golden_ks2d):
+    g = golden_ks2d
+    U, dx, dy, DT = g["U"].copy(), float(g["dx"]), float(g["dy"]), float(g["DT"])
+    U[4, 7, 3] = np.nan
+    U[9, 0, 0] = np.inf
+    names, X, y = ks_rows(U, dx, dy, DT, "true", False, (3, 8, 8))
+    stats, bad = ops.fd_lib_gram(U, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8),
+                                 variant=L.VARIANT_GENERIC, return_nonfinite=True)
+    n_all = 5 * 3 * 2
+    assert int(bad.item()) == n_all - len(y) > 0
+    assert_stats_close(stats.cpu().numpy()[0], gram.pack_stats(X, y), 3)
+
+
+def test_c_abi_error_codes(L):
+    """Bad arguments come back as PG_EINVAL with a message, never as a crash."""
+    import torch
+
+    lib = L.load()
+    U = torch.zeros((3, 8, 8), dtype=torch.float64, device="cuda")
+    out = torch.zeros(64, dtype=torch.float64, device="cuda")
+    rc = lib.pg_fd_lib_gram(U.data_ptr(), 3, 8, 8, 1.0, 1.0, 1.0, 0, 0, 0, 1, 1, None, None, 1, out.data_ptr(), None, 0, None)
+    assert rc == -1 and b"block sizes" in lib.pg_last_error()
+    rc = lib.pg_fd_lib_gram(U.data_ptr(), 3, 8, 8, 1.0, 1.0, 1.0, 0, L.LIB_BASIC, 1, 1, 1, None, None, 1, out.data_ptr(), None, 0, None)
+    assert rc == -1 and b"KS dialect" in lib.pg_last_error()
+    rc = lib.pg_fd_lib_gram(U.data_ptr(), 3, 8, 8, 1.0, 1.0, 1.0, 0, 0, 1, 1, 1, None, None, 99, out.data_ptr(), None, 0, None)
+    assert rc == -1 and b"n_folds" in lib.pg_last_error()
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("c1", dict(method="pointwise", dictionary="true")),
+    ("c2", dict(method="blockwise", dictionary="true")),
+    ("c2_rich_sweep", dict(method="blockwise", dictionary="rich", grid_search=True)),
+])
+def test_reference_configs_fused(K, ks_default_stack, golden_configs, tag, kw):
+    """BASELINE configs[0] and [1] end to end on the GPU (field -> K1 -> K3), against the numbers
+    the unmodified reference main() printed and its full-precision replay."""
+    U, dx, dy, DT = ks_default_stack
+    if tag != "c1":
+        U = O.add_noise(U, 0.05, seed=999)
+    out = K.fit_from_field(U, dx, dy, DT, **kw)
+    gold, full = golden_configs[tag], golden_configs["full_precision"][tag]
+    assert list(out["X_shape"]) == gold["X_shape"]
+    hyper = gold["hyper"]
+    assert (out["alpha"], out["threshold"], out["n_active"]) == (hyper["alpha"], hyper["threshold"], hyper["n_active"])
+    best_row = [r for r in full["table"] if (r["alpha"], r["threshold"]) == (out["alpha"], out["threshold"])][0]
+    assert_coef_close(out["coeffs"], np.array(best_row["coeffs"]), what=tag)
+    if tag == "c1":
+        # exact fit: r2 == 1 to rounding; ss_res from statistics cancels (documented), so only r2 is pinned
+        assert abs(out["r2_test"] - 1.0) < 1e-9
+    else:
+        np.testing.assert_allclose(out["r2_test"], hyper["r2_test"], rtol=1e-7)
+        np.testing.assert_allclose(out["rmse_test"], hyper["rmse_test"], rtol=1e-7)
+    if "table" in out and kw.get("grid_search"):
+        for (a, thr, r2, err, na), row in zip(out["table"], full["table"]):
+            assert (a, thr, na) == (row["alpha"], row["threshold"], row["n_active"])
+            np.testing.assert_allclose(r2, row["r2_test"], rtol=1e-7)
+            assert_coef_close(out["coef_grid"][O.GRID_ALPHAS.index(a), O.GRID_THRESHOLDS.index(thr)],
+                              np.array(row["coeffs"]), what=f"{tag} sweep {a} {thr}")
+
+
+def test_reference_script_runs_with_rebound_functions(K, ks_default_stack, golden_configs):
+    """Drop-in: a stand-in for the reference module's globals, rebound by patch_reference, then
+    driven exactly as main() drives them (ks2d:1508-1550, 1638-1718) for config C2."""
+    import types
+
+    import pde_b200
+
+    m = types.SimpleNamespace(**{n: getattr(O, n) for n in ("gradients", "laplacian", "build_dictionary",
+                                                            "build_dictionary_true", "build_blockwise_dataset",
+                                                            "standardize_fit", "ridge_fit", "stridge")})
+    done = pde_b200.patch_reference(m, "ks2d")
+    assert set(done) == {"gradients", "laplacian", "build_dictionary", "build_dictionary_true",
+                         "build_blockwise_dataset", "standardize_fit", "ridge_fit", "stridge"}
+    U, dx, dy, DT = ks_default_stack
+    U = O.add_noise(U, 0.05, seed=999)[:301]  # 300 row-frames keep the materialised path small
+    rng = np.random.default_rng(0)
+    Ut = (U[1:] - U[:-1]) / DT
+    names, terms = m.build_dictionary_true(U[:-1], dx=dx, dy=dy, deriv="finite", spectral_cutoff=1.0, include_advection=False)
+    X, y = m.build_blockwise_dataset(Ut, terms, names, block_t=3, block_x=8, block_y=8)
+    tr, te, scale = O.split_and_scale(names, X, y, rng)
+    c = m.stridge(X[tr] / scale, y[tr], alpha=1e-6, threshold=1e-10, max_iter=25) / scale
+    ref = O.run_config(U, dx, dy, DT, method="blockwise", dictionary="true")
+    assert X.shape == ref["X_shape"]
+    assert_coef_close(c, ref["coeffs"], what="rebound C2 (300 frames)")
+
+
+@pytest.mark.parametrize("shape,block", [((9, 64, 96), (1, 1, 1)), ((13, 128, 64), (3, 8, 8)), ((7, 40, 72), (2, 8, 8))])
+def test_slab_additivity_and_variants(ops, L, shape, block):
+    """Size-independent properties: statistics are additive over time slabs (what the multi-GPU
+    path relies on) and the AUTO variant (tiled where available) equals the generic kernel."""
+    U = ops.synth_field(*shape, seed=3, noise=0.05)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_RICH, block=block)
+    full = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()[0]
+    auto = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_AUTO, **kw).cpu().numpy()[0]
+    assert_stats_close(auto, full, 9)
+    cut = block[0] * max(1, (shape[0] // 2) // block[0])
+    a = ops.fd_lib_gram(U[: cut + 1], 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()[0]
+    b = ops.fd_lib_gram(U[cut:], 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()[0]
+    assert_stats_close(a + b, full, 9)
+    # and against the oracle on the same device-generated field
+    names, X, y = ks_rows(U.cpu().numpy(), 0.5, 0.5, 1e-3, "rich", False, block)
+    assert_stats_close(full, gram.pack_stats(X, y), 9)
