@@ -82,6 +82,8 @@ extern "C" {
 
 PG_API int pg_version(void);
 PG_API const char *pg_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+PG_API int64_t pg_launch_count(void);
 /* frees the per-device scratch of the current device */
 PG_API int pg_shutdown(void);
 /* number of columns of a library, or PG_EINVAL */

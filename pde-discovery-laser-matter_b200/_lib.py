@@ -42,6 +42,7 @@ _i64, _i32, _dbl, _ptr, _u64 = C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_u
 _PROTOS = {
     "pg_version": (C.c_int, []),
     "pg_last_error": (C.c_char_p, []),
+    "pg_launch_count": (C.c_int64, []),
     "pg_shutdown": (C.c_int, []),
     "pg_library_width": (C.c_int, [_i32]),
     "pg_fd_lib_gram": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -20,6 +21,9 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // One scratch buffer per (device, stream): calls on one stream are ordered, so reuse is safe.
 struct Scratch {
@@ -97,6 +101,7 @@ using namespace pg;
 extern "C" {
 
 int pg_version(void) { return PG_VERSION; }
+int64_t pg_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 const char *pg_last_error(void) { return g_err; }
 int pg_library_width(int library_id) {
     const int w = library_width(library_id);

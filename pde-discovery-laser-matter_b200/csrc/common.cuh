@@ -21,8 +21,13 @@ void set_error(const char *fmt, ...);
         if (e__ != cudaSuccess) PG_FAIL(PG_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
-// per-device scratch (grown on demand, freed by pg_shutdown)
-int scratch_get(size_t bytes, void **ptr);
+// every kernel launch of the library goes through this: counts it (pg_launch_count) and checks it
+void count_launch();
+#define PG_LAUNCHED()                \
+    do {                             \
+        pg::count_launch();          \
+        PG_CUDA(cudaGetLastError()); \
+    } while (0)
 
 // ----------------------------------------------------------------------------- library traits
 template <int LIB> struct Lib;

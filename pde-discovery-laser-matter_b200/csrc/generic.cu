@@ -313,7 +313,7 @@ template <int LIB> static int launch_k1_generic_t(const K1Params &P, int n_parts
     const size_t smem = sizeof(double) * (GW * P.n_folds * S + GW * 32 * (p + 2)) + 2 * S + 16;
     PG_CUDA(cudaFuncSetAttribute(k1_generic_kernel<LIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k1_generic_kernel<LIB><<<n_parts_cta, GW * 32, smem, st>>>(P);
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     return PG_OK;
 }
 
@@ -331,7 +331,7 @@ int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st) {
 int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate,
                            cudaStream_t st) {
     reduce_partials_kernel<<<(unsigned)((len + 127) / 128), 128, 0, st>>>(partials, n_parts, len, out, accumulate);
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     return PG_OK;
 }
 
@@ -353,7 +353,7 @@ int launch_fd_terms(int dialect, int lib, const double *U, int64_t T, int64_t A0
             default: PG_FAIL(PG_EINVAL, "library %d is not a KS-dialect library", lib);
         }
     }
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     return PG_OK;
 }
 
@@ -368,7 +368,7 @@ int launch_fd_gather(int lib, const K1Params &P, const int64_t *flat_idx, int64_
 #undef PG_CASE
         default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_gather_rows", lib);
     }
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     return PG_OK;
 }
 
@@ -379,7 +379,7 @@ int launch_block_means(const double *stack, int k, int64_t T, int64_t A0, int64_
     if (total <= 0) return PG_OK;
     block_means_kernel<<<grid_for(total, 128, 148 * 16), 128, 0, st>>>(stack, k, T, A0, A1, bt, b0, b1, nBt, nB0, nB1,
                                                                       out);
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     return PG_OK;
 }
 
@@ -393,12 +393,12 @@ int launch_rows_gram(const RowsParams &P, double *stats, double *colminmax, cuda
     const size_t smem = rows_gram_smem(P.p, P.n_folds);
     PG_CUDA(cudaFuncSetAttribute(rows_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rows_gram_kernel<<<(unsigned)(P.chunks * P.B), GW * 32, smem, st>>>(P);
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     const int len = P.n_folds * S, mmlen = P.n_folds * 2 * P.p;
     const int64_t work = P.B * (int64_t)(len > mmlen ? len : mmlen);
     rows_reduce_kernel<<<(unsigned)((work + 127) / 128), 128, 0, st>>>(P.partials, P.mm_partials, P.B, P.chunks * GW,
                                                                        len, mmlen, P.p, stats, colminmax);
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     return PG_OK;
 }
 

@@ -75,7 +75,7 @@ int launch_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, 
         poly_rows_kernel<double><<<(unsigned)g, PW * 32, smem, st>>>((const double *)U, T, H, W, pts, n, W6, rt, rs,
                                                                      mode, X, y, counters);
     }
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     return PG_OK;
 }
 
@@ -114,7 +114,7 @@ int launch_synth(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset,
     int64_t g = (total + 255) / 256;
     if (g > 148 * 32) g = 148 * 32;
     synth_kernel<<<(unsigned)g, 256, 0, st>>>(U, T, A0, A1, t_offset, T_total, seed, kind, noise);
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     return PG_OK;
 }
 

@@ -286,11 +286,11 @@ int launch_stridge(const StridgeParams &P, int32_t *best_out, cudaStream_t st) {
     const int64_t njobs = P.B * P.na * P.nt;
     if (njobs <= 0) return PG_OK;
     stridge_kernel<<<(unsigned)((njobs + SW - 1) / SW), SW * 32, 0, st>>>(P);
-    PG_CUDA(cudaGetLastError());
+    PG_LAUNCHED();
     if (best_out && P.metrics_out) {
         stridge_best_kernel<<<(unsigned)((P.B + 127) / 128), 128, 0, st>>>(P.coef_out, P.metrics_out, P.B, P.p,
                                                                           P.na * P.nt, best_out);
-        PG_CUDA(cudaGetLastError());
+        PG_LAUNCHED();
     }
     return PG_OK;
 }

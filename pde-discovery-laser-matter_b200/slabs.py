@@ -1,0 +1,117 @@
+"""Time-slab sharding of the fused path: one process per GPU, contiguous frame
+ranges per rank, a one-frame trailing halo (the forward u_t of ks2d:1511 needs u(t+1)), and a
+single small all-reduce of the per-fold statistics.  ``torch.distributed`` is the plumbing
+(NCCL over NVLink on GPUs; gloo in the CPU tests); the data path has exactly these two
+exchanges.  Slab edges are aligned to ``block_t`` so no block straddles two ranks.
+
+Also here: ``fit_streamed`` for host-resident stacks (slabs copied from pinned host memory on
+a copy stream while the previous slab is reduced on the compute stream).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+
+
+def slab_bounds(n_row_frames: int, block_t: int, world: int):
+    """Row-frame ranges [lo, hi) per rank: whole t-blocks, as even as possible; a ragged last
+    t-block (ks2d:384) stays with the last rank."""
+    n_tb = -(-n_row_frames // block_t)
+    base, extra = divmod(n_tb, world)
+    out, tb = [], 0
+    for r in range(world):
+        k = base + (1 if r < extra else 0)
+        lo, hi = tb * block_t, min(n_row_frames, (tb + k) * block_t)
+        out.append((lo, max(lo, hi)))
+        tb += k
+    return out
+
+
+def exchange_halo(U_local, group=None):
+    """Fill the trailing halo frame U_local[-1] with frame 0 of the next rank's slab.
+
+    Rank r sends its first frame to rank r-1 and receives rank r+1's first frame; the last
+    rank keeps its own trailing frame (it is part of the global stack)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return U_local
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, U_local[0], rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.irecv, U_local[-1], rank + 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return U_local
+
+
+def allreduce_stats(stats, group=None):
+    """Sum the per-fold statistics over ranks, in place (one all-reduce of n_folds*S doubles)."""
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def sharded_stats(U_local, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_frame=None, fold_of_row=None,
+                  n_folds=1, variant=L.VARIANT_AUTO, group=None, halo=True, stats_fn=None):
+    """Per-rank K1 over this rank's slab (own frames + trailing halo frame) followed by the
+    all-reduce.  ``stats_fn`` lets the CPU tests stand in for the CUDA kernel."""
+    if halo:
+        exchange_halo(U_local, group)
+    if stats_fn is None:
+        from . import ops
+
+        stats = ops.fd_lib_gram(U_local, d0, d1, dt, dialect=dialect, library=library, block=block,
+                                fold_of_frame=fold_of_frame, fold_of_row=fold_of_row, n_folds=n_folds, variant=variant)
+    else:
+        stats = stats_fn(U_local)
+    return allreduce_stats(stats, group)
+
+
+def fit_streamed(U_host, d0, d1, dt, *, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8),
+                 fold_of_frame=None, n_folds=1, slab_frames=96, variant=L.VARIANT_AUTO, buffers=None):
+    """Statistics of a HOST-resident stack: slabs of ``slab_frames`` row frames (+1 halo frame)
+    are copied host->device on a copy stream into two device buffers while the compute stream
+    runs K1 on the previous slab; per-slab statistics are summed on the device.
+
+    U_host: (T, A0, A1) float64 torch tensor in pinned memory (or a NumPy array, which is copied
+    through pageable memory and is slower).  Returns the [n_folds][S] statistics tensor (device).
+    """
+    torch = L.torch_cuda()
+    from . import ops
+
+    if isinstance(U_host, np.ndarray):
+        U_host = torch.from_numpy(np.ascontiguousarray(U_host, dtype=np.float64))
+    T, A0, A1 = U_host.shape
+    bt = int(block[0])
+    slab_frames = max(bt, (slab_frames // bt) * bt)
+    p = L.LIB_WIDTH[library]
+    total = torch.zeros((n_folds, L.stats_len(p)), dtype=torch.float64, device="cuda")
+    if buffers is None:
+        buffers = [torch.empty((slab_frames + 1, A0, A1), dtype=torch.float64, device="cuda") for _ in range(2)]
+    fof = None if fold_of_frame is None else torch.as_tensor(np.asarray(fold_of_frame), dtype=torch.int32).cuda()
+    compute = torch.cuda.current_stream()
+    copy = torch.cuda.Stream()
+    filled = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    starts = list(range(0, T - 1, slab_frames))
+    for k, lo in enumerate(starts):
+        hi = min(T - 1, lo + slab_frames)
+        b = k % 2
+        with torch.cuda.stream(copy):
+            if k >= 2:
+                copy.wait_event(freed[b])
+            buffers[b][: hi - lo + 1].copy_(U_host[lo:hi + 1], non_blocking=True)
+            filled[b].record(copy)
+        compute.wait_event(filled[b])
+        s = ops.fd_lib_gram(buffers[b][: hi - lo + 1], d0, d1, dt, dialect=dialect, library=library, block=block,
+                            fold_of_frame=None if fof is None else fof[lo:hi], n_folds=n_folds, variant=variant)
+        total += s
+        freed[b].record(compute)
+    return total

@@ -172,7 +172,7 @@ def test_patch_ensemble_larger_vs_oracle(P):
     U = synthetic_stack((24, 64, 80), seed=1)
     out = P.fit_patches(U, seed=3)
     ref = OP.run_patches(U, seed=3)
-    assert out["C"].shape == ref["C"].shape and len(out["C"]) == 5 * 6
+    assert out["C"].shape == ref["C"].shape and len(out["C"]) == 4 * 6
     assert np.array_equal(out["C"] != 0, ref["C"] != 0)
     np.testing.assert_allclose(out["C"], ref["C"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(out["agg"], ref["agg"], rtol=1e-6, atol=1e-9)

@@ -1,0 +1,82 @@
+"""Host logic of the multi-GPU path on CPU: world_size-2 gloo processes exercise the slab
+partition, the one-frame halo exchange and the statistics all-reduce of pde_b200.slabs.  The
+per-rank kernel is stood in for by the oracle (test-only), so what is pinned here is that
+"sum over ranks of slab statistics == statistics of the whole stack"."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import assert_stats_close, ks_rows
+from oracle import gram
+
+
+def test_slab_bounds():
+    from pde_b200.slabs import slab_bounds
+
+    assert slab_bounds(1023, 3, 1) == [(0, 1023)]
+    b = slab_bounds(1023, 3, 8)
+    assert b[0][0] == 0 and b[-1][1] == 1023 and all(lo % 3 == 0 for lo, _ in b)
+    assert all(b[k][1] == b[k + 1][0] for k in range(7))
+    assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 3
+    assert slab_bounds(10, 3, 2) == [(0, 6), (6, 10)]            # ragged last t-block stays last
+    assert slab_bounds(4, 3, 4) == [(0, 3), (3, 4), (4, 4), (4, 4)]  # more ranks than t-blocks
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, block, q):
+    import torch
+    import torch.distributed as dist
+
+    from pde_b200 import _lib as L
+    from pde_b200 import slabs
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        U = rng.standard_normal((14, 16, 24))
+        dx, dy, DT = 0.5, 0.25, 1e-2
+        lo, hi = slabs.slab_bounds(U.shape[0] - 1, block[0], world)[rank]
+        U_local = torch.from_numpy(U[lo:hi + 1].copy())
+        if rank < world - 1:
+            U_local[-1].zero_()  # the halo frame must come from the neighbour
+
+        def stats_fn(Ul):
+            names, X, y = ks_rows(Ul.numpy(), dx, dy, DT, "rich", False, block)
+            return torch.from_numpy(gram.pack_stats(X, y))[None].clone()
+
+        s = slabs.sharded_stats(U_local, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_RICH, block=block,
+                                stats_fn=stats_fn)
+        assert torch.equal(U_local[-1], torch.from_numpy(U[hi]))
+        q.put((rank, s.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("block", [(1, 1, 1), (3, 8, 8)])
+def test_two_rank_halo_and_allreduce(block):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, block, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    U = np.random.default_rng(0).standard_normal((14, 16, 24))
+    names, X, y = ks_rows(U, 0.5, 0.25, 1e-2, "rich", False, block)
+    ref = gram.pack_stats(X, y)
+    assert np.array_equal(res[0], res[1])        # every rank holds the reduced statistics
+    assert_stats_close(res[0][0], ref, 9, rtol=1e-12)

@@ -1,0 +1,69 @@
+"""Quick K1 timing probe (developer tool, not the contract bench): times pg_fd_lib_gram variants
+on a synthetic stack with CUDA events and prints achieved algorithmic GB/s (8 B per grid point)."""
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+import torch  # noqa: E402
+
+from pde_b200 import _lib as L  # noqa: E402
+from pde_b200 import ops  # noqa: E402
+
+
+def time_call(fn, warmup=2, iters=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for k in range(iters):
+        fn()
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    ts = [ev[k].elapsed_time(ev[k + 1]) for k in range(iters)]
+    return min(ts), sum(ts) / len(ts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--generic", action="store_true")
+    args = ap.parse_args()
+    T, A = args.frames, args.size
+    U = ops.synth_field(T, A, A, seed=0, noise=0.05)
+    torch.cuda.synchronize()
+    pts = T * A * A
+    fof = (torch.arange(T - 1) >= int(0.7 * (T - 1))).to(torch.int32)
+    out = []
+    cases = [("true_b388_tiled", L.LIB_KS_TRUE, (3, 8, 8), L.VARIANT_TILED, 1),
+             ("true_b388_tiled_2folds", L.LIB_KS_TRUE, (3, 8, 8), L.VARIANT_TILED, 2),
+             ("rich_b388_tiled_2folds", L.LIB_KS_RICH, (3, 8, 8), L.VARIANT_TILED, 2),
+             ("adv_b388_tiled", L.LIB_KS_TRUE_ADV, (3, 8, 8), L.VARIANT_TILED, 1)]
+    if args.generic:
+        cases += [("true_b388_generic", L.LIB_KS_TRUE, (3, 8, 8), L.VARIANT_GENERIC, 1),
+                  ("true_pointwise_generic", L.LIB_KS_TRUE, (1, 1, 1), L.VARIANT_GENERIC, 1),
+                  ("rich_pointwise_generic", L.LIB_KS_RICH, (1, 1, 1), L.VARIANT_GENERIC, 1)]
+    for name, lib, block, variant, nf in cases:
+        kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=block, variant=variant, n_folds=nf)
+        if nf == 2:
+            kw["fold_of_frame"] = fof
+        best, avg = time_call(lambda: ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, **kw), iters=args.iters)
+        rec = dict(case=name, ms_best=round(best, 3), ms_avg=round(avg, 3), gpts_per_s=round(pts / best / 1e6, 2),
+                   alg_GBps=round(8 * pts / best / 1e6, 1))
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+    # plain device copy of the same bytes for scale (read + write)
+    V = torch.empty_like(U[: T // 2])
+    best, _ = time_call(lambda: V.copy_(U[: T // 2]), iters=args.iters)
+    print(json.dumps(dict(case="torch_copy_half", ms_best=round(best, 3),
+                          GBps_rw=round(2 * 8 * V.numel() / best / 1e6, 1))))
+
+
+if __name__ == "__main__":
+    main()
