@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the fused FD + library + Gram hot path (BASELINE.json metric: grid points/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over the rank's synthetic stack: (N>1: one-frame halo
+exchange) -> K1 pg_fd_lib_gram over the whole stack with two time-holdout folds -> (N>1: one
+all-reduce of the 2 x S statistics) -> K3 batched STRidge (the reference's 5 x 6 sweep with
+held-out r2/rmse).  Workload (config.workload): BASELINE configs[3], a 2048 x 2048 x 1024 float64
+stack per GPU in the KS-2D dialect with the reference's default true dictionary (p = 3) and
+(3, 8, 8) block averaging (configs[1]'s estimator at configs[3]'s size).  N > 1 shards contiguous
+time slabs, one per GPU, weak scaling (the global stack is N x 1023 row frames + 1).
+
+Printed: ONE JSON line (rank 0) with the contract keys plus `roofline`, `cpu_baseline`, `e2e`,
+`gpu_launches`, `clocks` and `variants` (other libraries / estimators, fewer steps).
+`--impl reference` times the CPU port of the reference path (oracle/, NumPy, one process per host
+core over time slabs) on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "grid points/sec (fused FD+library+Gram)"
+UNIT = "grid-points/s"
+D0 = D1 = 0.5
+DT = 1e-3
+BLOCK = (3, 8, 8)
+
+
+def workload_text(args, world):
+    return (f"c4: synthetic {args.size}x{args.size}x{args.frames} float64 stack per GPU, KS periodic dialect, "
+            f"true dictionary p=3, block average (3,8,8), 2 time-holdout folds (70/30), 5x6 STRidge sweep; "
+            f"{world} time slab(s)")
+
+
+# ----------------------------------------------------------------------------- CPU port (reference arm / cpu_baseline)
+_CPU = {}  # sample stack shared with the forked worker processes (no pickling)
+
+
+def _cpu_slab_stats(a):
+    lo, hi, dictionary = a
+    from oracle import gram, ks2d as O
+
+    sl = _CPU["U"][lo:hi + 1]
+    if dictionary == "true":
+        names, terms = O.build_dictionary_true(sl[:-1], D0, D1)
+    else:
+        names, terms = O.build_dictionary(sl[:-1], D0, D1)
+    X, y = O.build_blockwise_dataset((sl[1:] - sl[:-1]) / DT, terms, names, block_t=BLOCK[0], block_x=BLOCK[1],
+                                     block_y=BLOCK[2])
+    return gram.pack_stats(X, y)
+
+
+def cpu_port_step(U, workers, pool, dictionary="true"):
+    """The reference algorithm (oracle port) for one pass over sample U: per-time-slab FD +
+    dictionary + block means + Gram in `workers` processes, then the STRidge sweep."""
+    from oracle import gram, ks2d as O
+    from pde_b200.slabs import slab_bounds
+
+    bounds = [b for b in slab_bounds(U.shape[0] - 1, BLOCK[0], workers) if b[1] > b[0]]
+    parts = pool.map(_cpu_slab_stats, [(lo, hi, dictionary) for lo, hi in bounds])
+    n_tr = max(1, int(0.7 * len(parts)))
+    s_tr, s_te = sum(parts[:n_tr]), sum(parts[n_tr:]) if len(parts) > n_tr else sum(parts)
+    p = 3 if dictionary == "true" else 9
+    return gram.ks_fit_from_stats(s_tr, s_te, p, alphas=O.GRID_ALPHAS, thresholds=O.GRID_THRESHOLDS,
+                                  const_cols=() if dictionary == "true" else (0,))
+
+
+def cpu_sample(frames=25, size=512, seed=0):
+    """Bounded sample of the workload for the CPU arm: same generator family, same dialect /
+    library / block, (frames x size x size) float64."""
+    rng = np.random.default_rng(seed)
+    i = np.arange(size) * (2 * np.pi / size)
+    t = np.arange(frames) * (2 * np.pi / 1024)
+    a, b, s = i[None, :, None], i[None, None, :], t[:, None, None]
+    U = (0.5 * np.sin(3 * a + 2 * b - 5 * s) + 0.3 * np.sin(7 * a - 4 * b + 3 * s + 0.7)
+         + 0.15 * np.sin(13 * a + 11 * b - 9 * s + 1.9) + 0.05 * np.cos(29 * a - 17 * b + 2 * s))
+    return U + 0.05 * (rng.random(U.shape) - 0.5)
+
+
+def time_cpu_port(steps, warmup, frames, size):
+    import multiprocessing as mp
+
+    workers = max(1, min(os.cpu_count() or 1, (frames - 1) // BLOCK[0]))
+    U = cpu_sample(frames, size)
+    _CPU["U"] = U
+    with mp.get_context("fork").Pool(workers) as pool:
+        for _ in range(warmup):
+            cpu_port_step(U, workers, pool)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_port_step(U, workers, pool)
+        dt = (time.perf_counter() - t0) / steps
+    pts = frames * size * size
+    return pts / dt, dt, workers, f"{frames}x{size}x{size} float64 sub-stack, same dialect/library/block, {workers} worker processes over time slabs"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 2))
+    frames, size = 97, 1024
+    t_budget = time.perf_counter()
+    value, dt, workers, sample = time_cpu_port(min(steps, 5), warmup, frames, size)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": min(steps, 5),
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_text(args, args.gpus), "note": "reference is CPU-only pure Python; timed as the NumPy port (oracle/) on a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_budget,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import pde_b200
+    from pde_b200 import _lib as L
+    from pde_b200 import ks2d as K
+    from pde_b200 import ops, slabs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = pde_b200.load()
+    T, A = args.frames, args.size
+    rows = T - 1
+    # global stack = world*(T-1) row frames + 1; this rank owns row frames [rank*rows, (rank+1)*rows)
+    U = torch.empty((T, A, A), dtype=torch.float64, device="cuda")
+    ops.synth_field(T if rank == world - 1 else T - 1, A, A, t_offset=rank * rows, T_total=1024, seed=0, noise=0.05, out=U)
+    if rank < world - 1:
+        U[-1].zero_()
+    g_rows = world * rows
+    fof = ((np.arange(rows) + rank * rows) >= int(0.7 * g_rows) // BLOCK[0] * BLOCK[0]).astype(np.int32)
+    fof_d = torch.from_numpy(fof).cuda()
+    names = K.TRUE_NAMES
+    alphas = ops._dev(np.array(K.GRID_ALPHAS))
+    thrs = ops._dev(np.array(K.GRID_THRESHOLDS))
+    k1_ev = []
+
+    def step(library=L.LIB_KS_TRUE, block=BLOCK, variant=L.VARIANT_AUTO, record=False):
+        if world > 1:
+            slabs.exchange_halo(U)
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        stats = ops.fd_lib_gram(U, D0, D1, DT, dialect=L.FD_KS_PERIODIC, library=library, block=block,
+                                fold_of_frame=fof_d, n_folds=2, variant=variant)
+        if record:
+            e1.record()
+            k1_ev.append((e0, e1))
+        slabs.allreduce_stats(stats)
+        p = L.LIB_WIDTH[library]
+        return ops.stridge_batched(stats[0], p, dialect=L.STRIDGE_KS, flags=L.STRIDGE_RMS_PRESCALE, alphas=alphas,
+                                   thresholds=thrs, max_iter=25, const_cols=[0] if p in (7, 9) else [],
+                                   eval_stats=stats[1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- parity gate on a small slab of the same field before any timing (rank 0)
+    if rank == 0:
+        from oracle import gram, ks2d as O
+
+        small = U[:7, :64, :128].contiguous()
+        s_gpu = ops.fd_lib_gram(small, D0, D1, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=BLOCK).cpu().numpy()[0]
+        sn = small.cpu().numpy()
+        nm, terms = O.build_dictionary_true(sn[:-1], D0, D1)
+        X, y = O.build_blockwise_dataset((sn[1:] - sn[:-1]) / DT, terms, nm, block_t=3, block_x=8, block_y=8)
+        ref = gram.pack_stats(X, y)
+        assert s_gpu[0] == ref[0] and np.abs(s_gpu - ref).max() <= 1e-10 * np.abs(ref).max(), "parity gate failed"
+
+    # ---- main timed region
+    sampler = ClockSampler(local)
+    launches0 = lib.pg_launch_count()
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = lib.pg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step(record=True)
+    e1.record()
+    barrier()
+    launches = lib.pg_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_t.item())
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1_ev]))
+    pts_rank = T * A * A
+    value = world * pts_rank * args.steps / (ms_total * 1e-3)
+
+    best = int(out["best"].cpu()[0])
+    coef = out["coef"].cpu().numpy()[0].reshape(-1, len(names))[best]
+
+    # ---- end to end through the public API with pinned HOST buffers (bounded sample per rank)
+    e2e_frames = min(T, args.e2e_frames)
+    e2e_value, h2d, ms_e2e = None, 0, None
+    if not args.skip_e2e:
+      host = torch.empty((e2e_frames, A, A), dtype=torch.float64).pin_memory()
+      host.copy_(U[:e2e_frames])
+      torch.cuda.synchronize()
+      bufs = [torch.empty((96 + 1, A, A), dtype=torch.float64, device="cuda") for _ in range(2)]
+      fof_e = (np.arange(e2e_frames - 1) >= int(0.7 * (e2e_frames - 1)) // 3 * 3).astype(np.int32)
+      res_host = torch.empty((30, len(names)), dtype=torch.float64).pin_memory()
+
+      def e2e_step():
+          st = slabs.fit_streamed(host, D0, D1, DT, library=L.LIB_KS_TRUE, block=BLOCK, fold_of_frame=fof_e, n_folds=2,
+                                  slab_frames=96, buffers=bufs)
+          slabs.allreduce_stats(st)
+          o = ops.stridge_batched(st[0], 3, dialect=L.STRIDGE_KS, flags=L.STRIDGE_RMS_PRESCALE, alphas=alphas,
+                                  thresholds=thrs, max_iter=25, eval_stats=st[1])
+          res_host.copy_(o["coef"].reshape(30, 3), non_blocking=False)
+
+      e2e_steps = max(2, min(args.steps, 5))
+      ms_e2e = timed(e2e_step, e2e_steps, 1)
+      e2e_value = world * e2e_frames * A * A * e2e_steps / (ms_e2e * 1e-3)
+      n_slabs = -(-(e2e_frames - 1) // 96)
+      h2d = (e2e_frames + n_slabs - 1) * A * A * 8
+      del host, bufs
+
+    # ---- variants (fewer steps): other libraries / estimators on the same stack
+    variants = {}
+    if not args.skip_variants:
+        for name, kw in [("rich_p9_block388", dict(library=L.LIB_KS_RICH)),
+                         ("true_adv_p5_block388", dict(library=L.LIB_KS_TRUE_ADV))]:
+            ms = timed(lambda: step(**kw), 3, 1)
+            variants[name] = {"value": world * pts_rank * 3 / (ms * 1e-3), "unit": UNIT,
+                              "alg_GBps_per_gpu": 8 * pts_rank * 3 / (ms * 1e-3) / 1e9}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    achieved = 8.0 * pts_rank / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "k1_traffic.json"
+    if tf.exists():
+        tj = json.loads(tf.read_text())
+        if tj.get("frames") and tj.get("size"):
+            traffic = tj["dram_bytes_per_launch"] * (T * A * A) / (tj["frames"] * tj["size"] ** 2)
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, dt_cpu, workers, sample = time_cpu_port(3, 1, 97, 1024)
+        cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_text(args, world), "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (pts_rank * 8 / 1e9),
+                   "parallelism": f"time slabs x{world}, 1-frame halo, all-reduce of 2x18 doubles" if world > 1 else "single GPU",
+                   "selected": {"alpha": float(alphas.cpu()[best // 6]), "threshold": float(thrs.cpu()[best % 6]),
+                                "coeffs": dict(zip(names, [float(c) for c in coef]))}},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "k1_tiled_b88<KS_TRUE,2 folds>", "k1_ms": k1_ms,
+                     "algorithmic_bytes": 8 * pts_rank, "peak_source": peak_src,
+                     "frac_of_nominal_8TBps": achieved / 8000.0},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 30 * 3 * 8,
+                "sample": f"{e2e_frames} frames per GPU streamed from pinned host memory in 96-frame slabs (double-buffered), "
+                          "through pde_b200.slabs.fit_streamed + stridge_batched"},
+        "gpu_launches": int(launches), "clocks": clocks, "variants": variants,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU (default: BASELINE configs[3])")
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--skip-variants", action="store_true", help="profiling runs: skip the other libraries")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,36 +3,51 @@
 // One CTA owns a 64 x 128 spatial tile and marches through a chunk of frames.  Each frame's
 // (64+4) x (128+4) halo tile is brought into shared memory ONCE by a 3-D TMA tensor copy
 // (cp.async.bulk.tensor, mbarrier completion) into a 3-stage ring: stage f is the frame being
-// differentiated, stage f+1 supplies u(t+1) for the forward u_t and becomes "current" next
-// iteration, stage f+2 is in flight.  Periodic wrap: TMA zero-fills the out-of-bounds halo of a
+// differentiated, stages f+1 and f+2 are in flight (two loads ahead: a single outstanding 72 KB
+// load per SM cannot cover the HBM latency-bandwidth product).  The forward u_t never touches
+// frame t+1 pointwise: over a t-block it telescopes to (sum u(t0+bt) - sum u(t0)) / dt, and every
+// frame's block sum of u is formed while that frame is current.  Periodic wrap: TMA zero-fills the out-of-bounds halo of a
 // border tile; the wrapped values are prefetched with plain loads one iteration ahead and stored
 // over the zero fill after the copy has landed.
 //
 // Inside a frame, warp w owns rows [8w, 8w+8) (one block row) and lane l owns columns
-// [4l, 4l+4) (half a block), marching down 12 tile rows with a register sliding window: two
-// LDS.128 per row give u at columns own-2 .. own+5, so the unscaled Laplacian L' is formed at
-// own-1 .. own+4 without any exchange between lanes.  Block sums of the linear terms use row
-// sums and the discrete divergence theorem (sum over a block of lap(L') = differences of L'
-// across the block boundary), so only the nonlinear terms cost per-point fp64 work.  At the end
+// [4l, 4l+4) (half a block), marching down 12 tile rows with a register sliding window: four
+// conflict-free LDS.128 per row give u at columns own-2 .. own+5, with no exchange between
+// lanes.  Block sums of the linear terms (lap, bih, u_x, u_y, u, u_t) reduce by the discrete
+// divergence theorem to per-row boundary scalars (see march_frame), so only the nonlinear
+// terms cost per-point fp64 work: about 8 fp64 ops per grid point for the true library.  At the end
 // of a t-block the two lanes of a block pair-reduce by shuffle, form the block-mean row and the
 // warp adds its 16 rows to lane-owned Gram entries held in registers.
 //
 // No tensor cores: p <= 9 and the kernel is HBM / fp64-issue bound.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "launch.h"
 
 namespace pg {
 
-constexpr int TI = 64, TJ = 128;            // tile rows / cols
-constexpr int HR = TI + 4, HC = TJ + 4;     // halo tile
+constexpr int TJ = 128;                     // tile columns (32 lanes x 4)
+constexpr int HC = TJ + 4;                  // halo tile columns
 constexpr int NSTAGE = 3;
-constexpr int STAGE_DOUBLES = HR * HC;      // 8976
-constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
-constexpr int TW = 8;                       // warps per CTA
-constexpr int MAXWRAP = 4;                  // wrap cells per thread (<= 4*256 >= 2*2*68 + 2*2*132)
+
+// Tile geometry for NW warps per CTA (one 8-row block band per warp).  NW = 8: 64 x 128 tile,
+// one CTA per SM; NW = 4: 32 x 128 tile, two CTAs per SM (independent barriers overlap each
+// other's TMA waits at the cost of a taller relative halo).
+template <int NW> struct Geo {
+    static constexpr int TI = 8 * NW;
+    static constexpr int HR = TI + 4;
+    static constexpr int STAGE_DOUBLES = HR * HC;
+    static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+    static constexpr int THREADS = 32 * NW;
+    static constexpr int MAXWRAP = (4 * HR + 4 * HC + THREADS - 1) / THREADS;   // wrap cells per thread
+    static constexpr int CTAS_PER_SM = NW == 8 ? 1 : 2;
+    // block rows staged per Gram-update batch (shared memory is the scarce resource at 2 CTAs/SM)
+    __host__ __device__ static constexpr int slots(int p) { return NW == 8 ? 8 : (p <= 5 ? 4 : 2); }
+    __host__ __device__ static constexpr size_t smem(int p) { return (size_t)NSTAGE * STAGE_BYTES + 64 + sizeof(double) * NW * slots(p) * (p + 2); }
+};
 
 struct TiledParams {
     const double *U;
@@ -49,7 +64,7 @@ struct TiledParams {
     const uint8_t *fold_of_row;
     const int32_t *fold_of_frame;
     int n_folds;
-    double *partials;         // [gridDim.x*TW][n_folds][S]
+    double *partials;         // [gridDim.x*NW][n_folds][S]
     unsigned long long *counters;
 };
 
@@ -86,106 +101,138 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- per-lane block sums
-template <int LIB> struct Acc {
-    // unscaled sums over the lane's half block; which ones exist depends on the library
-    double SL = 0, SE1 = 0, SE2 = 0, SGx = 0, SGy = 0, SY = 0;   // all libraries
-    double SDx = 0, SDy = 0;                                     // advection columns
-    double SU = 0, SU2 = 0, SUL = 0;                             // rich
-    __device__ __forceinline__ void reset() { SL = SE1 = SE2 = SGx = SGy = SY = SDx = SDy = SU = SU2 = SUL = 0.0; }
+// Unscaled sums over the lane's half block (4 columns x 8 rows x frames); which ones are live
+// depends on the library.  FrameSums holds one frame's contribution, Acc the running t-block.
+struct Sums {
+    double SL = 0, SE1 = 0, SE2 = 0, SGx = 0, SGy = 0;   // all libraries
+    double SU = 0;                                      // sum of u: rich column, and u_t by telescoping
+    double SDx = 0, SDy = 0;                            // advection columns
+    double SU2 = 0, SUL = 0;                            // rich
 };
 
 template <int LIB> constexpr bool kNeedAdv = (LIB == PG_LIB_KS_TRUE_ADV || LIB == PG_LIB_KS_RICH);
 template <int LIB> constexpr bool kRich = (LIB == PG_LIB_KS_RICH || LIB == PG_LIB_KS_RICH_NOADV);
 
-// One frame of one warp band: 12 tile rows march through the register window.
+// 16-byte chunk pair (k, k+1) of a lane's row segment.  Lanes are 32 B apart, so a plain LDS.128
+// would hit every bank group twice per quarter-warp; lanes with bit 2 set fetch the two chunks
+// in the opposite order (conflict-free) and swap them back.
+__device__ __forceinline__ void load_pair(const double2 *src, int k, int sw, double2 &lo, double2 &hi) {
+    const double2 x = src[k + sw], y = src[k + (sw ^ 1)];
+    lo = sw ? y : x;
+    hi = sw ? x : y;
+}
+
+// One frame of one warp band: 12 tile rows march through a 3-row register window.
 //   cur : halo tile of frame t (row pitch HC), pointing at the warp's first tile row, lane's first column
-//   nxt : halo tile of frame t+1, pointing at the warp's first OUTPUT row, lane's first own column
+//
+// With w[0..7] the lane's row segment (columns own-2 .. own+5, own = q 2..5) and band rows
+// s = 0..11 (outputs are rows 2..9), every block sum of a LINEAR term reduces, by the discrete
+// divergence theorem, to a few per-row scalars:
+//   rsU(s) = w2+w3+w4+w5                      D(s) = (w1-w2) + (w6-w5)        e(s) = (w0-w3) + (w7-w4)
+//   rsL(s) = sum_own L'(s,.) = rho*(rsU(s+1) + rsU(s-1) - 2 rsU(s)) + D(s)
+//   SL  = sum_{2..9} rsL           = rho*((rsU10 - rsU9) - (rsU2 - rsU1)) + sum_{2..9} D
+//   SE1 = a0-flux of L' through the block = rsL1 - rsL2 + rsL10 - rsL9
+//   SE2 = a1-flux of L' through the block = -3 sum_{2..9} D + rho*(D10 + D1 - D2 - D9) + sum_{2..9} e
+// (L' = rho*(u[i+1]+u[i-1]) + (u[j+1]+u[j-1]) + kappa*u with kappa = -2(1+rho); lap = r1*L',
+// block sum of bih = r1^2*(rho*SE1 + SE2)).  Only the nonlinear terms (|grad u|^2, and for the
+// rich library u^2 and u*L') cost per-point fp64 work.
 template <int LIB>
-__device__ __forceinline__ void march_frame(const double *__restrict__ cur, const double *__restrict__ nxt,
-                                            const TiledParams &P, Acc<LIB> &A, const int sw) {
-    double uA[8], uB[8], uC[8], uZ[4];       // rows s-2, s-1, s (cols own-2..own+5), row s-3 (own cols)
-    double Lc[6], Ln[6];                     // L' rows s-2, s-1 at cols own-1..own+4 (index q-1, q = 1..6)
-    double rsM = 0, rsC = 0, rsN = 0;        // row sums of L' over the own columns
-    double rsU_m1 = 0;                       // row sum of u over own columns, previous output-side row
-    (void)rsU_m1;
+__device__ __forceinline__ void march_frame(const double *__restrict__ cur, const TiledParams &P, Sums &F, const int sw) {
+    double wp[4], wc[8], wn[8];              // own columns of row s-2; rows s-1 and s (all 8 columns)
+    double rsU[12], D[12];
+    // per-column partial sums of the nonlinear terms: four independent FMA chains per quantity
+    double gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0}, u2[4] = {0, 0, 0, 0}, ul[4] = {0, 0, 0, 0};
+    double sD = 0, sE = 0, sU = 0, sDy = 0;
 #pragma unroll
     for (int s = 0; s < 12; ++s) {
-        // ---- load tile row s: 8 doubles as four 16-byte chunks.  Lanes are 32 B apart, so a plain
-        // LDS.128 would hit every bank group twice per quarter-warp; lanes with bit 2 set fetch the
-        // two chunks of each pair in the opposite order (conflict-free) and swap them back.
         const double2 *src = reinterpret_cast<const double2 *>(cur + s * HC);
-        const double2 p0 = src[sw], p1 = src[sw ^ 1], p2 = src[2 + sw], p3 = src[2 + (sw ^ 1)];
-        const double2 a0 = sw ? p1 : p0, a1 = sw ? p0 : p1, a2 = sw ? p3 : p2, a3 = sw ? p2 : p3;
-        uC[0] = a0.x; uC[1] = a0.y; uC[2] = a1.x; uC[3] = a1.y; uC[4] = a2.x; uC[5] = a2.y; uC[6] = a3.x; uC[7] = a3.y;
-        if (s >= 2) {
-            // ---- L' of tile row s-1 at q = 1..6
-#pragma unroll
-            for (int q = 1; q <= 6; ++q) {
-                const double v = uC[q] + uA[q];
-                const double h = uB[q + 1] + uB[q - 1];
-                Ln[q - 1] = fma(P.kappa, uB[q], fma(P.rho, v, h));
-            }
-            rsN = (Ln[1] + Ln[2]) + (Ln[3] + Ln[4]);
+        double2 a0, a1, a2, a3;
+        load_pair(src, 0, sw, a0, a1);
+        load_pair(src, 2, sw, a2, a3);
+        wn[0] = a0.x; wn[1] = a0.y; wn[2] = a1.x; wn[3] = a1.y; wn[4] = a2.x; wn[5] = a2.y; wn[6] = a3.x; wn[7] = a3.y;
+        rsU[s] = (wn[2] + wn[3]) + (wn[4] + wn[5]);
+        D[s] = (wn[1] - wn[2]) + (wn[6] - wn[5]);
+        if (s >= 2 && s <= 9) {
+            sD += D[s];
+            sE += (wn[0] - wn[3]) + (wn[7] - wn[4]);
+            sU += rsU[s];
+            if constexpr (kNeedAdv<LIB>) sDy += (wn[6] + wn[5]) - (wn[2] + wn[1]);
         }
-        if (s == 3) {
-            // L rows 1 (in Lc) and 2 (in Ln) exist: top boundary flux of the block, d/da0 direction
-            A.SE1 += rsC - rsN;
-        }
-        if (s >= 4) {
-            // ---- output tile row s-2 (u in uA, L' in Lc), neighbours: rows s-3 (uZ, rsM) and s-1 (uB, Ln)
-            A.SL += rsC;
-            A.SE2 += (Lc[0] - Lc[1]) + (Lc[5] - Lc[4]);
-            const double2 *ns = reinterpret_cast<const double2 *>(nxt + (s - 4) * HC);
-            const double2 m0 = ns[sw], m1 = ns[sw ^ 1];
-            const double2 n0 = sw ? m1 : m0, n1 = sw ? m0 : m1;
-            const double un[4] = {n0.x, n0.y, n1.x, n1.y};
-            const double rsU = (uA[2] + uA[3]) + (uA[4] + uA[5]);
-            A.SY += ((un[0] + un[1]) + (un[2] + un[3])) - rsU;
-            if constexpr (kRich<LIB>) A.SU += rsU;
-            if constexpr (kNeedAdv<LIB>) A.SDy += (uA[6] + uA[5]) - (uA[2] + uA[1]);
+        if (s >= 3 && s <= 10) {
+            // ---- nonlinear terms of output row s-1 (u in wc); rows s-2 (wp) and s (wn) are its a0-neighbours
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int q = c + 2;
-                const double dx = uB[q] - uZ[c];
-                const double dy = uA[q + 1] - uA[q - 1];
-                A.SGx = fma(dx, dx, A.SGx);
-                A.SGy = fma(dy, dy, A.SGy);
-                if constexpr (kNeedAdv<LIB>) A.SDx += dx;
+                const double dx = wn[q] - wp[c];
+                const double dy = wc[q + 1] - wc[q - 1];
+                gx[c] = fma(dx, dx, gx[c]);
+                gy[c] = fma(dy, dy, gy[c]);
                 if constexpr (kRich<LIB>) {
-                    A.SU2 = fma(uA[q], uA[q], A.SU2);
-                    A.SUL = fma(uA[q], Lc[q - 1], A.SUL);
+                    const double Lq = fma(P.kappa, wc[q], fma(P.rho, wn[q] + wp[c], wc[q + 1] + wc[q - 1]));
+                    u2[c] = fma(wc[q], wc[q], u2[c]);
+                    ul[c] = fma(wc[q], Lq, ul[c]);
                 }
             }
         }
-        if (s == 11) {
-            // L rows 9 (in Lc) and 10 (in Ln): bottom boundary flux
-            A.SE1 += rsN - rsC;
-        }
         // ---- rotate the window
 #pragma unroll
-        for (int c = 0; c < 4; ++c) uZ[c] = uA[c + 2];
+        for (int c = 0; c < 4; ++c) wp[c] = wc[c + 2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { uA[q] = uB[q]; uB[q] = uC[q]; }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) Lc[q] = Ln[q];
-        rsM = rsC; rsC = rsN;
+        for (int q = 0; q < 8; ++q) wc[q] = wn[q];
     }
-    (void)rsM;
+    const double rsL1 = fma(P.rho, (rsU[2] + rsU[0]) - 2.0 * rsU[1], D[1]);
+    const double rsL2 = fma(P.rho, (rsU[3] + rsU[1]) - 2.0 * rsU[2], D[2]);
+    const double rsL9 = fma(P.rho, (rsU[10] + rsU[8]) - 2.0 * rsU[9], D[9]);
+    const double rsL10 = fma(P.rho, (rsU[11] + rsU[9]) - 2.0 * rsU[10], D[10]);
+    F.SL = fma(P.rho, (rsU[10] - rsU[9]) - (rsU[2] - rsU[1]), sD);
+    F.SE1 = (rsL1 - rsL2) + (rsL10 - rsL9);
+    F.SE2 = fma(P.rho, (D[10] + D[1]) - (D[2] + D[9]), fma(-3.0, sD, sE));
+    F.SU = sU;
+    F.SGx = (gx[0] + gx[1]) + (gx[2] + gx[3]);
+    F.SGy = (gy[0] + gy[1]) + (gy[2] + gy[3]);
+    if constexpr (kNeedAdv<LIB>) {
+        F.SDy = sDy;
+        F.SDx = (rsU[10] + rsU[9]) - (rsU[2] + rsU[1]);   // sum_{2..9} (rsU(s+1) - rsU(s-1))
+    }
+    if constexpr (kRich<LIB>) {
+        F.SU2 = (u2[0] + u2[1]) + (u2[2] + u2[3]);
+        F.SUL = (ul[0] + ul[1]) + (ul[2] + ul[3]);
+    }
 }
 
-template <int LIB, int NF>
-__global__ void __launch_bounds__(TW * 32, 1) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap, TiledParams P) {
+// Sum of u over the lane's own 8 rows x 4 columns (the frame after a chunk only feeds u_t).
+//   own : halo tile, pointing at the warp's first OUTPUT row and the lane's first OWN column
+__device__ __forceinline__ double sum_frame_u(const double *__restrict__ own, const int sw) {
+    double s0 = 0, s1 = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        double2 a, b;
+        load_pair(reinterpret_cast<const double2 *>(own + r * HC), 0, sw, a, b);
+        s0 += a.x + a.y;
+        s1 += b.x + b.y;
+    }
+    return s0 + s1;
+}
+
+template <int LIB, int NF, int NW>
+__global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap,
+                                                                              TiledParams P) {
+    using G_ = Geo<NW>;
+    constexpr int TI = G_::TI, HR = G_::HR, STAGE_DOUBLES = G_::STAGE_DOUBLES, STAGE_BYTES = G_::STAGE_BYTES;
+    constexpr int MAXWRAP = G_::MAXWRAP, THREADS = G_::THREADS;
     constexpr int p = Lib<LIB>::P;
     constexpr int S = PG_STATS_LEN(p);
     constexpr int W = p + 2;
     constexpr int NE = (S + 31) / 32;   // lane-owned statistics entries
+    constexpr int SB = G_::slots(p);    // block rows per staging batch
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NSTAGE * STAGE_BYTES);
-    double *ext_all = reinterpret_cast<double *>(smem_raw + NSTAGE * STAGE_BYTES + 64);  // [TW][8][W]
+    double *ext_all = reinterpret_cast<double *>(smem_raw + NSTAGE * STAGE_BYTES + 64);  // [NW][SB][W]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    double *ext = ext_all + warp * 8 * W;
+    const int sw = (lane >> 2) & 1;
+    double *ext = ext_all + warp * SB * W;
 
     int ea[NE], eb[NE];
     bool ev[NE];
@@ -213,21 +260,46 @@ __global__ void __launch_bounds__(TW * 32, 1) k1_tiled_b88(const __grid_constant
     const int n_tiles = P.n_tiles0 * P.n_tiles1;
     const int64_t n_items = (int64_t)n_tiles * P.n_chunks;
     unsigned long long bad_rows = 0, bad_fold = 0;
-    uint32_t G = 0;  // loads issued so far by this CTA (stage = G % 3, parity = (G / 3) & 1)
-    Acc<LIB> A;
 
-    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // item -> (tile origin, first frame, number of row frames)
+    auto geometry = [&](int64_t item, int &i0, int &j0, int64_t &tb0, int &nf) {
         const int tile = (int)(item % n_tiles), chunk = (int)(item / n_tiles);
-        const int tj = tile % P.n_tiles1, ti = tile / P.n_tiles1;
-        const int64_t tb0 = (int64_t)chunk * P.chunk_tb;
-        const int64_t tb1 = min(P.nbt, tb0 + P.chunk_tb);
-        const int64_t t0 = tb0 * P.bt;
-        const int nf = (int)((tb1 - tb0) * P.bt);   // row frames; frames t0 .. t0+nf are loaded
-        const int i0 = ti * TI, j0 = tj * TJ;
+        i0 = (tile / P.n_tiles1) * TI;
+        j0 = (tile % P.n_tiles1) * TJ;
+        tb0 = (int64_t)chunk * P.chunk_tb;
+        nf = (int)((min(P.nbt, tb0 + P.chunk_tb) - tb0) * P.bt);
+    };
+
+    // ---- producer (thread 0): one continuous stream of frame loads over all items of this CTA,
+    // always two loads ahead of the consumer, so the pipeline never drains between items
+    int64_t p_item = blockIdx.x;
+    int p_f = 0;
+    uint32_t p_g = 0;
+    auto produce = [&]() {
+        if (p_item >= n_items) return;
+        int i0, j0, nf;
+        int64_t tb0;
+        geometry(p_item, i0, j0, tb0, nf);
+        uint64_t *bar = &bars[p_g % NSTAGE];
+        fence_proxy_async();
+        mbar_expect_tx(bar, STAGE_BYTES);
+        tma_load_3d(stages + (p_g % NSTAGE) * STAGE_DOUBLES, &tmap, bar, j0 - 2, i0 - 2, (int)(tb0 * P.bt + p_f));
+        ++p_g;
+        if (++p_f > nf) { p_f = 0; p_item += gridDim.x; }
+    };
+    if (tid == 0) { produce(); produce(); }
+
+    uint32_t G = 0;  // consumer load index (stage = G % 3, parity = (G / 3) & 1)
+    Sums A;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int i0, j0, nf;
+        int64_t tb0;
+        geometry(item, i0, j0, tb0, nf);
+        const int64_t t0 = tb0 * P.bt;   // frames t0 .. t0+nf are loaded; the last one only feeds u_t
         const bool wl = j0 == 0, wr = j0 + TJ == P.A1, wt = i0 == 0, wb = i0 + TI == P.A0;
         const bool border = wl || wr || wt || wb;
 
-        // wrap cells of this tile handled by this thread: tile offset (row*HC+col) and global offset in a frame
+        // periodic wrap cells of this tile handled by this thread: tile offset and offset inside a frame
         int w_off[MAXWRAP];
         int64_t w_src[MAXWRAP];
 #pragma unroll
@@ -235,7 +307,7 @@ __global__ void __launch_bounds__(TW * 32, 1) k1_tiled_b88(const __grid_constant
         if (border) {
 #pragma unroll
             for (int k = 0; k < MAXWRAP; ++k) {
-                int c = tid + k * (TW * 32), R = -1, C = -1;
+                int c = tid + k * THREADS, R = -1, C = -1;
                 if (wl) { if (c >= 0 && c < 2 * HR) { R = c >> 1; C = c & 1; } c -= 2 * HR; }
                 if (wr) { if (c >= 0 && c < 2 * HR) { R = c >> 1; C = HC - 2 + (c & 1); } c -= 2 * HR; }
                 if (wt) { if (c >= 0 && c < 2 * HC) { R = c / HC; C = c % HC; } c -= 2 * HC; }
@@ -257,47 +329,29 @@ __global__ void __launch_bounds__(TW * 32, 1) k1_tiled_b88(const __grid_constant
             for (int k = 0; k < MAXWRAP; ++k)
                 if (w_off[k] >= 0) stage[w_off[k]] = w_val[k];
         };
-        auto issue = [&](uint32_t g, int64_t t) {   // thread 0 only
-            uint64_t *bar = &bars[g % NSTAGE];
-            fence_proxy_async();
-            mbar_expect_tx(bar, STAGE_BYTES);
-            tma_load_3d(stages + (g % NSTAGE) * STAGE_DOUBLES, &tmap, bar, j0 - 2, i0 - 2, (int)t);
-        };
+        if (border) wrap_fetch(t0);
 
-        __syncthreads();  // every warp has left the previous item: its stages may be overwritten
-        const uint32_t G0 = G;
-        if (tid == 0) {
-            issue(G0, t0);
-            issue(G0 + 1, t0 + 1);
-        }
-        if (border) {
-            wrap_fetch(t0);
-            mbar_wait(&bars[G0 % NSTAGE], (G0 / NSTAGE) & 1);
-            wrap_store(stages + (G0 % NSTAGE) * STAGE_DOUBLES);
-            wrap_fetch(t0 + 1);
-        } else {
-            mbar_wait(&bars[G0 % NSTAGE], (G0 / NSTAGE) & 1);
-        }
+        int fold = 0;
+        double su_first = 0.0;
+        const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lane >> 1);
+        for (int f = 0; f <= nf; ++f, ++G) {
+            double *st = stages + (G % NSTAGE) * STAGE_DOUBLES;
+            mbar_wait(&bars[G % NSTAGE], (G / NSTAGE) & 1);
+            if (border) wrap_store(st);
+            __syncthreads();  // wrap stores visible; every warp finished the previous frame, whose stage is free
+            if (tid == 0) produce();                       // load G+2 -> the stage just freed
+            if (border && f < nf) wrap_fetch(t0 + f + 1);  // consumed after the next barrier wait
 
-        for (int f = 0; f < nf; ++f) {
-            const uint32_t gc = G0 + f, gn = gc + 1;
-            double *st_c = stages + (gc % NSTAGE) * STAGE_DOUBLES;
-            double *st_n = stages + (gn % NSTAGE) * STAGE_DOUBLES;
-            mbar_wait(&bars[gn % NSTAGE], (gn / NSTAGE) & 1);
-            if (border) wrap_store(st_n);
-            __syncthreads();  // wrap stores visible; every warp finished frame f-1 (stage (gc+2)%3 is free)
-            if (f + 2 <= nf) {
-                if (tid == 0) issue(gc + 2, t0 + f + 2);
-                if (border) wrap_fetch(t0 + f + 2);
-            }
-            march_frame<LIB>(st_c + (warp * 8) * HC + lane * 4, st_n + (warp * 8 + 2) * HC + lane * 4 + 2, P, A,
-                             (lane >> 2) & 1);
+            Sums F;
+            if (f < nf) march_frame<LIB>(st + (warp * 8) * HC + lane * 4, P, F, sw);
+            else F.SU = sum_frame_u(st + (warp * 8 + 2) * HC + lane * 4 + 2, sw);
 
-            if ((f + 1) % P.bt == 0) {
-                // ---- end of a t-block: the lane pair (2m, 2m+1) holds one block's sums
-                const int64_t tb = tb0 + f / P.bt;
+            if (f % P.bt == 0 && f > 0) {
+                // ---- the t-block that ended at frame f-1: u_t telescopes to (sum u(f) - sum u(f-bt)) / dt.
+                // The lane pair (2m, 2m+1) holds one block's sums.
+                double SY = F.SU - su_first;
 #define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 1)
-                PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(A.SY);
+                PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
                 if constexpr (kNeedAdv<LIB>) { PG_PAIR(A.SDx); PG_PAIR(A.SDy); }
                 if constexpr (kRich<LIB>) { PG_PAIR(A.SU); PG_PAIR(A.SU2); PG_PAIR(A.SUL); }
 #undef PG_PAIR
@@ -305,7 +359,7 @@ __global__ void __launch_bounds__(TW * 32, 1) k1_tiled_b88(const __grid_constant
                 const double lap = P.r1 * A.SL * invN;
                 const double bih = P.r1 * P.r1 * fma(P.rho, A.SE1, A.SE2) * invN;
                 const double gsq = fma(P.q0, A.SGx, P.q1 * A.SGy) * invN;
-                const double y = A.SY * P.rdt * invN;
+                const double y = SY * P.rdt * invN;
                 double th[p];
                 if constexpr (LIB == PG_LIB_KS_TRUE) {
                     th[0] = lap; th[1] = bih; th[2] = gsq;
@@ -318,22 +372,18 @@ __global__ void __launch_bounds__(TW * 32, 1) k1_tiled_b88(const __grid_constant
                     th[0] = 1.0; th[1] = A.SU * invN; th[2] = A.SU2 * invN; th[3] = lap; th[4] = bih; th[5] = gsq;
                     th[6] = P.r1 * A.SUL * invN;
                 }
-                A.reset();
+                A = Sums();
                 bool fin = isfinite(y);
 #pragma unroll
                 for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
-                const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lane >> 1);
-                int fold = 0;
-                if (P.fold_of_row) fold = P.fold_of_row[(tb * P.nB0 + ib) * P.nB1 + jb];
-                else if (P.fold_of_frame) fold = P.fold_of_frame[tb * P.bt];
                 bool valid = (lane & 1) == 0;
                 if (valid && !fin) { valid = false; ++bad_rows; }
                 else if (valid && (fold < 0 || fold >= NF)) { valid = false; ++bad_fold; }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const bool mine = valid && (lane >> 4) == h;
+                for (int h = 0; h < 16 / SB; ++h) {
+                    const bool mine = valid && (lane >> 1) / SB == h;
                     if (mine) {
-                        double *r = ext + ((lane >> 1) & 7) * W;
+                        double *r = ext + ((lane >> 1) % SB) * W;
                         r[0] = 1.0; r[1] = y;
 #pragma unroll
                         for (int k = 0; k < p; ++k) r[2 + k] = th[k];
@@ -341,8 +391,8 @@ __global__ void __launch_bounds__(TW * 32, 1) k1_tiled_b88(const __grid_constant
                     __syncwarp();
                     const unsigned vm = __ballot_sync(0xffffffffu, mine);
 #pragma unroll
-                    for (int slot = 0; slot < 8; ++slot) {
-                        const int src = h * 16 + slot * 2;
+                    for (int slot = 0; slot < SB; ++slot) {
+                        const int src = (h * SB + slot) * 2;
                         if (!((vm >> src) & 1u)) continue;
                         const int fr = __shfl_sync(0xffffffffu, fold, src);
                         const double *r = ext + slot * W;
@@ -357,12 +407,23 @@ __global__ void __launch_bounds__(TW * 32, 1) k1_tiled_b88(const __grid_constant
                     __syncwarp();
                 }
             }
+            if (f < nf) {
+                if (f % P.bt == 0) {
+                    // a t-block starts at this frame: remember sum u, fetch its fold id (used at its end)
+                    su_first = F.SU;
+                    const int64_t tbs = tb0 + f / P.bt;
+                    if (P.fold_of_row) fold = P.fold_of_row[(tbs * P.nB0 + ib) * P.nB1 + jb];
+                    else if (P.fold_of_frame) fold = P.fold_of_frame[tbs * P.bt];
+                }
+                A.SL += F.SL; A.SE1 += F.SE1; A.SE2 += F.SE2; A.SGx += F.SGx; A.SGy += F.SGy;
+                if constexpr (kNeedAdv<LIB>) { A.SDx += F.SDx; A.SDy += F.SDy; }
+                if constexpr (kRich<LIB>) { A.SU += F.SU; A.SU2 += F.SU2; A.SUL += F.SUL; }
+            }
         }
-        G = G0 + nf + 1;
     }
     if (bad_rows) atomicAdd(&P.counters[0], bad_rows);
     if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
-    double *out = P.partials + ((int64_t)blockIdx.x * TW + warp) * NF * S;
+    double *out = P.partials + ((int64_t)blockIdx.x * NW + warp) * NF * S;
 #pragma unroll
     for (int f = 0; f < NF; ++f)
 #pragma unroll
@@ -387,7 +448,12 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static size_t tiled_smem(int p) { return (size_t)NSTAGE * STAGE_BYTES + 64 + sizeof(double) * TW * 8 * (p + 2); }
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+// warps per CTA: 4 (two CTAs per SM) or 8 (one CTA per SM); PG_TILED_WARPS overrides for experiments
+static int tiled_warps() { return env_int("PG_TILED_WARPS", 4) == 8 ? 8 : 4; }
 
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan) {
     if (P.dialect != PG_FD_KS_PERIODIC) return false;
@@ -396,6 +462,10 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     if (P.b0 != 8 || P.b1 != 8) return false;
     if (P.n_folds > 2) return false;
     if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // TMA: 16-byte strides / base
+    const int NW = tiled_warps();
+    if (NW == 4 && P.A0 / 32 < 1) return false;
+    const int TI = 8 * NW;
+    const int workers = n_sm * (NW == 8 ? 1 : 2);
     const int64_t nt0 = P.A0 / TI, nt1 = P.A1 / TJ;
     const int64_t nbt = (P.T - 1) / P.bt;   // full t-blocks only; a ragged last one goes to the generic kernel
     if (nt0 < 1 || nt1 < 1 || nbt < 1) return false;
@@ -409,7 +479,7 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     for (int64_t c = 1; c <= nbt && c <= 4096; ++c) {
         const int64_t ctb = (nbt + c - 1) / c;
         const int64_t cc = (nbt + ctb - 1) / ctb;           // chunks actually produced
-        const int64_t rounds = (n_tiles * cc + n_sm - 1) / n_sm;
+        const int64_t rounds = (n_tiles * cc + workers - 1) / workers;
         const double cost = (double)rounds * ((double)ctb * P.bt + 4.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_c = cc; }
     }
@@ -418,26 +488,27 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     plan.chunk_t = (int)ctb; plan.n_chunks = (nbt + ctb - 1) / ctb;
     plan.n_tiles0 = nt0; plan.n_tiles1 = nt1;
     const int64_t items = n_tiles * plan.n_chunks;
-    plan.grid = (int)(items < n_sm ? items : n_sm);
-    plan.n_parts = (int64_t)plan.grid * TW;
+    plan.grid = (int)(items < workers ? items : workers);
+    plan.n_parts = (int64_t)plan.grid * NW;
     plan.extra_scratch = 0;
     plan.kernel_id = lib;
     plan.tile0 = TI; plan.tile1 = TJ;
     return true;
 }
 
-template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const TiledParams &tp, int n_folds, int grid,
-                                             cudaStream_t st) {
-    const size_t smem = tiled_smem(Lib<LIB>::P);
-    if (n_folds == 1) {
-        PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1_tiled_b88<LIB, 1><<<grid, TW * 32, smem, st>>>(map, tp);
-    } else {
-        PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1_tiled_b88<LIB, 2><<<grid, TW * 32, smem, st>>>(map, tp);
-    }
+template <int LIB, int NF, int NW> static int launch_tiled_k(const CUtensorMap &map, const TiledParams &tp, int grid,
+                                                            cudaStream_t st) {
+    const size_t smem = Geo<NW>::smem(Lib<LIB>::P);
+    PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_tiled_b88<LIB, NF, NW><<<grid, 32 * NW, smem, st>>>(map, tp);
     PG_LAUNCHED();
     return PG_OK;
+}
+
+template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const TiledParams &tp, int n_folds, int nw, int grid,
+                                             cudaStream_t st) {
+    if (nw == 8) return n_folds == 1 ? launch_tiled_k<LIB, 1, 8>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 8>(map, tp, grid, st);
+    return n_folds == 1 ? launch_tiled_k<LIB, 1, 4>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 4>(map, tp, grid, st);
 }
 
 int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *, cudaStream_t st) {
@@ -446,10 +517,11 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     CUtensorMap map;
     const cuuint64_t gdim[3] = {(cuuint64_t)P.A1, (cuuint64_t)P.A0, (cuuint64_t)P.T};
     const cuuint64_t gstr[2] = {(cuuint64_t)P.A1 * 8, (cuuint64_t)P.A0 * (cuuint64_t)P.A1 * 8};
-    const cuuint32_t box[3] = {HC, HR, 1};
+    const int NW = plan.tile0 / 8;
+    const cuuint32_t box[3] = {HC, (cuuint32_t)(plan.tile0 + 4), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(P.U), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)env_int("PG_TMA_L2PROMO", 3),
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     TiledParams tp{};
@@ -468,10 +540,10 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     tp.fold_of_row = P.fold_of_row; tp.fold_of_frame = P.fold_of_frame; tp.n_folds = P.n_folds;
     tp.partials = partials; tp.counters = P.counters;
     switch (lib) {
-        case PG_LIB_KS_TRUE: return launch_tiled_t<PG_LIB_KS_TRUE>(map, tp, P.n_folds, plan.grid, st);
-        case PG_LIB_KS_TRUE_ADV: return launch_tiled_t<PG_LIB_KS_TRUE_ADV>(map, tp, P.n_folds, plan.grid, st);
-        case PG_LIB_KS_RICH: return launch_tiled_t<PG_LIB_KS_RICH>(map, tp, P.n_folds, plan.grid, st);
-        case PG_LIB_KS_RICH_NOADV: return launch_tiled_t<PG_LIB_KS_RICH_NOADV>(map, tp, P.n_folds, plan.grid, st);
+        case PG_LIB_KS_TRUE: return launch_tiled_t<PG_LIB_KS_TRUE>(map, tp, P.n_folds, NW, plan.grid, st);
+        case PG_LIB_KS_TRUE_ADV: return launch_tiled_t<PG_LIB_KS_TRUE_ADV>(map, tp, P.n_folds, NW, plan.grid, st);
+        case PG_LIB_KS_RICH: return launch_tiled_t<PG_LIB_KS_RICH>(map, tp, P.n_folds, NW, plan.grid, st);
+        case PG_LIB_KS_RICH_NOADV: return launch_tiled_t<PG_LIB_KS_RICH_NOADV>(map, tp, P.n_folds, NW, plan.grid, st);
         default: PG_FAIL(PG_EUNSUPPORTED, "no tiled kernel for library %d", lib);
     }
 }

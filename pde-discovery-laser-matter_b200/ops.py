@@ -163,11 +163,17 @@ def stridge_batched(stats, p, *, dialect, alphas, thresholds, max_iter, flags=0,
     lib = L.load()
     stats = _dev(stats, torch.float64).reshape(-1, L.stats_len(p)).contiguous()
     B = stats.shape[0]
-    al = _dev(np.atleast_1d(np.asarray(alphas, dtype=np.float64)))
-    th = _dev(np.atleast_1d(np.asarray(thresholds, dtype=np.float64)))
+    def vec(v):  # sweep grids may already live on the device (no per-call copy)
+        if isinstance(v, torch.Tensor):
+            return _dev(v, torch.float64).reshape(-1)
+        return _dev(np.atleast_1d(np.asarray(v, dtype=np.float64)))
+
+    al, th = vec(alphas), vec(thresholds)
     na, nt = al.numel(), th.numel()
     cm = None
-    if len(tuple(const_cols)):
+    if isinstance(const_cols, torch.Tensor):
+        cm = _dev(const_cols, torch.uint8)
+    elif len(tuple(const_cols)):
         m = np.zeros(p, dtype=np.uint8)
         m[list(const_cols)] = 1
         cm = _dev(m)

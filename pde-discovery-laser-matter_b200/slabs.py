@@ -23,7 +23,7 @@ def slab_bounds(n_row_frames: int, block_t: int, world: int):
     out, tb = [], 0
     for r in range(world):
         k = base + (1 if r < extra else 0)
-        lo, hi = tb * block_t, min(n_row_frames, (tb + k) * block_t)
+        lo, hi = min(n_row_frames, tb * block_t), min(n_row_frames, (tb + k) * block_t)
         out.append((lo, max(lo, hi)))
         tb += k
     return out

@@ -3,6 +3,7 @@ on a synthetic stack with CUDA events and prints achieved algorithmic GB/s (8 B 
 
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -34,12 +35,14 @@ def main():
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--only", default=None, help="run a single named case")
     args = ap.parse_args()
     T, A = args.frames, args.size
     U = ops.synth_field(T, A, A, seed=0, noise=0.05)
     torch.cuda.synchronize()
     pts = T * A * A
-    fof = (torch.arange(T - 1) >= int(0.7 * (T - 1))).to(torch.int32)
+    fof = (torch.arange(T - 1) >= int(0.7 * (T - 1))).to(torch.int32).cuda()  # on the device: no per-call copy
     out = []
     cases = [("true_b388_tiled", L.LIB_KS_TRUE, (3, 8, 8), L.VARIANT_TILED, 1),
              ("true_b388_tiled_2folds", L.LIB_KS_TRUE, (3, 8, 8), L.VARIANT_TILED, 2),
@@ -50,6 +53,8 @@ def main():
                   ("true_pointwise_generic", L.LIB_KS_TRUE, (1, 1, 1), L.VARIANT_GENERIC, 1),
                   ("rich_pointwise_generic", L.LIB_KS_RICH, (1, 1, 1), L.VARIANT_GENERIC, 1)]
     for name, lib, block, variant, nf in cases:
+        if args.only and name != args.only:
+            continue
         kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=block, variant=variant, n_folds=nf)
         if nf == 2:
             kw["fold_of_frame"] = fof
@@ -58,6 +63,18 @@ def main():
                    alg_GBps=round(8 * pts / best / 1e6, 1))
         print(json.dumps(rec), flush=True)
         out.append(rec)
+    if args.sweep:
+        # tile geometry (warps per CTA) x TMA L2 promotion, read by the planner at every call
+        for nw in (8, 4):
+            for promo in (0, 1, 2, 3):
+                os.environ["PG_TILED_WARPS"], os.environ["PG_TMA_L2PROMO"] = str(nw), str(promo)
+                for name, lib, nf in (("true", L.LIB_KS_TRUE, 2), ("rich", L.LIB_KS_RICH, 2), ("true1f", L.LIB_KS_TRUE, 1)):
+                    kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=(3, 8, 8), variant=L.VARIANT_TILED, n_folds=nf)
+                    if nf == 2:
+                        kw["fold_of_frame"] = fof
+                    best, avg = time_call(lambda: ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, **kw), iters=args.iters)
+                    print(json.dumps(dict(case=f"{name}_nw{nw}_promo{promo}", ms_best=round(best, 3), ms_avg=round(avg, 3),
+                                          alg_GBps=round(8 * pts / best / 1e6, 1))), flush=True)
     # plain device copy of the same bytes for scale (read + write)
     V = torch.empty_like(U[: T // 2])
     best, _ = time_call(lambda: V.copy_(U[: T // 2]), iters=args.iters)
