@@ -33,19 +33,25 @@ constexpr int TJ = 128;                     // tile columns (32 lanes x 4)
 constexpr int HC = TJ + 4;                  // halo tile columns
 constexpr int NSTAGE = 3;
 
-// Tile geometry for NW warps per CTA (one 8-row block band per warp).  NW = 8: 64 x 128 tile,
-// one CTA per SM; NW = 4: 32 x 128 tile, two CTAs per SM (independent barriers overlap each
-// other's TMA waits at the cost of a taller relative halo).
+// Tile geometry for NW warps per CTA.  KC = columns per lane, BANDS = 8-row block bands per tile.
+//   NW = 16: 64 x 128 tile, KC = 2 (each band is split between two warps), one CTA per SM,
+//            <= 128 registers: 16 resident warps hide the fp64 / shared-memory latencies
+//   NW = 8 : 64 x 128 tile, KC = 4, one CTA per SM
+//   NW = 4 : 32 x 128 tile, KC = 4, two CTAs per SM
 template <int NW> struct Geo {
-    static constexpr int TI = 8 * NW;
+    static constexpr int KC = NW == 16 ? 2 : 4;
+    static constexpr int BANDS = NW == 16 ? 8 : NW;
+    static constexpr int TI = 8 * BANDS;
     static constexpr int HR = TI + 4;
     static constexpr int STAGE_DOUBLES = HR * HC;
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
     static constexpr int THREADS = 32 * NW;
     static constexpr int MAXWRAP = (4 * HR + 4 * HC + THREADS - 1) / THREADS;   // wrap cells per thread
-    static constexpr int CTAS_PER_SM = NW == 8 ? 1 : 2;
+    static constexpr int CTAS_PER_SM = NW == 4 ? 2 : 1;
+    static constexpr int LPB = 8 / KC;          // lanes per 8-column block
+    static constexpr int RPW = 32 / LPB;        // block rows a warp emits per t-block
     // block rows staged per Gram-update batch (shared memory is the scarce resource at 2 CTAs/SM)
-    __host__ __device__ static constexpr int slots(int p) { return NW == 8 ? 8 : (p <= 5 ? 4 : 2); }
+    __host__ __device__ static constexpr int slots(int p) { return NW == 4 ? (p <= 5 ? 4 : 2) : 8; }
     __host__ __device__ static constexpr size_t smem(int p) { return (size_t)NSTAGE * STAGE_BYTES + 64 + sizeof(double) * NW * slots(p) * (p + 2); }
 };
 
@@ -200,6 +206,78 @@ __device__ __forceinline__ void march_frame(const double *__restrict__ cur, cons
     }
 }
 
+// KC = 2 variant: the lane owns two columns (w[2], w[3] of the six-value segment own-2 .. own+3);
+// lanes are 16 B apart, so the three LDS.128 per row are conflict-free as they stand.  Same
+// scalars as above with D(s) = (w1-w2) + (w4-w3), e(s) = (w0-w3) + (w5-w2), rsU(s) = w2+w3.
+template <int LIB>
+__device__ __forceinline__ void march_frame2(const double *__restrict__ cur, const TiledParams &P, Sums &F) {
+    double wp[2], wc[6], wn[6];
+    double rsU[12], D[12];
+    double gx[2] = {0, 0}, gy[2] = {0, 0}, u2[2] = {0, 0}, ul[2] = {0, 0};
+    double sD = 0, sE = 0, sU = 0, sDy = 0;
+#pragma unroll
+    for (int s = 0; s < 12; ++s) {
+        const double2 *src = reinterpret_cast<const double2 *>(cur + s * HC);
+        const double2 a0 = src[0], a1 = src[1], a2 = src[2];
+        wn[0] = a0.x; wn[1] = a0.y; wn[2] = a1.x; wn[3] = a1.y; wn[4] = a2.x; wn[5] = a2.y;
+        rsU[s] = wn[2] + wn[3];
+        D[s] = (wn[1] - wn[2]) + (wn[4] - wn[3]);
+        if (s >= 2 && s <= 9) {
+            sD += D[s];
+            sE += (wn[0] - wn[3]) + (wn[5] - wn[2]);
+            sU += rsU[s];
+            if constexpr (kNeedAdv<LIB>) sDy += (wn[3] + wn[4]) - (wn[1] + wn[2]);
+        }
+        if (s >= 3 && s <= 10) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int q = c + 2;
+                const double dx = wn[q] - wp[c];
+                const double dy = wc[q + 1] - wc[q - 1];
+                gx[c] = fma(dx, dx, gx[c]);
+                gy[c] = fma(dy, dy, gy[c]);
+                if constexpr (kRich<LIB>) {
+                    const double Lq = fma(P.kappa, wc[q], fma(P.rho, wn[q] + wp[c], wc[q + 1] + wc[q - 1]));
+                    u2[c] = fma(wc[q], wc[q], u2[c]);
+                    ul[c] = fma(wc[q], Lq, ul[c]);
+                }
+            }
+        }
+        wp[0] = wc[2]; wp[1] = wc[3];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) wc[q] = wn[q];
+    }
+    const double rsL1 = fma(P.rho, (rsU[2] + rsU[0]) - 2.0 * rsU[1], D[1]);
+    const double rsL2 = fma(P.rho, (rsU[3] + rsU[1]) - 2.0 * rsU[2], D[2]);
+    const double rsL9 = fma(P.rho, (rsU[10] + rsU[8]) - 2.0 * rsU[9], D[9]);
+    const double rsL10 = fma(P.rho, (rsU[11] + rsU[9]) - 2.0 * rsU[10], D[10]);
+    F.SL = fma(P.rho, (rsU[10] - rsU[9]) - (rsU[2] - rsU[1]), sD);
+    F.SE1 = (rsL1 - rsL2) + (rsL10 - rsL9);
+    F.SE2 = fma(P.rho, (D[10] + D[1]) - (D[2] + D[9]), fma(-3.0, sD, sE));
+    F.SU = sU;
+    F.SGx = gx[0] + gx[1];
+    F.SGy = gy[0] + gy[1];
+    if constexpr (kNeedAdv<LIB>) {
+        F.SDy = sDy;
+        F.SDx = (rsU[10] + rsU[9]) - (rsU[2] + rsU[1]);
+    }
+    if constexpr (kRich<LIB>) {
+        F.SU2 = u2[0] + u2[1];
+        F.SUL = ul[0] + ul[1];
+    }
+}
+
+__device__ __forceinline__ double sum_frame_u2(const double *__restrict__ own) {
+    double s0 = 0, s1 = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const double2 a = *reinterpret_cast<const double2 *>(own + r * HC);
+        s0 += a.x;
+        s1 += a.y;
+    }
+    return s0 + s1;
+}
+
 // Sum of u over the lane's own 8 rows x 4 columns (the frame after a chunk only feeds u_t).
 //   own : halo tile, pointing at the warp's first OUTPUT row and the lane's first OWN column
 __device__ __forceinline__ double sum_frame_u(const double *__restrict__ own, const int sw) {
@@ -225,6 +303,7 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
     constexpr int W = p + 2;
     constexpr int NE = (S + 31) / 32;   // lane-owned statistics entries
     constexpr int SB = G_::slots(p);    // block rows per staging batch
+    constexpr int KC = G_::KC, LPB = G_::LPB, RPW = G_::RPW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NSTAGE * STAGE_BYTES);
@@ -232,6 +311,8 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sw = (lane >> 2) & 1;
+    const int band = KC == 4 ? warp : warp >> 1;                   // 8-row block band of the tile
+    const int col0 = (KC == 4 ? 0 : (warp & 1) * 64) + lane * KC;   // tile column where the lane's segment starts
     double *ext = ext_all + warp * SB * W;
 
     int ea[NE], eb[NE];
@@ -248,6 +329,16 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
     for (int f = 0; f < NF; ++f)
 #pragma unroll
         for (int k = 0; k < NE; ++k) acc[f][k] = 0.0;
+    // Small libraries (p <= 5): every lane that owns a block row keeps a PRIVATE copy of the whole
+    // statistics vector in registers (S <= 33 FMAs per emitted row, no staging, no shuffles);
+    // larger ones stage rows in shared memory and spread the S entries over the lanes.
+    constexpr bool PRIV = S * NF <= 36 && NW != 16;   // register budget: true library (S = 18), or p = 5 with one fold
+    constexpr int SP = PRIV ? S : 1;
+    double pacc[NF][SP];
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int e = 0; e < SP; ++e) pacc[f][e] = 0.0;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
@@ -271,21 +362,36 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
     };
 
     // ---- producer (thread 0): one continuous stream of frame loads over all items of this CTA,
-    // always two loads ahead of the consumer, so the pipeline never drains between items
+    // always two loads ahead of the consumer, so the pipeline never drains between items.  The
+    // cursor is advanced incrementally: the divisions of geometry() run once per item, not per frame.
     int64_t p_item = blockIdx.x;
-    int p_f = 0;
+    int p_i0 = 0, p_j0 = 0, p_t = 0, p_left = 0;
     uint32_t p_g = 0;
-    auto produce = [&]() {
-        if (p_item >= n_items) return;
-        int i0, j0, nf;
+    if (tid == 0 && p_item < n_items) {
+        int nf;
         int64_t tb0;
-        geometry(p_item, i0, j0, tb0, nf);
+        geometry(p_item, p_i0, p_j0, tb0, nf);
+        p_t = (int)(tb0 * P.bt);
+        p_left = nf + 1;
+    }
+    auto produce = [&]() {
+        if (p_left == 0) return;
         uint64_t *bar = &bars[p_g % NSTAGE];
         fence_proxy_async();
         mbar_expect_tx(bar, STAGE_BYTES);
-        tma_load_3d(stages + (p_g % NSTAGE) * STAGE_DOUBLES, &tmap, bar, j0 - 2, i0 - 2, (int)(tb0 * P.bt + p_f));
+        tma_load_3d(stages + (p_g % NSTAGE) * STAGE_DOUBLES, &tmap, bar, p_j0 - 2, p_i0 - 2, p_t);
         ++p_g;
-        if (++p_f > nf) { p_f = 0; p_item += gridDim.x; }
+        ++p_t;
+        if (--p_left == 0) {
+            p_item += gridDim.x;
+            if (p_item < n_items) {
+                int nf;
+                int64_t tb0;
+                geometry(p_item, p_i0, p_j0, tb0, nf);
+                p_t = (int)(tb0 * P.bt);
+                p_left = nf + 1;
+            }
+        }
     };
     if (tid == 0) { produce(); produce(); }
 
@@ -333,7 +439,7 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
 
         int fold = 0;
         double su_first = 0.0;
-        const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lane >> 1);
+        const int64_t ib = (int64_t)(i0 >> 3) + band, jb = (int64_t)((j0 + col0) >> 3);
         for (int f = 0; f <= nf; ++f, ++G) {
             double *st = stages + (G % NSTAGE) * STAGE_DOUBLES;
             mbar_wait(&bars[G % NSTAGE], (G / NSTAGE) & 1);
@@ -343,14 +449,23 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
             if (border && f < nf) wrap_fetch(t0 + f + 1);  // consumed after the next barrier wait
 
             Sums F;
-            if (f < nf) march_frame<LIB>(st + (warp * 8) * HC + lane * 4, P, F, sw);
-            else F.SU = sum_frame_u(st + (warp * 8 + 2) * HC + lane * 4 + 2, sw);
+            if constexpr (KC == 4) {
+                if (f < nf) march_frame<LIB>(st + (band * 8) * HC + col0, P, F, sw);
+                else F.SU = sum_frame_u(st + (band * 8 + 2) * HC + col0 + 2, sw);
+            } else {
+                if (f < nf) march_frame2<LIB>(st + (band * 8) * HC + col0, P, F);
+                else F.SU = sum_frame_u2(st + (band * 8 + 2) * HC + col0 + 2);
+            }
 
             if (f % P.bt == 0 && f > 0) {
                 // ---- the t-block that ended at frame f-1: u_t telescopes to (sum u(f) - sum u(f-bt)) / dt.
-                // The lane pair (2m, 2m+1) holds one block's sums.
+                // The LPB lanes of an 8-column block hold one block's sums.
                 double SY = F.SU - su_first;
-#define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 1)
+#define PG_PAIR(x)                                                  \
+    do {                                                            \
+        x += __shfl_xor_sync(0xffffffffu, x, 1);                    \
+        if constexpr (LPB == 4) x += __shfl_xor_sync(0xffffffffu, x, 2); \
+    } while (0)
                 PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
                 if constexpr (kNeedAdv<LIB>) { PG_PAIR(A.SDx); PG_PAIR(A.SDy); }
                 if constexpr (kRich<LIB>) { PG_PAIR(A.SU); PG_PAIR(A.SU2); PG_PAIR(A.SUL); }
@@ -376,14 +491,36 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
                 bool fin = isfinite(y);
 #pragma unroll
                 for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
-                bool valid = (lane & 1) == 0;
+                bool valid = (lane % LPB) == 0;
                 if (valid && !fin) { valid = false; ++bad_rows; }
                 else if (valid && (fold < 0 || fold >= NF)) { valid = false; ++bad_fold; }
+                if constexpr (PRIV) {
+                    if (valid) {
+                        double m[NF];
 #pragma unroll
-                for (int h = 0; h < 16 / SB; ++h) {
-                    const bool mine = valid && (lane >> 1) / SB == h;
+                        for (int ff = 0; ff < NF; ++ff) m[ff] = (NF == 1 || fold == ff) ? 1.0 : 0.0;
+                        auto add = [&](int e, double v) {
+#pragma unroll
+                            for (int ff = 0; ff < NF; ++ff) pacc[ff][e] = fma(v, m[ff], pacc[ff][e]);
+                        };
+                        add(0, 1.0);
+                        add(1, y);
+                        add(2, y * y);
+                        int e = 3 + 2 * p;
+#pragma unroll
+                        for (int i = 0; i < p; ++i) {
+                            add(3 + i, th[i]);
+                            add(3 + p + i, th[i] * y);
+#pragma unroll
+                            for (int j = i; j < p; ++j) add(e++, th[i] * th[j]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                for (int h = 0; h < RPW / SB; ++h) {
+                    const bool mine = valid && (lane / LPB) / SB == h;
                     if (mine) {
-                        double *r = ext + ((lane >> 1) % SB) * W;
+                        double *r = ext + ((lane / LPB) % SB) * W;
                         r[0] = 1.0; r[1] = y;
 #pragma unroll
                         for (int k = 0; k < p; ++k) r[2 + k] = th[k];
@@ -392,7 +529,7 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
                     const unsigned vm = __ballot_sync(0xffffffffu, mine);
 #pragma unroll
                     for (int slot = 0; slot < SB; ++slot) {
-                        const int src = (h * SB + slot) * 2;
+                        const int src = (h * SB + slot) * LPB;
                         if (!((vm >> src) & 1u)) continue;
                         const int fr = __shfl_sync(0xffffffffu, fold, src);
                         const double *r = ext + slot * W;
@@ -405,6 +542,7 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
                         }
                     }
                     __syncwarp();
+                }
                 }
             }
             if (f < nf) {
@@ -424,11 +562,23 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
     if (bad_rows) atomicAdd(&P.counters[0], bad_rows);
     if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
     double *out = P.partials + ((int64_t)blockIdx.x * NW + warp) * NF * S;
+    if constexpr (PRIV) {
 #pragma unroll
-    for (int f = 0; f < NF; ++f)
+        for (int f = 0; f < NF; ++f)
 #pragma unroll
-        for (int k = 0; k < NE; ++k)
-            if (ev[k]) out[f * S + lane + 32 * k] = acc[f][k];
+            for (int e = 0; e < S; ++e) {
+                double v = pacc[f][e];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == (e & 31)) out[f * S + e] = v;
+            }
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int k = 0; k < NE; ++k)
+                if (ev[k]) out[f * S + lane + 32 * k] = acc[f][k];
+    }
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -452,8 +602,11 @@ static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
-// warps per CTA: 4 (two CTAs per SM) or 8 (one CTA per SM); PG_TILED_WARPS overrides for experiments
-static int tiled_warps() { return env_int("PG_TILED_WARPS", 4) == 8 ? 8 : 4; }
+// warps per CTA (see Geo): 16, 8 or 4; PG_TILED_WARPS overrides the default for experiments
+static int tiled_warps() {
+    const int w = env_int("PG_TILED_WARPS", 8);
+    return w == 4 || w == 16 ? w : 8;
+}
 
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan) {
     if (P.dialect != PG_FD_KS_PERIODIC) return false;
@@ -463,9 +616,8 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     if (P.n_folds > 2) return false;
     if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // TMA: 16-byte strides / base
     const int NW = tiled_warps();
-    if (NW == 4 && P.A0 / 32 < 1) return false;
-    const int TI = 8 * NW;
-    const int workers = n_sm * (NW == 8 ? 1 : 2);
+    const int TI = NW == 4 ? 32 : 64;
+    const int workers = n_sm * (NW == 4 ? 2 : 1);
     const int64_t nt0 = P.A0 / TI, nt1 = P.A1 / TJ;
     const int64_t nbt = (P.T - 1) / P.bt;   // full t-blocks only; a ragged last one goes to the generic kernel
     if (nt0 < 1 || nt1 < 1 || nbt < 1) return false;
@@ -491,7 +643,7 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     plan.grid = (int)(items < workers ? items : workers);
     plan.n_parts = (int64_t)plan.grid * NW;
     plan.extra_scratch = 0;
-    plan.kernel_id = lib;
+    plan.kernel_id = NW;
     plan.tile0 = TI; plan.tile1 = TJ;
     return true;
 }
@@ -507,6 +659,7 @@ template <int LIB, int NF, int NW> static int launch_tiled_k(const CUtensorMap &
 
 template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const TiledParams &tp, int n_folds, int nw, int grid,
                                              cudaStream_t st) {
+    if (nw == 16) return n_folds == 1 ? launch_tiled_k<LIB, 1, 16>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 16>(map, tp, grid, st);
     if (nw == 8) return n_folds == 1 ? launch_tiled_k<LIB, 1, 8>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 8>(map, tp, grid, st);
     return n_folds == 1 ? launch_tiled_k<LIB, 1, 4>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 4>(map, tp, grid, st);
 }
@@ -517,7 +670,7 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     CUtensorMap map;
     const cuuint64_t gdim[3] = {(cuuint64_t)P.A1, (cuuint64_t)P.A0, (cuuint64_t)P.T};
     const cuuint64_t gstr[2] = {(cuuint64_t)P.A1 * 8, (cuuint64_t)P.A0 * (cuuint64_t)P.A1 * 8};
-    const int NW = plan.tile0 / 8;
+    const int NW = plan.kernel_id;
     const cuuint32_t box[3] = {HC, (cuuint32_t)(plan.tile0 + 4), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(P.U), gdim, gstr, box, estr,

@@ -15,6 +15,50 @@ from pde_b200 import _lib as L  # noqa: E402
 from pde_b200 import ops  # noqa: E402
 
 
+class Nvml:
+    """SM clock / power sampler (pynvml, ~2 ms period) for the timed loops."""
+
+    def __init__(self):
+        import threading
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        self.n, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+        self.rows, self.run = [], False
+        self.t = threading.Thread(target=self._loop, daemon=True)
+
+    def _loop(self):
+        import time
+
+        while self.run:
+            try:
+                self.rows.append((self.n.nvmlDeviceGetClockInfo(self.h, self.n.NVML_CLOCK_SM),
+                                  self.n.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                  self.n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        self.run = True
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.run = False
+        self.t.join()
+
+    def summary(self):
+        import statistics
+
+        if not self.rows:
+            return {}
+        return dict(sm_mhz_median=statistics.median(r[0] for r in self.rows), sm_mhz_min=min(r[0] for r in self.rows),
+                    power_w_max=round(max(r[1] for r in self.rows), 1), reasons=hex(max(r[2] for r in self.rows)),
+                    samples=len(self.rows))
+
+
 def time_call(fn, warmup=2, iters=5):
     for _ in range(warmup):
         fn()
@@ -58,9 +102,10 @@ def main():
         kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=block, variant=variant, n_folds=nf)
         if nf == 2:
             kw["fold_of_frame"] = fof
-        best, avg = time_call(lambda: ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, **kw), iters=args.iters)
+        with Nvml() as nv:
+            best, avg = time_call(lambda: ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, **kw), iters=args.iters)
         rec = dict(case=name, ms_best=round(best, 3), ms_avg=round(avg, 3), gpts_per_s=round(pts / best / 1e6, 2),
-                   alg_GBps=round(8 * pts / best / 1e6, 1))
+                   alg_GBps=round(8 * pts / best / 1e6, 1), clocks=nv.summary())
         print(json.dumps(rec), flush=True)
         out.append(rec)
     if args.sweep:
