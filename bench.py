@@ -130,38 +130,53 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed region, sampled through NVML
+    (nvidia_ml_py, ~2 ms period; `nvidia-smi -lms` cannot resolve a sub-second region)."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.run, self.thread, self.h = [], False, None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.n = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # pragma: no cover
+            self.err = repr(exc)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+        if self.h is None:
+            return
+        self.run = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        n = self.n
+        while self.run:
+            try:
+                self.rows.append((n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM), n.nvmlDeviceGetPowerUsage(self.h) / 1e3,
+                                  n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.run = False
         self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self.max_sm, "reasons": sorted(v for k, v in self.REASONS.items() if bits & k),
+                "power_w_max": max((r[1] for r in self.rows), default=None), "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------- our arm

@@ -107,19 +107,27 @@ __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
     for (int e = lane; e < P.n_folds * S; e += 32) out[e] = wacc[e];
 }
 
-// out[e] (+)= sum over parts of partials[part][e], fixed order, Kahan-compensated.
-__global__ void reduce_partials_kernel(const double *__restrict__ partials, int64_t n_parts, int64_t len,
-                                       double *__restrict__ out, int accumulate) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= len) return;
-    double s = accumulate ? out[e] : 0.0, comp = 0.0;
-    for (int64_t k = 0; k < n_parts; ++k) {
+// out[e] (+)= sum over parts of partials[part][e].  One CTA per entry: thread k adds parts
+// k, k+128, ... (Kahan-compensated), then a fixed-order tree in shared memory, so the result does
+// not depend on scheduling (run-to-run bit-identical).
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__restrict__ partials, int64_t n_parts,
+                                                              int64_t len, double *__restrict__ out, int accumulate) {
+    __shared__ double sh[128];
+    const int64_t e = blockIdx.x;
+    double s = 0.0, comp = 0.0;
+    for (int64_t k = threadIdx.x; k < n_parts; k += 128) {
         const double x = __dsub_rn(partials[k * len + e], comp);
         const double t = __dadd_rn(s, x);
         comp = __dsub_rn(__dsub_rn(t, s), x);
         s = t;
     }
-    out[e] = s;
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[e] = accumulate ? __dadd_rn(out[e], sh[0]) : sh[0];
 }
 
 // ----------------------------------------------------------------------------- term stacks
@@ -330,7 +338,8 @@ int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st) {
 
 int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate,
                            cudaStream_t st) {
-    reduce_partials_kernel<<<(unsigned)((len + 127) / 128), 128, 0, st>>>(partials, n_parts, len, out, accumulate);
+    if (len <= 0) return PG_OK;
+    reduce_partials_kernel<<<(unsigned)len, 128, 0, st>>>(partials, n_parts, len, out, accumulate);
     PG_LAUNCHED();
     return PG_OK;
 }

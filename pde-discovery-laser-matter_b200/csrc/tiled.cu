@@ -1,23 +1,27 @@
 // K1 tiled: fused FD + library + block mean + Gram for the KS dialect with (bt, 8, 8) blocks.
 //
-// One CTA owns a 64 x 128 spatial tile and marches through a chunk of frames.  Each frame's
-// (64+4) x (128+4) halo tile is brought into shared memory ONCE by a 3-D TMA tensor copy
-// (cp.async.bulk.tensor, mbarrier completion) into a 3-stage ring: stage f is the frame being
-// differentiated, stages f+1 and f+2 are in flight (two loads ahead: a single outstanding 72 KB
-// load per SM cannot cover the HBM latency-bandwidth product).  The forward u_t never touches
-// frame t+1 pointwise: over a t-block it telescopes to (sum u(t0+bt) - sum u(t0)) / dt, and every
-// frame's block sum of u is formed while that frame is current.  Periodic wrap: TMA zero-fills the out-of-bounds halo of a
-// border tile; the wrapped values are prefetched with plain loads one iteration ahead and stored
-// over the zero fill after the copy has landed.
+// One persistent CTA owns a TI x 128 spatial tile and marches through a chunk of frames.  Each
+// frame's (TI+4) x 128 row-halo tile is brought into shared memory ONCE by a 3-D TMA tensor copy
+// (cp.async.bulk.tensor, mbarrier completion) into a 3-stage ring: stage g is the frame being
+// differentiated, stages g+1 and g+2 are in flight (two loads ahead: a single outstanding load
+// per SM cannot cover the HBM latency-bandwidth product).  The TMA box is exactly 128 columns =
+// whole 128-byte lines; the two halo columns on either side are fetched separately as one 16-byte
+// load per row and side (a 32-byte sector instead of a 128/256-byte line: this is what keeps
+// DRAM traffic near the algorithmic 8 B/point), which also gives the periodic wrap along a1 for
+// free.  Wrap along a0: TMA zero-fills the out-of-bounds rows of a border tile and the wrapped
+// rows are stored over the zero fill after the copy has landed.
+//
+// The forward u_t never touches frame t+1 pointwise: over a t-block it telescopes to
+// (sum u(t0+bt) - sum u(t0)) / dt, and every frame's block sum of u is formed while that frame
+// is current.
 //
 // Inside a frame, warp w owns rows [8w, 8w+8) (one block row) and lane l owns columns
 // [4l, 4l+4) (half a block), marching down 12 tile rows with a register sliding window: four
 // conflict-free LDS.128 per row give u at columns own-2 .. own+5, with no exchange between
 // lanes.  Block sums of the linear terms (lap, bih, u_x, u_y, u, u_t) reduce by the discrete
 // divergence theorem to per-row boundary scalars (see march_frame), so only the nonlinear
-// terms cost per-point fp64 work: about 8 fp64 ops per grid point for the true library.  At the end
-// of a t-block the two lanes of a block pair-reduce by shuffle, form the block-mean row and the
-// warp adds its 16 rows to lane-owned Gram entries held in registers.
+// terms cost per-point fp64 work: about 8 fp64 ops per grid point for the true library.  At the
+// end of a t-block the two lanes of a block pair-reduce by shuffle and form the block-mean row.
 //
 // No tensor cores: p <= 9 and the kernel is HBM / fp64-issue bound.
 #include <cuda.h>
@@ -29,30 +33,28 @@
 
 namespace pg {
 
-constexpr int TJ = 128;                     // tile columns (32 lanes x 4)
-constexpr int HC = TJ + 4;                  // halo tile columns
+constexpr int TJ = 128;                     // tile columns (32 lanes x 4) = TMA box width
+constexpr int PITCH = TJ + 4;               // doubles per tile row in a stage incl. its 4 halo-column slots
 constexpr int NSTAGE = 3;
 
-// Tile geometry for NW warps per CTA.  KC = columns per lane, BANDS = 8-row block bands per tile.
-//   NW = 16: 64 x 128 tile, KC = 2 (each band is split between two warps), one CTA per SM,
-//            <= 128 registers: 16 resident warps hide the fp64 / shared-memory latencies
-//   NW = 8 : 64 x 128 tile, KC = 4, one CTA per SM
-//   NW = 4 : 32 x 128 tile, KC = 4, two CTAs per SM
+// Tile geometry for NW warps per CTA (one 8-row block band per warp).
+//   NW = 8 : 64 x 128 tile, one CTA per SM;   NW = 4 : 32 x 128 tile, two CTAs per SM
+// Stage layout (doubles): tile [HR][TJ] written by TMA, then hcol [HR][4] = (left2, right2) per row.
 template <int NW> struct Geo {
-    static constexpr int KC = NW == 16 ? 2 : 4;
-    static constexpr int BANDS = NW == 16 ? 8 : NW;
-    static constexpr int TI = 8 * BANDS;
+    static constexpr int TI = 8 * NW;
     static constexpr int HR = TI + 4;
-    static constexpr int STAGE_DOUBLES = HR * HC;
+    static constexpr int HOFF = HR * TJ;                        // start of hcol inside a stage
+    static constexpr int STAGE_DOUBLES = HR * PITCH;
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+    static constexpr int TMA_BYTES = HR * TJ * 8;
     static constexpr int THREADS = 32 * NW;
-    static constexpr int MAXWRAP = (4 * HR + 4 * HC + THREADS - 1) / THREADS;   // wrap cells per thread
+    static constexpr int MAXC = (2 * HR + 2 * TJ + THREADS - 1) / THREADS;   // 16-byte side cells per thread
     static constexpr int CTAS_PER_SM = NW == 4 ? 2 : 1;
-    static constexpr int LPB = 8 / KC;          // lanes per 8-column block
-    static constexpr int RPW = 32 / LPB;        // block rows a warp emits per t-block
     // block rows staged per Gram-update batch (shared memory is the scarce resource at 2 CTAs/SM)
     __host__ __device__ static constexpr int slots(int p) { return NW == 4 ? (p <= 5 ? 4 : 2) : 8; }
-    __host__ __device__ static constexpr size_t smem(int p) { return (size_t)NSTAGE * STAGE_BYTES + 64 + sizeof(double) * NW * slots(p) * (p + 2); }
+    __host__ __device__ static constexpr size_t smem(int p) {
+        return (size_t)NSTAGE * STAGE_BYTES + 64 + sizeof(double) * NW * slots(p) * (p + 2);
+    }
 };
 
 struct TiledParams {
@@ -108,7 +110,7 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 
 // ----------------------------------------------------------------------------- per-lane block sums
 // Unscaled sums over the lane's half block (4 columns x 8 rows x frames); which ones are live
-// depends on the library.  FrameSums holds one frame's contribution, Acc the running t-block.
+// depends on the library.
 struct Sums {
     double SL = 0, SE1 = 0, SE2 = 0, SGx = 0, SGy = 0;   // all libraries
     double SU = 0;                                      // sum of u: rich column, and u_t by telescoping
@@ -119,17 +121,31 @@ struct Sums {
 template <int LIB> constexpr bool kNeedAdv = (LIB == PG_LIB_KS_TRUE_ADV || LIB == PG_LIB_KS_RICH);
 template <int LIB> constexpr bool kRich = (LIB == PG_LIB_KS_RICH || LIB == PG_LIB_KS_RICH_NOADV);
 
-// 16-byte chunk pair (k, k+1) of a lane's row segment.  Lanes are 32 B apart, so a plain LDS.128
-// would hit every bank group twice per quarter-warp; lanes with bit 2 set fetch the two chunks
-// in the opposite order (conflict-free) and swap them back.
-__device__ __forceinline__ void load_pair(const double2 *src, int k, int sw, double2 &lo, double2 &hi) {
-    const double2 x = src[k + sw], y = src[k + (sw ^ 1)];
-    lo = sw ? y : x;
-    hi = sw ? x : y;
+// Where a lane finds its four 16-byte chunks (columns own-2,-1 | own0,1 | own2,3 | own+4,+5) of
+// band row 0, as element offsets into a stage, plus the per-row stride of each.  Chunks 0 and 3
+// of the edge lanes live in the halo-column array (stride 4) instead of the tile (stride TJ).
+// Lanes are 32 B apart, so a plain LDS.128 would hit every bank group twice per quarter-warp:
+// lanes with bit 2 set (sw) fetch the two chunks of each pair in the opposite order
+// (conflict-free) and swap them back.  a/b = first/second issued chunk of pair (c0,c1), (c2,c3).
+struct LaneMap {
+    int a0, sa0, a1, sa1, b0, sb0, b1, sb1, sw;
+};
+
+template <int NW> __device__ __forceinline__ LaneMap lane_map(int band, int lane) {
+    using G_ = Geo<NW>;
+    const int own = band * 8 * TJ + 4 * lane, hrow = G_::HOFF + band * 8 * 4;
+    const int c0 = lane > 0 ? own - 2 : hrow, s0 = lane > 0 ? TJ : 4;
+    const int c3 = lane < 31 ? own + 4 : hrow + 2, s3 = lane < 31 ? TJ : 4;
+    LaneMap m;
+    m.sw = (lane >> 2) & 1;
+    m.a0 = m.sw ? own : c0;       m.sa0 = m.sw ? TJ : s0;
+    m.a1 = m.sw ? c0 : own;       m.sa1 = m.sw ? s0 : TJ;
+    m.b0 = m.sw ? c3 : own + 2;   m.sb0 = m.sw ? s3 : TJ;
+    m.b1 = m.sw ? own + 2 : c3;   m.sb1 = m.sw ? TJ : s3;
+    return m;
 }
 
 // One frame of one warp band: 12 tile rows march through a 3-row register window.
-//   cur : halo tile of frame t (row pitch HC), pointing at the warp's first tile row, lane's first column
 //
 // With w[0..7] the lane's row segment (columns own-2 .. own+5, own = q 2..5) and band rows
 // s = 0..11 (outputs are rows 2..9), every block sum of a LINEAR term reduces, by the discrete
@@ -143,18 +159,20 @@ __device__ __forceinline__ void load_pair(const double2 *src, int k, int sw, dou
 // block sum of bih = r1^2*(rho*SE1 + SE2)).  Only the nonlinear terms (|grad u|^2, and for the
 // rich library u^2 and u*L') cost per-point fp64 work.
 template <int LIB>
-__device__ __forceinline__ void march_frame(const double *__restrict__ cur, const TiledParams &P, Sums &F, const int sw) {
+__device__ __forceinline__ void march_frame(const double *__restrict__ st, const LaneMap &m, const TiledParams &P, Sums &F) {
     double wp[4], wc[8], wn[8];              // own columns of row s-2; rows s-1 and s (all 8 columns)
     double rsU[12], D[12];
     // per-column partial sums of the nonlinear terms: four independent FMA chains per quantity
     double gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0}, u2[4] = {0, 0, 0, 0}, ul[4] = {0, 0, 0, 0};
     double sD = 0, sE = 0, sU = 0, sDy = 0;
+    const int sw = m.sw;
 #pragma unroll
     for (int s = 0; s < 12; ++s) {
-        const double2 *src = reinterpret_cast<const double2 *>(cur + s * HC);
-        double2 a0, a1, a2, a3;
-        load_pair(src, 0, sw, a0, a1);
-        load_pair(src, 2, sw, a2, a3);
+        const double2 x0 = *reinterpret_cast<const double2 *>(st + m.a0 + s * m.sa0);
+        const double2 x1 = *reinterpret_cast<const double2 *>(st + m.a1 + s * m.sa1);
+        const double2 y0 = *reinterpret_cast<const double2 *>(st + m.b0 + s * m.sb0);
+        const double2 y1 = *reinterpret_cast<const double2 *>(st + m.b1 + s * m.sb1);
+        const double2 a0 = sw ? x1 : x0, a1 = sw ? x0 : x1, a2 = sw ? y1 : y0, a3 = sw ? y0 : y1;
         wn[0] = a0.x; wn[1] = a0.y; wn[2] = a1.x; wn[3] = a1.y; wn[4] = a2.x; wn[5] = a2.y; wn[6] = a3.x; wn[7] = a3.y;
         rsU[s] = (wn[2] + wn[3]) + (wn[4] + wn[5]);
         D[s] = (wn[1] - wn[2]) + (wn[6] - wn[5]);
@@ -206,88 +224,15 @@ __device__ __forceinline__ void march_frame(const double *__restrict__ cur, cons
     }
 }
 
-// KC = 2 variant: the lane owns two columns (w[2], w[3] of the six-value segment own-2 .. own+3);
-// lanes are 16 B apart, so the three LDS.128 per row are conflict-free as they stand.  Same
-// scalars as above with D(s) = (w1-w2) + (w4-w3), e(s) = (w0-w3) + (w5-w2), rsU(s) = w2+w3.
-template <int LIB>
-__device__ __forceinline__ void march_frame2(const double *__restrict__ cur, const TiledParams &P, Sums &F) {
-    double wp[2], wc[6], wn[6];
-    double rsU[12], D[12];
-    double gx[2] = {0, 0}, gy[2] = {0, 0}, u2[2] = {0, 0}, ul[2] = {0, 0};
-    double sD = 0, sE = 0, sU = 0, sDy = 0;
-#pragma unroll
-    for (int s = 0; s < 12; ++s) {
-        const double2 *src = reinterpret_cast<const double2 *>(cur + s * HC);
-        const double2 a0 = src[0], a1 = src[1], a2 = src[2];
-        wn[0] = a0.x; wn[1] = a0.y; wn[2] = a1.x; wn[3] = a1.y; wn[4] = a2.x; wn[5] = a2.y;
-        rsU[s] = wn[2] + wn[3];
-        D[s] = (wn[1] - wn[2]) + (wn[4] - wn[3]);
-        if (s >= 2 && s <= 9) {
-            sD += D[s];
-            sE += (wn[0] - wn[3]) + (wn[5] - wn[2]);
-            sU += rsU[s];
-            if constexpr (kNeedAdv<LIB>) sDy += (wn[3] + wn[4]) - (wn[1] + wn[2]);
-        }
-        if (s >= 3 && s <= 10) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int q = c + 2;
-                const double dx = wn[q] - wp[c];
-                const double dy = wc[q + 1] - wc[q - 1];
-                gx[c] = fma(dx, dx, gx[c]);
-                gy[c] = fma(dy, dy, gy[c]);
-                if constexpr (kRich<LIB>) {
-                    const double Lq = fma(P.kappa, wc[q], fma(P.rho, wn[q] + wp[c], wc[q + 1] + wc[q - 1]));
-                    u2[c] = fma(wc[q], wc[q], u2[c]);
-                    ul[c] = fma(wc[q], Lq, ul[c]);
-                }
-            }
-        }
-        wp[0] = wc[2]; wp[1] = wc[3];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) wc[q] = wn[q];
-    }
-    const double rsL1 = fma(P.rho, (rsU[2] + rsU[0]) - 2.0 * rsU[1], D[1]);
-    const double rsL2 = fma(P.rho, (rsU[3] + rsU[1]) - 2.0 * rsU[2], D[2]);
-    const double rsL9 = fma(P.rho, (rsU[10] + rsU[8]) - 2.0 * rsU[9], D[9]);
-    const double rsL10 = fma(P.rho, (rsU[11] + rsU[9]) - 2.0 * rsU[10], D[10]);
-    F.SL = fma(P.rho, (rsU[10] - rsU[9]) - (rsU[2] - rsU[1]), sD);
-    F.SE1 = (rsL1 - rsL2) + (rsL10 - rsL9);
-    F.SE2 = fma(P.rho, (D[10] + D[1]) - (D[2] + D[9]), fma(-3.0, sD, sE));
-    F.SU = sU;
-    F.SGx = gx[0] + gx[1];
-    F.SGy = gy[0] + gy[1];
-    if constexpr (kNeedAdv<LIB>) {
-        F.SDy = sDy;
-        F.SDx = (rsU[10] + rsU[9]) - (rsU[2] + rsU[1]);
-    }
-    if constexpr (kRich<LIB>) {
-        F.SU2 = u2[0] + u2[1];
-        F.SUL = ul[0] + ul[1];
-    }
-}
-
-__device__ __forceinline__ double sum_frame_u2(const double *__restrict__ own) {
-    double s0 = 0, s1 = 0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const double2 a = *reinterpret_cast<const double2 *>(own + r * HC);
-        s0 += a.x;
-        s1 += a.y;
-    }
-    return s0 + s1;
-}
-
 // Sum of u over the lane's own 8 rows x 4 columns (the frame after a chunk only feeds u_t).
-//   own : halo tile, pointing at the warp's first OUTPUT row and the lane's first OWN column
-__device__ __forceinline__ double sum_frame_u(const double *__restrict__ own, const int sw) {
+__device__ __forceinline__ double sum_frame_u(const double *__restrict__ st, int band, int lane, int sw) {
+    const double2 *own = reinterpret_cast<const double2 *>(st + (band * 8 + 2) * TJ + 4 * lane);
     double s0 = 0, s1 = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        double2 a, b;
-        load_pair(reinterpret_cast<const double2 *>(own + r * HC), 0, sw, a, b);
-        s0 += a.x + a.y;
-        s1 += b.x + b.y;
+        const double2 x = own[r * (TJ / 2) + sw], y = own[r * (TJ / 2) + (sw ^ 1)];
+        s0 += x.x + x.y;
+        s1 += y.x + y.y;
     }
     return s0 + s1;
 }
@@ -296,23 +241,20 @@ template <int LIB, int NF, int NW>
 __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap,
                                                                               TiledParams P) {
     using G_ = Geo<NW>;
-    constexpr int TI = G_::TI, HR = G_::HR, STAGE_DOUBLES = G_::STAGE_DOUBLES, STAGE_BYTES = G_::STAGE_BYTES;
-    constexpr int MAXWRAP = G_::MAXWRAP, THREADS = G_::THREADS;
+    constexpr int TI = G_::TI, HR = G_::HR, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES;
+    constexpr int MAXC = G_::MAXC, THREADS = G_::THREADS;
     constexpr int p = Lib<LIB>::P;
     constexpr int S = PG_STATS_LEN(p);
     constexpr int W = p + 2;
     constexpr int NE = (S + 31) / 32;   // lane-owned statistics entries
     constexpr int SB = G_::slots(p);    // block rows per staging batch
-    constexpr int KC = G_::KC, LPB = G_::LPB, RPW = G_::RPW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NSTAGE * STAGE_BYTES);
-    double *ext_all = reinterpret_cast<double *>(smem_raw + NSTAGE * STAGE_BYTES + 64);  // [NW][SB][W]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NSTAGE * G_::STAGE_BYTES);
+    double *ext_all = reinterpret_cast<double *>(smem_raw + NSTAGE * G_::STAGE_BYTES + 64);  // [NW][SB][W]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int sw = (lane >> 2) & 1;
-    const int band = KC == 4 ? warp : warp >> 1;                   // 8-row block band of the tile
-    const int col0 = (KC == 4 ? 0 : (warp & 1) * 64) + lane * KC;   // tile column where the lane's segment starts
+    const LaneMap lm = lane_map<NW>(warp, lane);
     double *ext = ext_all + warp * SB * W;
 
     int ea[NE], eb[NE];
@@ -329,10 +271,10 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
     for (int f = 0; f < NF; ++f)
 #pragma unroll
         for (int k = 0; k < NE; ++k) acc[f][k] = 0.0;
-    // Small libraries (p <= 5): every lane that owns a block row keeps a PRIVATE copy of the whole
-    // statistics vector in registers (S <= 33 FMAs per emitted row, no staging, no shuffles);
-    // larger ones stage rows in shared memory and spread the S entries over the lanes.
-    constexpr bool PRIV = S * NF <= 36 && NW != 16;   // register budget: true library (S = 18), or p = 5 with one fold
+    // Small libraries: every lane that owns a block row keeps a PRIVATE copy of the whole statistics
+    // vector in registers (S FMAs per emitted row, no staging, no shuffles); larger ones stage rows
+    // in shared memory and spread the S entries over the lanes.
+    constexpr bool PRIV = S * NF <= 36;   // register budget: true library (S = 18), or p = 5 with one fold
     constexpr int SP = PRIV ? S : 1;
     double pacc[NF][SP];
 #pragma unroll
@@ -352,7 +294,7 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
     const int64_t n_items = (int64_t)n_tiles * P.n_chunks;
     unsigned long long bad_rows = 0, bad_fold = 0;
 
-    // item -> (tile origin, first frame, number of row frames)
+    // item -> (tile origin, first t-block, number of row frames)
     auto geometry = [&](int64_t item, int &i0, int &j0, int64_t &tb0, int &nf) {
         const int tile = (int)(item % n_tiles), chunk = (int)(item / n_tiles);
         i0 = (tile / P.n_tiles1) * TI;
@@ -378,8 +320,8 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
         if (p_left == 0) return;
         uint64_t *bar = &bars[p_g % NSTAGE];
         fence_proxy_async();
-        mbar_expect_tx(bar, STAGE_BYTES);
-        tma_load_3d(stages + (p_g % NSTAGE) * STAGE_DOUBLES, &tmap, bar, p_j0 - 2, p_i0 - 2, p_t);
+        mbar_expect_tx(bar, G_::TMA_BYTES);
+        tma_load_3d(stages + (p_g % NSTAGE) * STAGE_DOUBLES, &tmap, bar, p_j0, p_i0 - 2, p_t);
         ++p_g;
         ++p_t;
         if (--p_left == 0) {
@@ -402,70 +344,62 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
         int64_t tb0;
         geometry(item, i0, j0, tb0, nf);
         const int64_t t0 = tb0 * P.bt;   // frames t0 .. t0+nf are loaded; the last one only feeds u_t
-        const bool wl = j0 == 0, wr = j0 + TJ == P.A1, wt = i0 == 0, wb = i0 + TI == P.A0;
-        const bool border = wl || wr || wt || wb;
+        const bool wt = i0 == 0, wb = i0 + TI == P.A0;
 
-        // periodic wrap cells of this tile handled by this thread: tile offset and offset inside a frame
-        int w_off[MAXWRAP];
-        int64_t w_src[MAXWRAP];
+        // 16-byte "side cells" of this tile handled by this thread (stage offset, offset inside a frame):
+        // the two halo columns left and right of every row (always), and the wrapped rows that TMA
+        // zero-filled when the tile touches the top / bottom of the periodic domain.
+        int c_off[MAXC];
+        int64_t c_src[MAXC];
 #pragma unroll
-        for (int k = 0; k < MAXWRAP; ++k) w_off[k] = -1;
-        if (border) {
-#pragma unroll
-            for (int k = 0; k < MAXWRAP; ++k) {
-                int c = tid + k * THREADS, R = -1, C = -1;
-                if (wl) { if (c >= 0 && c < 2 * HR) { R = c >> 1; C = c & 1; } c -= 2 * HR; }
-                if (wr) { if (c >= 0 && c < 2 * HR) { R = c >> 1; C = HC - 2 + (c & 1); } c -= 2 * HR; }
-                if (wt) { if (c >= 0 && c < 2 * HC) { R = c / HC; C = c % HC; } c -= 2 * HC; }
-                if (wb) { if (c >= 0 && c < 2 * HC) { R = HR - 2 + c / HC; C = c % HC; } c -= 2 * HC; }
-                if (R >= 0) {
-                    w_off[k] = R * HC + C;
-                    w_src[k] = wrap((int64_t)i0 - 2 + R, P.A0) * P.A1 + wrap((int64_t)j0 - 2 + C, P.A1);
-                }
+        for (int k = 0; k < MAXC; ++k) {
+            int c = tid + k * THREADS, R = -1, C = 0;
+            c_off[k] = -1;
+            if (c < 2 * HR) {
+                R = c >> 1;
+                const int side = c & 1;
+                c_off[k] = HOFF + R * 4 + side * 2;
+                C = side ? j0 + TJ : j0 - 2;
+            } else {
+                c -= 2 * HR;
+                if (wt) { if (c >= 0 && c < TJ) { R = c / (TJ / 2); C = j0 + 2 * (c % (TJ / 2)); c_off[k] = R * TJ + (C - j0); } c -= TJ; }
+                if (wb) { if (c >= 0 && c < TJ) { R = HR - 2 + c / (TJ / 2); C = j0 + 2 * (c % (TJ / 2)); c_off[k] = R * TJ + (C - j0); } c -= TJ; }
             }
+            if (c_off[k] >= 0) c_src[k] = wrap((int64_t)i0 - 2 + R, P.A0) * P.A1 + wrap((int64_t)C, P.A1);
         }
-        double w_val[MAXWRAP];
-        auto wrap_fetch = [&](int64_t t) {
+        double2 c_val[MAXC];
+        auto side_fetch = [&](int64_t t) {
 #pragma unroll
-            for (int k = 0; k < MAXWRAP; ++k)
-                if (w_off[k] >= 0) w_val[k] = __ldg(P.U + t * frame + w_src[k]);
+            for (int k = 0; k < MAXC; ++k)
+                if (c_off[k] >= 0) c_val[k] = __ldg(reinterpret_cast<const double2 *>(P.U + t * frame + c_src[k]));
         };
-        auto wrap_store = [&](double *stage) {
+        auto side_store = [&](double *stage) {
 #pragma unroll
-            for (int k = 0; k < MAXWRAP; ++k)
-                if (w_off[k] >= 0) stage[w_off[k]] = w_val[k];
+            for (int k = 0; k < MAXC; ++k)
+                if (c_off[k] >= 0) *reinterpret_cast<double2 *>(stage + c_off[k]) = c_val[k];
         };
-        if (border) wrap_fetch(t0);
+        side_fetch(t0);
 
         int fold = 0;
         double su_first = 0.0;
-        const int64_t ib = (int64_t)(i0 >> 3) + band, jb = (int64_t)((j0 + col0) >> 3);
+        const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lane >> 1);
         for (int f = 0; f <= nf; ++f, ++G) {
             double *st = stages + (G % NSTAGE) * STAGE_DOUBLES;
             mbar_wait(&bars[G % NSTAGE], (G / NSTAGE) & 1);
-            if (border) wrap_store(st);
-            __syncthreads();  // wrap stores visible; every warp finished the previous frame, whose stage is free
-            if (tid == 0) produce();                       // load G+2 -> the stage just freed
-            if (border && f < nf) wrap_fetch(t0 + f + 1);  // consumed after the next barrier wait
+            side_store(st);
+            __syncthreads();  // side cells visible; every warp finished the previous frame, whose stage is free
+            if (tid == 0) produce();             // load G+2 -> the stage just freed
+            if (f < nf) side_fetch(t0 + f + 1);  // consumed after the next barrier wait
 
             Sums F;
-            if constexpr (KC == 4) {
-                if (f < nf) march_frame<LIB>(st + (band * 8) * HC + col0, P, F, sw);
-                else F.SU = sum_frame_u(st + (band * 8 + 2) * HC + col0 + 2, sw);
-            } else {
-                if (f < nf) march_frame2<LIB>(st + (band * 8) * HC + col0, P, F);
-                else F.SU = sum_frame_u2(st + (band * 8 + 2) * HC + col0 + 2);
-            }
+            if (f < nf) march_frame<LIB>(st, lm, P, F);
+            else F.SU = sum_frame_u(st, warp, lane, lm.sw);
 
             if (f % P.bt == 0 && f > 0) {
                 // ---- the t-block that ended at frame f-1: u_t telescopes to (sum u(f) - sum u(f-bt)) / dt.
-                // The LPB lanes of an 8-column block hold one block's sums.
+                // The lane pair (2m, 2m+1) holds one block's sums.
                 double SY = F.SU - su_first;
-#define PG_PAIR(x)                                                  \
-    do {                                                            \
-        x += __shfl_xor_sync(0xffffffffu, x, 1);                    \
-        if constexpr (LPB == 4) x += __shfl_xor_sync(0xffffffffu, x, 2); \
-    } while (0)
+#define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 1)
                 PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
                 if constexpr (kNeedAdv<LIB>) { PG_PAIR(A.SDx); PG_PAIR(A.SDy); }
                 if constexpr (kRich<LIB>) { PG_PAIR(A.SU); PG_PAIR(A.SU2); PG_PAIR(A.SUL); }
@@ -491,7 +425,7 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
                 bool fin = isfinite(y);
 #pragma unroll
                 for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
-                bool valid = (lane % LPB) == 0;
+                bool valid = (lane & 1) == 0;
                 if (valid && !fin) { valid = false; ++bad_rows; }
                 else if (valid && (fold < 0 || fold >= NF)) { valid = false; ++bad_fold; }
                 if constexpr (PRIV) {
@@ -517,32 +451,32 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
                     }
                 } else {
 #pragma unroll
-                for (int h = 0; h < RPW / SB; ++h) {
-                    const bool mine = valid && (lane / LPB) / SB == h;
-                    if (mine) {
-                        double *r = ext + ((lane / LPB) % SB) * W;
-                        r[0] = 1.0; r[1] = y;
+                    for (int h = 0; h < 16 / SB; ++h) {
+                        const bool mine = valid && (lane >> 1) / SB == h;
+                        if (mine) {
+                            double *r = ext + ((lane >> 1) % SB) * W;
+                            r[0] = 1.0; r[1] = y;
 #pragma unroll
-                        for (int k = 0; k < p; ++k) r[2 + k] = th[k];
-                    }
-                    __syncwarp();
-                    const unsigned vm = __ballot_sync(0xffffffffu, mine);
-#pragma unroll
-                    for (int slot = 0; slot < SB; ++slot) {
-                        const int src = (h * SB + slot) * LPB;
-                        if (!((vm >> src) & 1u)) continue;
-                        const int fr = __shfl_sync(0xffffffffu, fold, src);
-                        const double *r = ext + slot * W;
-#pragma unroll
-                        for (int k = 0; k < NE; ++k) {
-                            if (!ev[k]) continue;
-                            const double prod = r[ea[k]] * r[eb[k]];
-#pragma unroll
-                            for (int ff = 0; ff < NF; ++ff) acc[ff][k] += (fr == ff) ? prod : 0.0;
+                            for (int k = 0; k < p; ++k) r[2 + k] = th[k];
                         }
+                        __syncwarp();
+                        const unsigned vm = __ballot_sync(0xffffffffu, mine);
+#pragma unroll
+                        for (int slot = 0; slot < SB; ++slot) {
+                            const int src = (h * SB + slot) * 2;
+                            if (!((vm >> src) & 1u)) continue;
+                            const int fr = __shfl_sync(0xffffffffu, fold, src);
+                            const double *r = ext + slot * W;
+#pragma unroll
+                            for (int k = 0; k < NE; ++k) {
+                                if (!ev[k]) continue;
+                                const double prod = r[ea[k]] * r[eb[k]];
+#pragma unroll
+                                for (int ff = 0; ff < NF; ++ff) acc[ff][k] += (fr == ff) ? prod : 0.0;
+                            }
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
-                }
                 }
             }
             if (f < nf) {
@@ -602,11 +536,8 @@ static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
-// warps per CTA (see Geo): 16, 8 or 4; PG_TILED_WARPS overrides the default for experiments
-static int tiled_warps() {
-    const int w = env_int("PG_TILED_WARPS", 8);
-    return w == 4 || w == 16 ? w : 8;
-}
+// warps per CTA (see Geo): 8 or 4; PG_TILED_WARPS overrides the default for experiments
+static int tiled_warps() { return env_int("PG_TILED_WARPS", 8) == 4 ? 4 : 8; }
 
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan) {
     if (P.dialect != PG_FD_KS_PERIODIC) return false;
@@ -614,9 +545,9 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
         return false;
     if (P.b0 != 8 || P.b1 != 8) return false;
     if (P.n_folds > 2) return false;
-    if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // TMA: 16-byte strides / base
+    if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // TMA / LDG.128: 16-byte strides, base
     const int NW = tiled_warps();
-    const int TI = NW == 4 ? 32 : 64;
+    const int TI = 8 * NW;
     const int workers = n_sm * (NW == 4 ? 2 : 1);
     const int64_t nt0 = P.A0 / TI, nt1 = P.A1 / TJ;
     const int64_t nbt = (P.T - 1) / P.bt;   // full t-blocks only; a ragged last one goes to the generic kernel
@@ -625,14 +556,14 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     if (!encode_fn()) return false;
     (void)nBt;
     const int64_t n_tiles = nt0 * nt1;
-    // choose the number of frame chunks: balance the persistent CTAs, pay one extra frame + pipeline refill per item
+    // choose the number of frame chunks: balance the persistent CTAs, pay one extra frame per item
     int64_t best_c = 1;
     double best_cost = 1e300;
     for (int64_t c = 1; c <= nbt && c <= 4096; ++c) {
         const int64_t ctb = (nbt + c - 1) / c;
         const int64_t cc = (nbt + ctb - 1) / ctb;           // chunks actually produced
         const int64_t rounds = (n_tiles * cc + workers - 1) / workers;
-        const double cost = (double)rounds * ((double)ctb * P.bt + 4.0);
+        const double cost = (double)rounds * ((double)ctb * P.bt + 2.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_c = cc; }
     }
     const int64_t ctb = (nbt + best_c - 1) / best_c;
@@ -659,7 +590,6 @@ template <int LIB, int NF, int NW> static int launch_tiled_k(const CUtensorMap &
 
 template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const TiledParams &tp, int n_folds, int nw, int grid,
                                              cudaStream_t st) {
-    if (nw == 16) return n_folds == 1 ? launch_tiled_k<LIB, 1, 16>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 16>(map, tp, grid, st);
     if (nw == 8) return n_folds == 1 ? launch_tiled_k<LIB, 1, 8>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 8>(map, tp, grid, st);
     return n_folds == 1 ? launch_tiled_k<LIB, 1, 4>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 4>(map, tp, grid, st);
 }
@@ -671,11 +601,11 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     const cuuint64_t gdim[3] = {(cuuint64_t)P.A1, (cuuint64_t)P.A0, (cuuint64_t)P.T};
     const cuuint64_t gstr[2] = {(cuuint64_t)P.A1 * 8, (cuuint64_t)P.A0 * (cuuint64_t)P.A1 * 8};
     const int NW = plan.kernel_id;
-    const cuuint32_t box[3] = {HC, (cuuint32_t)(plan.tile0 + 4), 1};
+    const cuuint32_t box[3] = {TJ, (cuuint32_t)(plan.tile0 + 4), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(P.U), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)env_int("PG_TMA_L2PROMO", 3),
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           (CUtensorMapL2promotion)env_int("PG_TMA_L2PROMO", 2), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     TiledParams tp{};
     tp.U = P.U; tp.T = P.T; tp.A0 = P.A0; tp.A1 = P.A1;
