@@ -1,0 +1,57 @@
+"""CPU checks of bench.py's reference arm (the only leg that may execute oracle/ outside tests):
+the port runs on a tiny sample, recovers the same model as the single-process oracle, and the
+printed line carries the contract keys."""
+
+import importlib.util
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["bench"] = mod  # multiprocessing pickles the worker function by module name
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_cpu_port_matches_single_process_oracle():
+    import multiprocessing as mp
+
+    from oracle import gram, ks2d as O
+
+    b = _bench()
+    U = b.cpu_sample(frames=13, size=32)
+    b._CPU["U"] = U
+    with mp.get_context("fork").Pool(2) as pool:
+        best = b.cpu_port_step(U, 2, pool)
+    names, terms = O.build_dictionary_true(U[:-1], b.D0, b.D1)
+    X, y = O.build_blockwise_dataset((U[1:] - U[:-1]) / b.DT, terms, names, block_t=3, block_x=8, block_y=8)
+    rows_per_tb = len(y) // 4
+    s_tr, s_te = gram.pack_stats(X[: 2 * rows_per_tb], y[: 2 * rows_per_tb]), gram.pack_stats(X[2 * rows_per_tb:], y[2 * rows_per_tb:])
+    ref = gram.ks_fit_from_stats(s_tr, s_te, 3, alphas=O.GRID_ALPHAS, thresholds=O.GRID_THRESHOLDS)
+    assert (best["alpha"], best["threshold"]) == (ref["alpha"], ref["threshold"])
+    np.testing.assert_allclose(best["coeffs"], ref["coeffs"], rtol=1e-9)
+
+
+def test_reference_arm_prints_contract_line(tmp_path):
+    code = (
+        "import sys; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0'];"
+        "import bench; bench.time_cpu_port.__defaults__=None;"
+        "orig=bench.time_cpu_port; bench.time_cpu_port=lambda s,w,f,z: orig(1,0,13,64); bench.main()"
+    )
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
