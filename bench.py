@@ -194,6 +194,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = pde_b200.load()
     T, A = args.frames, args.size
@@ -323,6 +324,57 @@ def run_ours(args):
             variants[name] = {"value": world * pts_rank * 3 / (ms * 1e-3), "unit": UNIT,
                               "alg_GBps_per_gpu": 8 * pts_rank * 3 / (ms * 1e-3) / 1e9}
 
+    # ---- BASELINE configs[2]: patch-based spatial ensemble on a laser-image-shaped 1024x1024x500 float32 stack,
+    # 8464 patches x (120 train + 40 test) sampled points: K2 (245-tap polynomial stencil rows) -> per-patch
+    # statistics -> K3 (scikit-learn dialect).  Patches are embarrassingly parallel; every rank runs the same set.
+    patch = None
+    if not args.skip_variants and rank == 0:
+        from pde_b200 import patch as PP
+
+        del U
+        torch.cuda.empty_cache()
+        Tp, Hp = (500, 1024) if args.frames >= 1024 else (40, 256)
+        U32 = ops.synth_field(Tp, Hp, Hp, seed=1, kind=1, noise=0.02).float()
+        _, t_train, t_test = PP.time_split(Tp, 2, 0.7)
+        coords = PP.patch_grid(Hp, Hp, 21, 10)
+        tr_pts, te_pts = PP.sample_patch_points(np.random.default_rng(0), coords, Hp, Hp, 21, 3, t_train, t_test, 120)
+        B = tr_pts.shape[0]
+        W6 = ops._dev(PP.poly_stencil(2, 3, 3, 1.0, 0.1, 0.1))
+        tr_d, te_d = ops._dev(tr_pts.reshape(-1, 3)), ops._dev(te_pts.reshape(-1, 3))
+        a_d, t_d = ops._dev(np.array([0.01])), ops._dev(np.array([1e-5]))
+
+        def patch_step():
+            X, y = ops.poly_rows(U32, tr_d, W6, 2, 3, library=L.LIB_PATCH_FULL)
+            Xt, yt = ops.poly_rows(U32, te_d, W6, 2, 3, library=L.LIB_PATCH_FULL)
+            X, y, Xt, yt = X.view(B, 120, 8), y.view(B, 120), Xt.view(B, 40, 8), yt.view(B, 40)
+            shift = X[:, 0, :].contiguous()
+            st, mm = ops.rows_gram(X, y, shift=shift, want_minmax=True)
+            se = ops.rows_gram(Xt, yt, shift=shift)
+            return ops.stridge_batched(st[:, 0], 8, dialect=L.STRIDGE_SKLEARN, alphas=a_d, thresholds=t_d, max_iter=25,
+                                       colminmax=mm[:, 0], shift=shift, eval_stats=se[:, 0])
+
+        for _ in range(2):
+            patch_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            patch_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        patch = {"workload": f"c3: {Hp}x{Hp}x{Tp} float32 stack, {B} patches x (120 train + 40 test) points, p=8, rt=2 rs=3 deg=3",
+                 "stridge_fits_per_s": B / (ms * 1e-3), "stencil_points_per_s": B * 160 / (ms * 1e-3), "ms_per_pass": ms}
+        if not args.no_cpu:
+            from oracle import patch as OP
+
+            n_cpu = 24
+            Uh = U32.cpu().numpy()
+            t0c = time.perf_counter()
+            OP.run_patches(Uh, seed=0, max_patches=n_cpu)
+            patch["cpu_port_fits_per_s"] = n_cpu / (time.perf_counter() - t0c)
+            patch["cpu_port_sample"] = f"first {n_cpu} patches, fixed-stencil NumPy port, 1 core (the reference's per-point lstsq is ~100x slower)"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -364,7 +416,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 30 * 3 * 8,
                 "sample": f"{e2e_frames} frames per GPU streamed from pinned host memory in 96-frame slabs (double-buffered), "
                           "through pde_b200.slabs.fit_streamed + stridge_batched"},
-        "gpu_launches": int(launches), "clocks": clocks, "variants": variants,
+        "gpu_launches": int(launches), "clocks": clocks, "variants": variants, "patch_ensemble": patch,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
