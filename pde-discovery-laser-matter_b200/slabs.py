@@ -29,23 +29,37 @@ def slab_bounds(n_row_frames: int, block_t: int, world: int):
     return out
 
 
-def exchange_halo(U_local, group=None):
-    """Fill the trailing halo frame U_local[-1] with frame 0 of the next rank's slab.
+def exchange_halo_begin(U_local, group=None):
+    """Start filling the trailing halo frame U_local[-1] with frame 0 of the next rank's slab.
 
     Rank r sends its first frame to rank r-1 and receives rank r+1's first frame; the last
-    rank keeps its own trailing frame (it is part of the global stack)."""
+    rank keeps its own trailing frame (it is part of the global stack).  Returns the pending
+    requests; the transfer runs on the communication stream and overlaps whatever the caller
+    launches next, as long as that does not read U_local[-1]."""
     import torch.distributed as dist
 
+    if not dist.is_initialized():
+        return []
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if world == 1:
-        return U_local
+        return []
     ops = []
     if rank > 0:
         ops.append(dist.P2POp(dist.isend, U_local[0], rank - 1, group))
     if rank < world - 1:
         ops.append(dist.P2POp(dist.irecv, U_local[-1], rank + 1, group))
-    for req in dist.batch_isend_irecv(ops):
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+def exchange_halo_end(reqs):
+    """Make the current stream wait for the halo transfer started by exchange_halo_begin."""
+    for req in reqs:
         req.wait()
+
+
+def exchange_halo(U_local, group=None):
+    """Blocking form: begin + end."""
+    exchange_halo_end(exchange_halo_begin(U_local, group))
     return U_local
 
 
@@ -61,16 +75,29 @@ def allreduce_stats(stats, group=None):
 def sharded_stats(U_local, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_frame=None, fold_of_row=None,
                   n_folds=1, variant=L.VARIANT_AUTO, group=None, halo=True, stats_fn=None):
     """Per-rank K1 over this rank's slab (own frames + trailing halo frame) followed by the
-    all-reduce.  ``stats_fn`` lets the CPU tests stand in for the CUDA kernel."""
-    if halo:
-        exchange_halo(U_local, group)
-    if stats_fn is None:
-        from . import ops
+    all-reduce.  ``stats_fn`` lets the CPU tests stand in for the CUDA kernel.
 
-        stats = ops.fd_lib_gram(U_local, d0, d1, dt, dialect=dialect, library=library, block=block,
-                                fold_of_frame=fold_of_frame, fold_of_row=fold_of_row, n_folds=n_folds, variant=variant)
+    The halo frame is only read by the LAST t-block of the slab, so the exchange is started first,
+    K1 runs on everything before that t-block while the frame is in flight, and only the small tail
+    launch waits for it (the transfer is hidden; statistics are additive over time slabs)."""
+    reqs = exchange_halo_begin(U_local, group) if halo else []
+    if stats_fn is not None:
+        exchange_halo_end(reqs)
+        return allreduce_stats(stats_fn(U_local), group)
+    from . import ops
+
+    bt = int(block[0])
+    rows = U_local.shape[0] - 1
+    cut = ((rows - 1) // bt) * bt          # first frame of the last (possibly ragged) t-block
+    kw = dict(dialect=dialect, library=library, block=block, n_folds=n_folds, variant=variant)
+    if not reqs or cut <= 0 or fold_of_row is not None:
+        exchange_halo_end(reqs)
+        stats = ops.fd_lib_gram(U_local, d0, d1, dt, fold_of_frame=fold_of_frame, fold_of_row=fold_of_row, **kw)
     else:
-        stats = stats_fn(U_local)
+        fof = None if fold_of_frame is None else ops._dev(fold_of_frame)
+        stats = ops.fd_lib_gram(U_local[:cut + 1], d0, d1, dt, fold_of_frame=None if fof is None else fof[:cut], **kw)
+        exchange_halo_end(reqs)
+        stats = stats + ops.fd_lib_gram(U_local[cut:], d0, d1, dt, fold_of_frame=None if fof is None else fof[cut:], **kw)
     return allreduce_stats(stats, group)
 
 
