@@ -148,29 +148,34 @@ int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0
     const int64_t nBt = (Trows + bt - 1) / bt;
     P.nB0 = (P.R0 + b0 - 1) / b0; P.nB1 = (P.R1 + b1 - 1) / b1;
 
-    // Tiled TMA kernel over the region it supports; the generic kernel covers what is left.
+    // Tiled TMA kernels over the region they support; the generic kernel covers what is left.
     TiledPlan plan{};
-    bool tiled = false;
+    bool tiled = false, pointwise = false;
     if (variant != PG_VARIANT_GENERIC) {
-        tiled = tiled_plan(P, library_id, nBt, sm_count(), plan);
+        pointwise = bt == 1 && b0 == 1 && b1 == 1;
+        tiled = pointwise ? tiled_pw_plan(P, library_id, sm_count(), plan) : tiled_plan(P, library_id, nBt, sm_count(), plan);
         if (!tiled && variant == PG_VARIANT_TILED)
             PG_FAIL(PG_EUNSUPPORTED, "no tiled kernel for dialect %d library %d block (%d,%d,%d) shape (%lld,%lld,%lld)",
                     fd_dialect, library_id, bt, b0, b1, (long long)T, (long long)A0, (long long)A1);
     }
-    // generic launches: up to 3 boxes of block indices (the whole space when not tiled)
+    // generic launches: up to 4 boxes of block indices (the whole space when not tiled).  Box 0 of the
+    // pointwise path is its conditional fallback: the tiled region again, run only if that kernel saw a
+    // non-finite accumulator (the reference drops such rows; the generic kernel does it exactly).
     struct Box { int64_t t0, t1, a0, a1, c0, c1; };
-    Box boxes[3];
+    Box boxes[4];
     int nbox = 0;
+    const bool fallback = tiled && pointwise;
     if (!tiled) {
         boxes[nbox++] = {0, nBt, 0, P.nB0, 0, P.nB1};
     } else {
         // plan covers block indices [0,plan.nbt) x [0,plan.nb0) x [0,plan.nb1)
+        if (fallback) boxes[nbox++] = {0, plan.nbt, 0, plan.nb0, 0, plan.nb1};
         if (plan.nbt < nBt) boxes[nbox++] = {plan.nbt, nBt, 0, P.nB0, 0, P.nB1};
         if (plan.nb0 < P.nB0) boxes[nbox++] = {0, plan.nbt, plan.nb0, P.nB0, 0, P.nB1};
         if (plan.nb1 < P.nB1) boxes[nbox++] = {0, plan.nbt, 0, plan.nb0, plan.nb1, P.nB1};
     }
     const int max_ctas = sm_count() * 8;
-    int box_ctas[3] = {0, 0, 0};
+    int box_ctas[4] = {0, 0, 0, 0};
     int64_t gen_parts = 0;
     for (int k = 0; k < nbox; ++k) {
         const int64_t items = (boxes[k].t1 - boxes[k].t0) * (boxes[k].a1 - boxes[k].a0) * (boxes[k].c1 - boxes[k].c0);
@@ -189,7 +194,8 @@ int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0
     P.counters = counters;
     int64_t part_off = 0;
     if (tiled) {
-        rc = tiled_launch(P, library_id, plan, partials, (char *)(partials + (gen_parts + tiled_parts) * len), st);
+        rc = pointwise ? tiled_pw_launch(P, library_id, plan, partials, st)
+                       : tiled_launch(P, library_id, plan, partials, (char *)(partials + (gen_parts + tiled_parts) * len), st);
         if (rc) return rc;
         part_off = tiled_parts;
     }
@@ -198,11 +204,16 @@ int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0
         Q.tb_lo = boxes[k].t0; Q.tb_hi = boxes[k].t1; Q.i0_lo = boxes[k].a0; Q.i0_hi = boxes[k].a1;
         Q.i1_lo = boxes[k].c0; Q.i1_hi = boxes[k].c1;
         Q.partials = partials + part_off * len;
+        Q.run_if = (fallback && k == 0) ? counters + 2 : nullptr;
         rc = launch_k1_generic(library_id, Q, box_ctas[k], st);
         if (rc) return rc;
         part_off += (int64_t)box_ctas[k] * GW_WARPS;
     }
-    rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st);
+    if (fallback)
+        rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st, counters + 2, tiled_parts,
+                                    (int64_t)box_ctas[0] * GW_WARPS);
+    else
+        rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st);
     if (rc) return rc;
     if (nonfinite_out)
         PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
     constexpr int p = Lib<LIB>::P;
     constexpr int S = PG_STATS_LEN(p);
     extern __shared__ double sm[];
+    if (P.run_if && *P.run_if == 0) return;                  // conditional fallback launch: nothing to redo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *wacc_all = sm;                                   // [GW][n_folds][S]
     double *ext_all = wacc_all + GW * P.n_folds * S;         // [GW][32][p+2]
@@ -111,11 +112,19 @@ __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
 // k, k+128, ... (Kahan-compensated), then a fixed-order tree in shared memory, so the result does
 // not depend on scheduling (run-to-run bit-identical).
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__restrict__ partials, int64_t n_parts,
-                                                              int64_t len, double *__restrict__ out, int accumulate) {
+                                                              int64_t len, double *__restrict__ out, int accumulate,
+                                                              const unsigned long long *__restrict__ flag, int64_t n_a,
+                                                              int64_t n_b) {
     __shared__ double sh[128];
     const int64_t e = blockIdx.x;
     double s = 0.0, comp = 0.0;
+    int64_t skip_lo = 0, skip_hi = 0;
+    if (flag) {
+        if (*flag != 0) skip_hi = n_a;
+        else { skip_lo = n_a; skip_hi = n_a + n_b; }
+    }
     for (int64_t k = threadIdx.x; k < n_parts; k += 128) {
+        if (k >= skip_lo && k < skip_hi) continue;
         const double x = __dsub_rn(partials[k * len + e], comp);
         const double t = __dadd_rn(s, x);
         comp = __dsub_rn(__dsub_rn(t, s), x);
@@ -337,9 +346,9 @@ int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st) {
 }
 
 int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate,
-                           cudaStream_t st) {
+                           cudaStream_t st, const unsigned long long *flag, int64_t n_a, int64_t n_b) {
     if (len <= 0) return PG_OK;
-    reduce_partials_kernel<<<(unsigned)len, 128, 0, st>>>(partials, n_parts, len, out, accumulate);
+    reduce_partials_kernel<<<(unsigned)len, 128, 0, st>>>(partials, n_parts, len, out, accumulate, flag, n_a, n_b);
     PG_LAUNCHED();
     return PG_OK;
 }

@@ -25,7 +25,9 @@ struct K1Params {
     const int32_t *fold_of_frame;
     int n_folds;
     double *partials;               // [parts][n_folds][S]
-    unsigned long long *counters;   // [0] non-finite rows, [1] rows with an out-of-range fold id / index
+    unsigned long long *counters;   // [0] non-finite rows, [1] rows with an out-of-range fold id / index,
+                                    // [2] set by the tiled pointwise kernel when a flushed accumulator was not finite
+    const unsigned long long *run_if;  // nullable: the generic kernel only runs if *run_if != 0 (fallback launch)
 };
 
 struct RowsParams {
@@ -68,7 +70,10 @@ struct TiledPlan {
 };
 
 int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st);
-int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate, cudaStream_t st);
+// Sum of partials[k][.] over k.  With `flag`: parts [0, n_a) are skipped if *flag != 0 and parts [n_a, n_a + n_b)
+// are skipped if *flag == 0 (fast path and its conditional fallback, see tiled_pw.cu).
+int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate, cudaStream_t st,
+                           const unsigned long long *flag = nullptr, int64_t n_a = 0, int64_t n_b = 0);
 int launch_fd_terms(int dialect, int lib, const double *U, int64_t T, int64_t A0, int64_t A1, const FdConsts &c, double *out, cudaStream_t st);
 int launch_fd_gather(int lib, const K1Params &P, const int64_t *flat_idx, int64_t n, double *X, double *y, cudaStream_t st);
 int launch_block_means(const double *stack, int k, int64_t T, int64_t A0, int64_t A1, int bt, int b0, int b1, double *out, cudaStream_t st);
@@ -77,7 +82,11 @@ int launch_stridge(const StridgeParams &P, int32_t *best_out, cudaStream_t st);
 int launch_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, const int32_t *pts, int64_t n, const double *W6, int rt, int rs, int mode, double *X, double *y, unsigned long long *counters, cudaStream_t st);
 int launch_synth(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total, uint64_t seed, int kind, double noise, cudaStream_t st);
 
-// tiled.cu
+// tiled_pw.cu (pointwise rows)
+bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan);
+int tiled_pw_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, cudaStream_t st);
+
+// tiled.cu ((bt,8,8) block means)
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan);
 int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st);
 

@@ -1,0 +1,566 @@
+// K1 tiled, pointwise rows: fused FD + library + Gram where EVERY grid point is a row (block (1,1,1)).
+// Serves the full-grid configurations: basic_usage (basic:32-101,123-124: Theta over all interior points,
+// p = 6) and the KS dialect with every point a row and time-holdout folds (SURVEY 8d, C4 i/ii).
+//
+// Data movement is the one of tiled.cu: a persistent CTA owns a TI x 128 tile, each frame's (TI+4) x 128
+// row-halo tile arrives by one 3-D TMA copy, halo columns as 16-byte cells.  Differences:
+//   * u_t is pointwise here, so frame t+1 must be resident while frame t is differentiated: a 4-stage ring
+//     (current, next, two in flight), TI = 48 (4 x 54.9 KB).
+//   * every point contributes an outer product, so the kernel is fp64-ISSUE bound, not HBM bound
+//     (B200: 64 DFMA/clk/SM; ~32 fp64 ops per point for the p = 3 KS library, ~35 for basic p = 6,
+//     against ~23 available per point at the HBM roof).  The design therefore minimises fp64 operations:
+//     - all terms are accumulated UNSCALED (differences / stencil sums without their 1/h factors) and the
+//       statistics are scaled once when a warp flushes its accumulators;
+//     - the '1' column and the duplicates it creates in the statistics vector (sum theta_j == G_0j) are
+//       not accumulated twice: the accumulators are the unique pairs of [1, y, non-constant columns];
+//     - each lane keeps the whole set of accumulators in registers (no staging, no shuffles per point);
+//     - n is counted in integers.
+//   * folds are time-holdout folds (one id per frame): a warp accumulates for ONE fold at a time and
+//     flushes its registers to its private partial slot when the fold of the next frame differs, so any
+//     number of folds costs nothing per point.
+//   * rows with a non-finite value: the reference drops them (ks2d:1633-1636).  Testing every point would
+//     cost issue slots, so the kernel accumulates unconditionally and raises counters[2] when a flushed
+//     accumulator is not finite; the API then lets the generic kernel (exact drop semantics) redo the
+//     region, and the reduction ignores this kernel's partials.
+//   * basic_usage rows are the interior [2:-2, 2:-2] of each frame: boundary tiles mask rows (warp-uniform)
+//     and columns (selects, only instantiated for tiles that touch the left / right border).  The KS
+//     dialect wraps periodically; a ragged last tile row (A0 not a multiple of 48) is handled here, ragged
+//     columns go to the generic kernel.
+#include <cuda.h>
+#include <math.h>
+
+#include <utility>
+
+#include "common.cuh"
+#include "launch.h"
+#include "tiled_common.cuh"
+
+namespace pg {
+
+constexpr int PW_NSTAGE = 4;
+
+template <int R_, int NW_> struct GeoPw {
+    static constexpr int R = R_, NW = NW_;
+    static constexpr int TI = R * NW;                 // tile rows: one R-row band per warp
+    static constexpr int HR = TI + 4;
+    static constexpr int HOFF = HR * TJ;
+    static constexpr int STAGE_DOUBLES = HR * PITCH;
+    static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+    static constexpr int TMA_BYTES = HR * TJ * 8;
+    static constexpr int THREADS = 32 * NW;
+    static constexpr int MAXC = (2 * HR + 2 * TJ + THREADS - 1) / THREADS;
+    static constexpr size_t SMEM = (size_t)PW_NSTAGE * STAGE_BYTES + 64;
+};
+
+struct PwParams {
+    const double *U;
+    int64_t T, A0, A1;
+    double rho, kappa;        // L' = rho*(u[i+1]+u[i-1]) + (u[j+1]+u[j-1]) + kappa*u ; lap = r1*L'
+    double r1, q1;            // 1/d1^2 ; 1/(2 d1)^2   (|grad|^2 = q1*(rho*dx^2 + dy^2))
+    double h0, h1;            // 1/(2 d0), 1/(2 d1)
+    double rdt;
+    int n_tiles0, n_tiles1, n_chunks, chunk_frames;
+    int64_t n_row_frames;     // T - 1
+    const int32_t *fold_of_frame;
+    int n_folds;
+    double *partials;         // [gridDim.x*NW][n_folds][S]
+    unsigned long long *counters;
+};
+
+// ----------------------------------------------------------------------------- accumulator layout
+// Unique extended row: index 0 = the constant one (implicit), 1 = y, then the library columns in order
+// without the '1' column.  Accumulators = upper-triangular pairs (a <= b) except (0,0), which is n.
+template <int LIB> struct Pw {
+    static constexpr bool KS = LIB != PG_LIB_BASIC;
+    static constexpr int P = Lib<LIB>::P;
+    static constexpr bool ONE = LIB == PG_LIB_KS_RICH || LIB == PG_LIB_KS_RICH_NOADV || LIB == PG_LIB_BASIC;
+    static constexpr int NU = 2 + P - (ONE ? 1 : 0);
+    static constexpr int NX = NU - 1;                  // values formed per point
+    static constexpr int NACC = NU * (NU + 1) / 2 - 1;
+    static constexpr int S = PG_STATS_LEN(P);
+};
+
+__host__ __device__ constexpr int pw_slot(int nu, int a, int b) { return a * nu - a * (a - 1) / 2 + (b - a) - 1; }
+
+// statistics entry e -> unique pair; same enumeration as stats_pair (common.cuh)
+struct PwPair { int a, b; };
+__host__ __device__ constexpr PwPair pw_entry(int e, int p, bool one) {
+    int a = 0, b = 0;
+    if (e == 0) { a = 0; b = 0; }
+    else if (e == 1) { a = 0; b = 1; }
+    else if (e == 2) { a = 1; b = 1; }
+    else if (e < 3 + p) { a = 0; b = 2 + (e - 3); }
+    else if (e < 3 + 2 * p) { a = 1; b = 2 + (e - 3 - p); }
+    else {
+        int k = e - 3 - 2 * p, i = 0;
+        while (k >= p - i) { k -= p - i; ++i; }
+        a = 2 + i; b = 2 + i + k;
+    }
+    // full extended index (0 one, 1 y, 2+k theta_k) -> unique index
+    const int ua = a < 2 ? a : (one ? (a == 2 ? 0 : a - 1) : a);
+    const int ub = b < 2 ? b : (one ? (b == 2 ? 0 : b - 1) : b);
+    return ua <= ub ? PwPair{ua, ub} : PwPair{ub, ua};
+}
+
+template <int NU, int NACC> __device__ __forceinline__ void pw_accumulate(double (&acc)[NACC], const double (&x)[NU - 1]) {
+    int k = 0;
+#pragma unroll
+    for (int b = 1; b < NU; ++b) acc[k++] += x[b - 1];
+#pragma unroll
+    for (int a = 1; a < NU; ++a)
+#pragma unroll
+        for (int b = a; b < NU; ++b) { acc[k] = fma(x[a - 1], x[b - 1], acc[k]); ++k; }
+}
+
+// scale of each unique entry (the factor its unscaled accumulation lacks)
+template <int LIB> __device__ __forceinline__ void pw_scales(const PwParams &P, double (&sc)[Pw<LIB>::NU]) {
+    sc[0] = 1.0;
+    sc[1] = P.rdt;
+    const double lap = P.r1, bih = P.r1 * P.r1, g = P.q1;
+    if constexpr (LIB == PG_LIB_KS_TRUE) { sc[2] = lap; sc[3] = bih; sc[4] = g; }
+    else if constexpr (LIB == PG_LIB_KS_TRUE_ADV) { sc[2] = lap; sc[3] = bih; sc[4] = g; sc[5] = P.h0; sc[6] = P.h1; }
+    else if constexpr (LIB == PG_LIB_KS_RICH) {
+        sc[2] = 1.0; sc[3] = 1.0; sc[4] = P.h0; sc[5] = P.h1; sc[6] = lap; sc[7] = bih; sc[8] = g; sc[9] = lap;
+    } else if constexpr (LIB == PG_LIB_KS_RICH_NOADV) {
+        sc[2] = 1.0; sc[3] = 1.0; sc[4] = lap; sc[5] = bih; sc[6] = g; sc[7] = lap;
+    } else {  // BASIC: 1, u, u_x (a1), u_y (a0), lap, u^2
+        sc[2] = 1.0; sc[3] = P.h1; sc[4] = P.h0; sc[5] = lap; sc[6] = 1.0;
+    }
+}
+
+// ----------------------------------------------------------------------------- lane addressing
+// As LaneMap in tiled.cu, for bands of R rows: the four 16-byte chunks (columns own-2,-1 | own0,1 |
+// own2,3 | own+4,+5) of band row 0 and their row strides; lanes with bit 2 set issue each pair in the
+// opposite order (conflict-free LDS.128) and swap back.
+struct LaneMapPw {
+    int a0, sa0, a1, sa1, b0, sb0, b1, sb1, sw, own;
+};
+
+template <int R, int NW> __device__ __forceinline__ LaneMapPw lane_map_pw(int band, int lane) {
+    using G_ = GeoPw<R, NW>;
+    const int own = band * R * TJ + 4 * lane, hrow = G_::HOFF + band * R * 4;
+    const int c0 = lane > 0 ? own - 2 : hrow, s0 = lane > 0 ? TJ : 4;
+    const int c3 = lane < 31 ? own + 4 : hrow + 2, s3 = lane < 31 ? TJ : 4;
+    LaneMapPw m;
+    m.sw = (lane >> 2) & 1;
+    m.own = own;
+    m.a0 = m.sw ? own : c0;       m.sa0 = m.sw ? TJ : s0;
+    m.a1 = m.sw ? c0 : own;       m.sa1 = m.sw ? s0 : TJ;
+    m.b0 = m.sw ? c3 : own + 2;   m.sb0 = m.sw ? s3 : TJ;
+    m.b1 = m.sw ? own + 2 : c3;   m.sb1 = m.sw ? TJ : s3;
+    return m;
+}
+
+// columns own-2 .. own+5 of band row s
+__device__ __forceinline__ void load_row8(const double *__restrict__ st, const LaneMapPw &m, int s, double (&w)[8]) {
+    const double2 x0 = *reinterpret_cast<const double2 *>(st + m.a0 + s * m.sa0);
+    const double2 x1 = *reinterpret_cast<const double2 *>(st + m.a1 + s * m.sa1);
+    const double2 y0 = *reinterpret_cast<const double2 *>(st + m.b0 + s * m.sb0);
+    const double2 y1 = *reinterpret_cast<const double2 *>(st + m.b1 + s * m.sb1);
+    const double2 a0 = m.sw ? x1 : x0, a1 = m.sw ? x0 : x1, a2 = m.sw ? y1 : y0, a3 = m.sw ? y0 : y1;
+    w[0] = a0.x; w[1] = a0.y; w[2] = a1.x; w[3] = a1.y; w[4] = a2.x; w[5] = a2.y; w[6] = a3.x; w[7] = a3.y;
+}
+// own columns only (own0 .. own3) of band row s, conflict-free
+__device__ __forceinline__ void load_row4(const double *__restrict__ st, const LaneMapPw &m, int s, double (&w)[4]) {
+    const double2 *own = reinterpret_cast<const double2 *>(st + m.own + s * TJ);
+    const double2 x = own[m.sw], y = own[m.sw ^ 1];
+    const double2 lo = m.sw ? y : x, hi = m.sw ? x : y;
+    w[0] = lo.x; w[1] = lo.y; w[2] = hi.x; w[3] = hi.y;
+}
+
+// ----------------------------------------------------------------------------- one frame of one warp band
+// st = current frame's stage, stn = next frame's stage (u_t).  Band rows s = 0..R+3 are stage rows
+// band*R + s; the warp's own rows are s = 2..R+1 (bit r of rowmask = own row r is a row of the data set).
+template <int LIB, int R, bool MASKED>
+__device__ __forceinline__ void march_pw(const double *__restrict__ st, const double *__restrict__ stn, const LaneMapPw &m,
+                                         const PwParams &P, unsigned rowmask, unsigned colmask,
+                                         double (&acc)[Pw<LIB>::NACC], unsigned &cnt) {
+    using X_ = Pw<LIB>;
+    constexpr int NU = X_::NU, NX = X_::NX, NACC = X_::NACC;
+    const unsigned ncol = MASKED ? __popc(colmask) : 4u;
+    if constexpr (X_::KS) {
+        double u[R + 4][8];
+        double L[R + 4][6];   // L[s][k]: L' of band row s at window column k+1 (own-1 .. own+4)
+#pragma unroll
+        for (int s = 0; s < R + 4; ++s) {
+            if (s == 0 || s == R + 3) {
+                double w4[4];
+                load_row4(st, m, s, w4);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) u[s][c + 2] = w4[c];
+            } else {
+                load_row8(st, m, s, u[s]);
+            }
+            if (s >= 2) {
+                const int r = s - 1;   // L' of band row r (rows 1 and R+2 only feed the a0-neighbours: own columns)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    if ((r == 1 || r == R + 2) && (k == 0 || k == 5)) continue;
+                    const int q = k + 1;
+                    L[r][k] = fma(P.kappa, u[r][q], fma(P.rho, u[r + 1][q] + u[r - 1][q], u[r][q + 1] + u[r][q - 1]));
+                }
+            }
+            if (s >= 4) {
+                const int r = s - 2;   // own row r: all of its neighbours' L' are known now
+                if ((rowmask >> (r - 2)) & 1u) {
+                    double nx[4];
+                    load_row4(stn, m, r, nx);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int q = c + 2, k = c + 1;
+                        const double uc = u[r][q];
+                        const double Y = nx[c] - uc;
+                        const double dx = u[r + 1][q] - u[r - 1][q];
+                        const double dy = u[r][q + 1] - u[r][q - 1];
+                        const double Gq = fma(P.rho * dx, dx, dy * dy);
+                        const double Lc = L[r][k];
+                        const double B = fma(P.kappa, Lc, fma(P.rho, L[r + 1][k] + L[r - 1][k], L[r][k + 1] + L[r][k - 1]));
+                        double x[NX];
+                        if constexpr (LIB == PG_LIB_KS_TRUE) { x[0] = Y; x[1] = Lc; x[2] = B; x[3] = Gq; }
+                        else if constexpr (LIB == PG_LIB_KS_TRUE_ADV) { x[0] = Y; x[1] = Lc; x[2] = B; x[3] = Gq; x[4] = dx; x[5] = dy; }
+                        else if constexpr (LIB == PG_LIB_KS_RICH) {
+                            x[0] = Y; x[1] = uc; x[2] = uc * uc; x[3] = dx; x[4] = dy; x[5] = Lc; x[6] = B; x[7] = Gq; x[8] = uc * Lc;
+                        } else {
+                            x[0] = Y; x[1] = uc; x[2] = uc * uc; x[3] = Lc; x[4] = B; x[5] = Gq; x[6] = uc * Lc;
+                        }
+                        pw_accumulate<NU, NACC>(acc, x);
+                    }
+                    cnt += 4u;
+                }
+            }
+        }
+    } else {
+        // basic_usage: 5-point stencils only; band rows 1 .. R+2 are needed
+        double u[R + 4][8];
+#pragma unroll
+        for (int s = 1; s < R + 3; ++s) {
+            if (s == 1 || s == R + 2) {
+                double w4[4];
+                load_row4(st, m, s, w4);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) u[s][c + 2] = w4[c];
+            } else {
+                load_row8(st, m, s, u[s]);
+            }
+            if (s >= 3) {
+                const int r = s - 1;
+                if ((rowmask >> (r - 2)) & 1u) {
+                    double nx[4];
+                    load_row4(stn, m, r, nx);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int q = c + 2;
+                        double uc = u[r][q];
+                        double Y = nx[c] - uc;
+                        double dxj = u[r][q + 1] - u[r][q - 1];          // u_x * 2 d1   (basic:58)
+                        double dxi = u[r + 1][q] - u[r - 1][q];          // u_y * 2 d0   (basic:59)
+                        double Lc = fma(P.kappa, uc, fma(P.rho, u[r + 1][q] + u[r - 1][q], u[r][q + 1] + u[r][q - 1]));
+                        if constexpr (MASKED) {
+                            const bool ok = (colmask >> c) & 1u;
+                            uc = ok ? uc : 0.0; Y = ok ? Y : 0.0; dxj = ok ? dxj : 0.0; dxi = ok ? dxi : 0.0; Lc = ok ? Lc : 0.0;
+                        }
+                        const double x[NX] = {Y, uc, dxj, dxi, Lc, uc * uc};
+                        pw_accumulate<NU, NACC>(acc, x);
+                    }
+                    cnt += ncol;
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- flush
+template <int LIB, int E> __device__ __forceinline__ void pw_emit(const double (&acc)[Pw<LIB>::NACC], const double (&sc)[Pw<LIB>::NU],
+                                                                  double n, int lane, double *out) {
+    using X_ = Pw<LIB>;
+    constexpr PwPair pr = pw_entry(E, X_::P, X_::ONE);
+    if (lane == (E & 31)) {
+        double v;
+        if constexpr (pr.a == 0 && pr.b == 0) v = n;
+        else v = acc[pw_slot(X_::NU, pr.a, pr.b)] * (sc[pr.a] * sc[pr.b]);
+        out[E] += v;
+    }
+}
+template <int LIB, int... Es>
+__device__ __forceinline__ void pw_emit_all(std::integer_sequence<int, Es...>, const double (&acc)[Pw<LIB>::NACC],
+                                            const double (&sc)[Pw<LIB>::NU], double n, int lane, double *out) {
+    (pw_emit<LIB, Es>(acc, sc, n, lane, out), ...);
+}
+
+// Warp-reduce the lane accumulators, scale, and add them to this warp's partial slot of `fold`.
+// Returns true if some accumulator was not finite (a row the reference would have dropped, or overflow).
+template <int LIB>
+__device__ __forceinline__ bool pw_flush(double (&acc)[Pw<LIB>::NACC], unsigned &cnt, const PwParams &P, int lane, double *out) {
+    using X_ = Pw<LIB>;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < X_::NACC; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[k] = v;
+        bad = bad || !isfinite(v);
+    }
+    unsigned c = cnt;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    double sc[X_::NU];
+    pw_scales<LIB>(P, sc);
+    pw_emit_all<LIB>(std::make_integer_sequence<int, X_::S>{}, acc, sc, (double)c, lane, out);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < X_::NACC; ++k) acc[k] = 0.0;
+    cnt = 0;
+    return bad;
+}
+
+template <int LIB, int R, int NW>
+__global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant__ CUtensorMap tmap, PwParams P) {
+    using G_ = GeoPw<R, NW>;
+    using X_ = Pw<LIB>;
+    constexpr int TI = G_::TI, HR = G_::HR, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES;
+    constexpr int MAXC = G_::MAXC, THREADS = G_::THREADS, NS = PW_NSTAGE;
+    constexpr int S = X_::S;
+    constexpr bool KS = X_::KS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stages = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NS * G_::STAGE_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const LaneMapPw lm = lane_map_pw<R, NW>(warp, lane);
+
+    double acc[X_::NACC];
+#pragma unroll
+    for (int k = 0; k < X_::NACC; ++k) acc[k] = 0.0;
+    unsigned cnt = 0;           // rows accumulated by this lane since the last flush (< 2^32: flushed per item)
+    int cur_fold = -1;
+    bool poisoned = false;
+    unsigned long long bad_fold = 0;
+
+    double *slot = P.partials + ((int64_t)blockIdx.x * NW + warp) * P.n_folds * S;
+    for (int e = lane; e < P.n_folds * S; e += 32) slot[e] = 0.0;
+    __syncwarp();
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const int64_t frame = P.A0 * P.A1;
+    const int n_tiles = P.n_tiles0 * P.n_tiles1;
+    const int64_t n_items = (int64_t)n_tiles * P.n_chunks;
+
+    auto geometry = [&](int64_t item, int &i0, int &j0, int &t0, int &nf) {
+        const int tile = (int)(item % n_tiles), chunk = (int)(item / n_tiles);
+        i0 = (tile / P.n_tiles1) * TI;
+        j0 = (tile % P.n_tiles1) * TJ;
+        t0 = chunk * P.chunk_frames;
+        nf = (int)min((int64_t)P.chunk_frames, P.n_row_frames - t0);
+    };
+
+    // ---- producer (thread 0): a continuous stream of frame loads, three ahead of the consumer
+    int64_t p_item = blockIdx.x;
+    int p_i0 = 0, p_j0 = 0, p_t = 0, p_left = 0;
+    uint32_t p_g = 0;
+    if (tid == 0 && p_item < n_items) {
+        int nf;
+        geometry(p_item, p_i0, p_j0, p_t, nf);
+        p_left = nf + 1;
+    }
+    auto produce = [&]() {
+        if (p_left == 0) return;
+        uint64_t *bar = &bars[p_g % NS];
+        fence_proxy_async();
+        mbar_expect_tx(bar, G_::TMA_BYTES);
+        tma_load_3d(stages + (p_g % NS) * STAGE_DOUBLES, &tmap, bar, p_j0, p_i0 - 2, p_t);
+        ++p_g;
+        ++p_t;
+        if (--p_left == 0) {
+            p_item += gridDim.x;
+            if (p_item < n_items) {
+                int nf;
+                geometry(p_item, p_i0, p_j0, p_t, nf);
+                p_left = nf + 1;
+            }
+        }
+    };
+    if (tid == 0) { produce(); produce(); produce(); }
+
+    uint32_t G = 0;  // consumer load index (stage = G % NS, parity = (G / NS) & 1)
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int i0, j0, t0, nf;
+        geometry(item, i0, j0, t0, nf);
+        const int vrows = (int)min((int64_t)TI, P.A0 - i0);      // tile rows inside the frame
+        const bool wt = KS && i0 == 0, wb = KS && i0 + TI >= P.A0;
+
+        // rows / columns of this warp / lane that are rows of the data set
+        unsigned rowmask = 0, colmask = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t i = (int64_t)i0 + warp * R + r;
+            const bool ok = KS ? (i < P.A0) : (i >= 2 && i < P.A0 - 2);
+            rowmask |= ok ? (1u << r) : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int64_t j = (int64_t)j0 + 4 * lane + c;
+            const bool ok = KS ? true : (j >= 2 && j < P.A1 - 2);
+            colmask |= ok ? (1u << c) : 0u;
+        }
+        const bool edge_cols = !KS && (j0 < 2 || (int64_t)j0 + TJ > P.A1 - 2);   // CTA-uniform
+        const unsigned rows_per_frame = (unsigned)__popc(rowmask) * (unsigned)__popc(colmask);
+
+        // 16-byte side cells handled by this thread: the two halo columns on either side of every stage row,
+        // and (KS) the periodic wrap rows that TMA zero-filled.  c_src < 0: cell outside the frame -> zeros.
+        int c_off[MAXC];
+        int64_t c_src[MAXC];
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            int c = tid + k * THREADS, Rr = -1, C = 0;
+            c_off[k] = -1;
+            c_src[k] = -1;
+            if (c < 2 * HR) {
+                Rr = c >> 1;
+                const int side = c & 1;
+                c_off[k] = HOFF + Rr * 4 + side * 2;
+                C = side ? j0 + TJ : j0 - 2;
+            } else {
+                c -= 2 * HR;
+                if (wt) { if (c >= 0 && c < TJ) { Rr = c / (TJ / 2); C = j0 + 2 * (c % (TJ / 2)); c_off[k] = Rr * TJ + (C - j0); } c -= TJ; }
+                if (wb) { if (c >= 0 && c < TJ) { Rr = vrows + 2 + c / (TJ / 2); C = j0 + 2 * (c % (TJ / 2)); c_off[k] = Rr * TJ + (C - j0); } c -= TJ; }
+            }
+            if (c_off[k] >= 0) {
+                const int64_t gi = (int64_t)i0 - 2 + Rr;
+                if constexpr (KS) c_src[k] = wrap(gi, P.A0) * P.A1 + wrap((int64_t)C, P.A1);
+                else if (gi >= 0 && gi < P.A0 && C >= 0 && C < P.A1) c_src[k] = gi * P.A1 + C;
+            }
+        }
+        double2 c_val[MAXC];
+        auto side_fetch = [&](int64_t t) {
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                c_val[k] = make_double2(0.0, 0.0);
+                if (c_src[k] >= 0) c_val[k] = __ldg(reinterpret_cast<const double2 *>(P.U + t * frame + c_src[k]));
+            }
+        };
+        auto side_store = [&](double *stage) {
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k)
+                if (c_off[k] >= 0) *reinterpret_cast<double2 *>(stage + c_off[k]) = c_val[k];
+        };
+        side_fetch(t0);
+        int fold_next = P.fold_of_frame ? __ldg(P.fold_of_frame + t0) : 0;
+        mbar_wait(&bars[G % NS], (G / NS) & 1);
+
+        for (int f = 0; f <= nf; ++f, ++G) {
+            double *st = stages + (G % NS) * STAGE_DOUBLES;
+            const double *stn = stages + ((G + 1) % NS) * STAGE_DOUBLES;
+            if (f < nf) {
+                mbar_wait(&bars[(G + 1) % NS], ((G + 1) / NS) & 1);   // frame t+1 (u_t)
+                side_store(st);
+            }
+            __syncthreads();  // side cells visible; every warp is done with load G-1, whose stage is free
+            if (tid == 0) produce();                 // load G+3 -> the stage just freed
+            if (f >= nf) continue;
+            const int fold = fold_next;
+            if (f + 1 < nf) {
+                side_fetch((int64_t)t0 + f + 1);
+                if (P.fold_of_frame) fold_next = __ldg(P.fold_of_frame + t0 + f + 1);
+            }
+            if (fold < 0 || fold >= P.n_folds) { bad_fold += rows_per_frame; continue; }
+            if (fold != cur_fold) {
+                if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);
+                cur_fold = fold;
+            }
+            if (edge_cols) march_pw<LIB, R, !KS>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+            else march_pw<LIB, R, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+        }
+        // per-item flush: bounds the length of the per-lane summation chains (and cnt)
+        if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);
+    }
+    if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
+    if (poisoned && lane == 0) atomicAdd(&P.counters[2], 1ull);
+}
+
+// ----------------------------------------------------------------------------- host side
+constexpr int PW_R = 6, PW_NW = 8;
+
+bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
+    if (P.bt != 1 || P.b0 != 1 || P.b1 != 1) return false;
+    if (P.fold_of_row) return false;                        // per-row folds: generic kernel
+    const bool ks = P.dialect == PG_FD_KS_PERIODIC;
+    if (ks ? !(lib == PG_LIB_KS_TRUE || lib == PG_LIB_KS_TRUE_ADV || lib == PG_LIB_KS_RICH || lib == PG_LIB_KS_RICH_NOADV)
+           : lib != PG_LIB_BASIC)
+        return false;
+    if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // TMA / LDG.128 alignment
+    if (P.T < 2 || P.T > 0x7fffffff || P.A0 > 0x7fffffff || P.A1 > 0x7fffffff) return false;
+    if (P.A0 < 4 || P.A1 < TJ) return false;
+    if (!encode_fn()) return false;
+    constexpr int TI = GeoPw<PW_R, PW_NW>::TI;
+    const int64_t nt0 = (P.A0 + TI - 1) / TI;
+    const int64_t nt1 = ks ? P.A1 / TJ : (P.A1 + TJ - 1) / TJ;
+    const int64_t n_tiles = nt0 * nt1, nrf = P.T - 1;
+    // number of frame chunks: balance the persistent CTAs; every item pays one extra frame + pipeline fill
+    int64_t best_c = 1;
+    double best_cost = 1e300;
+    for (int64_t c = 1; c <= nrf && c <= 4096; ++c) {
+        const int64_t cf = (nrf + c - 1) / c, cc = (nrf + cf - 1) / cf;
+        const int64_t rounds = (n_tiles * cc + n_sm - 1) / n_sm;
+        const double cost = (double)rounds * ((double)cf + 2.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_c = cc; }
+    }
+    const int64_t cf = (nrf + best_c - 1) / best_c;
+    plan = TiledPlan{};
+    plan.nbt = nrf;
+    plan.nb0 = P.R0;
+    plan.nb1 = ks ? nt1 * TJ : P.R1;
+    plan.chunk_t = (int)cf;
+    plan.n_chunks = (nrf + cf - 1) / cf;
+    plan.n_tiles0 = nt0; plan.n_tiles1 = nt1;
+    const int64_t items = n_tiles * plan.n_chunks;
+    plan.grid = (int)(items < n_sm ? items : n_sm);
+    plan.n_parts = (int64_t)plan.grid * PW_NW;
+    plan.extra_scratch = 0;
+    plan.kernel_id = 100;
+    plan.tile0 = TI; plan.tile1 = TJ;
+    return true;
+}
+
+template <int LIB> static int launch_pw_t(const CUtensorMap &map, const PwParams &pp, int grid, cudaStream_t st) {
+    using G_ = GeoPw<PW_R, PW_NW>;
+    PG_CUDA(cudaFuncSetAttribute(k1_tiled_pw<LIB, PW_R, PW_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
+    k1_tiled_pw<LIB, PW_R, PW_NW><<<grid, G_::THREADS, G_::SMEM, st>>>(map, pp);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
+int tiled_pw_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, cudaStream_t st) {
+    CUtensorMap map;
+    const CUresult r = encode_field_map(&map, P.U, P.T, P.A0, P.A1, GeoPw<PW_R, PW_NW>::HR);
+    if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    PwParams pp{};
+    pp.U = P.U; pp.T = P.T; pp.A0 = P.A0; pp.A1 = P.A1;
+    pp.rho = P.c.d1sq / P.c.d0sq;
+    pp.kappa = -2.0 * (1.0 + pp.rho);
+    pp.r1 = 1.0 / P.c.d1sq;
+    pp.q1 = 1.0 / (P.c.two_d1 * P.c.two_d1);
+    pp.h0 = 1.0 / P.c.two_d0; pp.h1 = 1.0 / P.c.two_d1;
+    pp.rdt = 1.0 / P.c.dt;
+    pp.n_tiles0 = (int)plan.n_tiles0; pp.n_tiles1 = (int)plan.n_tiles1; pp.n_chunks = (int)plan.n_chunks;
+    pp.chunk_frames = plan.chunk_t;
+    pp.n_row_frames = P.T - 1;
+    pp.fold_of_frame = P.fold_of_frame; pp.n_folds = P.n_folds;
+    pp.partials = partials; pp.counters = P.counters;
+    switch (lib) {
+        case PG_LIB_KS_TRUE: return launch_pw_t<PG_LIB_KS_TRUE>(map, pp, plan.grid, st);
+        case PG_LIB_KS_TRUE_ADV: return launch_pw_t<PG_LIB_KS_TRUE_ADV>(map, pp, plan.grid, st);
+        case PG_LIB_KS_RICH: return launch_pw_t<PG_LIB_KS_RICH>(map, pp, plan.grid, st);
+        case PG_LIB_KS_RICH_NOADV: return launch_pw_t<PG_LIB_KS_RICH_NOADV>(map, pp, plan.grid, st);
+        case PG_LIB_BASIC: return launch_pw_t<PG_LIB_BASIC>(map, pp, plan.grid, st);
+        default: PG_FAIL(PG_EUNSUPPORTED, "no tiled pointwise kernel for library %d", lib);
+    }
+}
+
+}  // namespace pg

@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--generic", action="store_true")
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--pointwise", action="store_true", help="time the tiled pointwise kernel (every point a row)")
     ap.add_argument("--only", default=None, help="run a single named case")
     args = ap.parse_args()
     T, A = args.frames, args.size
@@ -92,6 +93,14 @@ def main():
              ("true_b388_tiled_2folds", L.LIB_KS_TRUE, (3, 8, 8), L.VARIANT_TILED, 2),
              ("rich_b388_tiled_2folds", L.LIB_KS_RICH, (3, 8, 8), L.VARIANT_TILED, 2),
              ("adv_b388_tiled", L.LIB_KS_TRUE_ADV, (3, 8, 8), L.VARIANT_TILED, 1)]
+    if args.pointwise:
+        cases = [("ks_true_pointwise_tiled", L.LIB_KS_TRUE, (1, 1, 1), L.VARIANT_TILED, 1),
+                 ("ks_true_pointwise_tiled_2folds", L.LIB_KS_TRUE, (1, 1, 1), L.VARIANT_TILED, 2),
+                 ("ks_adv_pointwise_tiled", L.LIB_KS_TRUE_ADV, (1, 1, 1), L.VARIANT_TILED, 1),
+                 ("ks_richnoadv_pointwise_tiled", L.LIB_KS_RICH_NOADV, (1, 1, 1), L.VARIANT_TILED, 1),
+                 ("ks_rich_pointwise_tiled", L.LIB_KS_RICH, (1, 1, 1), L.VARIANT_TILED, 1),
+                 ("basic_pointwise_tiled", L.LIB_BASIC, (1, 1, 1), L.VARIANT_TILED, 1),
+                 ("basic_pointwise_tiled_2folds", L.LIB_BASIC, (1, 1, 1), L.VARIANT_TILED, 2)]
     if args.generic:
         cases += [("true_b388_generic", L.LIB_KS_TRUE, (3, 8, 8), L.VARIANT_GENERIC, 1),
                   ("true_pointwise_generic", L.LIB_KS_TRUE, (1, 1, 1), L.VARIANT_GENERIC, 1),
@@ -99,7 +108,8 @@ def main():
     for name, lib, block, variant, nf in cases:
         if args.only and name != args.only:
             continue
-        kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=block, variant=variant, n_folds=nf)
+        kw = dict(dialect=L.FD_BASIC_TRIM if lib == L.LIB_BASIC else L.FD_KS_PERIODIC, library=lib, block=block,
+                  variant=variant, n_folds=nf)
         if nf == 2:
             kw["fold_of_frame"] = fof
         with Nvml() as nv:
