@@ -48,8 +48,7 @@ template <int R_, int NW_> struct GeoPw {
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
     static constexpr int TMA_BYTES = HR * TJ * 8;
     static constexpr int THREADS = 32 * NW;
-    static constexpr int MAXC = (2 * HR + 2 * TJ + THREADS - 1) / THREADS;
-    static constexpr size_t SMEM = (size_t)PW_NSTAGE * STAGE_BYTES + 64;
+    static constexpr size_t SMEM = (size_t)PW_NSTAGE * STAGE_BYTES + 128;   // + full[4], empty[4] mbarriers
 };
 
 struct PwParams {
@@ -314,17 +313,34 @@ __device__ __forceinline__ bool pw_flush(double (&acc)[Pw<LIB>::NACC], unsigned 
     return bad;
 }
 
+// ----------------------------------------------------------------------------- async 16-byte cells
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool zero) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(zero ? 0 : 16) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// The kernel.  Warps are DECOUPLED: there is no block-wide barrier per frame.  full[s] (TMA complete_tx)
+// says stage s holds its frame; empty[s] counts the NW warps that are done with it, and the producer
+// (lane 0 of warp 0, at the end of its own iteration) waits on it before re-arming the stage, so warps
+// drift apart by up to a frame and one warp's bookkeeping overlaps the others' fp64 work.  Each warp
+// copies the 16-byte side cells its own window needs (halo columns of its R+4 rows; the periodic wrap
+// rows if they fall inside its window) with cp.async, one frame ahead, so they need warp-level visibility
+// only.
 template <int LIB, int R, int NW>
 __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant__ CUtensorMap tmap, PwParams P) {
     using G_ = GeoPw<R, NW>;
     using X_ = Pw<LIB>;
-    constexpr int TI = G_::TI, HR = G_::HR, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES;
-    constexpr int MAXC = G_::MAXC, THREADS = G_::THREADS, NS = PW_NSTAGE;
+    constexpr int TI = G_::TI, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES, NS = PW_NSTAGE;
     constexpr int S = X_::S;
     constexpr bool KS = X_::KS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NS * G_::STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NS * G_::STAGE_BYTES);
+    uint64_t *empty = full + NS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const LaneMapPw lm = lane_map_pw<R, NW>(warp, lane);
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
     double acc[X_::NACC];
 #pragma unroll
     for (int k = 0; k < X_::NACC; ++k) acc[k] = 0.0;
-    unsigned cnt = 0;           // rows accumulated by this lane since the last flush (< 2^32: flushed per item)
+    unsigned cnt = 0;           // rows accumulated by this lane since the last flush
     int cur_fold = -1;
     bool poisoned = false;
     unsigned long long bad_fold = 0;
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
     __syncwarp();
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -360,7 +376,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
         nf = (int)min((int64_t)P.chunk_frames, P.n_row_frames - t0);
     };
 
-    // ---- producer (thread 0): a continuous stream of frame loads, three ahead of the consumer
+    // ---- producer (thread 0): a continuous stream of frame loads, NS-1 ahead of its own consumption
     int64_t p_item = blockIdx.x;
     int p_i0 = 0, p_j0 = 0, p_t = 0, p_left = 0;
     uint32_t p_g = 0;
@@ -371,10 +387,10 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
     }
     auto produce = [&]() {
         if (p_left == 0) return;
-        uint64_t *bar = &bars[p_g % NS];
-        fence_proxy_async();
-        mbar_expect_tx(bar, G_::TMA_BYTES);
-        tma_load_3d(stages + (p_g % NS) * STAGE_DOUBLES, &tmap, bar, p_j0, p_i0 - 2, p_t);
+        const uint32_t s = p_g % NS;
+        if (p_g >= NS) mbar_wait(&empty[s], ((p_g / NS) - 1) & 1);   // every warp released the stage's previous frame
+        mbar_expect_tx(&full[s], G_::TMA_BYTES);
+        tma_load_3d(stages + s * STAGE_DOUBLES, &tmap, &full[s], p_j0, p_i0 - 2, p_t);
         ++p_g;
         ++p_t;
         if (--p_left == 0) {
@@ -412,80 +428,85 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
         const bool edge_cols = !KS && (j0 < 2 || (int64_t)j0 + TJ > P.A1 - 2);   // CTA-uniform
         const unsigned rows_per_frame = (unsigned)__popc(rowmask) * (unsigned)__popc(colmask);
 
-        // 16-byte side cells handled by this thread: the two halo columns on either side of every stage row,
-        // and (KS) the periodic wrap rows that TMA zero-filled.  c_src < 0: cell outside the frame -> zeros.
-        int c_off[MAXC];
-        int64_t c_src[MAXC];
-#pragma unroll
-        for (int k = 0; k < MAXC; ++k) {
-            int c = tid + k * THREADS, Rr = -1, C = 0;
-            c_off[k] = -1;
-            c_src[k] = -1;
-            if (c < 2 * HR) {
-                Rr = c >> 1;
-                const int side = c & 1;
-                c_off[k] = HOFF + Rr * 4 + side * 2;
-                C = side ? j0 + TJ : j0 - 2;
-            } else {
-                c -= 2 * HR;
-                if (wt) { if (c >= 0 && c < TJ) { Rr = c / (TJ / 2); C = j0 + 2 * (c % (TJ / 2)); c_off[k] = Rr * TJ + (C - j0); } c -= TJ; }
-                if (wb) { if (c >= 0 && c < TJ) { Rr = vrows + 2 + c / (TJ / 2); C = j0 + 2 * (c % (TJ / 2)); c_off[k] = Rr * TJ + (C - j0); } c -= TJ; }
-            }
-            if (c_off[k] >= 0) {
-                const int64_t gi = (int64_t)i0 - 2 + Rr;
-                if constexpr (KS) c_src[k] = wrap(gi, P.A0) * P.A1 + wrap((int64_t)C, P.A1);
-                else if (gi >= 0 && gi < P.A0 && C >= 0 && C < P.A1) c_src[k] = gi * P.A1 + C;
-            }
+        // Side cells of this warp's window (stage rows warp*R .. warp*R + R+3):
+        //   lanes 0 .. 2(R+4)-1: one halo-column cell each (left / right pair of one row);
+        //   KS tiles at the top / bottom of the periodic domain: the wrap rows TMA zero-filled (stage rows
+        //   0, 1 and vrows+2, vrows+3), 64 cells per row = 2 per lane, if the row lies in the window.
+        int h_off = -1;
+        int64_t h_src = -1;       // < 0: outside the frame (basic_usage) -> zero-filled
+        if (lane < 2 * (R + 4)) {
+            const int Rr = warp * R + (lane >> 1), side = lane & 1;
+            const int C = side ? j0 + TJ : j0 - 2;
+            const int64_t gi = (int64_t)i0 - 2 + Rr;
+            h_off = HOFF + Rr * 4 + side * 2;
+            if constexpr (KS) h_src = wrap(gi, P.A0) * P.A1 + wrap((int64_t)C, P.A1);
+            else if (gi >= 0 && gi < P.A0 && C >= 0 && C < P.A1) h_src = gi * P.A1 + C;
         }
-        double2 c_val[MAXC];
-        auto side_fetch = [&](int64_t t) {
+        int w_row[4];             // stage rows to patch (-1: none), warp-uniform
+        int64_t w_src[4];
 #pragma unroll
-            for (int k = 0; k < MAXC; ++k) {
-                c_val[k] = make_double2(0.0, 0.0);
-                if (c_src[k] >= 0) c_val[k] = __ldg(reinterpret_cast<const double2 *>(P.U + t * frame + c_src[k]));
+        for (int k = 0; k < 4; ++k) {
+            const int Rr = k < 2 ? k : vrows + k;           // 0, 1, vrows+2, vrows+3
+            const bool need = (k < 2 ? wt : wb) && Rr >= warp * R && Rr <= warp * R + R + 3;
+            w_row[k] = need ? Rr : -1;
+            w_src[k] = wrap((int64_t)i0 - 2 + Rr, P.A0) * P.A1 + j0;
+        }
+        auto issue_cells = [&](double *stage, int64_t t) {
+            const double *Ft = P.U + t * frame;
+            if (h_off >= 0) cp_async16(stage + h_off, h_src >= 0 ? Ft + h_src : P.U, h_src < 0);
+            if constexpr (KS) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (w_row[k] >= 0) {
+                        cp_async16(stage + w_row[k] * TJ + 2 * lane, Ft + w_src[k] + 2 * lane, false);
+                        cp_async16(stage + w_row[k] * TJ + 64 + 2 * lane, Ft + w_src[k] + 64 + 2 * lane, false);
+                    }
             }
+            cp_async_commit();
         };
-        auto side_store = [&](double *stage) {
-#pragma unroll
-            for (int k = 0; k < MAXC; ++k)
-                if (c_off[k] >= 0) *reinterpret_cast<double2 *>(stage + c_off[k]) = c_val[k];
-        };
-        side_fetch(t0);
+
         int fold_next = P.fold_of_frame ? __ldg(P.fold_of_frame + t0) : 0;
-        mbar_wait(&bars[G % NS], (G / NS) & 1);
+        mbar_wait(&full[G % NS], (G / NS) & 1);
+        issue_cells(stages + (G % NS) * STAGE_DOUBLES, t0);
 
         for (int f = 0; f <= nf; ++f, ++G) {
-            double *st = stages + (G % NS) * STAGE_DOUBLES;
-            const double *stn = stages + ((G + 1) % NS) * STAGE_DOUBLES;
+            const double *st = stages + (G % NS) * STAGE_DOUBLES;
             if (f < nf) {
-                mbar_wait(&bars[(G + 1) % NS], ((G + 1) / NS) & 1);   // frame t+1 (u_t)
-                side_store(st);
+                double *stn = stages + ((G + 1) % NS) * STAGE_DOUBLES;
+                mbar_wait(&full[(G + 1) % NS], ((G + 1) / NS) & 1);   // frame t+1: u_t now, differentiated next
+                if (f + 1 < nf) issue_cells(stn, (int64_t)t0 + f + 1);
+                else cp_async_commit();
+                cp_async_wait<1>();                                    // this frame's cells have landed
+                __syncwarp();
+                const int fold = fold_next;
+                if (f + 1 < nf && P.fold_of_frame) fold_next = __ldg(P.fold_of_frame + t0 + f + 1);
+                if (fold < 0 || fold >= P.n_folds) {
+                    bad_fold += rows_per_frame;
+                } else {
+                    if (fold != cur_fold) {
+                        if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);
+                        cur_fold = fold;
+                    }
+                    if (edge_cols) march_pw<LIB, R, !KS>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                    else march_pw<LIB, R, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                }
             }
-            __syncthreads();  // side cells visible; every warp is done with load G-1, whose stage is free
-            if (tid == 0) produce();                 // load G+3 -> the stage just freed
-            if (f >= nf) continue;
-            const int fold = fold_next;
-            if (f + 1 < nf) {
-                side_fetch((int64_t)t0 + f + 1);
-                if (P.fold_of_frame) fold_next = __ldg(P.fold_of_frame + t0 + f + 1);
-            }
-            if (fold < 0 || fold >= P.n_folds) { bad_fold += rows_per_frame; continue; }
-            if (fold != cur_fold) {
-                if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);
-                cur_fold = fold;
-            }
-            if (edge_cols) march_pw<LIB, R, !KS>(st, stn, lm, P, rowmask, colmask, acc, cnt);
-            else march_pw<LIB, R, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+            // release the stage: this warp has read everything it needs from load G
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[G % NS]);
+            if (tid == 0) produce();                                   // load G+3 -> stage of load G-1
         }
-        // per-item flush: bounds the length of the per-lane summation chains (and cnt)
-        if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);
     }
+    cp_async_wait<0>();
+    if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);
     if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
     if (poisoned && lane == 0) atomicAdd(&P.counters[2], 1ull);
 }
 
 // ----------------------------------------------------------------------------- host side
-constexpr int PW_R = 6, PW_NW = 8;
+// Tile geometry: 48 rows as 8 warps x 6 rows (default) or 12 warps x 4 rows (PG_PW_GEO=1, experiments)
+static int pw_geo() { return env_int("PG_PW_GEO", 0) == 1 ? 1 : 0; }
 
 bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     if (P.bt != 1 || P.b0 != 1 || P.b1 != 1) return false;
@@ -498,7 +519,9 @@ bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     if (P.T < 2 || P.T > 0x7fffffff || P.A0 > 0x7fffffff || P.A1 > 0x7fffffff) return false;
     if (P.A0 < 4 || P.A1 < TJ) return false;
     if (!encode_fn()) return false;
-    constexpr int TI = GeoPw<PW_R, PW_NW>::TI;
+    constexpr int TI = 48;
+    const int geo = pw_geo();
+    const int NWg = geo == 1 ? 12 : 8;
     const int64_t nt0 = (P.A0 + TI - 1) / TI;
     const int64_t nt1 = ks ? P.A1 / TJ : (P.A1 + TJ - 1) / TJ;
     const int64_t n_tiles = nt0 * nt1, nrf = P.T - 1;
@@ -521,24 +544,27 @@ bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     plan.n_tiles0 = nt0; plan.n_tiles1 = nt1;
     const int64_t items = n_tiles * plan.n_chunks;
     plan.grid = (int)(items < n_sm ? items : n_sm);
-    plan.n_parts = (int64_t)plan.grid * PW_NW;
+    plan.n_parts = (int64_t)plan.grid * NWg;
     plan.extra_scratch = 0;
-    plan.kernel_id = 100;
+    plan.kernel_id = 100 + geo;
     plan.tile0 = TI; plan.tile1 = TJ;
     return true;
 }
 
-template <int LIB> static int launch_pw_t(const CUtensorMap &map, const PwParams &pp, int grid, cudaStream_t st) {
-    using G_ = GeoPw<PW_R, PW_NW>;
-    PG_CUDA(cudaFuncSetAttribute(k1_tiled_pw<LIB, PW_R, PW_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
-    k1_tiled_pw<LIB, PW_R, PW_NW><<<grid, G_::THREADS, G_::SMEM, st>>>(map, pp);
+template <int LIB, int R, int NW> static int launch_pw_g(const CUtensorMap &map, const PwParams &pp, int grid, cudaStream_t st) {
+    using G_ = GeoPw<R, NW>;
+    PG_CUDA(cudaFuncSetAttribute(k1_tiled_pw<LIB, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
+    k1_tiled_pw<LIB, R, NW><<<grid, G_::THREADS, G_::SMEM, st>>>(map, pp);
     PG_LAUNCHED();
     return PG_OK;
+}
+template <int LIB> static int launch_pw_t(const CUtensorMap &map, const PwParams &pp, int grid, int geo, cudaStream_t st) {
+    return geo == 1 ? launch_pw_g<LIB, 4, 12>(map, pp, grid, st) : launch_pw_g<LIB, 6, 8>(map, pp, grid, st);
 }
 
 int tiled_pw_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, cudaStream_t st) {
     CUtensorMap map;
-    const CUresult r = encode_field_map(&map, P.U, P.T, P.A0, P.A1, GeoPw<PW_R, PW_NW>::HR);
+    const CUresult r = encode_field_map(&map, P.U, P.T, P.A0, P.A1, 48 + 4);
     if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     PwParams pp{};
     pp.U = P.U; pp.T = P.T; pp.A0 = P.A0; pp.A1 = P.A1;
@@ -554,11 +580,11 @@ int tiled_pw_launch(const K1Params &P, int lib, const TiledPlan &plan, double *p
     pp.fold_of_frame = P.fold_of_frame; pp.n_folds = P.n_folds;
     pp.partials = partials; pp.counters = P.counters;
     switch (lib) {
-        case PG_LIB_KS_TRUE: return launch_pw_t<PG_LIB_KS_TRUE>(map, pp, plan.grid, st);
-        case PG_LIB_KS_TRUE_ADV: return launch_pw_t<PG_LIB_KS_TRUE_ADV>(map, pp, plan.grid, st);
-        case PG_LIB_KS_RICH: return launch_pw_t<PG_LIB_KS_RICH>(map, pp, plan.grid, st);
-        case PG_LIB_KS_RICH_NOADV: return launch_pw_t<PG_LIB_KS_RICH_NOADV>(map, pp, plan.grid, st);
-        case PG_LIB_BASIC: return launch_pw_t<PG_LIB_BASIC>(map, pp, plan.grid, st);
+        case PG_LIB_KS_TRUE: return launch_pw_t<PG_LIB_KS_TRUE>(map, pp, plan.grid, plan.kernel_id - 100, st);
+        case PG_LIB_KS_TRUE_ADV: return launch_pw_t<PG_LIB_KS_TRUE_ADV>(map, pp, plan.grid, plan.kernel_id - 100, st);
+        case PG_LIB_KS_RICH: return launch_pw_t<PG_LIB_KS_RICH>(map, pp, plan.grid, plan.kernel_id - 100, st);
+        case PG_LIB_KS_RICH_NOADV: return launch_pw_t<PG_LIB_KS_RICH_NOADV>(map, pp, plan.grid, plan.kernel_id - 100, st);
+        case PG_LIB_BASIC: return launch_pw_t<PG_LIB_BASIC>(map, pp, plan.grid, plan.kernel_id - 100, st);
         default: PG_FAIL(PG_EUNSUPPORTED, "no tiled pointwise kernel for library %d", lib);
     }
 }
