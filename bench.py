@@ -368,6 +368,22 @@ def run_ours(args):
             variants[name] = {"value": world * pts_rank * 3 / (ms * 1e-3), "unit": UNIT,
                               "alg_GBps_per_gpu": 8 * pts_rank * 3 / (ms * 1e-3) / 1e9}
 
+        # full-grid pointwise rows (every grid point a row; SURVEY 8d C4 i/ii): fp64-issue bound, not HBM bound
+        def pointwise_step(dialect, library, p, sdialect, flags):
+            s = ops.fd_lib_gram(U, D0, D1, DT, dialect=dialect, library=library, block=(1, 1, 1), fold_of_frame=fof_d,
+                                n_folds=2)
+            slabs.allreduce_stats(s)
+            return ops.stridge_batched(s[0], p, dialect=sdialect, flags=flags, alphas=alphas, thresholds=thrs,
+                                       max_iter=25 if sdialect == L.STRIDGE_KS else 10,
+                                       eval_stats=s[1])
+
+        for name, a in [("ks_true_p3_pointwise", (L.FD_KS_PERIODIC, L.LIB_KS_TRUE, 3, L.STRIDGE_KS, L.STRIDGE_RMS_PRESCALE)),
+                        ("basic_usage_p6_pointwise", (L.FD_BASIC_TRIM, L.LIB_BASIC, 6, L.STRIDGE_BASIC, 0))]:
+            ms = timed(lambda: pointwise_step(*a), 3, 1)
+            variants[name] = {"value": world * pts_rank * 3 / (ms * 1e-3), "unit": UNIT,
+                              "alg_GBps_per_gpu": 8 * pts_rank * 3 / (ms * 1e-3) / 1e9,
+                              "bound": "fp64 issue (64 DFMA/clk/SM): ~32-35 fp64 ops per point"}
+
     # ---- BASELINE configs[2]: patch-based spatial ensemble on a laser-image-shaped 1024x1024x500 float32 stack,
     # 8464 patches x (120 train + 40 test) sampled points: K2 (245-tap polynomial stencil rows) -> per-patch
     # statistics -> K3 (scikit-learn dialect).  Patches are embarrassingly parallel; every rank runs the same set.

@@ -482,18 +482,352 @@ __global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(co
     }
 }
 
+// ----------------------------------------------------------------------------- decoupled kernel
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// k1_tiled_b88d: the same tile march as k1_tiled_b88, with the warps DECOUPLED.
+//   * no warp is "the producer": every warp releases a stage when it has read what it needs (arrive on
+//     empty[s]), and the warp whose arrival completes the phase re-arms it at once with the TMA load
+//     of the frame three ahead, so the ring refills as early as possible and nobody waits for anybody's
+//     arithmetic (a ninth producer warp would cost a third warp on one SM sub-partition: 170 registers);
+//   * there is no block-wide barrier per frame: each consumer warp copies the 16-byte side cells of ITS
+//     window (halo columns of its 12 rows; the periodic wrap rows for the top / bottom band of a border
+//     tile) with cp.async one frame ahead, so they need warp-level visibility only, and waits on full[s];
+//     warps drift by up to a frame, so one warp's t-block epilogue (shuffles, row, Gram update: long
+//     dependent chains) overlaps the others' stencil work instead of idling the SM;
+//   * TIMEFOLD: folds given per frame (time-holdout folds) or no folds: a warp accumulates for ONE fold
+//     at a time in registers and flushes into its partial slot when the fold changes, so any number of
+//     folds runs at the single-fold cost.  !TIMEFOLD: fold_of_row, NF <= 2 masked accumulators as before.
+constexpr int DNW = 8;   // consumer warps
+
+template <int LIB, int NF, bool TIMEFOLD>
+__global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_constant__ CUtensorMap tmap, TiledParams P) {
+    constexpr int NW = DNW;
+    using G_ = Geo<NW>;
+    constexpr int TI = G_::TI, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES;
+    constexpr int p = Lib<LIB>::P;
+    constexpr int S = PG_STATS_LEN(p);
+    constexpr int W = p + 2;
+    constexpr int NE = (S + 31) / 32;   // lane-owned statistics entries
+    constexpr int SB = G_::slots(p);    // block rows per staging batch
+    static_assert(!TIMEFOLD || NF == 1, "time folds accumulate one fold at a time");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stages = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NSTAGE * G_::STAGE_BYTES);
+    uint64_t *empty = full + NSTAGE;
+    double *ext_all = reinterpret_cast<double *>(smem_raw + NSTAGE * G_::STAGE_BYTES + 64);  // [NW][SB][W]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const int64_t frame = P.A0 * P.A1;
+    const int n_tiles = P.n_tiles0 * P.n_tiles1;
+    const int64_t n_items = (int64_t)n_tiles * P.n_chunks;
+    auto geometry = [&](int64_t item, int &i0, int &j0, int64_t &tb0, int &nf) {
+        const int tile = (int)(item % n_tiles), chunk = (int)(item / n_tiles);
+        i0 = (tile / P.n_tiles1) * TI;
+        j0 = (tile % P.n_tiles1) * TJ;
+        tb0 = (int64_t)chunk * P.chunk_tb;
+        nf = (int)((min(P.nbt, tb0 + P.chunk_tb) - tb0) * P.bt);
+    };
+
+    // load index g of this CTA -> (tile origin, frame); g counts every frame of every item in order
+    auto issue_load = [&](uint32_t s, int i0, int j0, int t) {
+        fence_proxy_async();
+        mbar_expect_tx(&full[s], G_::TMA_BYTES);
+        tma_load_3d(stages + s * STAGE_DOUBLES, &tmap, &full[s], j0, i0 - 2, t);
+    };
+    // the load `ahead` frames after frame f of `item` (geometry i0, j0, t0, nf): walks into the following items
+    auto issue_ahead = [&](uint32_t s, int64_t item, int i0, int j0, int t0, int nf, int f, int ahead) {
+        int rem = f + ahead;
+        while (rem > nf) {
+            rem -= nf + 1;
+            item += gridDim.x;
+            if (item >= n_items) return;
+            int64_t tb0;
+            geometry(item, i0, j0, tb0, nf);
+            t0 = (int)(tb0 * P.bt);
+        }
+        issue_load(s, i0, j0, t0 + rem);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < n_items) {
+        int i0, j0, nf;
+        int64_t tb0;
+        geometry(blockIdx.x, i0, j0, tb0, nf);
+        for (int a = 0; a < NSTAGE; ++a) issue_ahead(a, blockIdx.x, i0, j0, (int)(tb0 * P.bt), nf, 0, a);
+    }
+
+    const LaneMap lm = lane_map<NW>(warp, lane);
+    double *ext = ext_all + warp * SB * W;
+    int ea[NE], eb[NE];
+    bool ev[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int e = lane + 32 * k;
+        ev[k] = e < S;
+        ea[k] = eb[k] = 0;
+        if (ev[k]) stats_pair(e, p, ea[k], eb[k]);
+    }
+    double acc[NF][NE];
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int k = 0; k < NE; ++k) acc[f][k] = 0.0;
+    constexpr bool PRIV = S * NF <= 36;   // every lane keeps the whole statistics vector in registers
+    constexpr int SP = PRIV ? S : 1;
+    double pacc[NF][SP];
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int e = 0; e < SP; ++e) pacc[f][e] = 0.0;
+
+    // this warp's partial slot [n_folds][S]: zeroed here, flushes add into it
+    double *slot = P.partials + ((int64_t)blockIdx.x * NW + warp) * P.n_folds * S;
+    for (int e = lane; e < P.n_folds * S; e += 32) slot[e] = 0.0;
+    __syncwarp();
+    // add the register accumulators of mask-fold f into slot[fold] and clear them (warp-collective)
+    auto flush = [&](int f, int fold) {
+        double *out = slot + fold * S;
+        if constexpr (PRIV) {
+#pragma unroll
+            for (int e = 0; e < S; ++e) {
+                double v = pacc[f][e];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == (e & 31)) out[e] += v;
+                pacc[f][e] = 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                if (ev[k]) out[lane + 32 * k] += acc[f][k];
+                acc[f][k] = 0.0;
+            }
+        }
+        __syncwarp();
+    };
+
+    unsigned long long bad_rows = 0, bad_fold = 0;
+    int cur_fold = -1;
+    uint32_t G = 0;  // consumer load index
+    Sums A;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int i0, j0, nf;
+        int64_t tb0;
+        geometry(item, i0, j0, tb0, nf);
+        const int64_t t0 = tb0 * P.bt;
+        const bool need_top = i0 == 0 && warp == 0, need_bot = i0 + TI == P.A0 && warp == NW - 1;
+
+        // side cells of this warp's window (stage rows 8*warp .. 8*warp+11): lanes 0..23 one halo-column cell
+        // each; the wrap rows TMA zero-filled (stage rows 0,1 / TI+2,TI+3) belong to the first / last band.
+        int h_off = -1;
+        int64_t h_src = 0;
+        if (lane < 24) {
+            const int Rr = warp * 8 + (lane >> 1), side = lane & 1;
+            h_off = HOFF + Rr * 4 + side * 2;
+            h_src = wrap((int64_t)i0 - 2 + Rr, P.A0) * P.A1 + wrap((int64_t)(side ? j0 + TJ : j0 - 2), P.A1);
+        }
+        const int64_t top_src = wrap((int64_t)i0 - 2, P.A0) * P.A1 + j0;      // rows i0-2, i0-1 (consecutive mod A0 when A0 >= 2)
+        const int64_t top_src1 = wrap((int64_t)i0 - 1, P.A0) * P.A1 + j0;
+        const int64_t bot_src = wrap((int64_t)i0 + TI, P.A0) * P.A1 + j0;
+        const int64_t bot_src1 = wrap((int64_t)i0 + TI + 1, P.A0) * P.A1 + j0;
+        auto issue_halo = [&](double *stage, int64_t t) {
+            if (h_off >= 0) cp_async16(stage + h_off, P.U + t * frame + h_src);
+        };
+        auto issue_wrap = [&](double *stage, int64_t t) {
+            const double *Ft = P.U + t * frame;
+            if (need_top) {
+                cp_async16(stage + 2 * lane, Ft + top_src + 2 * lane);
+                cp_async16(stage + 64 + 2 * lane, Ft + top_src + 64 + 2 * lane);
+                cp_async16(stage + TJ + 2 * lane, Ft + top_src1 + 2 * lane);
+                cp_async16(stage + TJ + 64 + 2 * lane, Ft + top_src1 + 64 + 2 * lane);
+            }
+            if (need_bot) {
+                cp_async16(stage + (TI + 2) * TJ + 2 * lane, Ft + bot_src + 2 * lane);
+                cp_async16(stage + (TI + 2) * TJ + 64 + 2 * lane, Ft + bot_src + 64 + 2 * lane);
+                cp_async16(stage + (TI + 3) * TJ + 2 * lane, Ft + bot_src1 + 2 * lane);
+                cp_async16(stage + (TI + 3) * TJ + 64 + 2 * lane, Ft + bot_src1 + 64 + 2 * lane);
+            }
+        };
+        // first frame of the item: its stage has landed => every warp released the stage's previous frame
+        mbar_wait(&full[G % NSTAGE], (G / NSTAGE) & 1);
+        issue_halo(stages + (G % NSTAGE) * STAGE_DOUBLES, t0);
+        issue_wrap(stages + (G % NSTAGE) * STAGE_DOUBLES, t0);
+        cp_async_commit();
+
+        int fold = 0;
+        double su_first = 0.0;
+        const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lane >> 1);
+        for (int f = 0; f <= nf; ++f, ++G) {
+            double *st = stages + (G % NSTAGE) * STAGE_DOUBLES;
+            if (f + 1 < nf) {
+                // side cells of the next frame, one frame ahead.  Its stage may still hold the frame two back:
+                // wait until every warp released that one (what the producer waits for as well).
+                const uint32_t g1 = G + 1, s1 = g1 % NSTAGE;
+                if (g1 >= NSTAGE) mbar_wait(&empty[s1], ((g1 / NSTAGE) - 1) & 1);
+                issue_halo(stages + s1 * STAGE_DOUBLES, t0 + f + 1);
+                if (need_top || need_bot) {
+                    mbar_wait(&full[s1], (g1 / NSTAGE) & 1);     // the wrap rows lie inside the TMA box
+                    issue_wrap(stages + s1 * STAGE_DOUBLES, t0 + f + 1);
+                }
+            }
+            cp_async_commit();
+            mbar_wait(&full[G % NSTAGE], (G / NSTAGE) & 1);
+            cp_async_wait<1>();
+            __syncwarp();
+
+            Sums F;
+            if (f < nf) march_frame<LIB>(st, lm, P, F);
+            else F.SU = sum_frame_u(st, warp, lane, lm.sw);
+
+            // release the stage (this warp has read everything it needs from load G); the warp whose arrival
+            // completes the phase re-arms it with the load NSTAGE ahead.  Only the wrap rows are generic-proxy
+            // writes inside the TMA box, so only their writers need the cross-proxy fence.
+            if (need_top || need_bot) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && mbar_arrive_pending(&empty[G % NSTAGE]) == 1)
+                issue_ahead(G % NSTAGE, item, i0, j0, (int)t0, nf, f, NSTAGE);
+
+            if (f % P.bt == 0 && f > 0) {
+                double SY = F.SU - su_first;
+#define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 1)
+                PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
+                if constexpr (kNeedAdv<LIB>) { PG_PAIR(A.SDx); PG_PAIR(A.SDy); }
+                if constexpr (kRich<LIB>) { PG_PAIR(A.SU); PG_PAIR(A.SU2); PG_PAIR(A.SUL); }
+#undef PG_PAIR
+                const double invN = 1.0 / (64.0 * (double)P.bt);
+                const double lap = P.r1 * A.SL * invN;
+                const double bih = P.r1 * P.r1 * fma(P.rho, A.SE1, A.SE2) * invN;
+                const double gsq = fma(P.q0, A.SGx, P.q1 * A.SGy) * invN;
+                const double y = SY * P.rdt * invN;
+                double th[p];
+                if constexpr (LIB == PG_LIB_KS_TRUE) {
+                    th[0] = lap; th[1] = bih; th[2] = gsq;
+                } else if constexpr (LIB == PG_LIB_KS_TRUE_ADV) {
+                    th[0] = lap; th[1] = bih; th[2] = gsq; th[3] = P.h0 * A.SDx * invN; th[4] = P.h1 * A.SDy * invN;
+                } else if constexpr (LIB == PG_LIB_KS_RICH) {
+                    th[0] = 1.0; th[1] = A.SU * invN; th[2] = A.SU2 * invN; th[3] = P.h0 * A.SDx * invN;
+                    th[4] = P.h1 * A.SDy * invN; th[5] = lap; th[6] = bih; th[7] = gsq; th[8] = P.r1 * A.SUL * invN;
+                } else {
+                    th[0] = 1.0; th[1] = A.SU * invN; th[2] = A.SU2 * invN; th[3] = lap; th[4] = bih; th[5] = gsq;
+                    th[6] = P.r1 * A.SUL * invN;
+                }
+                A = Sums();
+                bool fin = isfinite(y);
+#pragma unroll
+                for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
+                bool valid = (lane & 1) == 0;
+                if (valid && !fin) { valid = false; ++bad_rows; }
+                else if (valid && (fold < 0 || fold >= P.n_folds)) { valid = false; ++bad_fold; }
+                if constexpr (TIMEFOLD) {
+                    // fold is warp-uniform (one id per t-block): switch the accumulation target when it changes
+                    if (fold >= 0 && fold < P.n_folds && fold != cur_fold) {
+                        if (cur_fold >= 0) flush(0, cur_fold);
+                        cur_fold = fold;
+                    }
+                }
+                if constexpr (PRIV) {
+                    if (valid) {
+                        double m[NF];
+#pragma unroll
+                        for (int ff = 0; ff < NF; ++ff) m[ff] = (NF == 1 || fold == ff) ? 1.0 : 0.0;
+                        auto add = [&](int e, double v) {
+#pragma unroll
+                            for (int ff = 0; ff < NF; ++ff) pacc[ff][e] = NF == 1 ? pacc[ff][e] + v : fma(v, m[ff], pacc[ff][e]);
+                        };
+                        add(0, 1.0);
+                        add(1, y);
+                        add(2, y * y);
+                        int e = 3 + 2 * p;
+#pragma unroll
+                        for (int i = 0; i < p; ++i) {
+                            add(3 + i, th[i]);
+                            add(3 + p + i, th[i] * y);
+#pragma unroll
+                            for (int j = i; j < p; ++j) add(e++, th[i] * th[j]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 16 / SB; ++h) {
+                        const bool mine = valid && (lane >> 1) / SB == h;
+                        if (mine) {
+                            double *r = ext + ((lane >> 1) % SB) * W;
+                            r[0] = 1.0; r[1] = y;
+#pragma unroll
+                            for (int k = 0; k < p; ++k) r[2 + k] = th[k];
+                        }
+                        __syncwarp();
+                        const unsigned vm = __ballot_sync(0xffffffffu, mine);
+#pragma unroll
+                        for (int slot_i = 0; slot_i < SB; ++slot_i) {
+                            const int src = (h * SB + slot_i) * 2;
+                            if (!((vm >> src) & 1u)) continue;
+                            const int fr = TIMEFOLD ? 0 : __shfl_sync(0xffffffffu, fold, src);
+                            const double *r = ext + slot_i * W;
+#pragma unroll
+                            for (int k = 0; k < NE; ++k) {
+                                if (!ev[k]) continue;
+                                const double prod = r[ea[k]] * r[eb[k]];
+#pragma unroll
+                                for (int ff = 0; ff < NF; ++ff) acc[ff][k] += (NF == 1 || fr == ff) ? prod : 0.0;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            if (f < nf) {
+                if (f % P.bt == 0) {
+                    su_first = F.SU;
+                    const int64_t tbs = tb0 + f / P.bt;
+                    if constexpr (TIMEFOLD) fold = P.fold_of_frame ? P.fold_of_frame[tbs * P.bt] : 0;
+                    else fold = P.fold_of_row[(tbs * P.nB0 + ib) * P.nB1 + jb];
+                }
+                A.SL += F.SL; A.SE1 += F.SE1; A.SE2 += F.SE2; A.SGx += F.SGx; A.SGy += F.SGy;
+                if constexpr (kNeedAdv<LIB>) { A.SDx += F.SDx; A.SDy += F.SDy; }
+                if constexpr (kRich<LIB>) { A.SU += F.SU; A.SU2 += F.SU2; A.SUL += F.SUL; }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (bad_rows) atomicAdd(&P.counters[0], bad_rows);
+    if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
+    if constexpr (TIMEFOLD) {
+        if (cur_fold >= 0) flush(0, cur_fold);
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+            if (f < P.n_folds) flush(f, f);
+    }
+}
+
 // ----------------------------------------------------------------------------- host side
 // warps per CTA (see Geo): 8 or 4; PG_TILED_WARPS overrides the default for experiments
-static int tiled_warps() { return env_int("PG_TILED_WARPS", 8) == 4 ? 4 : 8; }
+// PG_TILED_WARPS: 9 (default) = decoupled kernel, 8 consumer warps + producer warp; 8 / 4 = legacy block-synchronous kernels
+static int tiled_warps() { const int w = env_int("PG_TILED_WARPS", 9); return w == 4 ? 4 : (w == 8 ? 8 : 9); }
 
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan) {
     if (P.dialect != PG_FD_KS_PERIODIC) return false;
     if (lib != PG_LIB_KS_TRUE && lib != PG_LIB_KS_TRUE_ADV && lib != PG_LIB_KS_RICH && lib != PG_LIB_KS_RICH_NOADV)
         return false;
     if (P.b0 != 8 || P.b1 != 8) return false;
-    if (P.n_folds > 2) return false;
+    const int NWsel = tiled_warps();
+    if (P.n_folds > 2 && (NWsel != 9 || P.fold_of_row)) return false;   // > 2 folds: time folds in the decoupled kernel only
     if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // TMA / LDG.128: 16-byte strides, base
-    const int NW = tiled_warps();
+    const int NW = NWsel == 9 ? 8 : NWsel;   // consumer warps
     const int TI = 8 * NW;
     const int workers = n_sm * (NW == 4 ? 2 : 1);
     const int64_t nt0 = P.A0 / TI, nt1 = P.A1 / TJ;
@@ -521,7 +855,7 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     plan.grid = (int)(items < workers ? items : workers);
     plan.n_parts = (int64_t)plan.grid * NW;
     plan.extra_scratch = 0;
-    plan.kernel_id = NW;
+    plan.kernel_id = NWsel;
     plan.tile0 = TI; plan.tile1 = TJ;
     return true;
 }
@@ -535,8 +869,21 @@ template <int LIB, int NF, int NW> static int launch_tiled_k(const CUtensorMap &
     return PG_OK;
 }
 
+template <int LIB, int NF, bool TIMEFOLD> static int launch_tiled_d(const CUtensorMap &map, const TiledParams &tp, int grid,
+                                                                     cudaStream_t st) {
+    const size_t smem = Geo<DNW>::smem(Lib<LIB>::P);
+    PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88d<LIB, NF, TIMEFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_tiled_b88d<LIB, NF, TIMEFOLD><<<grid, 32 * DNW, smem, st>>>(map, tp);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
 template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const TiledParams &tp, int n_folds, int nw, int grid,
                                              cudaStream_t st) {
+    if (nw == 9) {   // decoupled kernel: time folds / no folds at the single-fold cost, per-row folds masked (<= 2)
+        if (!tp.fold_of_row) return launch_tiled_d<LIB, 1, true>(map, tp, grid, st);
+        return launch_tiled_d<LIB, 2, false>(map, tp, grid, st);
+    }
     if (nw == 8) return n_folds == 1 ? launch_tiled_k<LIB, 1, 8>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 8>(map, tp, grid, st);
     return n_folds == 1 ? launch_tiled_k<LIB, 1, 4>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 4>(map, tp, grid, st);
 }

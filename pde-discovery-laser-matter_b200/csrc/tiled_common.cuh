@@ -41,6 +41,15 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// arrive (release.cta) and return how many arrivals the phase was still waiting for BEFORE this one
+// (1 => this arrival completed the phase)
+__device__ __forceinline__ uint32_t mbar_arrive_pending(uint64_t *bar) {
+    uint64_t state;
+    uint32_t pending;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
+    return pending;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 

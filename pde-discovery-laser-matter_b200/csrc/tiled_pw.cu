@@ -491,8 +491,9 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
                     else march_pw<LIB, R, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
                 }
             }
-            // release the stage: this warp has read everything it needs from load G
-            fence_proxy_async();
+            // release the stage: this warp has read everything it needs from load G (only the wrap rows are
+            // generic-proxy writes inside the TMA box: their writers fence towards the async proxy)
+            if (KS && (w_row[0] >= 0 || w_row[1] >= 0 || w_row[2] >= 0 || w_row[3] >= 0)) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[G % NS]);
             if (tid == 0) produce();                                   // load G+3 -> stage of load G-1

@@ -72,6 +72,34 @@ def test_tiled_folds(env):
     assert til[0][0] == 2 * 16 * 32 and til[1][0] == 16 * 32
 
 
+def test_tiled_many_time_folds(env):
+    """Time-holdout folds (one id per frame) are accumulated one fold at a time: 5 folds, an out-of-range
+    id, and folds that change inside a persistent CTA's chunk."""
+    L, ops = env
+    T, bt = 46, 3
+    U = field(ops, (T, 64, 256), seed=11)
+    fof = (np.arange(T - 1) // 9).astype(np.int32)          # 0..4, changes at t-block boundaries
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(bt, 8, 8), fold_of_frame=fof, n_folds=5)
+    gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    til = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    for f in range(5):
+        assert til[f][0] == gen[f][0] == 3 * 8 * 32
+        assert_stats_close(til[f], gen[f], 3)
+    fof[6:9] = 9                                             # one t-block with an id outside [0, 5): skipped
+    kw["fold_of_frame"] = fof
+    gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    til = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    assert til[0][0] == 2 * 8 * 32
+    for f in range(5):
+        assert_stats_close(til[f], gen[f], 3)
+    # the rich library keeps its statistics spread over the lanes (no private copy): same flush path
+    kw.update(library=L.LIB_KS_RICH, fold_of_frame=(np.arange(T - 1) // 9).astype(np.int32))
+    gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    til = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    for f in range(5):
+        assert_stats_close(til[f], gen[f], 9)
+
+
 def test_tiled_many_chunks_and_determinism(env):
     """A longer stack is cut into frame chunks across persistent CTAs; results are run-to-run
     bit-identical (fixed work assignment, fixed-order reduction: no floating-point atomics)."""
