@@ -1,27 +1,26 @@
 // K1 tiled: fused FD + library + block mean + Gram for the KS dialect with (bt, 8, 8) blocks.
 //
-// One persistent CTA owns a TI x 128 spatial tile and marches through a chunk of frames.  Each
-// frame's (TI+4) x 128 row-halo tile is brought into shared memory ONCE by a 3-D TMA tensor copy
-// (cp.async.bulk.tensor, mbarrier completion) into a 3-stage ring: stage g is the frame being
-// differentiated, stages g+1 and g+2 are in flight (two loads ahead: a single outstanding load
-// per SM cannot cover the HBM latency-bandwidth product).  The TMA box is exactly 128 columns =
-// whole 128-byte lines; the two halo columns on either side are fetched separately as one 16-byte
-// load per row and side (a 32-byte sector instead of a 128/256-byte line: this is what keeps
-// DRAM traffic near the algorithmic 8 B/point), which also gives the periodic wrap along a1 for
-// free.  Wrap along a0: TMA zero-fills the out-of-bounds rows of a border tile and the wrapped
-// rows are stored over the zero fill after the copy has landed.
+// One persistent CTA (8 warps) owns a 64 x 128 spatial tile and marches through a chunk of frames.  Each
+// frame's (64+4) x 128 row-halo tile is brought into shared memory ONCE by a 4-D TMA tensor copy
+// (cp.async.bulk.tensor, mbarrier completion, 128-byte swizzle: tiled_common.cuh) into a 3-stage ring.
+// The TMA box is exactly 128 columns = whole 128-byte lines; the two halo columns on either side are
+// fetched separately as one 16-byte cell per row and side (a 32-byte sector instead of a 128/256-byte
+// line: this is what keeps DRAM traffic near the algorithmic 8 B/point), which also gives the periodic
+// wrap along a1 for free.  Wrap along a0: TMA zero-fills the out-of-bounds rows of a border tile and the
+// wrapped rows are copied over the zero fill after the load has landed.
+//
+// The warps are DECOUPLED (no block-wide barrier per frame, no producer warp): see k1_tiled_b88 below.
 //
 // The forward u_t never touches frame t+1 pointwise: over a t-block it telescopes to
-// (sum u(t0+bt) - sum u(t0)) / dt, and every frame's block sum of u is formed while that frame
-// is current.
+// (sum u(t0+bt) - sum u(t0)) / dt, and every frame's block sum of u is formed while that frame is current.
 //
-// Inside a frame, warp w owns rows [8w, 8w+8) (one block row) and lane l owns columns
-// [4l, 4l+4) (half a block), marching down 12 tile rows with a register sliding window: four
-// conflict-free LDS.128 per row give u at columns own-2 .. own+5, with no exchange between
-// lanes.  Block sums of the linear terms (lap, bih, u_x, u_y, u, u_t) reduce by the discrete
-// divergence theorem to per-row boundary scalars (see march_frame), so only the nonlinear
-// terms cost per-point fp64 work: about 8 fp64 ops per grid point for the true library.  At the
-// end of a t-block the two lanes of a block pair-reduce by shuffle and form the block-mean row.
+// Inside a frame, warp w owns rows [8w, 8w+8) (one block row) and lane l owns the 4 columns of group
+// g(l) (half a block), marching down 12 tile rows with a register sliding window: four conflict-free
+// LDS.128 per row give u at columns own-2 .. own+5 in natural register order (the swizzle does the bank
+// spreading), with no exchange between lanes.  Block sums of the linear terms (lap, bih, u_x, u_y, u, u_t)
+// reduce by the discrete divergence theorem to per-row boundary scalars (see march_frame), so only the
+// nonlinear terms cost per-point fp64 work: about 8 fp64 ops per grid point for the true library.  At the
+// end of a t-block the two lanes of a block (l, l ^ 8) pair-reduce by shuffle and form the block-mean row.
 //
 // No tensor cores: p <= 9 and the kernel is HBM / fp64-issue bound.
 #include <cuda.h>
@@ -36,23 +35,20 @@ namespace pg {
 
 constexpr int NSTAGE = 3;
 
-// Tile geometry for NW warps per CTA (one 8-row block band per warp).
-//   NW = 8 : 64 x 128 tile, one CTA per SM;   NW = 4 : 32 x 128 tile, two CTAs per SM
-// Stage layout (doubles): tile [HR][TJ] written by TMA, then hcol [HR][4] = (left2, right2) per row.
+// Tile geometry: NW warps per CTA, one 8-row block band per warp (NW = 8: 64 x 128 tile, one CTA per SM).
+// Stage layout: swizzled tile [HR][TJ] written by TMA (tiled_common.cuh), then hcol [HR][4] = (left2, right2).
 template <int NW> struct Geo {
     static constexpr int TI = 8 * NW;
     static constexpr int HR = TI + 4;
     static constexpr int HOFF = HR * TJ;                        // start of hcol inside a stage
-    static constexpr int STAGE_DOUBLES = HR * PITCH;
-    static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+    static constexpr int STAGE_BYTES = stage_bytes_for(HR);     // 1024-byte multiple
+    static constexpr int STAGE_DOUBLES = STAGE_BYTES / 8;
     static constexpr int TMA_BYTES = HR * TJ * 8;
     static constexpr int THREADS = 32 * NW;
-    static constexpr int MAXC = (2 * HR + 2 * TJ + THREADS - 1) / THREADS;   // 16-byte side cells per thread
-    static constexpr int CTAS_PER_SM = NW == 4 ? 2 : 1;
-    // block rows staged per Gram-update batch (shared memory is the scarce resource at 2 CTAs/SM)
-    __host__ __device__ static constexpr int slots(int p) { return NW == 4 ? (p <= 5 ? 4 : 2) : 8; }
+    // block rows staged per Gram-update batch
+    __host__ __device__ static constexpr int slots(int p) { return 8; }
     __host__ __device__ static constexpr size_t smem(int p) {
-        return (size_t)NSTAGE * STAGE_BYTES + 64 + sizeof(double) * NW * slots(p) * (p + 2);
+        return (size_t)NSTAGE * STAGE_BYTES + 64 + sizeof(double) * NW * slots(p) * (p + 2) + 1024;   // + alignment slack
     }
 };
 
@@ -88,29 +84,10 @@ struct Sums {
 template <int LIB> constexpr bool kNeedAdv = (LIB == PG_LIB_KS_TRUE_ADV || LIB == PG_LIB_KS_RICH);
 template <int LIB> constexpr bool kRich = (LIB == PG_LIB_KS_RICH || LIB == PG_LIB_KS_RICH_NOADV);
 
-// Where a lane finds its four 16-byte chunks (columns own-2,-1 | own0,1 | own2,3 | own+4,+5) of
-// band row 0, as element offsets into a stage, plus the per-row stride of each.  Chunks 0 and 3
-// of the edge lanes live in the halo-column array (stride 4) instead of the tile (stride TJ).
-// Lanes are 32 B apart, so a plain LDS.128 would hit every bank group twice per quarter-warp:
-// lanes with bit 2 set (sw) fetch the two chunks of each pair in the opposite order
-// (conflict-free) and swap them back.  a/b = first/second issued chunk of pair (c0,c1), (c2,c3).
-struct LaneMap {
-    int a0, sa0, a1, sa1, b0, sb0, b1, sb1, sw;
-};
-
-template <int NW> __device__ __forceinline__ LaneMap lane_map(int band, int lane) {
-    using G_ = Geo<NW>;
-    const int own = band * 8 * TJ + 4 * lane, hrow = G_::HOFF + band * 8 * 4;
-    const int c0 = lane > 0 ? own - 2 : hrow, s0 = lane > 0 ? TJ : 4;
-    const int c3 = lane < 31 ? own + 4 : hrow + 2, s3 = lane < 31 ? TJ : 4;
-    LaneMap m;
-    m.sw = (lane >> 2) & 1;
-    m.a0 = m.sw ? own : c0;       m.sa0 = m.sw ? TJ : s0;
-    m.a1 = m.sw ? c0 : own;       m.sa1 = m.sw ? s0 : TJ;
-    m.b0 = m.sw ? c3 : own + 2;   m.sb0 = m.sw ? s3 : TJ;
-    m.b1 = m.sw ? own + 2 : c3;   m.sb1 = m.sw ? TJ : s3;
-    return m;
-}
+// Lane addressing: LaneMap / make_lane_map / load_row8 in tiled_common.cuh (swizzled tile, natural register
+// order).  A block (8 columns) is the two column groups 2m, 2m+1, owned by lanes l and l ^ 8; the lane with
+// bit 3 clear emits the block's row.
+__device__ __forceinline__ int block_lane(int b) { return 8 * ((2 * b) & 3) + (b >> 1); }   // lane owning group 2b
 
 // One frame of one warp band: 12 tile rows march through a 3-row register window.
 //
@@ -132,15 +109,9 @@ __device__ __forceinline__ void march_frame(const double *__restrict__ st, const
     // per-column partial sums of the nonlinear terms: four independent FMA chains per quantity
     double gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0}, u2[4] = {0, 0, 0, 0}, ul[4] = {0, 0, 0, 0};
     double sD = 0, sE = 0, sU = 0, sDy = 0;
-    const int sw = m.sw;
 #pragma unroll
     for (int s = 0; s < 12; ++s) {
-        const double2 x0 = *reinterpret_cast<const double2 *>(st + m.a0 + s * m.sa0);
-        const double2 x1 = *reinterpret_cast<const double2 *>(st + m.a1 + s * m.sa1);
-        const double2 y0 = *reinterpret_cast<const double2 *>(st + m.b0 + s * m.sb0);
-        const double2 y1 = *reinterpret_cast<const double2 *>(st + m.b1 + s * m.sb1);
-        const double2 a0 = sw ? x1 : x0, a1 = sw ? x0 : x1, a2 = sw ? y1 : y0, a3 = sw ? y0 : y1;
-        wn[0] = a0.x; wn[1] = a0.y; wn[2] = a1.x; wn[3] = a1.y; wn[4] = a2.x; wn[5] = a2.y; wn[6] = a3.x; wn[7] = a3.y;
+        load_row8(st, m, s, wn);
         rsU[s] = (wn[2] + wn[3]) + (wn[4] + wn[5]);
         D[s] = (wn[1] - wn[2]) + (wn[6] - wn[5]);
         if (s >= 2 && s <= 9) {
@@ -192,294 +163,16 @@ __device__ __forceinline__ void march_frame(const double *__restrict__ st, const
 }
 
 // Sum of u over the lane's own 8 rows x 4 columns (the frame after a chunk only feeds u_t).
-__device__ __forceinline__ double sum_frame_u(const double *__restrict__ st, int band, int lane, int sw) {
-    const double2 *own = reinterpret_cast<const double2 *>(st + (band * 8 + 2) * TJ + 4 * lane);
+__device__ __forceinline__ double sum_frame_u(const double *__restrict__ st, const LaneMap &m) {
     double s0 = 0, s1 = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const double2 x = own[r * (TJ / 2) + sw], y = own[r * (TJ / 2) + (sw ^ 1)];
-        s0 += x.x + x.y;
-        s1 += y.x + y.y;
+        double w[4];
+        load_row4(st, m, r + 2, w);
+        s0 += w[0] + w[1];
+        s1 += w[2] + w[3];
     }
     return s0 + s1;
-}
-
-template <int LIB, int NF, int NW>
-__global__ void __launch_bounds__(32 * NW, Geo<NW>::CTAS_PER_SM) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap,
-                                                                              TiledParams P) {
-    using G_ = Geo<NW>;
-    constexpr int TI = G_::TI, HR = G_::HR, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES;
-    constexpr int MAXC = G_::MAXC, THREADS = G_::THREADS;
-    constexpr int p = Lib<LIB>::P;
-    constexpr int S = PG_STATS_LEN(p);
-    constexpr int W = p + 2;
-    constexpr int NE = (S + 31) / 32;   // lane-owned statistics entries
-    constexpr int SB = G_::slots(p);    // block rows per staging batch
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stages = reinterpret_cast<double *>(smem_raw);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NSTAGE * G_::STAGE_BYTES);
-    double *ext_all = reinterpret_cast<double *>(smem_raw + NSTAGE * G_::STAGE_BYTES + 64);  // [NW][SB][W]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const LaneMap lm = lane_map<NW>(warp, lane);
-    double *ext = ext_all + warp * SB * W;
-
-    int ea[NE], eb[NE];
-    bool ev[NE];
-#pragma unroll
-    for (int k = 0; k < NE; ++k) {
-        const int e = lane + 32 * k;
-        ev[k] = e < S;
-        ea[k] = eb[k] = 0;
-        if (ev[k]) stats_pair(e, p, ea[k], eb[k]);
-    }
-    double acc[NF][NE];
-#pragma unroll
-    for (int f = 0; f < NF; ++f)
-#pragma unroll
-        for (int k = 0; k < NE; ++k) acc[f][k] = 0.0;
-    // Small libraries: every lane that owns a block row keeps a PRIVATE copy of the whole statistics
-    // vector in registers (S FMAs per emitted row, no staging, no shuffles); larger ones stage rows
-    // in shared memory and spread the S entries over the lanes.
-    constexpr bool PRIV = S * NF <= 36;   // register budget: true library (S = 18), or p = 5 with one fold
-    constexpr int SP = PRIV ? S : 1;
-    double pacc[NF][SP];
-#pragma unroll
-    for (int f = 0; f < NF; ++f)
-#pragma unroll
-        for (int e = 0; e < SP; ++e) pacc[f][e] = 0.0;
-
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    __syncthreads();
-
-    const int64_t frame = P.A0 * P.A1;
-    const int n_tiles = P.n_tiles0 * P.n_tiles1;
-    const int64_t n_items = (int64_t)n_tiles * P.n_chunks;
-    unsigned long long bad_rows = 0, bad_fold = 0;
-
-    // item -> (tile origin, first t-block, number of row frames)
-    auto geometry = [&](int64_t item, int &i0, int &j0, int64_t &tb0, int &nf) {
-        const int tile = (int)(item % n_tiles), chunk = (int)(item / n_tiles);
-        i0 = (tile / P.n_tiles1) * TI;
-        j0 = (tile % P.n_tiles1) * TJ;
-        tb0 = (int64_t)chunk * P.chunk_tb;
-        nf = (int)((min(P.nbt, tb0 + P.chunk_tb) - tb0) * P.bt);
-    };
-
-    // ---- producer (thread 0): one continuous stream of frame loads over all items of this CTA,
-    // always two loads ahead of the consumer, so the pipeline never drains between items.  The
-    // cursor is advanced incrementally: the divisions of geometry() run once per item, not per frame.
-    int64_t p_item = blockIdx.x;
-    int p_i0 = 0, p_j0 = 0, p_t = 0, p_left = 0;
-    uint32_t p_g = 0;
-    if (tid == 0 && p_item < n_items) {
-        int nf;
-        int64_t tb0;
-        geometry(p_item, p_i0, p_j0, tb0, nf);
-        p_t = (int)(tb0 * P.bt);
-        p_left = nf + 1;
-    }
-    auto produce = [&]() {
-        if (p_left == 0) return;
-        uint64_t *bar = &bars[p_g % NSTAGE];
-        fence_proxy_async();
-        mbar_expect_tx(bar, G_::TMA_BYTES);
-        tma_load_3d(stages + (p_g % NSTAGE) * STAGE_DOUBLES, &tmap, bar, p_j0, p_i0 - 2, p_t);
-        ++p_g;
-        ++p_t;
-        if (--p_left == 0) {
-            p_item += gridDim.x;
-            if (p_item < n_items) {
-                int nf;
-                int64_t tb0;
-                geometry(p_item, p_i0, p_j0, tb0, nf);
-                p_t = (int)(tb0 * P.bt);
-                p_left = nf + 1;
-            }
-        }
-    };
-    if (tid == 0) { produce(); produce(); }
-
-    uint32_t G = 0;  // consumer load index (stage = G % 3, parity = (G / 3) & 1)
-    Sums A;
-    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int i0, j0, nf;
-        int64_t tb0;
-        geometry(item, i0, j0, tb0, nf);
-        const int64_t t0 = tb0 * P.bt;   // frames t0 .. t0+nf are loaded; the last one only feeds u_t
-        const bool wt = i0 == 0, wb = i0 + TI == P.A0;
-
-        // 16-byte "side cells" of this tile handled by this thread (stage offset, offset inside a frame):
-        // the two halo columns left and right of every row (always), and the wrapped rows that TMA
-        // zero-filled when the tile touches the top / bottom of the periodic domain.
-        int c_off[MAXC];
-        int64_t c_src[MAXC];
-#pragma unroll
-        for (int k = 0; k < MAXC; ++k) {
-            int c = tid + k * THREADS, R = -1, C = 0;
-            c_off[k] = -1;
-            if (c < 2 * HR) {
-                R = c >> 1;
-                const int side = c & 1;
-                c_off[k] = HOFF + R * 4 + side * 2;
-                C = side ? j0 + TJ : j0 - 2;
-            } else {
-                c -= 2 * HR;
-                if (wt) { if (c >= 0 && c < TJ) { R = c / (TJ / 2); C = j0 + 2 * (c % (TJ / 2)); c_off[k] = R * TJ + (C - j0); } c -= TJ; }
-                if (wb) { if (c >= 0 && c < TJ) { R = HR - 2 + c / (TJ / 2); C = j0 + 2 * (c % (TJ / 2)); c_off[k] = R * TJ + (C - j0); } c -= TJ; }
-            }
-            if (c_off[k] >= 0) c_src[k] = wrap((int64_t)i0 - 2 + R, P.A0) * P.A1 + wrap((int64_t)C, P.A1);
-        }
-        double2 c_val[MAXC];
-        auto side_fetch = [&](int64_t t) {
-#pragma unroll
-            for (int k = 0; k < MAXC; ++k)
-                if (c_off[k] >= 0) c_val[k] = __ldg(reinterpret_cast<const double2 *>(P.U + t * frame + c_src[k]));
-        };
-        auto side_store = [&](double *stage) {
-#pragma unroll
-            for (int k = 0; k < MAXC; ++k)
-                if (c_off[k] >= 0) *reinterpret_cast<double2 *>(stage + c_off[k]) = c_val[k];
-        };
-        side_fetch(t0);
-
-        int fold = 0;
-        double su_first = 0.0;
-        const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lane >> 1);
-        for (int f = 0; f <= nf; ++f, ++G) {
-            double *st = stages + (G % NSTAGE) * STAGE_DOUBLES;
-            mbar_wait(&bars[G % NSTAGE], (G / NSTAGE) & 1);
-            side_store(st);
-            __syncthreads();  // side cells visible; every warp finished the previous frame, whose stage is free
-            if (tid == 0) produce();             // load G+2 -> the stage just freed
-            if (f < nf) side_fetch(t0 + f + 1);  // consumed after the next barrier wait
-
-            Sums F;
-            if (f < nf) march_frame<LIB>(st, lm, P, F);
-            else F.SU = sum_frame_u(st, warp, lane, lm.sw);
-
-            if (f % P.bt == 0 && f > 0) {
-                // ---- the t-block that ended at frame f-1: u_t telescopes to (sum u(f) - sum u(f-bt)) / dt.
-                // The lane pair (2m, 2m+1) holds one block's sums.
-                double SY = F.SU - su_first;
-#define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 1)
-                PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
-                if constexpr (kNeedAdv<LIB>) { PG_PAIR(A.SDx); PG_PAIR(A.SDy); }
-                if constexpr (kRich<LIB>) { PG_PAIR(A.SU); PG_PAIR(A.SU2); PG_PAIR(A.SUL); }
-#undef PG_PAIR
-                const double invN = 1.0 / (64.0 * (double)P.bt);
-                const double lap = P.r1 * A.SL * invN;
-                const double bih = P.r1 * P.r1 * fma(P.rho, A.SE1, A.SE2) * invN;
-                const double gsq = fma(P.q0, A.SGx, P.q1 * A.SGy) * invN;
-                const double y = SY * P.rdt * invN;
-                double th[p];
-                if constexpr (LIB == PG_LIB_KS_TRUE) {
-                    th[0] = lap; th[1] = bih; th[2] = gsq;
-                } else if constexpr (LIB == PG_LIB_KS_TRUE_ADV) {
-                    th[0] = lap; th[1] = bih; th[2] = gsq; th[3] = P.h0 * A.SDx * invN; th[4] = P.h1 * A.SDy * invN;
-                } else if constexpr (LIB == PG_LIB_KS_RICH) {
-                    th[0] = 1.0; th[1] = A.SU * invN; th[2] = A.SU2 * invN; th[3] = P.h0 * A.SDx * invN;
-                    th[4] = P.h1 * A.SDy * invN; th[5] = lap; th[6] = bih; th[7] = gsq; th[8] = P.r1 * A.SUL * invN;
-                } else {
-                    th[0] = 1.0; th[1] = A.SU * invN; th[2] = A.SU2 * invN; th[3] = lap; th[4] = bih; th[5] = gsq;
-                    th[6] = P.r1 * A.SUL * invN;
-                }
-                A = Sums();
-                bool fin = isfinite(y);
-#pragma unroll
-                for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
-                bool valid = (lane & 1) == 0;
-                if (valid && !fin) { valid = false; ++bad_rows; }
-                else if (valid && (fold < 0 || fold >= NF)) { valid = false; ++bad_fold; }
-                if constexpr (PRIV) {
-                    if (valid) {
-                        double m[NF];
-#pragma unroll
-                        for (int ff = 0; ff < NF; ++ff) m[ff] = (NF == 1 || fold == ff) ? 1.0 : 0.0;
-                        auto add = [&](int e, double v) {
-#pragma unroll
-                            for (int ff = 0; ff < NF; ++ff) pacc[ff][e] = fma(v, m[ff], pacc[ff][e]);
-                        };
-                        add(0, 1.0);
-                        add(1, y);
-                        add(2, y * y);
-                        int e = 3 + 2 * p;
-#pragma unroll
-                        for (int i = 0; i < p; ++i) {
-                            add(3 + i, th[i]);
-                            add(3 + p + i, th[i] * y);
-#pragma unroll
-                            for (int j = i; j < p; ++j) add(e++, th[i] * th[j]);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int h = 0; h < 16 / SB; ++h) {
-                        const bool mine = valid && (lane >> 1) / SB == h;
-                        if (mine) {
-                            double *r = ext + ((lane >> 1) % SB) * W;
-                            r[0] = 1.0; r[1] = y;
-#pragma unroll
-                            for (int k = 0; k < p; ++k) r[2 + k] = th[k];
-                        }
-                        __syncwarp();
-                        const unsigned vm = __ballot_sync(0xffffffffu, mine);
-#pragma unroll
-                        for (int slot = 0; slot < SB; ++slot) {
-                            const int src = (h * SB + slot) * 2;
-                            if (!((vm >> src) & 1u)) continue;
-                            const int fr = __shfl_sync(0xffffffffu, fold, src);
-                            const double *r = ext + slot * W;
-#pragma unroll
-                            for (int k = 0; k < NE; ++k) {
-                                if (!ev[k]) continue;
-                                const double prod = r[ea[k]] * r[eb[k]];
-#pragma unroll
-                                for (int ff = 0; ff < NF; ++ff) acc[ff][k] += (fr == ff) ? prod : 0.0;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            if (f < nf) {
-                if (f % P.bt == 0) {
-                    // a t-block starts at this frame: remember sum u, fetch its fold id (used at its end)
-                    su_first = F.SU;
-                    const int64_t tbs = tb0 + f / P.bt;
-                    if (P.fold_of_row) fold = P.fold_of_row[(tbs * P.nB0 + ib) * P.nB1 + jb];
-                    else if (P.fold_of_frame) fold = P.fold_of_frame[tbs * P.bt];
-                }
-                A.SL += F.SL; A.SE1 += F.SE1; A.SE2 += F.SE2; A.SGx += F.SGx; A.SGy += F.SGy;
-                if constexpr (kNeedAdv<LIB>) { A.SDx += F.SDx; A.SDy += F.SDy; }
-                if constexpr (kRich<LIB>) { A.SU += F.SU; A.SU2 += F.SU2; A.SUL += F.SUL; }
-            }
-        }
-    }
-    if (bad_rows) atomicAdd(&P.counters[0], bad_rows);
-    if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
-    double *out = P.partials + ((int64_t)blockIdx.x * NW + warp) * NF * S;
-    if constexpr (PRIV) {
-#pragma unroll
-        for (int f = 0; f < NF; ++f)
-#pragma unroll
-            for (int e = 0; e < S; ++e) {
-                double v = pacc[f][e];
-#pragma unroll
-                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == (e & 31)) out[f * S + e] = v;
-            }
-    } else {
-#pragma unroll
-        for (int f = 0; f < NF; ++f)
-#pragma unroll
-            for (int k = 0; k < NE; ++k)
-                if (ev[k]) out[f * S + lane + 32 * k] = acc[f][k];
-    }
 }
 
 // ----------------------------------------------------------------------------- decoupled kernel
@@ -492,7 +185,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// k1_tiled_b88d: the same tile march as k1_tiled_b88, with the warps DECOUPLED.
+// k1_tiled_b88: the warps are DECOUPLED.
 //   * no warp is "the producer": every warp releases a stage when it has read what it needs (arrive on
 //     empty[s]), and the warp whose arrival completes the phase re-arms it at once with the TMA load
 //     of the frame three ahead, so the ring refills as early as possible and nobody waits for anybody's
@@ -508,7 +201,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 constexpr int DNW = 8;   // consumer warps
 
 template <int LIB, int NF, bool TIMEFOLD>
-__global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_constant__ CUtensorMap tmap, TiledParams P) {
+__global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap, TiledParams P) {
     constexpr int NW = DNW;
     using G_ = Geo<NW>;
     constexpr int TI = G_::TI, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES;
@@ -518,7 +211,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
     constexpr int NE = (S + 31) / 32;   // lane-owned statistics entries
     constexpr int SB = G_::slots(p);    // block rows per staging batch
     static_assert(!TIMEFOLD || NF == 1, "time folds accumulate one fold at a time");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem_raw = align1024(smem_dyn);
     double *stages = reinterpret_cast<double *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NSTAGE * G_::STAGE_BYTES);
     uint64_t *empty = full + NSTAGE;
@@ -547,29 +241,34 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
     auto issue_load = [&](uint32_t s, int i0, int j0, int t) {
         fence_proxy_async();
         mbar_expect_tx(&full[s], G_::TMA_BYTES);
-        tma_load_3d(stages + s * STAGE_DOUBLES, &tmap, &full[s], j0, i0 - 2, t);
+        tma_load_4d(stages + s * STAGE_DOUBLES, &tmap, &full[s], 0, j0 >> 4, i0 - 2, t);
     };
-    // the load `ahead` frames after frame f of `item` (geometry i0, j0, t0, nf): walks into the following items
-    auto issue_ahead = [&](uint32_t s, int64_t item, int i0, int j0, int t0, int nf, int f, int ahead) {
+    // coordinates of the load `ahead` frames after frame f of `item` (geometry i0, j0, t0, nf); walks into the
+    // following items of this CTA; false when the CTA's stream of frames ends before that
+    auto ahead_coords = [&](int64_t item, int i0, int j0, int t0, int nf, int f, int ahead, int &ai0, int &aj0, int &at) {
         int rem = f + ahead;
         while (rem > nf) {
             rem -= nf + 1;
             item += gridDim.x;
-            if (item >= n_items) return;
+            if (item >= n_items) return false;
             int64_t tb0;
             geometry(item, i0, j0, tb0, nf);
             t0 = (int)(tb0 * P.bt);
         }
-        issue_load(s, i0, j0, t0 + rem);
+        ai0 = i0; aj0 = j0; at = t0 + rem;
+        return true;
     };
     if (tid == 0 && (int64_t)blockIdx.x < n_items) {
         int i0, j0, nf;
         int64_t tb0;
         geometry(blockIdx.x, i0, j0, tb0, nf);
-        for (int a = 0; a < NSTAGE; ++a) issue_ahead(a, blockIdx.x, i0, j0, (int)(tb0 * P.bt), nf, 0, a);
+        for (int a = 0; a < NSTAGE; ++a) {
+            int ai0, aj0, at;
+            if (ahead_coords(blockIdx.x, i0, j0, (int)(tb0 * P.bt), nf, 0, a, ai0, aj0, at)) issue_load(a, ai0, aj0, at);
+        }
     }
 
-    const LaneMap lm = lane_map<NW>(warp, lane);
+    const LaneMap lm = make_lane_map(warp * 8, HOFF, lane);
     double *ext = ext_all + warp * SB * W;
     int ea[NE], eb[NE];
     bool ev[NE];
@@ -649,16 +348,16 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
         auto issue_wrap = [&](double *stage, int64_t t) {
             const double *Ft = P.U + t * frame;
             if (need_top) {
-                cp_async16(stage + 2 * lane, Ft + top_src + 2 * lane);
-                cp_async16(stage + 64 + 2 * lane, Ft + top_src + 64 + 2 * lane);
-                cp_async16(stage + TJ + 2 * lane, Ft + top_src1 + 2 * lane);
-                cp_async16(stage + TJ + 64 + 2 * lane, Ft + top_src1 + 64 + 2 * lane);
+                cp_async16(stage + swz_cell(lane), Ft + top_src + 2 * lane);
+                cp_async16(stage + swz_cell(lane + 32), Ft + top_src + 64 + 2 * lane);
+                cp_async16(stage + TJ + swz_cell(lane), Ft + top_src1 + 2 * lane);
+                cp_async16(stage + TJ + swz_cell(lane + 32), Ft + top_src1 + 64 + 2 * lane);
             }
             if (need_bot) {
-                cp_async16(stage + (TI + 2) * TJ + 2 * lane, Ft + bot_src + 2 * lane);
-                cp_async16(stage + (TI + 2) * TJ + 64 + 2 * lane, Ft + bot_src + 64 + 2 * lane);
-                cp_async16(stage + (TI + 3) * TJ + 2 * lane, Ft + bot_src1 + 2 * lane);
-                cp_async16(stage + (TI + 3) * TJ + 64 + 2 * lane, Ft + bot_src1 + 64 + 2 * lane);
+                cp_async16(stage + (TI + 2) * TJ + swz_cell(lane), Ft + bot_src + 2 * lane);
+                cp_async16(stage + (TI + 2) * TJ + swz_cell(lane + 32), Ft + bot_src + 64 + 2 * lane);
+                cp_async16(stage + (TI + 3) * TJ + swz_cell(lane), Ft + bot_src1 + 2 * lane);
+                cp_async16(stage + (TI + 3) * TJ + swz_cell(lane + 32), Ft + bot_src1 + 64 + 2 * lane);
             }
         };
         // first frame of the item: its stage has landed => every warp released the stage's previous frame
@@ -669,9 +368,14 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
 
         int fold = 0;
         double su_first = 0.0;
-        const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lane >> 1);
+        const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lm.g >> 1);
         for (int f = 0; f <= nf; ++f, ++G) {
             double *st = stages + (G % NSTAGE) * STAGE_DOUBLES;
+            // where the stage of this frame goes next (known before the frame is even waited for, so the warp
+            // that releases it last can re-arm it without any arithmetic in between)
+            int n_i0 = i0, n_j0 = j0, n_t = (int)t0 + f + NSTAGE;
+            bool n_ok = true;
+            if (f + NSTAGE > nf) n_ok = ahead_coords(item, i0, j0, (int)t0, nf, f, NSTAGE, n_i0, n_j0, n_t);
             if (f + 1 < nf) {
                 // side cells of the next frame, one frame ahead.  Its stage may still hold the frame two back:
                 // wait until every warp released that one (what the producer waits for as well).
@@ -690,19 +394,18 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
 
             Sums F;
             if (f < nf) march_frame<LIB>(st, lm, P, F);
-            else F.SU = sum_frame_u(st, warp, lane, lm.sw);
+            else F.SU = sum_frame_u(st, lm);
 
             // release the stage (this warp has read everything it needs from load G); the warp whose arrival
             // completes the phase re-arms it with the load NSTAGE ahead.  Only the wrap rows are generic-proxy
             // writes inside the TMA box, so only their writers need the cross-proxy fence.
             if (need_top || need_bot) fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && mbar_arrive_pending(&empty[G % NSTAGE]) == 1)
-                issue_ahead(G % NSTAGE, item, i0, j0, (int)t0, nf, f, NSTAGE);
+            if (lane == 0 && mbar_arrive_pending(&empty[G % NSTAGE]) == 1 && n_ok) issue_load(G % NSTAGE, n_i0, n_j0, n_t);
 
             if (f % P.bt == 0 && f > 0) {
                 double SY = F.SU - su_first;
-#define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 1)
+#define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 8)
                 PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
                 if constexpr (kNeedAdv<LIB>) { PG_PAIR(A.SDx); PG_PAIR(A.SDy); }
                 if constexpr (kRich<LIB>) { PG_PAIR(A.SU); PG_PAIR(A.SU2); PG_PAIR(A.SUL); }
@@ -728,7 +431,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
                 bool fin = isfinite(y);
 #pragma unroll
                 for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
-                bool valid = (lane & 1) == 0;
+                bool valid = (lane & 8) == 0;
                 if (valid && !fin) { valid = false; ++bad_rows; }
                 else if (valid && (fold < 0 || fold >= P.n_folds)) { valid = false; ++bad_fold; }
                 if constexpr (TIMEFOLD) {
@@ -762,9 +465,9 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
                 } else {
 #pragma unroll
                     for (int h = 0; h < 16 / SB; ++h) {
-                        const bool mine = valid && (lane >> 1) / SB == h;
+                        const bool mine = valid && (lm.g >> 1) / SB == h;
                         if (mine) {
-                            double *r = ext + ((lane >> 1) % SB) * W;
+                            double *r = ext + ((lm.g >> 1) % SB) * W;
                             r[0] = 1.0; r[1] = y;
 #pragma unroll
                             for (int k = 0; k < p; ++k) r[2 + k] = th[k];
@@ -773,7 +476,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
                         const unsigned vm = __ballot_sync(0xffffffffu, mine);
 #pragma unroll
                         for (int slot_i = 0; slot_i < SB; ++slot_i) {
-                            const int src = (h * SB + slot_i) * 2;
+                            const int src = block_lane(h * SB + slot_i);
                             if (!((vm >> src) & 1u)) continue;
                             const int fr = TIMEFOLD ? 0 : __shfl_sync(0xffffffffu, fold, src);
                             const double *r = ext + slot_i * W;
@@ -816,20 +519,17 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88d(const __grid_consta
 
 // ----------------------------------------------------------------------------- host side
 // warps per CTA (see Geo): 8 or 4; PG_TILED_WARPS overrides the default for experiments
-// PG_TILED_WARPS: 9 (default) = decoupled kernel, 8 consumer warps + producer warp; 8 / 4 = legacy block-synchronous kernels
-static int tiled_warps() { const int w = env_int("PG_TILED_WARPS", 9); return w == 4 ? 4 : (w == 8 ? 8 : 9); }
 
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan) {
     if (P.dialect != PG_FD_KS_PERIODIC) return false;
     if (lib != PG_LIB_KS_TRUE && lib != PG_LIB_KS_TRUE_ADV && lib != PG_LIB_KS_RICH && lib != PG_LIB_KS_RICH_NOADV)
         return false;
     if (P.b0 != 8 || P.b1 != 8) return false;
-    const int NWsel = tiled_warps();
-    if (P.n_folds > 2 && (NWsel != 9 || P.fold_of_row)) return false;   // > 2 folds: time folds in the decoupled kernel only
-    if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // TMA / LDG.128: 16-byte strides, base
-    const int NW = NWsel == 9 ? 8 : NWsel;   // consumer warps
+    if (P.n_folds > 2 && P.fold_of_row) return false;   // per-row folds: two masked accumulator sets; time folds: any number
+    if (P.A1 % 16 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // 4-D swizzled TMA view: whole 128-byte groups
+    const int NW = DNW;
     const int TI = 8 * NW;
-    const int workers = n_sm * (NW == 4 ? 2 : 1);
+    const int workers = n_sm;
     const int64_t nt0 = P.A0 / TI, nt1 = P.A1 / TJ;
     const int64_t nbt = (P.T - 1) / P.bt;   // full t-blocks only; a ragged last one goes to the generic kernel
     if (nt0 < 1 || nt1 < 1 || nbt < 1) return false;
@@ -855,51 +555,33 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     plan.grid = (int)(items < workers ? items : workers);
     plan.n_parts = (int64_t)plan.grid * NW;
     plan.extra_scratch = 0;
-    plan.kernel_id = NWsel;
+    plan.kernel_id = 1;
     plan.tile0 = TI; plan.tile1 = TJ;
     return true;
-}
-
-template <int LIB, int NF, int NW> static int launch_tiled_k(const CUtensorMap &map, const TiledParams &tp, int grid,
-                                                            cudaStream_t st) {
-    const size_t smem = Geo<NW>::smem(Lib<LIB>::P);
-    PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1_tiled_b88<LIB, NF, NW><<<grid, 32 * NW, smem, st>>>(map, tp);
-    PG_LAUNCHED();
-    return PG_OK;
 }
 
 template <int LIB, int NF, bool TIMEFOLD> static int launch_tiled_d(const CUtensorMap &map, const TiledParams &tp, int grid,
                                                                      cudaStream_t st) {
     const size_t smem = Geo<DNW>::smem(Lib<LIB>::P);
-    PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88d<LIB, NF, TIMEFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1_tiled_b88d<LIB, NF, TIMEFOLD><<<grid, 32 * DNW, smem, st>>>(map, tp);
+    PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, TIMEFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_tiled_b88<LIB, NF, TIMEFOLD><<<grid, 32 * DNW, smem, st>>>(map, tp);
     PG_LAUNCHED();
     return PG_OK;
 }
 
 template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const TiledParams &tp, int n_folds, int nw, int grid,
                                              cudaStream_t st) {
-    if (nw == 9) {   // decoupled kernel: time folds / no folds at the single-fold cost, per-row folds masked (<= 2)
-        if (!tp.fold_of_row) return launch_tiled_d<LIB, 1, true>(map, tp, grid, st);
-        return launch_tiled_d<LIB, 2, false>(map, tp, grid, st);
-    }
-    if (nw == 8) return n_folds == 1 ? launch_tiled_k<LIB, 1, 8>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 8>(map, tp, grid, st);
-    return n_folds == 1 ? launch_tiled_k<LIB, 1, 4>(map, tp, grid, st) : launch_tiled_k<LIB, 2, 4>(map, tp, grid, st);
+    // time folds / no folds at the single-fold cost; per-row folds: two masked accumulator sets
+    (void)n_folds; (void)nw;
+    if (!tp.fold_of_row) return launch_tiled_d<LIB, 1, true>(map, tp, grid, st);
+    return launch_tiled_d<LIB, 2, false>(map, tp, grid, st);
 }
 
 int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *, cudaStream_t st) {
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) PG_FAIL(PG_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+    if (!encode_fn()) PG_FAIL(PG_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
     CUtensorMap map;
-    const cuuint64_t gdim[3] = {(cuuint64_t)P.A1, (cuuint64_t)P.A0, (cuuint64_t)P.T};
-    const cuuint64_t gstr[2] = {(cuuint64_t)P.A1 * 8, (cuuint64_t)P.A0 * (cuuint64_t)P.A1 * 8};
     const int NW = plan.kernel_id;
-    const cuuint32_t box[3] = {TJ, (cuuint32_t)(plan.tile0 + 4), 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(P.U), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           (CUtensorMapL2promotion)env_int("PG_TMA_L2PROMO", 2), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode_field_map(&map, P.U, P.T, P.A0, P.A1, plan.tile0 + 4);
     if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     TiledParams tp{};
     tp.U = P.U; tp.T = P.T; tp.A0 = P.A0; tp.A1 = P.A1;

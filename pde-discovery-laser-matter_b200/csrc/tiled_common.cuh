@@ -41,6 +41,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 // arrive (release.cta) and return how many arrivals the phase was still waiting for BEFORE this one
 // (1 => this arrival completed the phase)
 __device__ __forceinline__ uint32_t mbar_arrive_pending(uint64_t *bar) {
@@ -52,6 +59,53 @@ __device__ __forceinline__ uint32_t mbar_arrive_pending(uint64_t *bar) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------- swizzled tile layout
+// A stage holds a [rows][128] fp64 tile written by TMA through a 4-D view of the field
+// (16 doubles, A1/16 groups, A0, T) with CU_TENSOR_MAP_SWIZZLE_128B: inside every 128-byte segment the
+// 16-byte cells are XOR-permuted with the segment index (mod 8).  Lane l owns column group
+// g = (l >> 3) + 4 (l & 7) (columns 4g .. 4g+3 = cells 2g, 2g+1): the eight lanes of a quarter-warp then
+// sit in eight different segments at the same in-segment cell, which the swizzle spreads over all 32
+// banks -- every LDS.128 of "cell 2g + d" is conflict-free with the registers in natural order (no
+// operand swaps).  A stage is followed by its halo-column cells [rows][4] (left pair, right pair).
+__device__ __forceinline__ int lane_group(int lane) { return (lane >> 3) + 4 * (lane & 7); }
+// element offset, inside a row, of 16-byte cell `cell` (0..63)
+__host__ __device__ __forceinline__ int swz_cell(int cell) { return ((cell >> 3) << 4) + ((((cell & 7) ^ (cell >> 3)) & 7) << 1); }
+
+// Element offsets (inside a stage) of a lane's four cells 2g-1 .. 2g+2 in band row 0 and their row strides.
+// Cell -1 / 64 live in the halo-column array (stride 4) instead of the tile (stride TJ).
+struct LaneMap {
+    int a[4], s[4];
+    int g;
+};
+__device__ __forceinline__ LaneMap make_lane_map(int row0, int hoff, int lane) {
+    LaneMap m;
+    m.g = lane_group(lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int cell = 2 * m.g - 1 + k;
+        if (cell < 0) { m.a[k] = hoff + row0 * 4; m.s[k] = 4; }
+        else if (cell > 63) { m.a[k] = hoff + row0 * 4 + 2; m.s[k] = 4; }
+        else { m.a[k] = row0 * TJ + swz_cell(cell); m.s[k] = TJ; }
+    }
+    return m;
+}
+// columns own-2 .. own+5 of band row s
+__device__ __forceinline__ void load_row8(const double *__restrict__ st, const LaneMap &m, int s, double (&w)[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double2 x = *reinterpret_cast<const double2 *>(st + m.a[k] + s * m.s[k]);
+        w[2 * k] = x.x; w[2 * k + 1] = x.y;
+    }
+}
+// own columns only
+__device__ __forceinline__ void load_row4(const double *__restrict__ st, const LaneMap &m, int s, double (&w)[4]) {
+    const double2 x = *reinterpret_cast<const double2 *>(st + m.a[1] + s * TJ);
+    const double2 y = *reinterpret_cast<const double2 *>(st + m.a[2] + s * TJ);
+    w[0] = x.x; w[1] = x.y; w[2] = y.x; w[3] = y.y;
+}
+// bytes of a stage: tile + halo-column cells, padded so that every stage starts 1024-byte aligned (swizzle atom)
+__host__ __device__ constexpr int stage_bytes_for(int rows) { return ((rows * (TJ + 4) * 8 + 1023) / 1024) * 1024; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -74,17 +128,24 @@ inline int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-// 3-D tensor map over U[T][A0][A1] (fp64) with a (1, box_rows, TJ) box; out-of-bounds elements are zero-filled.
+// 4-D tensor map over U[T][A0][A1] (fp64) viewed as (16, A1/16, A0, T), box (16, 8, box_rows, 1), 128-byte swizzle;
+// out-of-bounds elements are zero-filled.  Requires A1 % 16 == 0.
 inline CUresult encode_field_map(CUtensorMap *map, const double *U, int64_t T, int64_t A0, int64_t A1, int box_rows) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return CUDA_ERROR_NOT_SUPPORTED;
-    const cuuint64_t gdim[3] = {(cuuint64_t)A1, (cuuint64_t)A0, (cuuint64_t)T};
-    const cuuint64_t gstr[2] = {(cuuint64_t)A1 * 8, (cuuint64_t)A0 * (cuuint64_t)A1 * 8};
-    const cuuint32_t box[3] = {TJ, (cuuint32_t)box_rows, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(U), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    const cuuint64_t gdim[4] = {16, (cuuint64_t)(A1 / 16), (cuuint64_t)A0, (cuuint64_t)T};
+    const cuuint64_t gstr[3] = {128, (cuuint64_t)A1 * 8, (cuuint64_t)A0 * (cuuint64_t)A1 * 8};
+    const cuuint32_t box[4] = {16, TJ / 16, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double *>(U), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                (CUtensorMapL2promotion)env_int("PG_TMA_L2PROMO", 2), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// first 1024-byte aligned address of the dynamic shared memory window (allocate 1024 bytes of slack)
+__device__ __forceinline__ unsigned char *align1024(unsigned char *p) {
+    const uint32_t a = smem_u32(p);
+    return p + (((a + 1023u) & ~1023u) - a);
 }
 
 }  // namespace pg

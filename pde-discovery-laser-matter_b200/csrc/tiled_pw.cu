@@ -5,7 +5,7 @@
 // Data movement is the one of tiled.cu: a persistent CTA owns a TI x 128 tile, each frame's (TI+4) x 128
 // row-halo tile arrives by one 3-D TMA copy, halo columns as 16-byte cells.  Differences:
 //   * u_t is pointwise here, so frame t+1 must be resident while frame t is differentiated: a 4-stage ring
-//     (current, next, two in flight), TI = 48 (4 x 54.9 KB).
+//     (current, next, two in flight), TI = 48 (4 x 54 KB), same swizzled stage layout and lane addressing.
 //   * every point contributes an outer product, so the kernel is fp64-ISSUE bound, not HBM bound
 //     (B200: 64 DFMA/clk/SM; ~32 fp64 ops per point for the p = 3 KS library, ~35 for basic p = 6,
 //     against ~23 available per point at the HBM roof).  The design therefore minimises fp64 operations:
@@ -44,11 +44,11 @@ template <int R_, int NW_> struct GeoPw {
     static constexpr int TI = R * NW;                 // tile rows: one R-row band per warp
     static constexpr int HR = TI + 4;
     static constexpr int HOFF = HR * TJ;
-    static constexpr int STAGE_DOUBLES = HR * PITCH;
-    static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+    static constexpr int STAGE_BYTES = stage_bytes_for(HR);       // tile + halo-column cells, 1024-byte multiple
+    static constexpr int STAGE_DOUBLES = STAGE_BYTES / 8;
     static constexpr int TMA_BYTES = HR * TJ * 8;
     static constexpr int THREADS = 32 * NW;
-    static constexpr size_t SMEM = (size_t)PW_NSTAGE * STAGE_BYTES + 128;   // + full[4], empty[4] mbarriers
+    static constexpr size_t SMEM = (size_t)PW_NSTAGE * STAGE_BYTES + 128 + 1024;   // + mbarriers + alignment slack
 };
 
 struct PwParams {
@@ -127,51 +127,11 @@ template <int LIB> __device__ __forceinline__ void pw_scales(const PwParams &P, 
     }
 }
 
-// ----------------------------------------------------------------------------- lane addressing
-// As LaneMap in tiled.cu, for bands of R rows: the four 16-byte chunks (columns own-2,-1 | own0,1 |
-// own2,3 | own+4,+5) of band row 0 and their row strides; lanes with bit 2 set issue each pair in the
-// opposite order (conflict-free LDS.128) and swap back.
-struct LaneMapPw {
-    int a0, sa0, a1, sa1, b0, sb0, b1, sb1, sw, own;
-};
-
-template <int R, int NW> __device__ __forceinline__ LaneMapPw lane_map_pw(int band, int lane) {
-    using G_ = GeoPw<R, NW>;
-    const int own = band * R * TJ + 4 * lane, hrow = G_::HOFF + band * R * 4;
-    const int c0 = lane > 0 ? own - 2 : hrow, s0 = lane > 0 ? TJ : 4;
-    const int c3 = lane < 31 ? own + 4 : hrow + 2, s3 = lane < 31 ? TJ : 4;
-    LaneMapPw m;
-    m.sw = (lane >> 2) & 1;
-    m.own = own;
-    m.a0 = m.sw ? own : c0;       m.sa0 = m.sw ? TJ : s0;
-    m.a1 = m.sw ? c0 : own;       m.sa1 = m.sw ? s0 : TJ;
-    m.b0 = m.sw ? c3 : own + 2;   m.sb0 = m.sw ? s3 : TJ;
-    m.b1 = m.sw ? own + 2 : c3;   m.sb1 = m.sw ? TJ : s3;
-    return m;
-}
-
-// columns own-2 .. own+5 of band row s
-__device__ __forceinline__ void load_row8(const double *__restrict__ st, const LaneMapPw &m, int s, double (&w)[8]) {
-    const double2 x0 = *reinterpret_cast<const double2 *>(st + m.a0 + s * m.sa0);
-    const double2 x1 = *reinterpret_cast<const double2 *>(st + m.a1 + s * m.sa1);
-    const double2 y0 = *reinterpret_cast<const double2 *>(st + m.b0 + s * m.sb0);
-    const double2 y1 = *reinterpret_cast<const double2 *>(st + m.b1 + s * m.sb1);
-    const double2 a0 = m.sw ? x1 : x0, a1 = m.sw ? x0 : x1, a2 = m.sw ? y1 : y0, a3 = m.sw ? y0 : y1;
-    w[0] = a0.x; w[1] = a0.y; w[2] = a1.x; w[3] = a1.y; w[4] = a2.x; w[5] = a2.y; w[6] = a3.x; w[7] = a3.y;
-}
-// own columns only (own0 .. own3) of band row s, conflict-free
-__device__ __forceinline__ void load_row4(const double *__restrict__ st, const LaneMapPw &m, int s, double (&w)[4]) {
-    const double2 *own = reinterpret_cast<const double2 *>(st + m.own + s * TJ);
-    const double2 x = own[m.sw], y = own[m.sw ^ 1];
-    const double2 lo = m.sw ? y : x, hi = m.sw ? x : y;
-    w[0] = lo.x; w[1] = lo.y; w[2] = hi.x; w[3] = hi.y;
-}
-
 // ----------------------------------------------------------------------------- one frame of one warp band
 // st = current frame's stage, stn = next frame's stage (u_t).  Band rows s = 0..R+3 are stage rows
 // band*R + s; the warp's own rows are s = 2..R+1 (bit r of rowmask = own row r is a row of the data set).
 template <int LIB, int R, bool MASKED>
-__device__ __forceinline__ void march_pw(const double *__restrict__ st, const double *__restrict__ stn, const LaneMapPw &m,
+__device__ __forceinline__ void march_pw(const double *__restrict__ st, const double *__restrict__ stn, const LaneMap &m,
                                          const PwParams &P, unsigned rowmask, unsigned colmask,
                                          double (&acc)[Pw<LIB>::NACC], unsigned &cnt) {
     using X_ = Pw<LIB>;
@@ -337,13 +297,14 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
     constexpr int TI = G_::TI, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES, NS = PW_NSTAGE;
     constexpr int S = X_::S;
     constexpr bool KS = X_::KS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem_raw = align1024(smem_dyn);
     double *stages = reinterpret_cast<double *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NS * G_::STAGE_BYTES);
     uint64_t *empty = full + NS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const LaneMapPw lm = lane_map_pw<R, NW>(warp, lane);
+    const LaneMap lm = make_lane_map(warp * R, HOFF, lane);
 
     double acc[X_::NACC];
 #pragma unroll
@@ -390,7 +351,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
         const uint32_t s = p_g % NS;
         if (p_g >= NS) mbar_wait(&empty[s], ((p_g / NS) - 1) & 1);   // every warp released the stage's previous frame
         mbar_expect_tx(&full[s], G_::TMA_BYTES);
-        tma_load_3d(stages + s * STAGE_DOUBLES, &tmap, &full[s], p_j0, p_i0 - 2, p_t);
+        tma_load_4d(stages + s * STAGE_DOUBLES, &tmap, &full[s], 0, p_j0 >> 4, p_i0 - 2, p_t);
         ++p_g;
         ++p_t;
         if (--p_left == 0) {
@@ -421,7 +382,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int64_t j = (int64_t)j0 + 4 * lane + c;
+            const int64_t j = (int64_t)j0 + 4 * lm.g + c;
             const bool ok = KS ? true : (j >= 2 && j < P.A1 - 2);
             colmask |= ok ? (1u << c) : 0u;
         }
@@ -458,8 +419,8 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (w_row[k] >= 0) {
-                        cp_async16(stage + w_row[k] * TJ + 2 * lane, Ft + w_src[k] + 2 * lane, false);
-                        cp_async16(stage + w_row[k] * TJ + 64 + 2 * lane, Ft + w_src[k] + 64 + 2 * lane, false);
+                        cp_async16(stage + w_row[k] * TJ + swz_cell(lane), Ft + w_src[k] + 2 * lane, false);
+                        cp_async16(stage + w_row[k] * TJ + swz_cell(lane + 32), Ft + w_src[k] + 64 + 2 * lane, false);
                     }
             }
             cp_async_commit();
@@ -516,7 +477,7 @@ bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     if (ks ? !(lib == PG_LIB_KS_TRUE || lib == PG_LIB_KS_TRUE_ADV || lib == PG_LIB_KS_RICH || lib == PG_LIB_KS_RICH_NOADV)
            : lib != PG_LIB_BASIC)
         return false;
-    if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // TMA / LDG.128 alignment
+    if (P.A1 % 16 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // 4-D swizzled TMA view: whole 128-byte groups
     if (P.T < 2 || P.T > 0x7fffffff || P.A0 > 0x7fffffff || P.A1 > 0x7fffffff) return false;
     if (P.A0 < 4 || P.A1 < TJ) return false;
     if (!encode_fn()) return false;

@@ -31,7 +31,7 @@ def field(ops, shape, seed):
 @pytest.mark.parametrize("libname", list(LIBS))
 @pytest.mark.parametrize("shape,bt", [((7, 64, 128), 3),      # one tile: wraps on all four sides, two t-blocks
                                       ((10, 128, 256), 3),    # 2 x 2 tiles, three t-blocks
-                                      ((9, 72, 136), 3),      # remainder rows/cols + ragged t -> generic boxes
+                                      ((9, 72, 144), 3),      # remainder rows/cols + ragged t -> generic boxes
                                       ((6, 64, 384), 1),      # bt = 1, three tiles in a row
                                       ((12, 192, 128), 5)])   # bt = 5, three tiles in a column, ragged t
 def test_tiled_vs_generic_and_oracle(env, libname, shape, bt):

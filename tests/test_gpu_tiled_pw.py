@@ -40,7 +40,7 @@ def basic_rows(U, d0, d1, dt):
                                    (4, 96, 256),      # 2 x 2 tiles
                                    (6, 64, 128),      # ragged last tile row (64 = 48 + 16): wrap rows inside the box
                                    (3, 20, 128),      # a single ragged tile: both wraps in one tile
-                                   (4, 100, 200)])    # ragged rows AND columns: remainder columns -> generic kernel
+                                   (4, 100, 208)])    # ragged rows AND columns: remainder columns -> generic kernel
 def test_ks_pointwise_tiled(env, libname, shape):
     L, ops = env
     lib = getattr(L, libname)
@@ -58,9 +58,9 @@ def test_ks_pointwise_tiled(env, libname, shape):
 
 
 @pytest.mark.parametrize("shape", [(4, 48, 128),      # one tile: all four borders masked
-                                   (5, 60, 140),      # ragged rows and columns (second tile column has 12 columns)
-                                   (3, 100, 300),     # 3 x 3 tiles, interior tile unmasked
-                                   (4, 50, 130),      # last tile row / column holds only border points
+                                   (5, 60, 144),      # ragged rows and columns (second tile column has 16 columns)
+                                   (3, 100, 304),     # 3 x 3 tiles, interior tile unmasked
+                                   (4, 50, 144),      # last tile row holds only border points
                                    (6, 7, 128)])      # fewer rows than one band
 def test_basic_pointwise_tiled(env, shape):
     L, ops = env
@@ -104,12 +104,12 @@ def test_pointwise_time_folds_and_chunks(env):
 def test_pointwise_basic_folds(env):
     L, ops = env
     T = 40
-    U = field(ops, (T, 100, 260), seed=3, kind=1)
+    U = field(ops, (T, 100, 272), seed=3, kind=1)
     fof = (np.arange(T - 1) >= 27).astype(np.int32)
     kw = dict(dialect=L.FD_BASIC_TRIM, library=L.LIB_BASIC, fold_of_frame=fof, n_folds=2)
     til = ops.fd_lib_gram(U, 0.3, 0.3, 0.1, variant=L.VARIANT_TILED, **kw).cpu().numpy()
     X, y = basic_rows(U.cpu().numpy(), 0.3, 0.3, 0.1)
-    fold_of_point = np.repeat(fof, 96 * 256)
+    fold_of_point = np.repeat(fof, 96 * 268)
     for f in range(2):
         assert_stats_close(til[f], gram.pack_stats(X[fold_of_point == f], y[fold_of_point == f]), 6)
 
@@ -153,6 +153,9 @@ def test_pointwise_unsupported_layouts_use_generic(env):
     with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
         ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, fold_of_row=fold,
                         variant=L.VARIANT_TILED)
+    odd = field(ops, (4, 48, 136), seed=7)      # the swizzled TMA view needs whole 128-byte column groups
+    with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
+        ops.fd_lib_gram(odd, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, variant=L.VARIANT_TILED)
     narrow = field(ops, (4, 48, 64), seed=7)
     with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
         ops.fd_lib_gram(narrow, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, variant=L.VARIANT_TILED)
