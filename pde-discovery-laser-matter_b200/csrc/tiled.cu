@@ -56,10 +56,9 @@ struct TiledParams {
     const double *U;
     int64_t T, A0, A1;
     double rho, kappa;        // L' = rho*(u[i+1]+u[i-1]) + (u[j+1]+u[j-1]) + kappa*u ; lap = r1*L'
-    double r1;                // 1/d1^2
-    double q0, q1;            // 1/(4 d0^2), 1/(4 d1^2)   (squares of the central-difference scales)
-    double h0, h1;            // 1/(2 d0), 1/(2 d1)
-    double rdt;               // 1/dt
+    // Rows are accumulated UNSCALED (block sums without 1/h^k, 1/dt and 1/(64 bt)); sc[] holds the factor each
+    // entry of the extended row [1, y, theta_0 ..] lacks, applied once per flush to the Gram products.
+    double sc[PG_MAX_P + 2];
     int bt;
     int n_tiles0, n_tiles1, n_chunks, chunk_tb;
     int64_t nbt;              // t-blocks covered
@@ -305,13 +304,15 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                 double v = pacc[f][e];
 #pragma unroll
                 for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == (e & 31)) out[e] += v;
+                int ea_, eb_;
+                stats_pair(e, p, ea_, eb_);
+                if (lane == (e & 31)) out[e] = fma(v, P.sc[ea_] * P.sc[eb_], out[e]);
                 pacc[f][e] = 0.0;
             }
         } else {
 #pragma unroll
             for (int k = 0; k < NE; ++k) {
-                if (ev[k]) out[lane + 32 * k] += acc[f][k];
+                if (ev[k]) out[lane + 32 * k] = fma(acc[f][k], P.sc[ea[k]] * P.sc[eb[k]], out[lane + 32 * k]);
                 acc[f][k] = 0.0;
             }
         }
@@ -320,7 +321,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
 
     unsigned long long bad_rows = 0, bad_fold = 0;
     int cur_fold = -1;
-    uint32_t G = 0;  // consumer load index
+    uint32_t G = 0;  // consumer load index; cs = G % NSTAGE and cph = (G / NSTAGE) & 1 are kept incrementally
+    uint32_t cs = 0, cph = 0;
     Sums A;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         int i0, j0, nf;
@@ -361,16 +363,18 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             }
         };
         // first frame of the item: its stage has landed => every warp released the stage's previous frame
-        mbar_wait(&full[G % NSTAGE], (G / NSTAGE) & 1);
-        issue_halo(stages + (G % NSTAGE) * STAGE_DOUBLES, t0);
-        issue_wrap(stages + (G % NSTAGE) * STAGE_DOUBLES, t0);
+        mbar_wait(&full[cs], cph);
+        issue_halo(stages + cs * STAGE_DOUBLES, t0);
+        issue_wrap(stages + cs * STAGE_DOUBLES, t0);
         cp_async_commit();
 
         int fold = 0;
         double su_first = 0.0;
         const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lm.g >> 1);
+        int fb = 0;               // f % bt, kept incrementally (no integer division in the frame loop)
+        int64_t tbs = tb0 - 1;    // t-block that starts at the latest frame with fb == 0
         for (int f = 0; f <= nf; ++f, ++G) {
-            double *st = stages + (G % NSTAGE) * STAGE_DOUBLES;
+            double *st = stages + cs * STAGE_DOUBLES;
             // where the stage of this frame goes next (known before the frame is even waited for, so the warp
             // that releases it last can re-arm it without any arithmetic in between)
             int n_i0 = i0, n_j0 = j0, n_t = (int)t0 + f + NSTAGE;
@@ -379,16 +383,16 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             if (f + 1 < nf) {
                 // side cells of the next frame, one frame ahead.  Its stage may still hold the frame two back:
                 // wait until every warp released that one (what the producer waits for as well).
-                const uint32_t g1 = G + 1, s1 = g1 % NSTAGE;
-                if (g1 >= NSTAGE) mbar_wait(&empty[s1], ((g1 / NSTAGE) - 1) & 1);
+                const uint32_t g1 = G + 1, s1 = cs + 1 == NSTAGE ? 0 : cs + 1, ph1 = s1 == 0 ? cph ^ 1 : cph;
+                if (g1 >= NSTAGE) mbar_wait(&empty[s1], ph1 ^ 1);
                 issue_halo(stages + s1 * STAGE_DOUBLES, t0 + f + 1);
                 if (need_top || need_bot) {
-                    mbar_wait(&full[s1], (g1 / NSTAGE) & 1);     // the wrap rows lie inside the TMA box
+                    mbar_wait(&full[s1], ph1);     // the wrap rows lie inside the TMA box
                     issue_wrap(stages + s1 * STAGE_DOUBLES, t0 + f + 1);
                 }
             }
             cp_async_commit();
-            mbar_wait(&full[G % NSTAGE], (G / NSTAGE) & 1);
+            mbar_wait(&full[cs], cph);
             cp_async_wait<1>();
             __syncwarp();
 
@@ -401,31 +405,29 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             // writes inside the TMA box, so only their writers need the cross-proxy fence.
             if (need_top || need_bot) fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && mbar_arrive_pending(&empty[G % NSTAGE]) == 1 && n_ok) issue_load(G % NSTAGE, n_i0, n_j0, n_t);
+            if (lane == 0 && mbar_arrive_pending(&empty[cs]) == 1 && n_ok) issue_load(cs, n_i0, n_j0, n_t);
+            if (++cs == NSTAGE) { cs = 0; cph ^= 1; }
 
-            if (f % P.bt == 0 && f > 0) {
+            if (fb == 0 && f > 0) {
                 double SY = F.SU - su_first;
 #define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 8)
                 PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
                 if constexpr (kNeedAdv<LIB>) { PG_PAIR(A.SDx); PG_PAIR(A.SDy); }
                 if constexpr (kRich<LIB>) { PG_PAIR(A.SU); PG_PAIR(A.SU2); PG_PAIR(A.SUL); }
 #undef PG_PAIR
-                const double invN = 1.0 / (64.0 * (double)P.bt);
-                const double lap = P.r1 * A.SL * invN;
-                const double bih = P.r1 * P.r1 * fma(P.rho, A.SE1, A.SE2) * invN;
-                const double gsq = fma(P.q0, A.SGx, P.q1 * A.SGy) * invN;
-                const double y = SY * P.rdt * invN;
+                // unscaled block-mean row (scales: TiledParams::sc); |grad u|^2 = q1 (rho SGx + SGy), bih = r1^2 (rho SE1 + SE2)
+                const double y = SY;
+                const double bih = fma(P.rho, A.SE1, A.SE2), gsq = fma(P.rho, A.SGx, A.SGy);
                 double th[p];
                 if constexpr (LIB == PG_LIB_KS_TRUE) {
-                    th[0] = lap; th[1] = bih; th[2] = gsq;
+                    th[0] = A.SL; th[1] = bih; th[2] = gsq;
                 } else if constexpr (LIB == PG_LIB_KS_TRUE_ADV) {
-                    th[0] = lap; th[1] = bih; th[2] = gsq; th[3] = P.h0 * A.SDx * invN; th[4] = P.h1 * A.SDy * invN;
+                    th[0] = A.SL; th[1] = bih; th[2] = gsq; th[3] = A.SDx; th[4] = A.SDy;
                 } else if constexpr (LIB == PG_LIB_KS_RICH) {
-                    th[0] = 1.0; th[1] = A.SU * invN; th[2] = A.SU2 * invN; th[3] = P.h0 * A.SDx * invN;
-                    th[4] = P.h1 * A.SDy * invN; th[5] = lap; th[6] = bih; th[7] = gsq; th[8] = P.r1 * A.SUL * invN;
+                    th[0] = 1.0; th[1] = A.SU; th[2] = A.SU2; th[3] = A.SDx; th[4] = A.SDy; th[5] = A.SL; th[6] = bih;
+                    th[7] = gsq; th[8] = A.SUL;
                 } else {
-                    th[0] = 1.0; th[1] = A.SU * invN; th[2] = A.SU2 * invN; th[3] = lap; th[4] = bih; th[5] = gsq;
-                    th[6] = P.r1 * A.SUL * invN;
+                    th[0] = 1.0; th[1] = A.SU; th[2] = A.SU2; th[3] = A.SL; th[4] = bih; th[5] = gsq; th[6] = A.SUL;
                 }
                 A = Sums();
                 bool fin = isfinite(y);
@@ -493,16 +495,17 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                 }
             }
             if (f < nf) {
-                if (f % P.bt == 0) {
+                if (fb == 0) {
                     su_first = F.SU;
-                    const int64_t tbs = tb0 + f / P.bt;
-                    if constexpr (TIMEFOLD) fold = P.fold_of_frame ? P.fold_of_frame[tbs * P.bt] : 0;
+                    ++tbs;
+                    if constexpr (TIMEFOLD) fold = P.fold_of_frame ? P.fold_of_frame[t0 + f] : 0;
                     else fold = P.fold_of_row[(tbs * P.nB0 + ib) * P.nB1 + jb];
                 }
                 A.SL += F.SL; A.SE1 += F.SE1; A.SE2 += F.SE2; A.SGx += F.SGx; A.SGy += F.SGy;
                 if constexpr (kNeedAdv<LIB>) { A.SDx += F.SDx; A.SDy += F.SDy; }
                 if constexpr (kRich<LIB>) { A.SU += F.SU; A.SU2 += F.SU2; A.SUL += F.SUL; }
             }
+            if (++fb == P.bt) fb = 0;
         }
     }
     cp_async_wait<0>();
@@ -588,10 +591,24 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     const double d0sq = P.c.d0sq, d1sq = P.c.d1sq;
     tp.rho = d1sq / d0sq;
     tp.kappa = -2.0 * (1.0 + tp.rho);
-    tp.r1 = 1.0 / d1sq;
-    tp.q0 = 1.0 / (P.c.two_d0 * P.c.two_d0); tp.q1 = 1.0 / (P.c.two_d1 * P.c.two_d1);
-    tp.h0 = 1.0 / P.c.two_d0; tp.h1 = 1.0 / P.c.two_d1;
-    tp.rdt = 1.0 / P.c.dt;
+    {
+        const double invN = 1.0 / (64.0 * (double)P.bt), r1 = 1.0 / d1sq, q1 = 1.0 / (P.c.two_d1 * P.c.two_d1);
+        const double h0 = 1.0 / P.c.two_d0, h1 = 1.0 / P.c.two_d1;
+        const double lapS = r1 * invN, bihS = r1 * r1 * invN, gS = q1 * invN;
+        double *sc = tp.sc;
+        for (int k = 0; k < PG_MAX_P + 2; ++k) sc[k] = 1.0;
+        sc[1] = invN / P.c.dt;
+        switch (lib) {
+            case PG_LIB_KS_TRUE: sc[2] = lapS; sc[3] = bihS; sc[4] = gS; break;
+            case PG_LIB_KS_TRUE_ADV: sc[2] = lapS; sc[3] = bihS; sc[4] = gS; sc[5] = h0 * invN; sc[6] = h1 * invN; break;
+            case PG_LIB_KS_RICH:
+                sc[3] = invN; sc[4] = invN; sc[5] = h0 * invN; sc[6] = h1 * invN; sc[7] = lapS; sc[8] = bihS; sc[9] = gS;
+                sc[10] = lapS;
+                break;
+            case PG_LIB_KS_RICH_NOADV: sc[3] = invN; sc[4] = invN; sc[5] = lapS; sc[6] = bihS; sc[7] = gS; sc[8] = lapS; break;
+            default: break;
+        }
+    }
     tp.bt = P.bt;
     tp.n_tiles0 = (int)plan.n_tiles0; tp.n_tiles1 = (int)plan.n_tiles1; tp.n_chunks = (int)plan.n_chunks;
     tp.chunk_tb = plan.chunk_t;
