@@ -283,10 +283,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// The kernel.  Warps are DECOUPLED: there is no block-wide barrier per frame.  full[s] (TMA complete_tx)
-// says stage s holds its frame; empty[s] counts the NW warps that are done with it, and the producer
-// (lane 0 of warp 0, at the end of its own iteration) waits on it before re-arming the stage, so warps
-// drift apart by up to a frame and one warp's bookkeeping overlaps the others' fp64 work.  Each warp
+// The kernel.  Warps are DECOUPLED: there is no block-wide barrier per frame and no producer warp.
+// full[s] (TMA complete_tx) says stage s holds its frame; empty[s] counts the NW warps that are done with
+// it, and the warp whose arrival completes that phase re-arms the stage with the load four frames ahead,
+// so warps drift apart by up to a frame and one warp's bookkeeping overlaps the others' fp64 work.  Each warp
 // copies the 16-byte side cells its own window needs (halo columns of its R+4 rows; the periodic wrap
 // rows if they fall inside its window) with cp.async, one frame ahead, so they need warp-level visibility
 // only.
@@ -337,33 +337,34 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
         nf = (int)min((int64_t)P.chunk_frames, P.n_row_frames - t0);
     };
 
-    // ---- producer (thread 0): a continuous stream of frame loads, NS-1 ahead of its own consumption
-    int64_t p_item = blockIdx.x;
-    int p_i0 = 0, p_j0 = 0, p_t = 0, p_left = 0;
-    uint32_t p_g = 0;
-    if (tid == 0 && p_item < n_items) {
-        int nf;
-        geometry(p_item, p_i0, p_j0, p_t, nf);
-        p_left = nf + 1;
-    }
-    auto produce = [&]() {
-        if (p_left == 0) return;
-        const uint32_t s = p_g % NS;
-        if (p_g >= NS) mbar_wait(&empty[s], ((p_g / NS) - 1) & 1);   // every warp released the stage's previous frame
+    // ---- loads: no warp is the producer.  Every warp releases a stage when it has read what it needs; the
+    // warp whose arrival completes the phase re-arms the stage with the load NS frames ahead.
+    auto issue_load = [&](uint32_t s, int i0, int j0, int t) {
+        fence_proxy_async();
         mbar_expect_tx(&full[s], G_::TMA_BYTES);
-        tma_load_4d(stages + s * STAGE_DOUBLES, &tmap, &full[s], 0, p_j0 >> 4, p_i0 - 2, p_t);
-        ++p_g;
-        ++p_t;
-        if (--p_left == 0) {
-            p_item += gridDim.x;
-            if (p_item < n_items) {
-                int nf;
-                geometry(p_item, p_i0, p_j0, p_t, nf);
-                p_left = nf + 1;
-            }
-        }
+        tma_load_4d(stages + s * STAGE_DOUBLES, &tmap, &full[s], 0, j0 >> 4, i0 - 2, t);
     };
-    if (tid == 0) { produce(); produce(); produce(); }
+    // coordinates of the load `ahead` frames after frame f of `item`; walks into the following items of this
+    // CTA; false when the CTA's stream of frames ends before that
+    auto ahead_coords = [&](int64_t item, int i0, int j0, int t0, int nf, int f, int ahead, int &ai0, int &aj0, int &at) {
+        int rem = f + ahead;
+        while (rem > nf) {
+            rem -= nf + 1;
+            item += gridDim.x;
+            if (item >= n_items) return false;
+            geometry(item, i0, j0, t0, nf);
+        }
+        ai0 = i0; aj0 = j0; at = t0 + rem;
+        return true;
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < n_items) {
+        int i0, j0, t0, nf;
+        geometry(blockIdx.x, i0, j0, t0, nf);
+        for (int a = 0; a < NS; ++a) {
+            int ai0, aj0, at;
+            if (ahead_coords(blockIdx.x, i0, j0, t0, nf, 0, a, ai0, aj0, at)) issue_load(a, ai0, aj0, at);
+        }
+    }
 
     uint32_t G = 0;  // consumer load index (stage = G % NS, parity = (G / NS) & 1)
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -432,6 +433,10 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
 
         for (int f = 0; f <= nf; ++f, ++G) {
             const double *st = stages + (G % NS) * STAGE_DOUBLES;
+            // where this frame's stage goes next, known up front so that re-arming it costs no arithmetic
+            int n_i0 = i0, n_j0 = j0, n_t = t0 + f + NS;
+            bool n_ok = true;
+            if (f + NS > nf) n_ok = ahead_coords(item, i0, j0, t0, nf, f, NS, n_i0, n_j0, n_t);
             if (f < nf) {
                 double *stn = stages + ((G + 1) % NS) * STAGE_DOUBLES;
                 mbar_wait(&full[(G + 1) % NS], ((G + 1) / NS) & 1);   // frame t+1: u_t now, differentiated next
@@ -456,8 +461,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
             // generic-proxy writes inside the TMA box: their writers fence towards the async proxy)
             if (KS && (w_row[0] >= 0 || w_row[1] >= 0 || w_row[2] >= 0 || w_row[3] >= 0)) fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[G % NS]);
-            if (tid == 0) produce();                                   // load G+3 -> stage of load G-1
+            if (lane == 0 && mbar_arrive_pending(&empty[G % NS]) == 1 && n_ok) issue_load(G % NS, n_i0, n_j0, n_t);
         }
     }
     cp_async_wait<0>();
