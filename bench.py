@@ -179,6 +179,21 @@ class ClockSampler:
                 "power_w_max": max((r[1] for r in self.rows), default=None), "samples": len(sm)}
 
 
+class _StdoutToStderr:
+    """NCCL prints its version banner to fd 1 from C; the contract is ONE JSON line on stdout.  Route fd 1
+    to fd 2 while the communicators are being created."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -193,9 +208,14 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    halo = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)          # creates the communicator (and prints NCCL's banner) now
+            torch.cuda.synchronize()
     lib = pde_b200.load()
     T, A = args.frames, args.size
     passes = 1
@@ -218,6 +238,15 @@ def run_ours(args):
     U = torch.empty((T, A, A), dtype=torch.float64, device="cuda")
     g_rows = world * rows_rank
     fof_pass = []
+    if world > 1:
+        with _StdoutToStderr():
+            halo = slabs.PeerHalo((A, A)) if os.environ.get("PG_HALO", "peer") != "send_recv" else None
+        if halo is None:
+            class _SendRecv:   # NCCL point-to-point path (A/B comparison: PG_HALO=send_recv)
+                mode = "send_recv"
+                begin = staticmethod(lambda U_: slabs.exchange_halo_begin(U_) or None)
+                end = staticmethod(lambda tok: slabs.exchange_halo_end(tok))
+            halo = _SendRecv()
 
     def fill(ps):
         """(Re)generate sub-slab `ps` of this rank's slab; the trailing frame of the rank's LAST sub-slab comes
@@ -247,21 +276,27 @@ def run_ours(args):
                 fill(ps)
             # the halo frame is only read by the last t-block: start the exchange, run K1 on everything before
             # that block while the frame is in flight, then the small tail launch (statistics are additive)
-            reqs = slabs.exchange_halo_begin(U) if (world > 1 and ps == passes - 1) else []
-            if record or passes > 1:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
+            token = halo.begin(U) if (world > 1 and ps == passes - 1) else None
             kw = dict(dialect=L.FD_KS_PERIODIC, library=library, block=block, n_folds=2, variant=variant)
-            cut = ((rows - 1) // block[0]) * block[0] if reqs else rows
+            cut = ((rows - 1) // block[0]) * block[0] if token is not None else rows
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if (record or passes > 1) else None
+            if ev:
+                ev[0].record()
             s = ops.fd_lib_gram(U[:cut + 1], D0, D1, DT, fold_of_frame=fof_pass[ps][:cut], **kw)
-            if reqs:
-                slabs.exchange_halo_end(reqs)
+            if ev:
+                ev[1].record()
+            if token is not None:
+                halo.end(token)
+                if ev:
+                    ev[2].record()
                 s = s + ops.fd_lib_gram(U[cut:], D0, D1, DT, fold_of_frame=fof_pass[ps][cut:], **kw)
-            if record or passes > 1:
-                e1.record()
+                if ev:
+                    ev[3].record()
+            if ev:
+                iv = [(ev[0], ev[1])] + ([(ev[2], ev[3])] if token is not None else [])
                 if record:
-                    k1_ev.append((e0, e1))
-                    pass_ev.append((e0, e1))
+                    k1_ev.append(iv)
+                pass_ev.append((ev[0], ev[3] if token is not None else ev[1]))
             stats = s if stats is None else stats + s
         slabs.allreduce_stats(stats)
         p = L.LIB_WIDTH[library]
@@ -322,10 +357,10 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_total = float(ms_t.item())
-    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1_ev]))
+    k1_ms = float(np.mean([sum(a.elapsed_time(b) for a, b in iv) for iv in k1_ev]))   # K1 launches only (bulk + tail)
     if passes > 1:
         # the refill between passes sits inside the bracketed region: count only the hot-path intervals (+ K3, < 0.1 ms)
-        ms_total = float(sum(a.elapsed_time(b) for a, b in pass_ev))
+        ms_total = float(sum(a.elapsed_time(b) for a, b in pass_ev[-passes * args.steps:]))
     pts_rank = T * A * A                      # points of one K1 launch (roofline)
     pts_step = (rows_rank + 1) * A * A        # points this rank processes per step
     value = world * pts_step * args.steps / (ms_total * 1e-3)
@@ -469,7 +504,7 @@ def run_ours(args):
                    f"c5: ONE synthetic {A}x{A}x{g_rows + 1} float64 stack in {world} time slab(s) of {rows_rank} row frames"
                    f"{' streamed through one buffer in %d passes (generator refill excluded)' % passes if passes > 1 else ''}, "
                    "KS periodic dialect, true dictionary p=3, block average (3,8,8), 2 time-holdout folds, 5x6 STRidge sweep", "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (pts_rank * 8 / 1e9),
-                   "parallelism": f"time slabs x{world}, 1-frame halo, all-reduce of 2x18 doubles" if world > 1 else "single GPU",
+                   "parallelism": f"time slabs x{world}, 1-frame halo ({halo.mode}), all-reduce of 2x18 doubles" if world > 1 else "single GPU",
                    "selected": {"alpha": float(alphas.cpu()[best // 6]), "threshold": float(thrs.cpu()[best % 6]),
                                 "coeffs": dict(zip(names, [float(c) for c in coef]))}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

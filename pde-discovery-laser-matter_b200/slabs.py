@@ -29,6 +29,76 @@ def slab_bounds(n_row_frames: int, block_t: int, world: int):
     return out
 
 
+class PeerHalo:
+    """Trailing-halo exchange through NVLink peer memory, with no SM involvement.
+
+    K1 is a persistent kernel that fills every SM (one CTA, ~218 KB of shared memory each), so a NCCL
+    send/recv kernel launched beside it cannot be scheduled until K1 retires: the exchange would serialise
+    behind the bulk launch instead of hiding under it.  Here every rank publishes its first frame in a
+    symmetric-memory buffer (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped into every
+    peer over NVSwitch), one small barrier kernel orders the publication BEFORE K1 starts, and the frame of
+    rank r+1 is then pulled by a copy engine (cudaMemcpyAsync on a side stream) while K1 owns the SMs.
+    Two buffers alternate, so a rank never overwrites a frame a slower neighbour may still be pulling.
+
+    Falls back to NCCL/gloo send-recv (``exchange_halo_begin``) when symmetric memory cannot be set up
+    (CPU tests, single GPU, unsupported platform); ``mode`` says which path is active.
+    """
+
+    def __init__(self, frame_shape, group=None, device=None):
+        import torch.distributed as dist
+
+        self.group, self.mode, self.k = group, "send_recv", 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.done = None
+        if self.world == 1:
+            self.mode = "none"
+            return
+        try:
+            torch = L.torch_cuda()
+            import torch.distributed._symmetric_memory as symm_mem
+
+            shape = (2,) + tuple(int(x) for x in frame_shape)
+            self.buf = symm_mem.empty(shape, dtype=torch.float64, device=device or torch.device("cuda", torch.cuda.current_device()))
+            self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            self.peer = self.hdl.get_buffer(self.rank + 1, shape, torch.float64) if self.rank < self.world - 1 else None
+            self.stream = torch.cuda.Stream()
+            self.mode = "peer_memory"
+        except Exception as exc:  # symmetric memory unavailable: keep the send/recv path
+            self.why = repr(exc)
+
+    def begin(self, U_local):
+        """Start filling U_local[-1] with the next rank's first frame; returns a token for end()."""
+        if self.mode == "none":
+            return None
+        if self.mode == "send_recv":
+            return exchange_halo_begin(U_local, self.group)
+        torch = L.torch_cuda()
+        b = self.k & 1
+        self.k += 1
+        self.buf[b].copy_(U_local[0])          # publish my first frame (local copy)
+        self.hdl.barrier(channel=0)            # every rank has published; tiny kernel, stream-ordered before K1
+        if self.peer is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            U_local[-1].copy_(self.peer[b], non_blocking=True)   # copy engine over NVLink
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return done
+
+    def end(self, token):
+        """Make the current stream wait for the halo frame."""
+        if token is None:
+            return
+        if self.mode == "send_recv":
+            exchange_halo_end(token)
+        else:
+            L.torch_cuda().cuda.current_stream().wait_event(token)
+
+
 def exchange_halo_begin(U_local, group=None):
     """Start filling the trailing halo frame U_local[-1] with frame 0 of the next rank's slab.
 
@@ -73,16 +143,23 @@ def allreduce_stats(stats, group=None):
 
 
 def sharded_stats(U_local, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_frame=None, fold_of_row=None,
-                  n_folds=1, variant=L.VARIANT_AUTO, group=None, halo=True, stats_fn=None):
+                  n_folds=1, variant=L.VARIANT_AUTO, group=None, halo=True, stats_fn=None, peer_halo=None):
     """Per-rank K1 over this rank's slab (own frames + trailing halo frame) followed by the
     all-reduce.  ``stats_fn`` lets the CPU tests stand in for the CUDA kernel.
 
     The halo frame is only read by the LAST t-block of the slab, so the exchange is started first,
     K1 runs on everything before that t-block while the frame is in flight, and only the small tail
     launch waits for it (the transfer is hidden; statistics are additive over time slabs)."""
-    reqs = exchange_halo_begin(U_local, group) if halo else []
+    if peer_halo is not None and halo:
+        # NVLink peer-memory exchange (PeerHalo): same begin / end protocol
+        token = peer_halo.begin(U_local)
+        reqs = [token] if token is not None else []
+        finish = lambda r: peer_halo.end(r[0]) if r else None   # noqa: E731
+    else:
+        reqs = exchange_halo_begin(U_local, group) if halo else []
+        finish = exchange_halo_end
     if stats_fn is not None:
-        exchange_halo_end(reqs)
+        finish(reqs)
         return allreduce_stats(stats_fn(U_local), group)
     from . import ops
 
@@ -91,12 +168,12 @@ def sharded_stats(U_local, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fol
     cut = ((rows - 1) // bt) * bt          # first frame of the last (possibly ragged) t-block
     kw = dict(dialect=dialect, library=library, block=block, n_folds=n_folds, variant=variant)
     if not reqs or cut <= 0 or fold_of_row is not None:
-        exchange_halo_end(reqs)
+        finish(reqs)
         stats = ops.fd_lib_gram(U_local, d0, d1, dt, fold_of_frame=fold_of_frame, fold_of_row=fold_of_row, **kw)
     else:
         fof = None if fold_of_frame is None else ops._dev(fold_of_frame)
         stats = ops.fd_lib_gram(U_local[:cut + 1], d0, d1, dt, fold_of_frame=None if fof is None else fof[:cut], **kw)
-        exchange_halo_end(reqs)
+        finish(reqs)
         stats = stats + ops.fd_lib_gram(U_local[cut:], d0, d1, dt, fold_of_frame=None if fof is None else fof[cut:], **kw)
     return allreduce_stats(stats, group)
 
