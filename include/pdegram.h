@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PG_VERSION 100
+#define PG_VERSION 101
 
 #if defined(__GNUC__)
 #define PG_API __attribute__((visibility("default")))
@@ -171,6 +171,9 @@ PG_API int pg_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t 
  *   alphas/thrs  [na] / [nt] DEVICE arrays: the sweep grid (ks2d:1720-1722)
  *   const_mask   nullable [p] uint8: columns known to be constant ('1'), forced to an exact
  *                zero coefficient as centring does in the reference
+ *   signs        nullable [p] int8 (-1 / 0 / +1), PG_STRIDGE_KS only: stridge_sign_constrained
+ *                (ks2d:552-600) -- a coefficient whose sign contradicts signs[j] is zeroed before the
+ *                threshold mask of every iteration and after every refit
  *   colminmax    nullable [B][2][p] from pg_rows_gram: adds exact constant detection
  *   shift        nullable [B][p]: the statistics (train and held-out) are of (X - shift)
  *   eval_stats   nullable [B][PG_STATS_LEN(p)]: held-out statistics -> metrics_out
@@ -180,7 +183,7 @@ PG_API int pg_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t 
  */
 PG_API int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect, int flags, const double *alphas,
                        int na, const double *thrs, int nt, int max_iter, const uint8_t *const_mask,
-                       const double *colminmax, const double *shift, const double *eval_stats,
+                       const int8_t *signs, const double *colminmax, const double *shift, const double *eval_stats,
                        double *coef_out, double *metrics_out, int32_t *best_out, void *stream);
 
 /*

@@ -99,9 +99,10 @@ def _solve(A, rhs, dialect):
 
 
 def stridge_from_stats(s, p: int, *, dialect: int, alpha: float, threshold: float, max_iter: int,
-                       const_cols=()):
+                       const_cols=(), signs=None):
     """STRidge on statistics.  ks2d:404-428 (DIALECT_KS), patch:78-98 (DIALECT_SKLEARN),
-    basic:104-143 (DIALECT_BASIC)."""
+    basic:104-143 (DIALECT_BASIC).  ``signs`` (KS dialect): stridge_sign_constrained, ks2d:552-600 --
+    wrong-signed coefficients are zeroed before the threshold mask and after every refit."""
     if dialect == DIALECT_BASIC:
         n, sy, syy, sx, b, G = unpack_stats(s, p)
         coef = np.ones(p)
@@ -118,7 +119,15 @@ def stridge_from_stats(s, p: int, *, dialect: int, alpha: float, threshold: floa
 
     C, r, scale = _standardised_system(s, p, dialect, const_cols)
     c = _solve(C + alpha * np.eye(p), r, dialect)
+
+    def enforce(c):
+        if signs is not None:
+            for j, sg in enumerate(signs):
+                if (sg == -1 and c[j] > 0) or (sg == 1 and c[j] < 0):
+                    c[j] = 0.0
+
     for _ in range(max_iter):
+        enforce(c)
         small = np.abs(c) < threshold
         if small.all():
             c = np.zeros(p)
@@ -128,6 +137,7 @@ def stridge_from_stats(s, p: int, *, dialect: int, alpha: float, threshold: floa
         cb = _solve(C[np.ix_(big, big)] + alpha * np.eye(k), r[big], dialect)
         c = np.zeros(p)
         c[big] = cb
+        enforce(c)
     return c / (scale + 1e-12)
 
 

@@ -239,6 +239,36 @@ def stridge(X, y, *, alpha: float = 1e-3, threshold: float = 1e-6, max_iter: int
     return c / (scale + 1e-12)
 
 
+def _enforce_signs(c, signs):
+    """ks2d:577-582 / 594-598: a coefficient whose sign contradicts signs[j] (-1 / +1) becomes 0."""
+    for j, sg in enumerate(signs):
+        if (sg == -1 and c[j] > 0) or (sg == 1 and c[j] < 0):
+            c[j] = 0.0
+
+
+def stridge_sign_constrained(X, y, *, alpha: float = 1e-3, threshold: float = 1e-6, max_iter: int = 25, signs=None):
+    """ks2d:552-600.  STRidge (same standardisation and refits as ks2d:404-428) where, inside every
+    iteration, wrong-signed coefficients are zeroed BEFORE the threshold mask is formed and again after
+    the refit; the initial full ridge fit is not sign-filtered when max_iter == 0."""
+    mean, scale = standardize_fit(X)
+    Xs = standardize_transform(X, mean, scale)
+    p = X.shape[1]
+    signs = [0] * p if signs is None else list(signs)
+    c = ridge_fit(Xs, y, alpha).copy()
+    for _ in range(max_iter):
+        _enforce_signs(c, signs)
+        small = np.abs(c) < threshold
+        if small.all():
+            c[:] = 0.0
+            break
+        big = ~small
+        cb = ridge_fit(Xs[:, big], y, alpha)
+        c = np.zeros_like(c)
+        c[big] = cb
+        _enforce_signs(c, signs)
+    return c / (scale + 1e-12)
+
+
 # --------------------------------------------------------------------------- main() hot path
 def make_dataset(U, dx, dy, DT, *, method: str = "pointwise", dictionary: str = "true",
                  include_advection: bool = False, n_sample: int = 50_000,

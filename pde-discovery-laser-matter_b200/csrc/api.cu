@@ -307,19 +307,21 @@ int pg_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, cons
 }
 
 int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect, int flags, const double *alphas, int na,
-                       const double *thrs, int nt, int max_iter, const uint8_t *const_mask, const double *colminmax,
+                       const double *thrs, int nt, int max_iter, const uint8_t *const_mask, const int8_t *signs,
+                       const double *colminmax,
                        const double *shift, const double *eval_stats, double *coef_out, double *metrics_out,
                        int32_t *best_out, void *stream) {
     if (p < 1 || p > PG_MAX_P) PG_FAIL(PG_EINVAL, "p must be in 1..%d", PG_MAX_P);
     if (dialect < PG_STRIDGE_KS || dialect > PG_STRIDGE_BASIC) PG_FAIL(PG_EINVAL, "unknown STRidge dialect %d", dialect);
     if (B < 0 || na < 1 || nt < 1 || max_iter < 0) PG_FAIL(PG_EINVAL, "bad sizes");
     if (!stats || !alphas || !thrs || !coef_out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (signs && dialect != PG_STRIDGE_KS) PG_FAIL(PG_EINVAL, "sign constraints belong to the ks2d dialect (ks2d:552-600)");
     if (dialect == PG_STRIDGE_BASIC && shift) PG_FAIL(PG_EINVAL, "the basic_usage dialect works on the raw Gram; shift must be null");
     if ((eval_stats != nullptr) != (metrics_out != nullptr)) PG_FAIL(PG_EINVAL, "eval_stats and metrics_out go together");
     if (best_out && !metrics_out) PG_FAIL(PG_EINVAL, "best_out needs eval_stats/metrics_out");
     StridgeParams P{};
     P.stats = stats; P.B = B; P.p = p; P.dialect = dialect; P.flags = flags; P.alphas = alphas; P.na = na;
-    P.thrs = thrs; P.nt = nt; P.max_iter = max_iter; P.const_mask = const_mask; P.colminmax = colminmax;
+    P.thrs = thrs; P.nt = nt; P.max_iter = max_iter; P.const_mask = const_mask; P.signs = signs; P.colminmax = colminmax;
     P.shift = shift; P.eval_stats = eval_stats; P.coef_out = coef_out; P.metrics_out = metrics_out;
     return launch_stridge(P, best_out, (cudaStream_t)stream);
 }

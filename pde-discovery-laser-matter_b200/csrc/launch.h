@@ -51,6 +51,7 @@ struct StridgeParams {
     const double *thrs; int nt;
     int max_iter;
     const uint8_t *const_mask;   // [p] or null
+    const int8_t *signs;         // [p] or null: sign constraints (-1 / 0 / +1), ks2d:552-600
     const double *colminmax;     // [B][2][p] or null
     const double *shift;         // [B][p] or null
     const double *eval_stats;    // [B][S] or null

@@ -104,6 +104,17 @@ __device__ void solve_active(WarpMem &w, int p, unsigned act, double alpha, bool
     __syncwarp();
 }
 
+// stridge_sign_constrained (ks2d:577-582, 594-598): a coefficient whose sign contradicts signs[j] becomes 0
+__device__ __forceinline__ void enforce_signs(WarpMem &w, int p, const int8_t *signs, int lane) {
+    if (!signs) return;
+    if (lane < p) {
+        const int sg = signs[lane];
+        const double c = w.c[lane];
+        if ((sg == -1 && c > 0.0) || (sg == 1 && c < 0.0)) w.c[lane] = 0.0;
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ unsigned big_mask(const WarpMem &w, int p, double thr, int lane) {
     const bool big = lane < p && !(fabs(w.c[lane]) < thr);
     return __ballot_sync(0xffffffffu, big);
@@ -207,6 +218,7 @@ __global__ void __launch_bounds__(SW * 32) stridge_kernel(StridgeParams P) {
         solve_active(w, p, all, alpha, cholesky, lane);
         unsigned prev = all;
         for (int it = 0; it < P.max_iter; ++it) {
+            enforce_signs(w, p, P.signs, lane);   // no-op after the first pass (already enforced after the refit)
             const unsigned big = big_mask(w, p, thr, lane);
             if (big == 0) {
                 if (lane < p) w.c[lane] = 0.0;
@@ -216,6 +228,7 @@ __global__ void __launch_bounds__(SW * 32) stridge_kernel(StridgeParams P) {
             if (big == prev && it > 0) break;  // same support -> the refit reproduces w.c
             if (big == all && it == 0) { prev = big; continue; }  // refit of the full system = initial solve
             solve_active(w, p, big, alpha, cholesky, lane);
+            enforce_signs(w, p, P.signs, lane);
             prev = big;
         }
     }

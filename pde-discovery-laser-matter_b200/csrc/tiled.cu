@@ -60,6 +60,11 @@ struct TiledParams {
     // entry of the extended row [1, y, theta_0 ..] lacks, applied once per flush to the Gram products.
     double sc[PG_MAX_P + 2];
     int bt;
+    int flags;                // experiments: bit 0 = issue the next frame's side cells after this frame has landed
+    // Pacing (see k1_tiled_b88): epoch_done[k] counts the CTAs that have consumed their k-th group of 2^epoch_shift
+    // frames; a CTA loads frames of epoch k only once every CTA is through epoch k - epoch_lead.
+    unsigned int *epoch_done;
+    int n_epochs, epoch_shift, epoch_lead;
     int n_tiles0, n_tiles1, n_chunks, chunk_tb;
     int64_t nbt;              // t-blocks covered
     int64_t nB0, nB1;         // block counts of the whole row space (row numbering)
@@ -194,6 +199,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 //     tile) with cp.async one frame ahead, so they need warp-level visibility only, and waits on full[s];
 //     warps drift by up to a frame, so one warp's t-block epilogue (shuffles, row, Gram update: long
 //     dependent chains) overlaps the others' stencil work instead of idling the SM;
+//   * PACING: neighbouring tiles share their halo rows / halo cells through L2, but only while the CTAs that
+//     own them work on nearby frames; persistent CTAs drift apart over a long chunk and the halo is then
+//     re-read from DRAM (measured: DRAM traffic 1.04x the algorithmic bytes over 256 frames, 1.12x over 1024).
+//     So the CTA-local frame stream is cut into epochs of 2^epoch_shift frames: the warp that re-arms a stage
+//     only issues a load of epoch k once every CTA has consumed epoch k - epoch_lead (one relaxed poll per
+//     epoch; the slowest CTA never waits, the others would only have finished early).  The poll gives up after
+//     a bounded number of tries: pacing is an optimisation, never a correctness requirement.
 //   * TIMEFOLD: folds given per frame (time-holdout folds) or no folds: a warp accumulates for ONE fold
 //     at a time in registers and flushes into its partial slot when the fold changes, so any number of
 //     folds runs at the single-fold cost.  !TIMEFOLD: fold_of_row, NF <= 2 masked accumulators as before.
@@ -237,7 +249,15 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
     };
 
     // load index g of this CTA -> (tile origin, frame); g counts every frame of every item in order
-    auto issue_load = [&](uint32_t s, int i0, int j0, int t) {
+    // gl = CTA-local index of the load (pacing); one lane calls this
+    auto issue_load = [&](uint32_t s, int i0, int j0, int t, uint32_t gl) {
+        if (P.epoch_done && (gl & ((1u << P.epoch_shift) - 1u)) == 0) {
+            const int k = (int)(gl >> P.epoch_shift) - P.epoch_lead;
+            if (k >= 0 && k < P.n_epochs) {
+                const volatile unsigned int *c = P.epoch_done + k;
+                for (int tries = 0; tries < (1 << 16) && *c < gridDim.x; ++tries) __nanosleep(64);
+            }
+        }
         fence_proxy_async();
         mbar_expect_tx(&full[s], G_::TMA_BYTES);
         tma_load_4d(stages + s * STAGE_DOUBLES, &tmap, &full[s], 0, j0 >> 4, i0 - 2, t);
@@ -263,7 +283,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         geometry(blockIdx.x, i0, j0, tb0, nf);
         for (int a = 0; a < NSTAGE; ++a) {
             int ai0, aj0, at;
-            if (ahead_coords(blockIdx.x, i0, j0, (int)(tb0 * P.bt), nf, 0, a, ai0, aj0, at)) issue_load(a, ai0, aj0, at);
+            if (ahead_coords(blockIdx.x, i0, j0, (int)(tb0 * P.bt), nf, 0, a, ai0, aj0, at)) issue_load(a, ai0, aj0, at, (uint32_t)a);
         }
     }
 
@@ -380,6 +400,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             int n_i0 = i0, n_j0 = j0, n_t = (int)t0 + f + NSTAGE;
             bool n_ok = true;
             if (f + NSTAGE > nf) n_ok = ahead_coords(item, i0, j0, (int)t0, nf, f, NSTAGE, n_i0, n_j0, n_t);
+            if (P.flags & 1) mbar_wait(&full[cs], cph);
             if (f + 1 < nf) {
                 // side cells of the next frame, one frame ahead.  Its stage may still hold the frame two back:
                 // wait until every warp released that one (what the producer waits for as well).
@@ -405,7 +426,12 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             // writes inside the TMA box, so only their writers need the cross-proxy fence.
             if (need_top || need_bot) fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && mbar_arrive_pending(&empty[cs]) == 1 && n_ok) issue_load(cs, n_i0, n_j0, n_t);
+            if (lane == 0 && mbar_arrive_pending(&empty[cs]) == 1) {
+                // every warp has consumed load G: count the epoch it closes, then re-arm the stage
+                if (P.epoch_done && ((G + 1) & ((1u << P.epoch_shift) - 1u)) == 0 && (int)(G >> P.epoch_shift) < P.n_epochs)
+                    atomicAdd(P.epoch_done + (G >> P.epoch_shift), 1u);
+                if (n_ok) issue_load(cs, n_i0, n_j0, n_t, G + NSTAGE);
+            }
             if (++cs == NSTAGE) { cs = 0; cph ^= 1; }
 
             if (fb == 0 && f > 0) {
@@ -509,6 +535,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         }
     }
     cp_async_wait<0>();
+    if (P.epoch_done && warp == 0 && lane == 0)
+        for (int k = (int)(G >> P.epoch_shift); k < P.n_epochs; ++k) atomicAdd(P.epoch_done + k, 1u);
     if (bad_rows) atomicAdd(&P.counters[0], bad_rows);
     if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
     if constexpr (TIMEFOLD) {
@@ -557,7 +585,12 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     const int64_t items = n_tiles * plan.n_chunks;
     plan.grid = (int)(items < workers ? items : workers);
     plan.n_parts = (int64_t)plan.grid * NW;
-    plan.extra_scratch = 0;
+    // pacing epochs: the longest CTA-local frame stream is rounds x (chunk frames + 1)
+    {
+        const int64_t rounds = (items + workers - 1) / workers;
+        const int64_t max_loads = rounds * ((int64_t)plan.chunk_t * P.bt + 1);
+        plan.extra_scratch = sizeof(unsigned int) * (size_t)((max_loads >> 2) + 2);
+    }
     plan.kernel_id = 1;
     plan.tile0 = TI; plan.tile1 = TJ;
     return true;
@@ -580,7 +613,7 @@ template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const Tiled
     return launch_tiled_d<LIB, 2, false>(map, tp, grid, st);
 }
 
-int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *, cudaStream_t st) {
+int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st) {
     if (!encode_fn()) PG_FAIL(PG_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
     CUtensorMap map;
     const int NW = plan.kernel_id;
@@ -610,6 +643,19 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
         }
     }
     tp.bt = P.bt;
+    tp.flags = env_int("PG_TILED_FLAGS", 0);
+    tp.epoch_shift = 2;                                   // epochs of 4 frames
+    // a CTA may run this many epochs ahead of the slowest (PG_TILED_LEAD < 0: no pacing).  Measured at C4: DRAM traffic
+    // 1.11x the algorithmic bytes without pacing, 1.01x with lead 2 (but the waits cost more than they save), lead 4
+    // is the fastest.  The lead must cover the ring depth (a CTA waits for its own epochs too): >= 2.
+    tp.epoch_lead = env_int("PG_TILED_LEAD", 4);
+    if (tp.epoch_lead >= 0 && tp.epoch_lead < 2) tp.epoch_lead = 2;
+    tp.n_epochs = (int)(plan.extra_scratch / sizeof(unsigned int)) - 1;
+    tp.epoch_done = nullptr;
+    if (tp.epoch_lead >= 0 && plan.grid > 1 && extra) {
+        tp.epoch_done = reinterpret_cast<unsigned int *>(extra);
+        PG_CUDA(cudaMemsetAsync(extra, 0, plan.extra_scratch, st));
+    }
     tp.n_tiles0 = (int)plan.n_tiles0; tp.n_tiles1 = (int)plan.n_tiles1; tp.n_chunks = (int)plan.n_chunks;
     tp.chunk_tb = plan.chunk_t;
     tp.nbt = plan.nbt; tp.nB0 = P.nB0; tp.nB1 = P.nB1;

@@ -131,6 +131,16 @@ def stridge(X, y, *, alpha: float = 1e-3, threshold: float = 1e-6, max_iter: int
     return _np(out["coef"])[0, 0, 0]
 
 
+def stridge_sign_constrained(X, y, *, alpha: float = 1e-3, threshold: float = 1e-6, max_iter: int = 25, signs=None):
+    """ks2d:552-600 on the GPU: STRidge with physics-informed sign constraints (signs[j] in {-1, 0, +1};
+    None = unconstrained).  Rows -> statistics -> K3 with the sign filter inside the thresholding loop."""
+    stats, mm, shift = _stats_of_rows(X, y)
+    out = ops.stridge_batched(stats, np.asarray(X).shape[1], dialect=L.STRIDGE_KS, alphas=[alpha],
+                              thresholds=[threshold], max_iter=int(max_iter), colminmax=mm, shift=shift,
+                              signs=None if signs is None else list(signs))
+    return _np(out["coef"])[0, 0, 0]
+
+
 # ------------------------------------------------------------------ fused path (ks2d:1508-1743)
 def library_of(dictionary: str, include_advection: bool = False, enforce_no_advection: bool = False):
     if dictionary == "true":
@@ -147,7 +157,8 @@ def split_folds(n_rows: int, rng):
     return fold, perm
 
 
-def fit_from_stats(stats_train, stats_test, names, *, alpha=1e-6, threshold=1e-10, grid_search=False, max_iter=25):
+def fit_from_stats(stats_train, stats_test, names, *, alpha=1e-6, threshold=1e-10, grid_search=False, max_iter=25,
+                   signs=None):
     """ks2d:1647-1779 on statistics: train-RMS scale, STRidge (or the 5x6 sweep), held-out
     r2/rmse and the reference's arg-max, all inside pg_stridge_batched."""
     p = len(names)
@@ -155,7 +166,8 @@ def fit_from_stats(stats_train, stats_test, names, *, alpha=1e-6, threshold=1e-1
     alphas = GRID_ALPHAS if grid_search else (alpha,)
     thrs = GRID_THRESHOLDS if grid_search else (threshold,)
     out = ops.stridge_batched(stats_train, p, dialect=L.STRIDGE_KS, flags=L.STRIDGE_RMS_PRESCALE, alphas=alphas,
-                              thresholds=thrs, max_iter=max_iter, const_cols=const_cols, eval_stats=stats_test)
+                              thresholds=thrs, max_iter=max_iter, const_cols=const_cols, eval_stats=stats_test,
+                              signs=signs)
     coef, met, best = _np(out["coef"])[0], _np(out["metrics"])[0], int(_np(out["best"])[0])
     ia, it = divmod(best, len(thrs))
     c = coef[ia, it]

@@ -157,7 +157,7 @@ def poly_rows(U, pts, W6, rt, rs, *, library):
 
 
 def stridge_batched(stats, p, *, dialect, alphas, thresholds, max_iter, flags=0, const_cols=(), colminmax=None,
-                    shift=None, eval_stats=None):
+                    shift=None, eval_stats=None, signs=None):
     """K3: pg_stridge_batched.  stats [B][S] -> dict(coef [B][na][nt][p], metrics, best)."""
     torch = L.torch_cuda()
     lib = L.load()
@@ -177,6 +177,12 @@ def stridge_batched(stats, p, *, dialect, alphas, thresholds, max_iter, flags=0,
         m = np.zeros(p, dtype=np.uint8)
         m[list(const_cols)] = 1
         cm = _dev(m)
+    sg = None
+    if signs is not None:
+        sg_h = np.asarray(list(signs), dtype=np.int64)
+        if sg_h.shape != (p,) or not np.isin(sg_h, (-1, 0, 1)).all():
+            raise ValueError("signs must hold p entries from {-1, 0, +1}")
+        sg = _dev(sg_h.astype(np.int8))
     mm = None if colminmax is None else _dev(colminmax, torch.float64).reshape(B, 2, p).contiguous()
     sh = None if shift is None else _dev(shift, torch.float64).reshape(B, p).contiguous()
     ev = None if eval_stats is None else _dev(eval_stats, torch.float64).reshape(B, L.stats_len(p)).contiguous()
@@ -184,7 +190,7 @@ def stridge_batched(stats, p, *, dialect, alphas, thresholds, max_iter, flags=0,
     metrics = torch.empty((B, na, nt, 2), dtype=torch.float64, device=stats.device) if ev is not None else None
     best = torch.empty((B,), dtype=torch.int32, device=stats.device) if ev is not None else None
     L.check(lib.pg_stridge_batched(L.ptr(stats), B, p, dialect, flags, L.ptr(al), na, L.ptr(th), nt, int(max_iter),
-                                   L.ptr(cm), L.ptr(mm), L.ptr(sh), L.ptr(ev), L.ptr(coef), L.ptr(metrics), L.ptr(best),
+                                   L.ptr(cm), L.ptr(sg), L.ptr(mm), L.ptr(sh), L.ptr(ev), L.ptr(coef), L.ptr(metrics), L.ptr(best),
                                    L.stream_ptr()))
     return dict(coef=coef, metrics=metrics, best=best)
 

@@ -85,6 +85,34 @@ def golden_ks2d_small(ks):
     np.savez_compressed(OUT / "ks2d_small.npz", **out)
 
 
+def golden_ks2d_signed(ks):
+    """stridge_sign_constrained (ks2d:552-600) on the rows stored in ks2d_small.npz: true (p=3, pointwise rows),
+    rich (p=9, pointwise and (4,5,3) block rows), several (alpha, threshold, signs) including constraints that
+    bite on the first pass, constraints that only bite after a refit, and the unconstrained default."""
+    g = np.load(OUT / "ks2d_small.npz")
+    cases = []
+    sets = {"true_pw": (g["bw111_X_true"], g["bw111_y"]), "rich_pw": (g["bw111_X_rich"], g["bw111_y"]),
+            "rich_453": (g["bw453_X_rich"], g["bw453_y"])}
+    grid = [(1e-6, 1e-10), (1e-3, 1e-6), (1e-2, 1e-2), (1e-2, 0.2)]
+    rng = np.random.default_rng(11)
+    out = {}
+    for tag, (X, y) in sets.items():
+        p = X.shape[1]
+        free = ks.stridge(X, y, alpha=1e-3, threshold=1e-6, max_iter=25)
+        sign_sets = [[0] * p, [-1] * p, [1] * p, [int(v) for v in np.sign(free)], [int(-v) for v in np.sign(free)]]
+        sign_sets += [[int(v) for v in rng.integers(-1, 2, size=p)] for _ in range(3)]
+        S, A, C = [], [], []
+        for signs in sign_sets:
+            for a, t in grid:
+                S.append(signs)
+                A.append((a, t))
+                C.append(ks.stridge_sign_constrained(X, y, alpha=a, threshold=t, max_iter=25, signs=list(signs)))
+        out[f"{tag}_signs"], out[f"{tag}_grid"], out[f"{tag}_coef"] = np.array(S, dtype=np.int8), np.array(A), np.stack(C)
+        out[f"{tag}_none"] = ks.stridge_sign_constrained(X, y, alpha=1e-3, threshold=1e-6, max_iter=25, signs=None)
+        out[f"{tag}_iter0"] = ks.stridge_sign_constrained(X, y, alpha=1e-3, threshold=1e-6, max_iter=0, signs=[-1] * p)
+    np.savez_compressed(OUT / "ks2d_signed.npz", **out)
+
+
 def _run_main(ks, argv):
     buf = io.StringIO()
     with mock.patch.object(sys, "argv", ["ks2d_stridge_benchmark.py"] + argv), contextlib.redirect_stdout(buf):
@@ -269,6 +297,7 @@ def golden_patch(pa):
 def main():
     ks, ba, pa = load_reference()
     golden_ks2d_small(ks)
+    golden_ks2d_signed(ks)
     golden_basic(ba)
     golden_patch(pa)
     golden_ks2d_configs(ks)

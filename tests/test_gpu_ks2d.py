@@ -273,3 +273,23 @@ def test_slab_additivity_and_variants(ops, L, shape, block):
     # and against the oracle on the same device-generated field
     names, X, y = ks_rows(U.cpu().numpy(), 0.5, 0.5, 1e-3, "rich", False, block)
     assert_stats_close(full, gram.pack_stats(X, y), 9)
+
+
+def test_stridge_sign_constrained_matches_reference():
+    """K3 with sign constraints (ks2d:552-600) against the reference's outputs on the golden rows: identical
+    support, coefficients to 1e-8, through the literal (X, y) signature."""
+    from conftest import GOLDEN
+    from pde_b200 import ks2d as K
+
+    gs, g = np.load(GOLDEN / "ks2d_signed.npz"), np.load(GOLDEN / "ks2d_small.npz")
+    for tag, xkey, ykey in [("true_pw", "bw111_X_true", "bw111_y"), ("rich_pw", "bw111_X_rich", "bw111_y"),
+                            ("rich_453", "bw453_X_rich", "bw453_y")]:
+        X, y = g[xkey], g[ykey]
+        for signs, (a, t), ref in zip(gs[f"{tag}_signs"], gs[f"{tag}_grid"], gs[f"{tag}_coef"]):
+            got = K.stridge_sign_constrained(X, y, alpha=a, threshold=t, max_iter=25, signs=[int(v) for v in signs])
+            assert_coef_close(got, ref, what=f"{tag} signs={signs} alpha={a} thr={t}")
+        assert_coef_close(K.stridge_sign_constrained(X, y, alpha=1e-3, threshold=1e-6, signs=None), gs[f"{tag}_none"])
+        assert_coef_close(K.stridge_sign_constrained(X, y, alpha=1e-3, threshold=1e-6, max_iter=0, signs=[-1] * X.shape[1]),
+                          gs[f"{tag}_iter0"])
+    with pytest.raises(ValueError):
+        K.stridge_sign_constrained(g["bw111_X_true"], g["bw111_y"], signs=[2, 0, 0])

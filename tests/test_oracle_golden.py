@@ -263,3 +263,36 @@ def test_patch_loop(golden_patch):
         assert np.array_equal(out[k], g[f"loop_{k}"])
     for k in ("median", "q25", "q75", "agg"):
         close(out[k], g[f"loop_{k}"], rtol=1e-6, atol=1e-9)
+
+
+# --------------------------------------------------------------------------- sign-constrained STRidge
+@pytest.fixture(scope="session")
+def golden_signed():
+    from conftest import GOLDEN
+
+    return np.load(GOLDEN / "ks2d_signed.npz")
+
+
+@pytest.mark.parametrize("tag,xkey,ykey", [("true_pw", "bw111_X_true", "bw111_y"), ("rich_pw", "bw111_X_rich", "bw111_y"),
+                                           ("rich_453", "bw453_X_rich", "bw453_y")])
+def test_sign_constrained_rows_and_stats_match_reference(golden_ks2d, golden_signed, tag, xkey, ykey):
+    """oracle.ks2d.stridge_sign_constrained (rows) and its statistics form against the outputs of the
+    reference's ks2d:552-600 on the same rows: identical support, coefficients to 1e-9 / 1e-8."""
+    from oracle import gram, ks2d
+
+    X, y, g = golden_ks2d[xkey], golden_ks2d[ykey], golden_signed
+    p = X.shape[1]
+    const = [j for j in range(p) if np.all(X[:, j] == X[0, j])]
+    stats = gram.pack_stats(X, y)
+    for signs, (a, t), ref in zip(g[f"{tag}_signs"], g[f"{tag}_grid"], g[f"{tag}_coef"]):
+        rows = ks2d.stridge_sign_constrained(X, y, alpha=a, threshold=t, max_iter=25, signs=[int(v) for v in signs])
+        assert np.array_equal(rows != 0, ref != 0), (tag, signs, a, t)
+        np.testing.assert_allclose(rows, ref, rtol=1e-9, atol=0)
+        st = gram.stridge_from_stats(stats, p, dialect=gram.DIALECT_KS, alpha=a, threshold=t, max_iter=25,
+                                     const_cols=const, signs=[int(v) for v in signs])
+        assert np.array_equal(st != 0, ref != 0), (tag, signs, a, t)
+        np.testing.assert_allclose(st, ref, rtol=1e-8, atol=0)
+    none = ks2d.stridge_sign_constrained(X, y, alpha=1e-3, threshold=1e-6, max_iter=25, signs=None)
+    np.testing.assert_allclose(none, g[f"{tag}_none"], rtol=1e-9)
+    it0 = ks2d.stridge_sign_constrained(X, y, alpha=1e-3, threshold=1e-6, max_iter=0, signs=[-1] * p)
+    np.testing.assert_allclose(it0, g[f"{tag}_iter0"], rtol=1e-9)
