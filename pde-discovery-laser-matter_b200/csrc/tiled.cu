@@ -227,10 +227,12 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
     double *stages = reinterpret_cast<double *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NSTAGE * G_::STAGE_BYTES);
     uint64_t *empty = full + NSTAGE;
+    volatile int *pace_off = reinterpret_cast<volatile int *>(empty + NSTAGE);   // set when a pacing poll timed out
     double *ext_all = reinterpret_cast<double *>(smem_raw + NSTAGE * G_::STAGE_BYTES + 64);  // [NW][SB][W]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
+        *pace_off = 0;
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
         fence_barrier_init();
         fence_proxy_async();
@@ -251,11 +253,13 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
     // load index g of this CTA -> (tile origin, frame); g counts every frame of every item in order
     // gl = CTA-local index of the load (pacing); one lane calls this
     auto issue_load = [&](uint32_t s, int i0, int j0, int t, uint32_t gl) {
-        if (P.epoch_done && (gl & ((1u << P.epoch_shift) - 1u)) == 0) {
+        if (P.epoch_done && (gl & ((1u << P.epoch_shift) - 1u)) == 0 && *pace_off == 0) {
             const int k = (int)(gl >> P.epoch_shift) - P.epoch_lead;
             if (k >= 0 && k < P.n_epochs) {
                 const volatile unsigned int *c = P.epoch_done + k;
-                for (int tries = 0; tries < (1 << 16) && *c < gridDim.x; ++tries) __nanosleep(64);
+                int tries = 0;
+                while (*c < gridDim.x && ++tries < (1 << 14)) __nanosleep(64);
+                if (tries >= (1 << 14)) *pace_off = 1;   // some CTA is not making progress (shared GPU?): stop pacing this CTA
             }
         }
         fence_proxy_async();

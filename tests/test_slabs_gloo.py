@@ -31,7 +31,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, block, q):
+def _worker(rank, world, port, block, q, use_peer=False):
     import torch
     import torch.distributed as dist
 
@@ -53,22 +53,27 @@ def _worker(rank, world, port, block, q):
             names, X, y = ks_rows(Ul.numpy(), dx, dy, DT, "rich", False, block)
             return torch.from_numpy(gram.pack_stats(X, y))[None].clone()
 
+        peer = None
+        if use_peer:
+            # no CUDA / symmetric memory here: PeerHalo must say so and take the send/recv path
+            peer = slabs.PeerHalo(U.shape[1:])
+            assert peer.mode == "send_recv" and peer.world == world
         s = slabs.sharded_stats(U_local, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_RICH, block=block,
-                                stats_fn=stats_fn)
+                                stats_fn=stats_fn, peer_halo=peer)
         assert torch.equal(U_local[-1], torch.from_numpy(U[hi]))
         q.put((rank, s.numpy()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("block", [(1, 1, 1), (3, 8, 8)])
-def test_two_rank_halo_and_allreduce(block):
+@pytest.mark.parametrize("block,use_peer", [((1, 1, 1), False), ((3, 8, 8), False), ((3, 8, 8), True)])
+def test_two_rank_halo_and_allreduce(block, use_peer):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, block, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, block, q, use_peer)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=120) for _ in range(2))
@@ -80,3 +85,11 @@ def test_two_rank_halo_and_allreduce(block):
     ref = gram.pack_stats(X, y)
     assert np.array_equal(res[0], res[1])        # every rank holds the reduced statistics
     assert_stats_close(res[0][0], ref, 9, rtol=1e-12)
+
+
+def test_peer_halo_single_process_is_a_no_op():
+    from pde_b200.slabs import PeerHalo
+
+    h = PeerHalo((4, 4))
+    assert h.mode == "none" and h.begin(None) is None
+    h.end(None)
