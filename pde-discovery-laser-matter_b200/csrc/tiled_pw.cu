@@ -130,7 +130,8 @@ template <int LIB> __device__ __forceinline__ void pw_scales(const PwParams &P, 
 // ----------------------------------------------------------------------------- one frame of one warp band
 // st = current frame's stage, stn = next frame's stage (u_t).  Band rows s = 0..R+3 are stage rows
 // band*R + s; the warp's own rows are s = 2..R+1 (bit r of rowmask = own row r is a row of the data set).
-template <int LIB, int R, bool MASKED>
+// ROWS_ALL: every own row is a row of the data set (no per-row branch: the whole march is one basic block).
+template <int LIB, int R, bool MASKED, bool ROWS_ALL>
 __device__ __forceinline__ void march_pw(const double *__restrict__ st, const double *__restrict__ stn, const LaneMap &m,
                                          const PwParams &P, unsigned rowmask, unsigned colmask,
                                          double (&acc)[Pw<LIB>::NACC], unsigned &cnt) {
@@ -161,7 +162,7 @@ __device__ __forceinline__ void march_pw(const double *__restrict__ st, const do
             }
             if (s >= 4) {
                 const int r = s - 2;   // own row r: all of its neighbours' L' are known now
-                if ((rowmask >> (r - 2)) & 1u) {
+                if (ROWS_ALL || ((rowmask >> (r - 2)) & 1u)) {
                     double nx[4];
                     load_row4(stn, m, r, nx);
 #pragma unroll
@@ -203,7 +204,7 @@ __device__ __forceinline__ void march_pw(const double *__restrict__ st, const do
             }
             if (s >= 3) {
                 const int r = s - 1;
-                if ((rowmask >> (r - 2)) & 1u) {
+                if (ROWS_ALL || ((rowmask >> (r - 2)) & 1u)) {
                     double nx[4];
                     load_row4(stn, m, r, nx);
 #pragma unroll
@@ -453,8 +454,15 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
                         if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);
                         cur_fold = fold;
                     }
-                    if (edge_cols) march_pw<LIB, R, !KS>(st, stn, lm, P, rowmask, colmask, acc, cnt);
-                    else march_pw<LIB, R, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                    const bool rows_all = rowmask == (1u << R) - 1u;   // warp-uniform
+                    if constexpr (KS) {
+                        if (rows_all) march_pw<LIB, R, false, true>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                        else march_pw<LIB, R, false, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                    } else {
+                        if (!edge_cols && rows_all) march_pw<LIB, R, false, true>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                        else if (!edge_cols) march_pw<LIB, R, false, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                        else march_pw<LIB, R, true, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                    }
                 }
             }
             // release the stage: this warp has read everything it needs from load G (only the wrap rows are
