@@ -187,6 +187,16 @@ PG_API int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect
                        double *coef_out, double *metrics_out, int32_t *best_out, void *stream);
 
 /*
+ * Rollout check of a discovered KS-dialect PDE (ks2d:1804-1838): explicit Euler from frame 0,
+ * u_hat <- u_hat + dt * sum_k coef[k] * theta_k(u_hat) with the periodic stencils of ks2d:63-73 (terms added in
+ * library order, |coef| < 1e-12 skipped), and rmse_out[k] = RMSE(U[k+1], u_hat after step k+1) (ks2d:29-32).
+ *   coef      [p] DEVICE coefficients in library order        work  [2][A0][A1] DEVICE scratch frames
+ *   n_steps   <= T-1                                          rmse_out [n_steps] DEVICE
+ */
+PG_API int pg_ks_rollout(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                  int library_id, const double *coef, int n_steps, double *work, double *rmse_out, void *stream);
+
+/*
  * Synthetic field generator for the large benchmark stacks: frames
  * t_offset..t_offset+T-1 of a smooth travelling-wave field plus counter-based noise,
  * written straight into HBM.  kind 0 = periodic (KS-shaped), 1 = laser-image-shaped [0,1].

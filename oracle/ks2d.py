@@ -269,6 +269,32 @@ def stridge_sign_constrained(X, y, *, alpha: float = 1e-3, threshold: float = 1e
     return c / (scale + 1e-12)
 
 
+def rollout_errors(U, dx, dy, DT, names, coeffs, n_steps: int = 50):
+    """ks2d:1804-1838: u_hat <- u_hat + DT * rhs_from_coeffs(u_hat) from U[0]; rmse(U[k+1], u_hat) per step.
+    rhs: out = zeros; for (name, c): skip |c| < 1e-12; out += c * value(name)."""
+    def rhs(u):
+        ux, uy = gradients(u, dx, dy)
+        lap = laplacian(u, dx, dy)
+        bih = laplacian(lap, dx, dy)
+        vals = {"1": 1.0, "u": u, "u^2": u ** 2, "u_x": ux, "u_y": uy, "∇²u": lap, "∇⁴u": bih,
+                "|∇u|²": ux ** 2 + uy ** 2, "u·∇²u": u * lap}
+        out = np.zeros_like(u, dtype=np.float64)
+        for name, c in zip(names, coeffs):
+            if abs(c) < 1e-12:
+                continue
+            v = vals[name]
+            out += c * (v if isinstance(v, np.ndarray) else float(v))
+        return out
+
+    n = int(min(n_steps, U.shape[0] - 1))
+    u_hat = U[0].copy()
+    errs = []
+    for k in range(n):
+        u_hat = u_hat + DT * rhs(u_hat)
+        errs.append(rmse(U[k + 1].ravel(), u_hat.ravel()))
+    return np.asarray(errs)
+
+
 # --------------------------------------------------------------------------- main() hot path
 def make_dataset(U, dx, dy, DT, *, method: str = "pointwise", dictionary: str = "true",
                  include_advection: bool = False, n_sample: int = 50_000,

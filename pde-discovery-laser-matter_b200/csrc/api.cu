@@ -326,6 +326,22 @@ int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect, int f
     return launch_stridge(P, best_out, (cudaStream_t)stream);
 }
 
+int pg_ks_rollout(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int library_id,
+                  const double *coef, int n_steps, double *work, double *rmse_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    K1Params P{};
+    int rc = describe(P, U, T, A0, A1, d0, d1, dt, PG_FD_KS_PERIODIC, library_id, true);
+    if (rc) return rc;
+    if (n_steps < 0 || n_steps > T - 1) PG_FAIL(PG_EINVAL, "n_steps must be in 0..T-1 (every step is compared with an observed frame)");
+    if (n_steps == 0) return PG_OK;
+    if (!coef || !work || !rmse_out) PG_FAIL(PG_EINVAL, "null buffer");
+    const int blocks = rollout_blocks(A0, A1, sm_count());
+    void *scr = nullptr;
+    rc = scratch_for(st, sizeof(double) * (size_t)blocks * (size_t)n_steps, &scr);
+    if (rc) return rc;
+    return launch_rollout(library_id, U, A0, A1, P.c, coef, n_steps, work, (double *)scr, blocks, rmse_out, st);
+}
+
 int pg_synth_field(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total, uint64_t seed,
                    int kind, double noise, void *stream) {
     if (!U) PG_FAIL(PG_EINVAL, "U is null");

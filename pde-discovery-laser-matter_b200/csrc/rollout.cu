@@ -1,0 +1,94 @@
+// Rollout check of a discovered KS-dialect PDE (ks2d:1804-1838): explicit Euler with the fitted right-hand
+// side, u_hat <- u_hat + DT * sum_k c_k theta_k(u_hat), started from frame 0, and the RMSE of u_hat against
+// the observed frame after every step.  The step after the solve; same stencils as K1 (reference arithmetic,
+// bit-identical to the NumPy evaluation: products and sums are not contracted, terms are added in library
+// order, coefficients with |c| < 1e-12 are skipped as the reference does).
+//
+// One launch per Euler step (a step needs the whole previous frame: a grid-wide dependency); a frame fits L2
+// (33 MB at 2048^2), so the 13-point stencil reads come from L2.  Squared-error partial sums go to
+// [blocks][steps] and are reduced once, in a fixed order, at the end.
+#include <math.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace pg {
+
+constexpr int RO_THREADS = 256;
+
+template <int LIB>
+__global__ void __launch_bounds__(RO_THREADS) rollout_step_kernel(const double *__restrict__ u_in, double *__restrict__ u_out,
+                                                                  const double *__restrict__ ref, int64_t A0, int64_t A1,
+                                                                  FdConsts c, const double *__restrict__ coef, int step,
+                                                                  int n_steps, double *__restrict__ partials) {
+    constexpr int p = Lib<LIB>::P;
+    __shared__ double sh[RO_THREADS];
+    double cf[p];
+#pragma unroll
+    for (int k = 0; k < p; ++k) cf[k] = coef[k];
+    const int64_t total = A0 * A1;
+    double se = 0.0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        PointVals v;
+        ks_point<Lib<LIB>::BIH>(u_in, A0, A1, idx / A1, idx % A1, c, v);
+        double row[p];
+        lib_row<LIB>(v, row);
+        double rhs = 0.0;   // out = zeros; out += c * v in library order (ks2d:1824-1830)
+#pragma unroll
+        for (int k = 0; k < p; ++k)
+            if (!(fabs(cf[k]) < 1e-12)) rhs = __dadd_rn(rhs, __dmul_rn(cf[k], row[k]));
+        const double un = __dadd_rn(v.u, __dmul_rn(c.dt, rhs));
+        u_out[idx] = un;
+        const double d = __dsub_rn(ref[idx], un);
+        se = __dadd_rn(se, __dmul_rn(d, d));
+    }
+    sh[threadIdx.x] = se;
+    __syncthreads();
+    for (int w = RO_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * n_steps + step] = sh[0];
+}
+
+__global__ void rollout_finish_kernel(double *__restrict__ rmse, int n_steps, double n_points) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_steps) rmse[k] = sqrt(rmse[k] / n_points);
+}
+
+template <int LIB>
+static int rollout_t(const double *U, int64_t A0, int64_t A1, const FdConsts &c, const double *coef, int n_steps,
+                     double *work, double *partials, int blocks, double *rmse, cudaStream_t st) {
+    const int64_t frame = A0 * A1;
+    for (int k = 0; k < n_steps; ++k) {
+        const double *in = k == 0 ? U : work + (int64_t)((k - 1) & 1) * frame;
+        double *out = work + (int64_t)(k & 1) * frame;
+        rollout_step_kernel<LIB><<<blocks, RO_THREADS, 0, st>>>(in, out, U + (int64_t)(k + 1) * frame, A0, A1, c, coef, k,
+                                                                n_steps, partials);
+        PG_LAUNCHED();
+    }
+    int rc = launch_reduce_partials(partials, blocks, n_steps, rmse, 0, st);
+    if (rc) return rc;
+    rollout_finish_kernel<<<(n_steps + 127) / 128, 128, 0, st>>>(rmse, n_steps, (double)frame);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
+int rollout_blocks(int64_t A0, int64_t A1, int n_sm) {
+    int64_t g = (A0 * A1 + RO_THREADS - 1) / RO_THREADS;
+    const int64_t cap = (int64_t)n_sm * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int launch_rollout(int lib, const double *U, int64_t A0, int64_t A1, const FdConsts &c, const double *coef, int n_steps,
+                   double *work, double *partials, int blocks, double *rmse, cudaStream_t st) {
+    switch (lib) {
+        case PG_LIB_KS_TRUE: return rollout_t<PG_LIB_KS_TRUE>(U, A0, A1, c, coef, n_steps, work, partials, blocks, rmse, st);
+        case PG_LIB_KS_TRUE_ADV: return rollout_t<PG_LIB_KS_TRUE_ADV>(U, A0, A1, c, coef, n_steps, work, partials, blocks, rmse, st);
+        case PG_LIB_KS_RICH: return rollout_t<PG_LIB_KS_RICH>(U, A0, A1, c, coef, n_steps, work, partials, blocks, rmse, st);
+        case PG_LIB_KS_RICH_NOADV: return rollout_t<PG_LIB_KS_RICH_NOADV>(U, A0, A1, c, coef, n_steps, work, partials, blocks, rmse, st);
+        default: PG_FAIL(PG_EINVAL, "library %d does not belong to the KS dialect", lib);
+    }
+}
+
+}  // namespace pg

@@ -141,6 +141,17 @@ def stridge_sign_constrained(X, y, *, alpha: float = 1e-3, threshold: float = 1e
     return _np(out["coef"])[0, 0, 0]
 
 
+def rollout_errors(U, dx, dy, DT, names, coeffs, n_steps: int = 50):
+    """ks2d:1804-1838: explicit-Euler rollout of the discovered PDE from U[0]; RMSE against U[k+1] per step.
+    ``names`` selects the library (true / true+advection / rich / rich without advection)."""
+    names = list(names)
+    lib = next((l for l, nm in _LIB_OF.values() if list(nm) == names), None)
+    if lib is None:
+        raise ValueError(f"no KS library with columns {names}")
+    n = int(min(n_steps, np.asarray(U).shape[0] - 1))       # ks2d:1832
+    return _np(ops.ks_rollout(U, dx, dy, DT, coeffs, n, library=lib))
+
+
 # ------------------------------------------------------------------ fused path (ks2d:1508-1743)
 def library_of(dictionary: str, include_advection: bool = False, enforce_no_advection: bool = False):
     if dictionary == "true":

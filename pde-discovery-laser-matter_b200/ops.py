@@ -195,6 +195,23 @@ def stridge_batched(stats, p, *, dialect, alphas, thresholds, max_iter, flags=0,
     return dict(coef=coef, metrics=metrics, best=best)
 
 
+def ks_rollout(U, d0, d1, dt, coef, n_steps, *, library):
+    """pg_ks_rollout: explicit-Euler rollout of the fitted PDE from frame 0 (ks2d:1804-1838) -> rmse [n_steps]."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, A0, A1 = U.shape
+    coef = _dev(np.asarray(coef, dtype=np.float64) if not isinstance(coef, torch.Tensor) else coef, torch.float64).reshape(-1)
+    if coef.numel() != L.LIB_WIDTH[library]:
+        raise ValueError("one coefficient per library column")
+    n_steps = int(n_steps)
+    work = torch.empty((2, A0, A1), dtype=torch.float64, device=U.device)
+    rmse = torch.empty((max(n_steps, 0),), dtype=torch.float64, device=U.device)
+    L.check(lib.pg_ks_rollout(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), library, L.ptr(coef), n_steps,
+                              L.ptr(work), L.ptr(rmse) if n_steps > 0 else None, L.stream_ptr()))
+    return rmse
+
+
 def synth_field(T, A0, A1, *, t_offset=0, T_total=None, seed=0, kind=0, noise=0.0, out=None):
     """pg_synth_field: synthetic benchmark stack generated in HBM (no host transfer)."""
     torch = L.torch_cuda()

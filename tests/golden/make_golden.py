@@ -134,6 +134,39 @@ def _parse_main(text: str):
     return res
 
 
+def golden_ks2d_rollout(ks):
+    """Rollout check of main() (ks2d:1804-1838) at full precision: main() calls rmse() on 1-D arrays of
+    Nx*Ny values only inside the rollout loop, so a recording wrapper around the module's rmse captures the
+    50 per-step errors (and the last u_hat) of C1, C2 and C2+rich+sweep exactly as the script computes them."""
+    runs = {
+        "c1": [],
+        "c2": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05"],
+        "c2_rich_sweep": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05",
+                          "--dictionary", "rich", "--grid-search"],
+    }
+    out = {}
+    orig = ks.rmse
+    for tag, argv in runs.items():
+        rec = []
+
+        def spy(a, b, _rec=rec):
+            v = orig(a, b)
+            if np.asarray(a).ndim == 1 and np.asarray(a).size == 100 * 100:
+                _rec.append((float(v), float(np.asarray(b).sum())))
+            return v
+
+        ks.rmse = spy
+        try:
+            text = _run_main(ks, argv)
+        finally:
+            ks.rmse = orig
+        m = re.search(r"Rollout RMSE over (\d+) steps: first=([\d.eE+-]+), last=([\d.eE+-]+), mean=([\d.eE+-]+)", text)
+        out[tag] = {"argv": argv, "n_steps": int(m.group(1)), "printed": [float(m.group(k)) for k in (2, 3, 4)],
+                    "errs": [r[0] for r in rec], "u_hat_sum_last": rec[-1][1]}
+        assert len(rec) == out[tag]["n_steps"]
+    (OUT / "ks2d_rollout.json").write_text(json.dumps(out, indent=1))
+
+
 def golden_ks2d_configs(ks):
     """C1 / C2 / C2+rich+sweep exactly as main() runs them."""
     runs = {
@@ -301,6 +334,7 @@ def main():
     golden_basic(ba)
     golden_patch(pa)
     golden_ks2d_configs(ks)
+    golden_ks2d_rollout(ks)
     for f in sorted(OUT.glob("*.npz")) + sorted(OUT.glob("*.json")):
         print(f.name, f.stat().st_size)
 

@@ -293,3 +293,24 @@ def test_stridge_sign_constrained_matches_reference():
                           gs[f"{tag}_iter0"])
     with pytest.raises(ValueError):
         K.stridge_sign_constrained(g["bw111_X_true"], g["bw111_y"], signs=[2, 0, 0])
+
+
+@pytest.mark.parametrize("tag", ["c1", "c2", "c2_rich_sweep"])
+def test_rollout_on_gpu_matches_reference_main(tag, golden_configs, ks_default_stack):
+    """pg_ks_rollout (explicit Euler with the fitted right-hand side, ks2d:1804-1838) against the per-step
+    RMSEs of the reference's own main() and against the oracle: same arithmetic per point (bit-identical
+    u_hat), only the order of the squared-error sum differs."""
+    import json
+
+    from conftest import GOLDEN
+    from pde_b200 import ks2d as K
+    from test_oracle_golden import _rollout_case
+
+    g = json.loads((GOLDEN / "ks2d_rollout.json").read_text())[tag]
+    Uo, dx, dy, DT, names, coef = _rollout_case(tag, golden_configs, ks_default_stack)
+    errs = K.rollout_errors(Uo, dx, dy, DT, names, coef, 50)
+    np.testing.assert_allclose(errs, g["errs"], rtol=1e-10, atol=0)
+    np.testing.assert_allclose(errs, O.rollout_errors(Uo, dx, dy, DT, names, coef, 50), rtol=1e-10, atol=0)
+    assert K.rollout_errors(Uo[:4], dx, dy, DT, names, coef, 50).shape == (3,)      # ks2d:1832: min(steps, T-1)
+    with pytest.raises(ValueError):
+        K.rollout_errors(Uo[:4], dx, dy, DT, ["u", "nonsense"], [1.0, 2.0])

@@ -296,3 +296,31 @@ def test_sign_constrained_rows_and_stats_match_reference(golden_ks2d, golden_sig
     np.testing.assert_allclose(none, g[f"{tag}_none"], rtol=1e-9)
     it0 = ks2d.stridge_sign_constrained(X, y, alpha=1e-3, threshold=1e-6, max_iter=0, signs=[-1] * p)
     np.testing.assert_allclose(it0, g[f"{tag}_iter0"], rtol=1e-9)
+
+
+# --------------------------------------------------------------------------- rollout check
+def _rollout_case(tag, golden_configs, ks_default_stack):
+    from oracle import ks2d
+
+    U, dx, dy, DT = ks_default_stack
+    Uo = U if tag == "c1" else ks2d.add_noise(U, 0.05)
+    fp, hyper = golden_configs["full_precision"][tag], golden_configs[tag]["hyper"]
+    best = [r for r in fp["table"] if r["alpha"] == hyper["alpha"] and r["threshold"] == hyper["threshold"]][0]
+    return Uo, dx, dy, DT, fp["names"], np.array(best["coeffs"])
+
+
+@pytest.mark.parametrize("tag", ["c1", "c2", "c2_rich_sweep"])
+def test_rollout_matches_reference_main(tag, golden_configs, ks_default_stack):
+    """oracle.ks2d.rollout_errors against the 50 per-step RMSEs the reference's main() computed (captured at
+    full precision by tests/golden/make_golden.py): bit-identical arithmetic."""
+    import json
+
+    from conftest import GOLDEN
+    from oracle import ks2d
+
+    g = json.loads((GOLDEN / "ks2d_rollout.json").read_text())[tag]
+    Uo, dx, dy, DT, names, coef = _rollout_case(tag, golden_configs, ks_default_stack)
+    errs = ks2d.rollout_errors(Uo, dx, dy, DT, names, coef, 50)
+    assert len(errs) == g["n_steps"] == 50
+    np.testing.assert_allclose(errs, g["errs"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose([errs[0], errs[-1], errs.mean()], g["printed"], rtol=2e-3)
