@@ -58,6 +58,109 @@ __global__ void __launch_bounds__(PW * 32) poly_rows_kernel(const TIn *__restric
     }
 }
 
+// Fast path for neighbourhoods of at most 256 taps (the script's default rt = 2, rs = 3: 245 taps).  The stencil
+// is the same for every point, so each lane keeps its (up to) 8 taps -- offsets and the 6 x 8 weights -- in
+// REGISTERS for the whole kernel: per point a lane issues 8 independent gathers and 48 FMAs, with no shared
+// memory and no index arithmetic.  NPT points are in flight per warp (NPT x 8 gathers per lane outstanding), and
+// the six accumulators are reduced with a packed butterfly (half of the lanes take over half of the values at
+// each step: 8 shuffles instead of 30).
+constexpr int PNE = 8;   // taps per lane
+constexpr int NPT = 4;   // points in flight per warp
+
+__device__ __forceinline__ void reduce6(double (&a)[6], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    // xor 16: bit4 = 0 keeps a0..a2, bit4 = 1 keeps a3..a5
+    double k0 = b4 ? a[3] : a[0], k1 = b4 ? a[4] : a[1], k2 = b4 ? a[5] : a[2];
+    k0 += __shfl_xor_sync(0xffffffffu, b4 ? a[0] : a[3], 16);
+    k1 += __shfl_xor_sync(0xffffffffu, b4 ? a[1] : a[4], 16);
+    k2 += __shfl_xor_sync(0xffffffffu, b4 ? a[2] : a[5], 16);
+    // xor 8: bit3 = 0 keeps (k0, k1), bit3 = 1 keeps k2
+    const double r = __shfl_xor_sync(0xffffffffu, b3 ? k0 : k2, 8);
+    const double r2 = __shfl_xor_sync(0xffffffffu, k1, 8);
+    double m0 = b3 ? k2 + r : k0 + r, m1 = k1 + r2;
+    // xor 4: bit3 = 0: bit2 = 0 keeps m0, bit2 = 1 keeps m1; bit3 = 1: plain add of m0
+    const double snd = b3 ? m0 : (b2 ? m0 : m1);
+    double m = (b3 ? m0 : (b2 ? m1 : m0)) + __shfl_xor_sync(0xffffffffu, snd, 4);
+    m += __shfl_xor_sync(0xffffffffu, m, 2);
+    m += __shfl_xor_sync(0xffffffffu, m, 1);
+    // value q now lives in lanes {0, 4, 8, 16, 20, 24}[q] (and their low-bit neighbours)
+    a[0] = __shfl_sync(0xffffffffu, m, 0);  a[1] = __shfl_sync(0xffffffffu, m, 4);  a[2] = __shfl_sync(0xffffffffu, m, 8);
+    a[3] = __shfl_sync(0xffffffffu, m, 16); a[4] = __shfl_sync(0xffffffffu, m, 20); a[5] = __shfl_sync(0xffffffffu, m, 24);
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(PW * 32) poly_rows_reg_kernel(const TIn *__restrict__ U, int64_t T, int64_t H, int64_t W,
+                                                               const int32_t *__restrict__ pts, int64_t n,
+                                                               const double *__restrict__ W6, int rt, int rs, int mode,
+                                                               double *__restrict__ X, double *__restrict__ y,
+                                                               unsigned long long *counters) {
+    const int side = 2 * rs + 1, nnb = (2 * rt + 1) * side * side;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = mode == 1 ? 8 : 6;
+    int64_t off[PNE];
+    double w[6][PNE];
+#pragma unroll
+    for (int k = 0; k < PNE; ++k) {
+        const int e = lane + 32 * k;
+        const bool has = e < nnb;
+        const int ee = has ? e : 0;
+        const int ox = ee % side, oy = (ee / side) % side, ot = ee / (side * side);
+        off[k] = ((int64_t)ot * H + oy) * W + ox;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) w[q][k] = has ? W6[q * nnb + e] : 0.0;   // absent taps: a valid address, weight 0
+    }
+    auto emit = [&](int64_t k, bool ok, double (&acc)[6]) {
+        reduce6(acc, lane);
+        if (lane != 0) return;
+        if (!ok) {  // the reference would raise on an out-of-range neighbourhood; poison the row
+            for (int c = 0; c < p; ++c) X[k * p + c] = nan("");
+            y[k] = nan("");
+            atomicAdd(&counters[1], 1ull);
+            return;
+        }
+        const double u = acc[0], ux = acc[2], uy = acc[3], lap = __dadd_rn(acc[4], acc[5]);
+        double *r = X + k * p;
+        if (mode == 2) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) r[q] = acc[q];
+        } else {
+            r[0] = 1.0; r[1] = u; r[2] = ux; r[3] = uy; r[4] = lap; r[5] = __dmul_rn(u, u);
+            if (mode == 1) { r[6] = __dmul_rn(u, ux); r[7] = __dmul_rn(u, uy); }
+        }
+        y[k] = acc[1];
+    };
+    auto base_of = [&](int64_t k, bool &ok) {
+        const int64_t t0 = pts[3 * k], y0 = pts[3 * k + 1], x0 = pts[3 * k + 2];
+        ok = t0 - rt >= 0 && t0 + rt < T && y0 - rs >= 0 && y0 + rs < H && x0 - rs >= 0 && x0 + rs < W;
+        return ok ? ((t0 - rt) * H + (y0 - rs)) * W + (x0 - rs) : (int64_t)0;
+    };
+    const int64_t stride = (int64_t)gridDim.x * PW;
+    for (int64_t k = (int64_t)blockIdx.x * PW + warp; k < n; k += NPT * stride) {
+        bool ok[NPT];
+        int64_t kk[NPT], base[NPT];
+        double v[NPT][PNE];
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            kk[j] = k + j * stride;
+            ok[j] = false;
+            base[j] = kk[j] < n ? base_of(kk[j], ok[j]) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < NPT; ++j)
+#pragma unroll
+            for (int e = 0; e < PNE; ++e) v[j][e] = ok[j] ? (double)U[base[j] + off[e]] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int e = 0; e < PNE; ++e)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) acc[q] = fma(w[q][e], v[j][e], acc[q]);
+            if (kk[j] < n) emit(kk[j], ok[j], acc);
+        }
+    }
+}
+
 int launch_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, const int32_t *pts, int64_t n,
                      const double *W6, int rt, int rs, int mode, double *X, double *y, unsigned long long *counters,
                      cudaStream_t st) {
@@ -66,6 +169,16 @@ int launch_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, 
     const size_t smem = sizeof(double) * 6 * nnb;
     int64_t g = (n + PW - 1) / PW;
     if (g > 148 * 8) g = 148 * 8;
+    if (nnb <= 32 * PNE) {   // taps fit the per-lane registers
+        int64_t gr = (n + NPT * PW - 1) / (NPT * PW);
+        if (gr > 148 * 2) gr = 148 * 2;
+        if (dtype == 0)
+            poly_rows_reg_kernel<float><<<(unsigned)gr, PW * 32, 0, st>>>((const float *)U, T, H, W, pts, n, W6, rt, rs, mode, X, y, counters);
+        else
+            poly_rows_reg_kernel<double><<<(unsigned)gr, PW * 32, 0, st>>>((const double *)U, T, H, W, pts, n, W6, rt, rs, mode, X, y, counters);
+        PG_LAUNCHED();
+        return PG_OK;
+    }
     if (dtype == 0) {
         PG_CUDA(cudaFuncSetAttribute(poly_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         poly_rows_kernel<float><<<(unsigned)g, PW * 32, smem, st>>>((const float *)U, T, H, W, pts, n, W6, rt, rs, mode,
