@@ -169,7 +169,11 @@ class ClockSampler:
         if self.h is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
         self.run = False
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["sampler disabled"]}
         self.thread.join(timeout=2)
+        if os.environ.get("PG_BENCH_CLOCK_TRACE"):
+            print("clock trace (sm MHz, W, reasons):", [(r[0], round(r[1]), hex(r[2])) for r in self.rows], file=sys.stderr)
         sm = [r[0] for r in self.rows]
         bits = 0
         for r in self.rows:
@@ -339,7 +343,7 @@ def run_ours(args):
     # ---- main timed region
     sampler = ClockSampler(local)
     launches0 = lib.pg_launch_count()
-    if rank == 0:
+    if rank == 0 and not os.environ.get("PG_BENCH_NO_SAMPLER"):
         sampler.start()
     for _ in range(args.warmup):
         step()

@@ -100,6 +100,24 @@ def test_tiled_many_time_folds(env):
         assert_stats_close(til[f], gen[f], 9)
 
 
+def test_tiled_row_folds_single_fold_and_two_frames(env):
+    """Degenerate layouts: fold_of_row with a single fold (all zeros), and the shortest stack that has one
+    t-block (bt + 1 frames)."""
+    L, ops = env
+    U = field(ops, (4, 64, 128), seed=12)
+    fold = np.zeros(8 * 16, dtype=np.uint8)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE_ADV, block=(3, 8, 8), fold_of_row=fold, n_folds=1)
+    gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    til = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    assert til.shape == (1, 28)
+    assert_stats_close(til[0], gen[0], 5)
+    U2 = field(ops, (2, 128, 128), seed=13)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_RICH_NOADV, block=(1, 8, 8))
+    gen = ops.fd_lib_gram(U2, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    til = ops.fd_lib_gram(U2, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    assert_stats_close(til[0], gen[0], 7)
+
+
 def test_tiled_many_chunks_and_determinism(env):
     """A longer stack is cut into frame chunks across persistent CTAs; results are run-to-run
     bit-identical (fixed work assignment, fixed-order reduction: no floating-point atomics)."""

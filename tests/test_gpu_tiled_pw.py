@@ -75,6 +75,25 @@ def test_basic_pointwise_tiled(env, shape):
     assert_stats_close(til, gram.pack_stats(X, y), 6)
 
 
+def test_pointwise_two_frames_and_eight_folds(env):
+    """The shortest stack (one row frame) and the maximum number of folds."""
+    L, ops = env
+    U = field(ops, (2, 96, 128), seed=21)
+    for dialect, lib, p in ((L.FD_KS_PERIODIC, L.LIB_KS_TRUE, 3), (L.FD_BASIC_TRIM, L.LIB_BASIC, 6)):
+        gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=dialect, library=lib, variant=L.VARIANT_GENERIC).cpu().numpy()
+        til = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=dialect, library=lib, variant=L.VARIANT_TILED).cpu().numpy()
+        assert_stats_close(til[0], gen[0], p)
+    T = 33
+    V = field(ops, (T, 48, 128), seed=22)
+    fof = (np.arange(T - 1) // 4).astype(np.int32)           # 8 folds of 4 frames
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE_ADV, fold_of_frame=fof, n_folds=8)
+    gen = ops.fd_lib_gram(V, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    til = ops.fd_lib_gram(V, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    for f in range(8):
+        assert til[f][0] == 4 * 48 * 128
+        assert_stats_close(til[f], gen[f], 5)
+
+
 def test_pointwise_time_folds_and_chunks(env):
     """A long thin stack is cut into many frame chunks; 5 time-holdout folds (fold id per frame) cost a
     flush per fold change; results are run-to-run bit-identical."""

@@ -91,8 +91,36 @@ def full(tag):
     print("\n".join(lines[-28:]))
 
 
+def pointwise(tag):
+    """ncu --set full captures of the tiled pointwise kernel (tools/quick_bench.py --pointwise --frames 256)."""
+    alg = 8 * 256 * 2048 * 2048
+    lines = ["# ncu --set full --clock-control none --import-source on -k regex:k1_tiled_pw -s 2 -c 1  "
+             "python tools/quick_bench.py --pointwise --frames 256 --only <case>",
+             f"# {tag}, B200, 2048x2048x256 fp64, every grid point a row; algorithmic bytes per launch = {alg / 1e9:.2f} GB",
+             "# bound: fp64 issue (64 DFMA/clk/SM), see sm__pipe_fp64_cycles_active"]
+    for rep, what in (("prof_pw_ks.ncu-rep", "KS dialect, true library p = 3"), ("prof_pw_basic.ncu-rep", "basic_usage dialect p = 6")):
+        f = SRC / rep
+        if not f.exists():
+            continue
+        raw = subprocess.run(["ncu", "-i", str(f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            lines.append(f"---- {what}")
+            for w in WANT:
+                if w in hdr:
+                    i = hdr.index(w)
+                    lines.append(f"{w} = {r[i]} {units[i]}")
+            ms = float(r[hdr.index("gpu__time_duration.sum")]) * TIME[units[hdr.index("gpu__time_duration.sum")]]
+            pts = 256 * 2048 * 2048
+            lines.append(f"derived: {pts / (ms / 1e3) / 1e9:.1f} G points/s; algorithmic GB/s = {alg / 1e9 / (ms / 1e3):.1f}")
+    (OUT / f"{tag}_k1_pointwise_ncu_summary.txt").write_text("\n".join(lines) + "\n")
+    print("\n".join(lines[-8:]))
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     OUT.mkdir(exist_ok=True)
     launches(tag)
     full(tag)
+    pointwise(tag)
