@@ -168,6 +168,29 @@ def split_folds(n_rows: int, rng):
     return fold, perm
 
 
+def split_space(extent: int, train_frac: float) -> int:
+    """analyze_results:282-299: index where the spatial hold-out region starts (floor(frac * extent), clipped so
+    that both regions are non-empty)."""
+    if not (0.4 <= train_frac <= 0.9):
+        raise ValueError("SPACE_TRAIN_FRAC should be in [0.4, 0.9]")
+    return max(1, min(extent - 1, int(np.floor(train_frac * extent))))
+
+
+def spatial_fold_of_row(n_row_frames: int, A0: int, A1: int, block=(1, 1, 1), *, split="left_right", train_frac=0.7):
+    """Spatial hold-out folds (analyze_results:282-299, 820-902) as one fold byte per (block) row in K1's row
+    order: 0 = train region, 1 = held-out region.  "left_right" splits the LAST frame axis (columns),
+    "top_bottom" the first one (rows); a block belongs to the region its first point lies in."""
+    bt, b0, b1 = (int(b) for b in block)
+    nbt, nb0, nb1 = -(-n_row_frames // bt), -(-A0 // b0), -(-A1 // b1)
+    if split == "left_right":
+        held = (np.arange(nb1) * b1 >= split_space(A1, train_frac))[None, None, :]
+    elif split == "top_bottom":
+        held = (np.arange(nb0) * b0 >= split_space(A0, train_frac))[None, :, None]
+    else:
+        raise ValueError("split must be 'left_right' or 'top_bottom'")
+    return np.broadcast_to(held, (nbt, nb0, nb1)).astype(np.uint8).reshape(-1)
+
+
 def fit_from_stats(stats_train, stats_test, names, *, alpha=1e-6, threshold=1e-10, grid_search=False, max_iter=25,
                    signs=None):
     """ks2d:1647-1779 on statistics: train-RMS scale, STRidge (or the 5x6 sweep), held-out
@@ -191,7 +214,7 @@ def fit_from_stats(stats_train, stats_test, names, *, alpha=1e-6, threshold=1e-1
 
 def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", include_advection=False,
                    enforce_no_advection=False, block=(3, 8, 8), n_sample=50_000, alpha=1e-6, threshold=1e-10,
-                   grid_search=False, fold_of_frame=None, seed=0, variant=L.VARIANT_AUTO):
+                   grid_search=False, fold_of_frame=None, seed=0, variant=L.VARIANT_AUTO, signs=None):
     """The reference's main() hot path for one config, fused on the GPU.
 
     method="blockwise": K1 forms block means and both folds' Grams in one pass over U; the
@@ -200,6 +223,9 @@ def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", incl
     method="pointwise": the 50 000-point sample (ks2d:1625-1636) is gathered by K1c, then split.
     method="full": every grid point is a row and ``fold_of_frame`` gives time-holdout folds
         (0 = train, 1 = test); this is the large-stack configuration C4/C5.
+    method="blockwise_left_right" / "blockwise_top_bottom": block means with a SPATIAL hold-out region
+        (analyze_results:282-299, 820-902) instead of the random row split.
+    ``signs``: optional sign constraints of stridge_sign_constrained (ks2d:552-600).
     """
     lib, names = library_of(dictionary, include_advection, enforce_no_advection)
     torch = L.torch_cuda()
@@ -224,6 +250,11 @@ def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", incl
             stats = ops.rows_gram(rows[:, 1:].contiguous(), rows[:, 0].contiguous(), fold_of_row=fold, n_folds=2)[0]
             n_rows = rows.shape[0]
         info["X_shape"] = (n_rows, len(names))
+    elif method in ("blockwise_left_right", "blockwise_top_bottom"):
+        fold = spatial_fold_of_row(T - 1, A0, A1, block, split=method[len("blockwise_"):])
+        stats = ops.fd_lib_gram(Ud, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib, block=block, fold_of_row=fold,
+                                n_folds=2, variant=variant)
+        info["X_shape"] = (fold.size, len(names))
     elif method == "pointwise":
         n_total = (T - 1) * A0 * A1
         flat_idx = rng.choice(n_total, size=int(min(n_sample, n_total)), replace=False)
@@ -242,6 +273,7 @@ def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", incl
         info["X_shape"] = ((T - 1) * A0 * A1, len(names))
     else:
         raise ValueError(method)
-    out = fit_from_stats(stats[0], stats[1], names, alpha=alpha, threshold=threshold, grid_search=grid_search)
+    out = fit_from_stats(stats[0], stats[1], names, alpha=alpha, threshold=threshold, grid_search=grid_search,
+                         signs=signs)
     out.update(info, stats=_np(stats))
     return out

@@ -314,3 +314,33 @@ def test_rollout_on_gpu_matches_reference_main(tag, golden_configs, ks_default_s
     assert K.rollout_errors(Uo[:4], dx, dy, DT, names, coef, 50).shape == (3,)      # ks2d:1832: min(steps, T-1)
     with pytest.raises(ValueError):
         K.rollout_errors(Uo[:4], dx, dy, DT, ["u", "nonsense"], [1.0, 2.0])
+
+
+@pytest.mark.parametrize("split", ["left_right", "top_bottom"])
+def test_spatial_holdout_folds(split):
+    """Spatial hold-out regions (analyze_results:282-299) through the tiled block kernel's per-row folds: the
+    statistics of each region equal the oracle's rows restricted to that region, and the fit follows."""
+    from pde_b200 import _lib as L
+    from pde_b200 import ks2d as K
+    from pde_b200 import ops
+
+    U = ops.synth_field(13, 128, 256, seed=31, noise=0.05)
+    Uh = U.cpu().numpy()
+    block = (3, 8, 8)
+    fold = K.spatial_fold_of_row(12, 128, 256, block, split=split, train_frac=0.7)
+    stats = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=block,
+                            fold_of_row=fold, n_folds=2, variant=L.VARIANT_TILED).cpu().numpy()
+    _, X, y = ks_rows(Uh, 0.5, 0.5, 1e-3, "true", False, block)
+    jb, ib = np.meshgrid(np.arange(32), np.arange(16))
+    held = (jb * 8 >= K.split_space(256, 0.7)) if split == "left_right" else (ib * 8 >= K.split_space(128, 0.7))
+    held = np.broadcast_to(held[None], (4, 16, 32)).reshape(-1)
+    assert np.array_equal(held.astype(np.uint8), fold)
+    for f in range(2):
+        assert_stats_close(stats[f], gram.pack_stats(X[held == f], y[held == f]), 3)
+    out = K.fit_from_field(U, 0.5, 0.5, 1e-3, method=f"blockwise_{split}", dictionary="true", grid_search=True)
+    ref = gram.ks_fit_from_stats(gram.pack_stats(X[~held], y[~held]), gram.pack_stats(X[held], y[held]), 3,
+                                 alphas=K.GRID_ALPHAS, thresholds=K.GRID_THRESHOLDS)
+    assert (out["alpha"], out["threshold"]) == (ref["alpha"], ref["threshold"])
+    assert_coef_close(out["coeffs"], ref["coeffs"], what=split)
+    with pytest.raises(ValueError):
+        K.split_space(100, 0.95)
