@@ -353,7 +353,11 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         int64_t tb0;
         geometry(item, i0, j0, tb0, nf);
         const int64_t t0 = tb0 * P.bt;
-        const bool need_top = i0 == 0 && warp == 0, need_bot = i0 + TI == P.A0 && warp == NW - 1;
+        // a ragged last tile row (A0 a multiple of 8 but not of 64): only the first vrows / 8 bands hold blocks; the
+        // periodic wrap rows then sit inside the TMA box, right below the last valid band
+        const int vrows = (int)min((int64_t)TI, P.A0 - i0);
+        const bool band_ok = warp * 8 < vrows;
+        const bool need_top = i0 == 0 && warp == 0, need_bot = i0 + TI >= P.A0 && warp == (vrows >> 3) - 1;
 
         // side cells of this warp's window (stage rows 8*warp .. 8*warp+11): lanes 0..23 one halo-column cell
         // each; the wrap rows TMA zero-filled (stage rows 0,1 / TI+2,TI+3) belong to the first / last band.
@@ -366,8 +370,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         }
         const int64_t top_src = wrap((int64_t)i0 - 2, P.A0) * P.A1 + j0;      // rows i0-2, i0-1 (consecutive mod A0 when A0 >= 2)
         const int64_t top_src1 = wrap((int64_t)i0 - 1, P.A0) * P.A1 + j0;
-        const int64_t bot_src = wrap((int64_t)i0 + TI, P.A0) * P.A1 + j0;
-        const int64_t bot_src1 = wrap((int64_t)i0 + TI + 1, P.A0) * P.A1 + j0;
+        const int64_t bot_src = wrap((int64_t)i0 + vrows, P.A0) * P.A1 + j0;
+        const int64_t bot_src1 = wrap((int64_t)i0 + vrows + 1, P.A0) * P.A1 + j0;
         auto issue_halo = [&](double *stage, int64_t t) {
             if (h_off >= 0) cp_async16(stage + h_off, P.U + t * frame + h_src);
         };
@@ -380,10 +384,10 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                 cp_async16(stage + TJ + swz_cell(lane + 32), Ft + top_src1 + 64 + 2 * lane);
             }
             if (need_bot) {
-                cp_async16(stage + (TI + 2) * TJ + swz_cell(lane), Ft + bot_src + 2 * lane);
-                cp_async16(stage + (TI + 2) * TJ + swz_cell(lane + 32), Ft + bot_src + 64 + 2 * lane);
-                cp_async16(stage + (TI + 3) * TJ + swz_cell(lane), Ft + bot_src1 + 2 * lane);
-                cp_async16(stage + (TI + 3) * TJ + swz_cell(lane + 32), Ft + bot_src1 + 64 + 2 * lane);
+                cp_async16(stage + (vrows + 2) * TJ + swz_cell(lane), Ft + bot_src + 2 * lane);
+                cp_async16(stage + (vrows + 2) * TJ + swz_cell(lane + 32), Ft + bot_src + 64 + 2 * lane);
+                cp_async16(stage + (vrows + 3) * TJ + swz_cell(lane), Ft + bot_src1 + 2 * lane);
+                cp_async16(stage + (vrows + 3) * TJ + swz_cell(lane + 32), Ft + bot_src1 + 64 + 2 * lane);
             }
         };
         // first frame of the item: its stage has landed => every warp released the stage's previous frame
@@ -422,8 +426,10 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             __syncwarp();
 
             Sums F;
-            if (f < nf) march_frame<LIB>(st, lm, P, F);
-            else F.SU = sum_frame_u(st, lm);
+            if (band_ok) {
+                if (f < nf) march_frame<LIB>(st, lm, P, F);
+                else F.SU = sum_frame_u(st, lm);
+            }
 
             // release the stage (this warp has read everything it needs from load G); the warp whose arrival
             // completes the phase re-arms it with the load NSTAGE ahead.  Only the wrap rows are generic-proxy
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             }
             if (++cs == NSTAGE) { cs = 0; cph ^= 1; }
 
-            if (fb == 0 && f > 0) {
+            if (fb == 0 && f > 0 && band_ok) {
                 double SY = F.SU - su_first;
 #define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 8)
                 PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                     }
                 }
             }
-            if (f < nf) {
+            if (f < nf && band_ok) {
                 if (fb == 0) {
                     su_first = F.SU;
                     ++tbs;
@@ -565,7 +571,8 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     const int NW = DNW;
     const int TI = 8 * NW;
     const int workers = n_sm;
-    const int64_t nt0 = P.A0 / TI, nt1 = P.A1 / TJ;
+    // tile rows: a ragged last one is handled in-kernel when it still consists of whole blocks
+    const int64_t nt0 = P.A0 % 8 == 0 ? (P.A0 + TI - 1) / TI : P.A0 / TI, nt1 = P.A1 / TJ;
     const int64_t nbt = (P.T - 1) / P.bt;   // full t-blocks only; a ragged last one goes to the generic kernel
     if (nt0 < 1 || nt1 < 1 || nbt < 1) return false;
     if (P.T > 0x7fffffff || P.A0 > 0x7fffffff || P.A1 > 0x7fffffff) return false;
@@ -583,7 +590,7 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
         if (cost < best_cost - 1e-9) { best_cost = cost; best_c = cc; }
     }
     const int64_t ctb = (nbt + best_c - 1) / best_c;
-    plan.nbt = nbt; plan.nb0 = nt0 * (TI / 8); plan.nb1 = nt1 * (TJ / 8);
+    plan.nbt = nbt; plan.nb0 = P.A0 % 8 == 0 ? P.A0 / 8 : nt0 * (TI / 8); plan.nb1 = nt1 * (TJ / 8);
     plan.chunk_t = (int)ctb; plan.n_chunks = (nbt + ctb - 1) / ctb;
     plan.n_tiles0 = nt0; plan.n_tiles1 = nt1;
     const int64_t items = n_tiles * plan.n_chunks;

@@ -33,7 +33,10 @@ def field(ops, shape, seed):
                                       ((10, 128, 256), 3),    # 2 x 2 tiles, three t-blocks
                                       ((9, 72, 144), 3),      # remainder rows/cols + ragged t -> generic boxes
                                       ((6, 64, 384), 1),      # bt = 1, three tiles in a row
-                                      ((12, 192, 128), 5)])   # bt = 5, three tiles in a column, ragged t
+                                      ((12, 192, 128), 5),    # bt = 5, three tiles in a column, ragged t
+                                      ((7, 88, 128), 3),      # ragged last tile row (88 = 64 + 24): wrap rows inside the box
+                                      ((7, 40, 256), 3),      # a single ragged tile row: top and bottom wrap in one tile
+                                      ((7, 1080 // 8 * 8 // 5, 128), 3)])   # 216 rows = 3 x 64 + 24
 def test_tiled_vs_generic_and_oracle(env, libname, shape, bt):
     L, ops = env
     lib = getattr(L, libname)
@@ -70,6 +73,17 @@ def test_tiled_folds(env):
     for f in range(2):
         assert_stats_close(til[f], gen[f], 9)
     assert til[0][0] == 2 * 16 * 32 and til[1][0] == 16 * 32
+
+
+def test_tiled_row_folds_on_ragged_tile_rows(env):
+    L, ops = env
+    U = field(ops, (10, 88, 256), seed=14)
+    fold = np.random.default_rng(3).integers(0, 2, size=3 * 11 * 32).astype(np.uint8)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8), fold_of_row=fold, n_folds=2)
+    gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    til = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    for f in range(2):
+        assert_stats_close(til[f], gen[f], 3)
 
 
 def test_tiled_many_time_folds(env):
