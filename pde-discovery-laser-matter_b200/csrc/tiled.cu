@@ -66,7 +66,8 @@ struct TiledParams {
     unsigned int *epoch_done;
     int n_epochs, epoch_shift, epoch_lead;
     int n_tiles0, n_tiles1, n_chunks, chunk_tb;
-    int64_t nbt;              // t-blocks covered
+    int64_t nbt;              // t-blocks covered (the last one may hold fewer than bt frames)
+    int64_t n_row_frames;     // T - 1
     int64_t nB0, nB1;         // block counts of the whole row space (row numbering)
     const uint8_t *fold_of_row;
     const int32_t *fold_of_frame;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         i0 = (tile / P.n_tiles1) * TI;
         j0 = (tile % P.n_tiles1) * TJ;
         tb0 = (int64_t)chunk * P.chunk_tb;
-        nf = (int)((min(P.nbt, tb0 + P.chunk_tb) - tb0) * P.bt);
+        nf = (int)(min(P.n_row_frames, (tb0 + P.chunk_tb) * P.bt) - tb0 * P.bt);   // a ragged last t-block is shorter
     };
 
     // load index g of this CTA -> (tile origin, frame); g counts every frame of every item in order
@@ -444,7 +445,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             }
             if (++cs == NSTAGE) { cs = 0; cph ^= 1; }
 
-            if (fb == 0 && f > 0 && band_ok) {
+            // a t-block ends after bt frames, or with the stack (ragged last block: fewer frames, ks2d:384-389)
+            if (((fb == 0 && f > 0) || (f == nf && fb != 0)) && band_ok) {
                 double SY = F.SU - su_first;
 #define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 8)
                 PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
@@ -466,7 +468,16 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                     th[0] = 1.0; th[1] = A.SU; th[2] = A.SU2; th[3] = A.SL; th[4] = bih; th[5] = gsq; th[6] = A.SUL;
                 }
                 A = Sums();
-                bool fin = isfinite(y);
+                double y_ = y;
+                if (fb != 0) {
+                    // ragged block of fb frames: the common scale assumes bt frames per block
+                    const double ratio = (double)P.bt / (double)fb;
+                    y_ *= ratio;
+#pragma unroll
+                    for (int k = 0; k < p; ++k)
+                        if (!(kRich<LIB> && k == 0)) th[k] *= ratio;
+                }
+                bool fin = isfinite(y_);
 #pragma unroll
                 for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
                 bool valid = (lane & 8) == 0;
@@ -489,13 +500,13 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                             for (int ff = 0; ff < NF; ++ff) pacc[ff][e] = NF == 1 ? pacc[ff][e] + v : fma(v, m[ff], pacc[ff][e]);
                         };
                         add(0, 1.0);
-                        add(1, y);
-                        add(2, y * y);
+                        add(1, y_);
+                        add(2, y_ * y_);
                         int e = 3 + 2 * p;
 #pragma unroll
                         for (int i = 0; i < p; ++i) {
                             add(3 + i, th[i]);
-                            add(3 + p + i, th[i] * y);
+                            add(3 + p + i, th[i] * y_);
 #pragma unroll
                             for (int j = i; j < p; ++j) add(e++, th[i] * th[j]);
                         }
@@ -506,7 +517,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                         const bool mine = valid && (lm.g >> 1) / SB == h;
                         if (mine) {
                             double *r = ext + ((lm.g >> 1) % SB) * W;
-                            r[0] = 1.0; r[1] = y;
+                            r[0] = 1.0; r[1] = y_;
 #pragma unroll
                             for (int k = 0; k < p; ++k) r[2 + k] = th[k];
                         }
@@ -573,7 +584,7 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     const int workers = n_sm;
     // tile rows: a ragged last one is handled in-kernel when it still consists of whole blocks
     const int64_t nt0 = P.A0 % 8 == 0 ? (P.A0 + TI - 1) / TI : P.A0 / TI, nt1 = P.A1 / TJ;
-    const int64_t nbt = (P.T - 1) / P.bt;   // full t-blocks only; a ragged last one goes to the generic kernel
+    const int64_t nbt = (P.T - 1 + P.bt - 1) / P.bt;   // a ragged last t-block (fewer frames) is handled in-kernel
     if (nt0 < 1 || nt1 < 1 || nbt < 1) return false;
     if (P.T > 0x7fffffff || P.A0 > 0x7fffffff || P.A1 > 0x7fffffff) return false;
     if (!encode_fn()) return false;
@@ -669,7 +680,7 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     }
     tp.n_tiles0 = (int)plan.n_tiles0; tp.n_tiles1 = (int)plan.n_tiles1; tp.n_chunks = (int)plan.n_chunks;
     tp.chunk_tb = plan.chunk_t;
-    tp.nbt = plan.nbt; tp.nB0 = P.nB0; tp.nB1 = P.nB1;
+    tp.nbt = plan.nbt; tp.n_row_frames = P.T - 1; tp.nB0 = P.nB0; tp.nB1 = P.nB1;
     tp.fold_of_row = P.fold_of_row; tp.fold_of_frame = P.fold_of_frame; tp.n_folds = P.n_folds;
     tp.partials = partials; tp.counters = P.counters;
     switch (lib) {
