@@ -463,7 +463,25 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
+        # K3 alone over the whole ensemble with the reference's 5 x 6 (alpha, threshold) sweep: B x 30 fits per launch
+        Xs, ys = ops.poly_rows(U32, tr_d, W6, 2, 3, library=L.LIB_PATCH_FULL)
+        Xs, ys = Xs.view(B, 120, 8), ys.view(B, 120)
+        sh = Xs[:, 0, :].contiguous()
+        st_all, mm_all = ops.rows_gram(Xs, ys, shift=sh, want_minmax=True)
+        k3 = lambda: ops.stridge_batched(st_all[:, 0], 8, dialect=L.STRIDGE_SKLEARN, alphas=alphas, thresholds=thrs,  # noqa: E731
+                                         max_iter=25, colminmax=mm_all[:, 0], shift=sh)
+        for _ in range(2):
+            k3()
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(5):
+            k3()
+        k1.record()
+        torch.cuda.synchronize()
+        ms_k3 = k0.elapsed_time(k1) / 5
         patch = {"workload": f"c3: {Hp}x{Hp}x{Tp} float32 stack, {B} patches x (120 train + 40 test) points, p=8, rt=2 rs=3 deg=3",
+                 "k3_sweep_fits_per_s": B * 30 / (ms_k3 * 1e-3), "k3_sweep_ms": ms_k3,
                  "stridge_fits_per_s": B / (ms * 1e-3), "stencil_points_per_s": B * 160 / (ms * 1e-3), "ms_per_pass": ms}
         if not args.no_cpu:
             from oracle import patch as OP

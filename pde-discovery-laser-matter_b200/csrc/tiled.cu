@@ -181,15 +181,6 @@ __device__ __forceinline__ double sum_frame_u(const double *__restrict__ st, con
 }
 
 // ----------------------------------------------------------------------------- decoupled kernel
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // k1_tiled_b88: the warps are DECOUPLED.
 //   * no warp is "the producer": every warp releases a stage when it has read what it needs (arrive on
 //     empty[s]), and the warp whose arrival completes the phase re-arms it at once with the TMA load

@@ -57,6 +57,12 @@ __device__ __forceinline__ uint32_t mbar_arrive_pending(uint64_t *bar) {
     asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
     return pending;
 }
+// 16-byte asynchronous global -> shared copy (generic proxy); zero = true writes zeros instead (src is not read)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool zero = false) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(zero ? 0 : 16) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 

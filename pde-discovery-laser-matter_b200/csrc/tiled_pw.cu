@@ -274,16 +274,6 @@ __device__ __forceinline__ bool pw_flush(double (&acc)[Pw<LIB>::NACC], unsigned 
     return bad;
 }
 
-// ----------------------------------------------------------------------------- async 16-byte cells
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool zero) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(zero ? 0 : 16) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // The kernel.  Warps are DECOUPLED: there is no block-wide barrier per frame and no producer warp.
 // full[s] (TMA complete_tx) says stage s holds its frame; empty[s] counts the NW warps that are done with
 // it, and the warp whose arrival completes that phase re-arms the stage with the load four frames ahead,
