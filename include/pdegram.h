@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PG_VERSION 101
+#define PG_VERSION 102
 
 #if defined(__GNUC__)
 #define PG_API __attribute__((visibility("default")))
@@ -195,6 +195,18 @@ PG_API int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect
  */
 PG_API int pg_ks_rollout(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
                   int library_id, const double *coef, int n_steps, double *work, double *rmse_out, void *stream);
+
+/*
+ * Optional denoising prologue of the ks2d script (ks2d:1448-1468), the step before the hot path.
+ * pg_time_moving_average: time_smooth_moving_average (ks2d:145-161), reflect-padded moving average along t
+ *   through a sequential cumulative sum; bit-identical to the NumPy formulation.  window odd, out != U.
+ * pg_periodic_conv: one axis of a separable circular convolution, out = sum_k weights[k] * in[.. - offsets[k] ..]
+ *   (periodic); two calls with the taps of the periodic Gaussian ifft(exp(-sigma^2 k^2 / 2)) reproduce
+ *   gaussian_smooth_periodic_2d (ks2d:125-142) without an FFT.  offsets / weights are DEVICE arrays.
+ */
+PG_API int pg_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, void *stream);
+PG_API int pg_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int axis, const int32_t *offsets,
+                     const double *weights, int n_taps, double *out, void *stream);
 
 /*
  * Synthetic field generator for the large benchmark stacks: frames

@@ -202,6 +202,33 @@ def build_blockwise_dataset_loops(Ut, terms, names, *, block_t: int, block_x: in
     return np.stack(rows), np.asarray(ys)
 
 
+# --------------------------------------------------------------------------- optional denoising prologue
+def gaussian_smooth_periodic_2d(frame, sigma_px: float):
+    """ks2d:125-142: multiply the 2-D FFT by exp(-sigma^2 (kx^2 + ky^2) / 2)."""
+    sigma_px = float(sigma_px)
+    if sigma_px <= 0:
+        return frame.astype(np.float64, copy=True)
+    nx, ny = frame.shape
+    kx = 2.0 * np.pi * np.fft.fftfreq(nx)
+    ky = 2.0 * np.pi * np.fft.fftfreq(ny)
+    KX, KY = np.meshgrid(kx, ky, indexing="ij")
+    H = np.exp(-0.5 * (sigma_px ** 2) * (KX ** 2 + KY ** 2))
+    return np.fft.ifft2(np.fft.fft2(frame.astype(np.float64, copy=False)) * H).real
+
+
+def time_smooth_moving_average(U, window: int):
+    """ks2d:145-161: reflect padding, cumulative sum, difference / window."""
+    window = int(window)
+    if window <= 1:
+        return U.astype(np.float64, copy=True)
+    if window % 2 == 0:
+        raise ValueError("time smoothing window must be odd")
+    pad = window // 2
+    U_pad = np.pad(U.astype(np.float64, copy=False), ((pad, pad), (0, 0), (0, 0)), mode="reflect")
+    cs = np.concatenate([np.zeros_like(U_pad[:1]), np.cumsum(U_pad, axis=0)], axis=0)
+    return (cs[window:] - cs[:-window]) / float(window)
+
+
 # --------------------------------------------------------------------------- STRidge
 def standardize_fit(X):
     """ks2d:43-48: column mean and population std; zero std -> 1."""

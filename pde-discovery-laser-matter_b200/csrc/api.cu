@@ -342,6 +342,24 @@ int pg_ks_rollout(const double *U, int64_t T, int64_t A0, int64_t A1, double d0,
     return launch_rollout(library_id, U, A0, A1, P.c, coef, n_steps, work, (double *)scr, blocks, rmse_out, st);
 }
 
+int pg_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, void *stream) {
+    if (!U || !out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (T < 1 || A0 < 1 || A1 < 1) PG_FAIL(PG_EINVAL, "bad shape");
+    if (window < 1 || window % 2 == 0) PG_FAIL(PG_EINVAL, "time smoothing window must be odd");   // ks2d:152-153
+    if (window / 2 > T - 1) PG_FAIL(PG_EINVAL, "reflect padding needs window // 2 <= T - 1");      // np.pad(mode='reflect')
+    if (U == out) PG_FAIL(PG_EINVAL, "in-place smoothing is not supported");
+    return launch_time_moving_average(U, T, A0, A1, window, out, (cudaStream_t)stream);
+}
+
+int pg_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int axis, const int32_t *offsets,
+                     const double *weights, int n_taps, double *out, void *stream) {
+    if (!in || !out || !offsets || !weights) PG_FAIL(PG_EINVAL, "null buffer");
+    if (T < 1 || A0 < 1 || A1 < 1 || n_taps < 1) PG_FAIL(PG_EINVAL, "bad shape");
+    if (axis != 0 && axis != 1) PG_FAIL(PG_EINVAL, "axis must be 0 or 1");
+    if (in == out) PG_FAIL(PG_EINVAL, "in-place convolution is not supported");
+    return launch_periodic_conv(in, T, A0, A1, axis, offsets, weights, n_taps, out, (cudaStream_t)stream);
+}
+
 int pg_synth_field(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total, uint64_t seed,
                    int kind, double noise, void *stream) {
     if (!U) PG_FAIL(PG_EINVAL, "U is null");

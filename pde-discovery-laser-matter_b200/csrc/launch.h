@@ -83,6 +83,11 @@ int launch_stridge(const StridgeParams &P, int32_t *best_out, cudaStream_t st);
 int launch_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, const int32_t *pts, int64_t n, const double *W6, int rt, int rs, int mode, double *X, double *y, unsigned long long *counters, cudaStream_t st);
 int launch_synth(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total, uint64_t seed, int kind, double noise, cudaStream_t st);
 
+// smooth.cu
+int launch_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, cudaStream_t st);
+int launch_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int axis, const int32_t *off, const double *w,
+                         int n_taps, double *out, cudaStream_t st);
+
 // rollout.cu
 int rollout_blocks(int64_t A0, int64_t A1, int n_sm);
 int launch_rollout(int lib, const double *U, int64_t A0, int64_t A1, const FdConsts &c, const double *coef, int n_steps,

@@ -49,6 +49,26 @@ def gradients(f2d, dx: float, dy: float):
     return g[0, 0], g[1, 0]
 
 
+# ------------------------------------------------------------------ optional denoising prologue (ks2d:125-161)
+def gaussian_smooth_periodic_2d(frame, sigma_px: float):
+    """ks2d:125-142: periodic Gaussian low-pass of one frame (sigma in pixels)."""
+    f = np.asarray(frame)
+    if float(sigma_px) <= 0:
+        return f.astype(np.float64, copy=True)
+    return _np(ops.gaussian_smooth_periodic(_frame(f), sigma_px))[0]
+
+
+def time_smooth_moving_average(U, window: int):
+    """ks2d:145-161: reflect-padded moving average along axis 0; window must be odd."""
+    window = int(window)
+    U = np.asarray(U)
+    if window <= 1:
+        return U.astype(np.float64, copy=True)
+    if window % 2 == 0:
+        raise ValueError("time smoothing window must be odd")
+    return _np(ops.time_moving_average(U, window))
+
+
 # ------------------------------------------------------------------ dictionaries (ks2d:1017-1104)
 def _dictionary(U, dx, dy, deriv, key):
     if deriv != "finite":

@@ -212,6 +212,50 @@ def ks_rollout(U, d0, d1, dt, coef, n_steps, *, library):
     return rmse
 
 
+def time_moving_average(U, window):
+    """pg_time_moving_average: reflect-padded moving average along t (ks2d:145-161)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, A0, A1 = U.shape
+    out = torch.empty_like(U)
+    L.check(lib.pg_time_moving_average(L.ptr(U), T, A0, A1, int(window), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def periodic_gaussian_taps(n, sigma_px):
+    """Taps (offsets, weights) of the periodic Gaussian g = ifft(exp(-sigma^2 k^2 / 2)) on n points
+    (ks2d:135-138).  When the transfer function is below 1e-17 at the Nyquist frequency (sigma >= 2.82 px) g is
+    numerically the wrapped Gaussian and is cut where it falls below 1e-17 of its peak; for smaller sigma the
+    spectral cut-off makes g ring with slowly decaying tails and all n taps are kept."""
+    sigma = float(sigma_px)
+    k = 2.0 * np.pi * np.fft.fftfreq(n)
+    g = np.fft.ifft(np.exp(-0.5 * sigma ** 2 * k ** 2)).real
+    r = int(np.ceil(sigma * np.sqrt(2.0 * np.log(1e17)))) + 1
+    if np.exp(-0.5 * sigma ** 2 * np.pi ** 2) < 1e-17 and 2 * r + 1 < n:
+        off = np.arange(-r, r + 1)
+    else:
+        off = np.arange(n)
+    return off.astype(np.int32), g[off % n].astype(np.float64)
+
+
+def gaussian_smooth_periodic(U, sigma_px):
+    """gaussian_smooth_periodic_2d (ks2d:125-142) for every frame of U: two passes of pg_periodic_conv."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, A0, A1 = U.shape
+    if float(sigma_px) <= 0:
+        return U.clone()
+    tmp, out = torch.empty_like(U), torch.empty_like(U)
+    for axis, src, dst, n in ((0, U, tmp, A0), (1, tmp, out, A1)):
+        off, w = periodic_gaussian_taps(n, sigma_px)
+        off_d, w_d = _dev(off), _dev(w)
+        L.check(lib.pg_periodic_conv(L.ptr(src), T, A0, A1, axis, L.ptr(off_d), L.ptr(w_d), len(off), L.ptr(dst),
+                                     L.stream_ptr()))
+    return out
+
+
 def synth_field(T, A0, A1, *, t_offset=0, T_total=None, seed=0, kind=0, noise=0.0, out=None):
     """pg_synth_field: synthetic benchmark stack generated in HBM (no host transfer)."""
     torch = L.torch_cuda()

@@ -134,6 +134,22 @@ def _parse_main(text: str):
     return res
 
 
+def golden_ks2d_smooth(ks):
+    """Optional denoising prologue (ks2d:125-161): periodic Gaussian and reflect-padded time moving average."""
+    rng = np.random.default_rng(21)
+    out = {}
+    for tag, shape in (("a", (100, 100)), ("b", (37, 50)), ("c", (8, 128))):
+        f = rng.standard_normal(shape)
+        out[f"frame_{tag}"] = f
+        for sig in (0.8, 1.5, 4.0):
+            out[f"gauss_{tag}_{sig}"] = ks.gaussian_smooth_periodic_2d(f, sig)
+    U = rng.standard_normal((9, 6, 10))
+    out["stack"] = U
+    for w in (3, 5, 9):
+        out[f"tavg_{w}"] = ks.time_smooth_moving_average(U, w)
+    np.savez_compressed(OUT / "ks2d_smooth.npz", **out)
+
+
 def golden_ks2d_rollout(ks):
     """Rollout check of main() (ks2d:1804-1838) at full precision: main() calls rmse() on 1-D arrays of
     Nx*Ny values only inside the rollout loop, so a recording wrapper around the module's rmse captures the
@@ -335,6 +351,7 @@ def main():
     golden_patch(pa)
     golden_ks2d_configs(ks)
     golden_ks2d_rollout(ks)
+    golden_ks2d_smooth(ks)
     for f in sorted(OUT.glob("*.npz")) + sorted(OUT.glob("*.json")):
         print(f.name, f.stat().st_size)
 

@@ -344,3 +344,24 @@ def test_spatial_holdout_folds(split):
     assert_coef_close(out["coeffs"], ref["coeffs"], what=split)
     with pytest.raises(ValueError):
         K.split_space(100, 0.95)
+
+
+def test_smoothing_prologue_on_gpu():
+    """pg_time_moving_average is bit-identical to the reference's cumulative-sum formulation; the two-pass
+    periodic stencil reproduces gaussian_smooth_periodic_2d (FFT) to rounding (ks2d:125-161)."""
+    from conftest import GOLDEN
+    from pde_b200 import ks2d as K
+
+    g = np.load(GOLDEN / "ks2d_smooth.npz")
+    for w in (3, 5, 9):
+        assert np.array_equal(K.time_smooth_moving_average(g["stack"], w), g[f"tavg_{w}"])
+    assert np.array_equal(K.time_smooth_moving_average(g["stack"], 1), g["stack"])
+    with pytest.raises(ValueError):
+        K.time_smooth_moving_average(g["stack"], 4)
+    for tag in "abc":
+        f = g[f"frame_{tag}"]
+        for sig in (0.8, 1.5, 4.0):
+            ref = g[f"gauss_{tag}_{sig}"]
+            got = K.gaussian_smooth_periodic_2d(f, sig)
+            assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), (tag, sig)
+    assert np.array_equal(K.gaussian_smooth_periodic_2d(g["frame_a"], 0.0), g["frame_a"])

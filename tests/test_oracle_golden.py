@@ -324,3 +324,30 @@ def test_rollout_matches_reference_main(tag, golden_configs, ks_default_stack):
     assert len(errs) == g["n_steps"] == 50
     np.testing.assert_allclose(errs, g["errs"], rtol=1e-12, atol=0)
     np.testing.assert_allclose([errs[0], errs[-1], errs.mean()], g["printed"], rtol=2e-3)
+
+
+# --------------------------------------------------------------------------- denoising prologue
+def test_smoothing_prologue_matches_reference():
+    """oracle restatements of ks2d:125-161 bit for bit, and the separable periodic-Gaussian taps the GPU path
+    uses (no FFT) against the reference's FFT result."""
+    from conftest import GOLDEN
+    from oracle import ks2d
+    from pde_b200.ops import periodic_gaussian_taps
+
+    g = np.load(GOLDEN / "ks2d_smooth.npz")
+    for tag in "abc":
+        f = g[f"frame_{tag}"]
+        for sig in (0.8, 1.5, 4.0):
+            ref = g[f"gauss_{tag}_{sig}"]
+            assert np.array_equal(ks2d.gaussian_smooth_periodic_2d(f, sig), ref)
+            tmp, out = np.zeros_like(f), np.zeros_like(f)
+            for o, w in zip(*periodic_gaussian_taps(f.shape[0], sig)):
+                tmp += w * np.roll(f, o, axis=0)
+            for o, w in zip(*periodic_gaussian_taps(f.shape[1], sig)):
+                out += w * np.roll(tmp, o, axis=1)
+            assert np.abs(out - ref).max() <= 1e-14 * np.abs(ref).max(), (tag, sig)
+    assert len(periodic_gaussian_taps(100, 4.0)[0]) < 100 and len(periodic_gaussian_taps(100, 0.8)[0]) == 100
+    for w in (3, 5, 9):
+        assert np.array_equal(ks2d.time_smooth_moving_average(g["stack"], w), g[f"tavg_{w}"])
+    with pytest.raises(ValueError):
+        ks2d.time_smooth_moving_average(g["stack"], 4)
