@@ -52,3 +52,15 @@ def synthetic_stack(shape, seed=0):
     a = gaussian_filter(np.random.default_rng(seed).standard_normal(shape), sigma=(1, 2, 2))
     a = (a - a.min()) / (a.max() - a.min())
     return a.astype(np.float32)
+
+
+def rollout_case(tag, golden_configs, ks_default_stack):
+    """Inputs of the rollout check of main() for one reference config: the (noisy) stack the script observed
+    and the full-precision coefficients of the configuration it selected."""
+    from oracle import ks2d
+
+    U, dx, dy, DT = ks_default_stack
+    Uo = U if tag == "c1" else ks2d.add_noise(U, 0.05)
+    fp, hyper = golden_configs["full_precision"][tag], golden_configs[tag]["hyper"]
+    best = [r for r in fp["table"] if r["alpha"] == hyper["alpha"] and r["threshold"] == hyper["threshold"]][0]
+    return Uo, dx, dy, DT, fp["names"], np.array(best["coeffs"])

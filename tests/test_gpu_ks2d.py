@@ -304,10 +304,10 @@ def test_rollout_on_gpu_matches_reference_main(tag, golden_configs, ks_default_s
 
     from conftest import GOLDEN
     from pde_b200 import ks2d as K
-    from test_oracle_golden import _rollout_case
+    from helpers import rollout_case
 
     g = json.loads((GOLDEN / "ks2d_rollout.json").read_text())[tag]
-    Uo, dx, dy, DT, names, coef = _rollout_case(tag, golden_configs, ks_default_stack)
+    Uo, dx, dy, DT, names, coef = rollout_case(tag, golden_configs, ks_default_stack)
     errs = K.rollout_errors(Uo, dx, dy, DT, names, coef, 50)
     np.testing.assert_allclose(errs, g["errs"], rtol=1e-10, atol=0)
     np.testing.assert_allclose(errs, O.rollout_errors(Uo, dx, dy, DT, names, coef, 50), rtol=1e-10, atol=0)

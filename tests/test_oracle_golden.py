@@ -299,16 +299,6 @@ def test_sign_constrained_rows_and_stats_match_reference(golden_ks2d, golden_sig
 
 
 # --------------------------------------------------------------------------- rollout check
-def _rollout_case(tag, golden_configs, ks_default_stack):
-    from oracle import ks2d
-
-    U, dx, dy, DT = ks_default_stack
-    Uo = U if tag == "c1" else ks2d.add_noise(U, 0.05)
-    fp, hyper = golden_configs["full_precision"][tag], golden_configs[tag]["hyper"]
-    best = [r for r in fp["table"] if r["alpha"] == hyper["alpha"] and r["threshold"] == hyper["threshold"]][0]
-    return Uo, dx, dy, DT, fp["names"], np.array(best["coeffs"])
-
-
 @pytest.mark.parametrize("tag", ["c1", "c2", "c2_rich_sweep"])
 def test_rollout_matches_reference_main(tag, golden_configs, ks_default_stack):
     """oracle.ks2d.rollout_errors against the 50 per-step RMSEs the reference's main() computed (captured at
@@ -319,7 +309,9 @@ def test_rollout_matches_reference_main(tag, golden_configs, ks_default_stack):
     from oracle import ks2d
 
     g = json.loads((GOLDEN / "ks2d_rollout.json").read_text())[tag]
-    Uo, dx, dy, DT, names, coef = _rollout_case(tag, golden_configs, ks_default_stack)
+    from helpers import rollout_case
+
+    Uo, dx, dy, DT, names, coef = rollout_case(tag, golden_configs, ks_default_stack)
     errs = ks2d.rollout_errors(Uo, dx, dy, DT, names, coef, 50)
     assert len(errs) == g["n_steps"] == 50
     np.testing.assert_allclose(errs, g["errs"], rtol=1e-12, atol=0)
