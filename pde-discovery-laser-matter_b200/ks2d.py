@@ -232,6 +232,40 @@ def fit_from_stats(stats_train, stats_test, names, *, alpha=1e-6, threshold=1e-1
                 coef_grid=coef)
 
 
+def time_fold_of_frame(n_row_frames: int, n_folds: int, block_t: int = 1):
+    """K contiguous time-holdout folds: fold id per row frame, boundaries aligned to whole
+    t-blocks so that no block straddles two folds."""
+    n_tb = -(-n_row_frames // int(block_t))
+    tb_fold = np.minimum(np.arange(n_tb) * int(n_folds) // max(n_tb, 1), n_folds - 1)
+    return np.repeat(tb_fold, int(block_t))[:n_row_frames].astype(np.int32)
+
+
+def fit_time_cv(U, dx, dy, DT, *, n_folds=5, dictionary="true", include_advection=False, enforce_no_advection=False,
+                block=(3, 8, 8), max_iter=25, variant=L.VARIANT_AUTO):
+    """K-fold time-holdout cross-validation of the 5 x 6 (alpha, threshold) sweep (ks2d:1720-1743 applied per
+    fold): ONE pass of K1 over the stack yields the statistics of the K time folds (they cost nothing extra),
+    the K train sets are sums of the other folds' statistics, and one K3 launch fits K x 30 models and scores
+    each on its held-out fold.  Returns the per-fold selections and the configuration with the best mean r2."""
+    lib, names = library_of(dictionary, include_advection, enforce_no_advection)
+    torch = L.torch_cuda()
+    Ud = ops.field(U)
+    T = Ud.shape[0]
+    fof = time_fold_of_frame(T - 1, n_folds, block[0])
+    stats = ops.fd_lib_gram(Ud, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib, block=block, fold_of_frame=fof,
+                            n_folds=n_folds, variant=variant)                      # [K][S]
+    p = len(names)
+    train = torch.stack([stats[[j for j in range(n_folds) if j != k_]].sum(dim=0) for k_ in range(n_folds)])
+    const_cols = [j for j, n in enumerate(names) if n == "1"]
+    out = ops.stridge_batched(train, p, dialect=L.STRIDGE_KS, flags=L.STRIDGE_RMS_PRESCALE, alphas=GRID_ALPHAS,
+                              thresholds=GRID_THRESHOLDS, max_iter=max_iter, const_cols=const_cols, eval_stats=stats)
+    coef, met, best = _np(out["coef"]), _np(out["metrics"]), _np(out["best"])
+    mean_r2 = met[..., 0].mean(axis=0)                                             # [na][nt]
+    ia, it = np.unravel_index(int(np.argmax(mean_r2)), mean_r2.shape)
+    return dict(names=list(names), fold_of_frame=fof, stats=_np(stats), coef_grid=coef, metrics=met,
+                best_per_fold=[divmod(int(b), len(GRID_THRESHOLDS)) for b in best], mean_r2=mean_r2,
+                alpha=GRID_ALPHAS[ia], threshold=GRID_THRESHOLDS[it], coeffs=coef[:, ia, it].mean(axis=0))
+
+
 def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", include_advection=False,
                    enforce_no_advection=False, block=(3, 8, 8), n_sample=50_000, alpha=1e-6, threshold=1e-10,
                    grid_search=False, fold_of_frame=None, seed=0, variant=L.VARIANT_AUTO, signs=None):

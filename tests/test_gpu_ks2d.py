@@ -365,3 +365,28 @@ def test_smoothing_prologue_on_gpu():
             got = K.gaussian_smooth_periodic_2d(f, sig)
             assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), (tag, sig)
     assert np.array_equal(K.gaussian_smooth_periodic_2d(g["frame_a"], 0.0), g["frame_a"])
+
+
+def test_time_holdout_cross_validation():
+    """K = 5 time-holdout folds from one K1 pass; K x 30 fits in one K3 launch; every fold's fit and held-out
+    score against the oracle on the rows of that fold ("also K = 5")."""
+    from pde_b200 import ks2d as K
+    from pde_b200 import ops
+
+    U = ops.synth_field(31, 64, 128, seed=41, noise=0.05)
+    Uh = U.cpu().numpy()
+    block = (3, 8, 8)
+    out = K.fit_time_cv(U, 0.5, 0.5, 1e-3, n_folds=5, dictionary="true", block=block)
+    fof = out["fold_of_frame"]
+    assert fof.shape == (30,) and set(fof) == {0, 1, 2, 3, 4} and all(len(set(fof[3 * k:3 * k + 3])) == 1 for k in range(10))
+    _, X, y = ks_rows(Uh, 0.5, 0.5, 1e-3, "true", False, block)
+    fold_of_row = np.repeat(fof[::3], 8 * 16)
+    for k in range(5):
+        tr, te = fold_of_row != k, fold_of_row == k
+        assert_stats_close(out["stats"][k], gram.pack_stats(X[te], y[te]), 3)
+        ref = gram.ks_fit_from_stats(gram.pack_stats(X[tr], y[tr]), gram.pack_stats(X[te], y[te]), 3,
+                                     alphas=K.GRID_ALPHAS, thresholds=K.GRID_THRESHOLDS)
+        ia, it = out["best_per_fold"][k]
+        assert (K.GRID_ALPHAS[ia], K.GRID_THRESHOLDS[it]) == (ref["alpha"], ref["threshold"])
+        assert_coef_close(out["coef_grid"][k, ia, it], ref["coeffs"], what=f"fold {k}")
+        np.testing.assert_allclose(out["metrics"][k, ia, it, 0], ref["r2_test"], rtol=1e-6, atol=1e-9)
