@@ -156,6 +156,16 @@ PG_API int pg_rows_gram(const double *X, const double *y, int64_t B, int64_t n, 
                  double *colminmax_out, void *stream);
 
 /*
+ * Statistics of B bootstrap resamples of ONE row set (ensemble_stridge, ks2d:603-642): weights [B][n] uint16 holds
+ * how many times resample b drew row i (np.bincount of the reference's rng.choice(n, n_sub, replace=True)); a
+ * resample's Gram is the multiplicity-weighted Gram, so the resampled rows are never materialised.  X [n][ldx],
+ * y [n], shift [p] (nullable) are shared; stats_out [B][PG_STATS_LEN(p)]; colminmax_out [B][2][p] (nullable)
+ * covers only the rows a resample drew.
+ */
+PG_API int pg_rows_gram_weighted(const double *X, const double *y, int64_t n, int p, int64_t ldx, const uint16_t *weights,
+                          int64_t B, const double *shift, double *stats_out, double *colminmax_out, void *stream);
+
+/*
  * K2 -- local-polynomial derivative rows (patch:193-280).  The lstsq fit of patch:231 has a
  * constant design matrix, so it is the fixed stencil W6 [6][(2rt+1)(2rs+1)^2] (rows u, u_t,
  * u_x, u_y, u_xx, u_yy; neighbour order t, y, x with x fastest).  U [T][H][W] is float32

@@ -296,6 +296,22 @@ def stridge_sign_constrained(X, y, *, alpha: float = 1e-3, threshold: float = 1e
     return c / (scale + 1e-12)
 
 
+def ensemble_stridge(X, y, *, alpha: float = 1e-3, threshold: float = 1e-6, max_iter: int = 25, n_bootstrap: int = 50,
+                     subsample_frac: float = 0.7, seed: int = 0, return_all: bool = False):
+    """ks2d:603-642 (use_huber=False): bootstrap resamples with replacement, stridge on each, median / std."""
+    rng = np.random.default_rng(seed)
+    n = len(y)
+    n_sub = max(int(n * subsample_frac), 1)
+    allc = []
+    for _ in range(n_bootstrap):
+        idx = rng.choice(n, size=n_sub, replace=True)
+        allc.append(stridge(X[idx], y[idx], alpha=alpha, threshold=threshold, max_iter=max_iter))
+    allc = np.stack(allc, axis=0)
+    if return_all:
+        return allc
+    return np.median(allc, axis=0), np.std(allc, axis=0)
+
+
 def rollout_errors(U, dx, dy, DT, names, coeffs, n_steps: int = 50):
     """ks2d:1804-1838: u_hat <- u_hat + DT * rhs_from_coeffs(u_hat) from U[0]; rmse(U[k+1], u_hat) per step.
     rhs: out = zeros; for (name, c): skip |c| < 1e-12; out += c * value(name)."""

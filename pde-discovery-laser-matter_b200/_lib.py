@@ -51,6 +51,7 @@ _PROTOS = {
     "pg_fd_gather_rows": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _ptr, _i64, _ptr, _ptr, _ptr]),
     "pg_block_means": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr]),
     "pg_rows_gram": (C.c_int, [_ptr, _ptr, _i64, _i64, _i32, _i64, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "pg_rows_gram_weighted": (C.c_int, [_ptr, _ptr, _i64, _i32, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
     "pg_poly_rows": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _ptr, _i64, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "pg_stridge_batched": (C.c_int, [_ptr, _i64, _i32, _i32, _i32, _ptr, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr,
                                      _ptr, _ptr, _ptr, _ptr, _ptr]),

@@ -289,6 +289,36 @@ int pg_rows_gram(const double *X, const double *y, int64_t B, int64_t n, int p, 
     return launch_rows_gram(R, stats_out, colminmax_out, st);
 }
 
+int pg_rows_gram_weighted(const double *X, const double *y, int64_t n, int p, int64_t ldx, const uint16_t *weights,
+                          int64_t B, const double *shift, double *stats_out, double *colminmax_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p < 1 || p > PG_MAX_P) PG_FAIL(PG_EINVAL, "p must be in 1..%d", PG_MAX_P);
+    if (B < 0 || n < 0 || ldx < p) PG_FAIL(PG_EINVAL, "bad shape B=%lld n=%lld ldx=%lld", (long long)B, (long long)n, (long long)ldx);
+    if (!stats_out || !weights) PG_FAIL(PG_EINVAL, "null buffer");
+    if (B == 0) return PG_OK;
+    if (n > 0 && (!X || !y)) PG_FAIL(PG_EINVAL, "null rows");
+    const int S = PG_STATS_LEN(p);
+    RowsParams R{};
+    R.X = X; R.y = y; R.B = B; R.n = n; R.ldx = ldx; R.p = p; R.fold_of_row = nullptr; R.n_folds = 1;
+    R.shift = shift; R.weights = weights;
+    int64_t chunks = (n + GW_THREADS * 64 - 1) / (GW_THREADS * 64);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (chunks * B > cap) chunks = cap / B;
+    if (chunks < 1) chunks = 1;
+    R.chunks = (int)chunks;
+    const int64_t parts = B * chunks * GW_WARPS;
+    const size_t b_stats = sizeof(double) * (size_t)(parts * S);
+    const size_t b_mm = colminmax_out ? sizeof(double) * (size_t)(parts * 2 * p) : 0;
+    void *scr = nullptr;
+    int rc = scratch_for(st, 64 + b_stats + b_mm, &scr);
+    if (rc) return rc;
+    PG_CUDA(cudaMemsetAsync(scr, 0, 64, st));
+    R.counters = (unsigned long long *)scr;
+    R.partials = (double *)((char *)scr + 64);
+    R.mm_partials = colminmax_out ? (double *)((char *)scr + 64 + b_stats) : nullptr;
+    return launch_rows_gram(R, stats_out, colminmax_out, st);
+}
+
 int pg_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, const int32_t *pts, int64_t n,
                  const double *W6, int rt, int rs, int library_id, double *X_out, double *y_out, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -243,16 +243,23 @@ __global__ void __launch_bounds__(GW * 32) rows_gram_kernel(RowsParams P) {
 
     const int64_t b = blockIdx.x / P.chunks;
     const int chunk = (int)(blockIdx.x % P.chunks);
-    const double *Xb = P.X + b * P.n * P.ldx;
-    const double *yb = P.y + b * P.n;
+    // weighted mode (bootstrap resamples, ks2d:603-642): every problem reads the same rows with its own multiplicities
+    const uint16_t *wb = P.weights ? P.weights + b * P.n : nullptr;
+    const double *Xb = P.X + (wb ? 0 : b * P.n * P.ldx);
+    const double *yb = P.y + (wb ? 0 : b * P.n);
     const uint8_t *fb = P.fold_of_row ? P.fold_of_row + b * P.n : nullptr;
-    const double *sh = P.shift ? P.shift + b * p : nullptr;
+    const double *sh = P.shift ? P.shift + (wb ? 0 : b * p) : nullptr;
     const int64_t stride = (int64_t)P.chunks * GW * 32;
     unsigned long long bad_fold = 0;
     for (int64_t base = ((int64_t)chunk * GW + warp) * 32; base < P.n; base += stride) {
         const int64_t r = base + lane;
         bool valid = r < P.n;
         int fold = 0;
+        double wgt = 1.0;
+        if (valid && wb) {
+            wgt = (double)wb[r];
+            valid = wgt > 0.0;              // rows the resample did not draw do not exist for it (min / max included)
+        }
         ext[lane * W] = 1.0;
         if (valid) {
             ext[lane * W + 1] = yb[r];
@@ -265,9 +272,10 @@ __global__ void __launch_bounds__(GW * 32) rows_gram_kernel(RowsParams P) {
         for (int l = 0; l < 32; ++l) {
             if (!((vmask >> l) & 1u)) continue;
             const int f = __shfl_sync(0xffffffffu, fold, l);
+            const double wl = __shfl_sync(0xffffffffu, wgt, l);
             const double *row = ext + l * W;
             double *acc = wacc + f * S;
-            for (int e = lane; e < S; e += 32) acc[e] = fma(row[pa[e]], row[pb[e]], acc[e]);
+            for (int e = lane; e < S; e += 32) acc[e] = fma(row[pa[e]] * wl, row[pb[e]], acc[e]);
             if (lane < p) {
                 // min/max of the UNSHIFTED column values
                 const double xv = sh ? Xb[(base + l) * P.ldx + lane] : row[2 + lane];

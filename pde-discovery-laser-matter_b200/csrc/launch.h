@@ -37,6 +37,7 @@ struct RowsParams {
     const uint8_t *fold_of_row;  // [B][n] or null
     int n_folds;
     const double *shift;         // [B][p] or null: statistics are of (X - shift)
+    const uint16_t *weights;     // [B][n] or null: row multiplicities (bootstrap resamples); X, y, shift are then SHARED by the B problems
     int chunks;                  // CTAs per problem
     double *partials;            // [B][chunks*GW_WARPS][n_folds][S]
     double *mm_partials;         // [B][chunks*GW_WARPS][n_folds][2][p] or null

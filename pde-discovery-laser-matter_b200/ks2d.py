@@ -161,6 +161,32 @@ def stridge_sign_constrained(X, y, *, alpha: float = 1e-3, threshold: float = 1e
     return _np(out["coef"])[0, 0, 0]
 
 
+def ensemble_stridge(X, y, *, alpha: float = 1e-3, threshold: float = 1e-6, max_iter: int = 25, n_bootstrap: int = 50,
+                     subsample_frac: float = 0.7, seed: int = 0, use_huber: bool = False, huber_delta: float = 1.35):
+    """ks2d:603-642 on the GPU: the reference draws ``rng.choice(n, n_sub, replace=True)`` per bootstrap and
+    fits stridge() on the materialised resample; a resample's Gram is the multiplicity-weighted Gram of the
+    original rows, so here the draws stay on the host RNG (same stream, same order), become a (n_bootstrap, n)
+    count table, one launch forms all weighted statistics and one K3 launch fits all resamples.  Returns
+    (median, std) over the resamples like the reference.  ``use_huber`` needs raw residuals: not supported."""
+    if use_huber:
+        raise NotImplementedError("the Huber inner solve iterates on raw residuals; only the ridge ensemble is GPU-accelerated")
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if X.ndim != 2 or y.shape != (X.shape[0],):
+        raise ValueError("X must be (n, p) and y (n,)")
+    rng = np.random.default_rng(seed)
+    n, p = X.shape
+    n_sub = max(int(n * subsample_frac), 1)
+    counts = np.stack([np.bincount(rng.choice(n, size=n_sub, replace=True), minlength=n) for _ in range(int(n_bootstrap))])
+    shift = X[:1].copy()
+    stats, mm = ops.rows_gram_weighted(X, y, counts.astype(np.uint16), shift=shift, want_minmax=True)
+    torch = L.torch_cuda()
+    out = ops.stridge_batched(stats, p, dialect=L.STRIDGE_KS, alphas=[alpha], thresholds=[threshold], max_iter=int(max_iter),
+                              colminmax=mm, shift=torch.as_tensor(shift).expand(int(n_bootstrap), p).contiguous())
+    C = _np(out["coef"])[:, 0, 0, :]
+    return np.median(C, axis=0), np.std(C, axis=0)
+
+
 def rollout_errors(U, dx, dy, DT, names, coeffs, n_steps: int = 50):
     """ks2d:1804-1838: explicit-Euler rollout of the discovered PDE from U[0]; RMSE against U[k+1] per step.
     ``names`` selects the library (true / true+advection / rich / rich without advection)."""

@@ -131,6 +131,29 @@ def rows_gram(X, y, *, fold_of_row=None, n_folds=1, shift=None, want_minmax=Fals
     return (stats, mm) if want_minmax else stats
 
 
+def rows_gram_weighted(X, y, weights, *, shift=None, want_minmax=False):
+    """pg_rows_gram_weighted: statistics of B resamples of one row set.  X [n][p], y [n], weights [B][n]
+    (multiplicities) -> stats [B][S] (+ colminmax [B][2][p] over the rows each resample drew)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    X = _dev(X, torch.float64)
+    y = _dev(y, torch.float64)
+    n, p = X.shape
+    w = _dev(weights).reshape(-1, n)
+    if w.dtype != torch.uint16:
+        if int(w.max()) > 65535:
+            raise ValueError("row multiplicities above 65535 are not supported")
+        w = w.to(torch.uint16)
+    w = w.contiguous()
+    B = w.shape[0]
+    sh = None if shift is None else _dev(shift, torch.float64).reshape(p).contiguous()
+    stats = torch.empty((B, L.stats_len(p)), dtype=torch.float64, device=X.device)
+    mm = torch.empty((B, 2, p), dtype=torch.float64, device=X.device) if want_minmax else None
+    L.check(lib.pg_rows_gram_weighted(L.ptr(X), L.ptr(y), n, p, p, L.ptr(w), B, L.ptr(sh), L.ptr(stats), L.ptr(mm),
+                                      L.stream_ptr()))
+    return (stats, mm) if want_minmax else stats
+
+
 def poly_rows(U, pts, W6, rt, rs, *, library):
     """K2: pg_poly_rows.  U float32 or float64 (T,H,W); pts [n][3] (t,y,x) -> (X [n][p], y [n])."""
     torch = L.torch_cuda()

@@ -150,6 +150,20 @@ def golden_ks2d_smooth(ks):
     np.savez_compressed(OUT / "ks2d_smooth.npz", **out)
 
 
+def golden_ks2d_ensemble(ks):
+    """ensemble_stridge (ks2d:603-642, use_huber=False) on the pointwise rows stored in ks2d_small.npz."""
+    g = np.load(OUT / "ks2d_small.npz")
+    out = {}
+    for tag, X in (("true", g["bw111_X_true"]), ("rich", g["bw111_X_rich"])):
+        y = g["bw111_y"]
+        for k, (a, t, nb, frac, seed) in enumerate([(1e-3, 1e-6, 12, 0.7, 0), (1e-2, 1e-2, 7, 0.5, 3)]):
+            med, std = ks.ensemble_stridge(X, y, alpha=a, threshold=t, max_iter=25, n_bootstrap=nb, subsample_frac=frac,
+                                           seed=seed)
+            out[f"{tag}_{k}_args"] = np.array([a, t, nb, frac, seed])
+            out[f"{tag}_{k}_median"], out[f"{tag}_{k}_std"] = med, std
+    np.savez_compressed(OUT / "ks2d_ensemble.npz", **out)
+
+
 def golden_ks2d_rollout(ks):
     """Rollout check of main() (ks2d:1804-1838) at full precision: main() calls rmse() on 1-D arrays of
     Nx*Ny values only inside the rollout loop, so a recording wrapper around the module's rmse captures the
@@ -351,6 +365,7 @@ def main():
     golden_patch(pa)
     golden_ks2d_configs(ks)
     golden_ks2d_rollout(ks)
+    golden_ks2d_ensemble(ks)
     golden_ks2d_smooth(ks)
     for f in sorted(OUT.glob("*.npz")) + sorted(OUT.glob("*.json")):
         print(f.name, f.stat().st_size)

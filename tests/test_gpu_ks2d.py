@@ -390,3 +390,32 @@ def test_time_holdout_cross_validation():
         assert (K.GRID_ALPHAS[ia], K.GRID_THRESHOLDS[it]) == (ref["alpha"], ref["threshold"])
         assert_coef_close(out["coef_grid"][k, ia, it], ref["coeffs"], what=f"fold {k}")
         np.testing.assert_allclose(out["metrics"][k, ia, it, 0], ref["r2_test"], rtol=1e-6, atol=1e-9)
+
+
+def test_ensemble_stridge_weighted_grams(golden_ks2d):
+    """ensemble_stridge (ks2d:603-642): every bootstrap resample is fitted from the multiplicity-weighted Gram of
+    the original rows; per-resample coefficients against the oracle's fits of the materialised resamples, and
+    (median, std) against the reference's outputs."""
+    from conftest import GOLDEN
+    from pde_b200 import _lib as L
+    from pde_b200 import ks2d as K
+    from pde_b200 import ops
+
+    g = np.load(GOLDEN / "ks2d_ensemble.npz")
+    y = golden_ks2d["bw111_y"]
+    for tag, X in (("true", golden_ks2d["bw111_X_true"]), ("rich", golden_ks2d["bw111_X_rich"])):
+        for k in range(2):
+            a, t, nb, frac, seed = g[f"{tag}_{k}_args"]
+            kw = dict(alpha=a, threshold=t, n_bootstrap=int(nb), subsample_frac=frac, seed=int(seed))
+            med, std = K.ensemble_stridge(X, y, **kw)
+            assert_coef_close(med, g[f"{tag}_{k}_median"], what=f"ensemble median {tag} {k}")
+            np.testing.assert_allclose(std, g[f"{tag}_{k}_std"], rtol=1e-6, atol=1e-12)
+    # weighted statistics == statistics of the materialised resample
+    X = golden_ks2d["bw111_X_rich"]
+    rng = np.random.default_rng(5)
+    idx = rng.choice(len(y), size=2000, replace=True)
+    w = np.bincount(idx, minlength=len(y))[None]
+    st = ops.rows_gram_weighted(X, y, w).cpu().numpy()[0]
+    assert_stats_close(st, gram.pack_stats(X[idx], y[idx]), 9)
+    with pytest.raises(NotImplementedError):
+        K.ensemble_stridge(X, y, use_huber=True)

@@ -343,3 +343,17 @@ def test_smoothing_prologue_matches_reference():
         assert np.array_equal(ks2d.time_smooth_moving_average(g["stack"], w), g[f"tavg_{w}"])
     with pytest.raises(ValueError):
         ks2d.time_smooth_moving_average(g["stack"], 4)
+
+
+# --------------------------------------------------------------------------- bootstrap ensemble (ks2d:603-642)
+def test_ensemble_stridge_matches_reference(golden_ks2d):
+    from conftest import GOLDEN
+    from oracle import ks2d
+
+    g = np.load(GOLDEN / "ks2d_ensemble.npz")
+    for tag, X in (("true", golden_ks2d["bw111_X_true"]), ("rich", golden_ks2d["bw111_X_rich"])):
+        for k in range(2):
+            a, t, nb, frac, seed = g[f"{tag}_{k}_args"]
+            med, std = ks2d.ensemble_stridge(X, golden_ks2d["bw111_y"], alpha=a, threshold=t, n_bootstrap=int(nb),
+                                             subsample_frac=frac, seed=int(seed))
+            assert np.array_equal(med, g[f"{tag}_{k}_median"]) and np.array_equal(std, g[f"{tag}_{k}_std"])
