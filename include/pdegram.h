@@ -207,6 +207,15 @@ PG_API int pg_ks_rollout(const double *U, int64_t T, int64_t A0, int64_t A1, dou
                   int library_id, const double *coef, int n_steps, double *work, double *rmse_out, void *stream);
 
 /*
+ * Sums behind the reference's fit metrics (rmse / r2_score ks2d:29-40; regression_metrics patch:47-65) of
+ * (y_true, y_pred), both DEVICE [n]; r = y_true - y_pred.  sums_out DEVICE [10]:
+ *   [0] sum r  [1] sum r^2  [2] sum |r|  [3] sum y  [4] sum yhat
+ *   [5] sum (y - mean y)^2  [6] sum (yhat - mean yhat)^2  [7] sum (y - mean y)(yhat - mean yhat)
+ *   [8] sum (r - mean r)^2  [9] unused (0)
+ */
+PG_API int pg_fit_metrics(const double *y_true, const double *y_pred, int64_t n, double *sums_out, void *stream);
+
+/*
  * Optional denoising prologue of the ks2d script (ks2d:1448-1468), the step before the hot path.
  * pg_time_moving_average: time_smooth_moving_average (ks2d:145-161), reflect-padded moving average along t
  *   through a sequential cumulative sum; bit-identical to the NumPy formulation.  window odd, out != U.

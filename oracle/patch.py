@@ -228,3 +228,18 @@ def run_patches(U, *, rt=2, rs=3, deg=3, patch=21, overlap=10, samples_per_patch
     out = stability_aggregate(C, threshold)
     out.update(C=C, samples=samples, rng=rng)
     return out
+
+
+def regression_metrics(y_true, y_pred) -> dict:
+    """patch:47-65 (r2 through sklearn.metrics.r2_score's formula 1 - ss_res / ss_tot)."""
+    y_true = np.asarray(y_true).ravel()
+    y_pred = np.asarray(y_pred).ravel()
+    resid = y_true - y_pred
+    rmse = float(np.sqrt(np.mean(resid ** 2)))
+    y_std = float(np.std(y_true))
+    ss_tot = float(np.sum((y_true - y_true.mean()) ** 2))
+    return {"r2": float(1.0 - np.sum(resid ** 2) / ss_tot), "rmse": rmse, "mae": float(np.mean(np.abs(resid))),
+            "nrmse": float(rmse / (y_std + 1e-12)),
+            "corr": float(np.corrcoef(y_true, y_pred)[0, 1]) if y_true.size > 1 else float("nan"),
+            "resid_mean": float(np.mean(resid)), "resid_std": float(np.std(resid)),
+            "resid_med_abs": float(np.median(np.abs(resid)))}

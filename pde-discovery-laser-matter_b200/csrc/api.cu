@@ -372,6 +372,19 @@ int pg_ks_rollout(const double *U, int64_t T, int64_t A0, int64_t A1, double d0,
     return launch_rollout(library_id, U, A0, A1, P.c, coef, n_steps, work, (double *)scr, blocks, rmse_out, st);
 }
 
+int pg_fit_metrics(const double *y_true, const double *y_pred, int64_t n, double *sums_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 1) PG_FAIL(PG_EINVAL, "n must be >= 1");
+    if (!y_true || !y_pred || !sums_out) PG_FAIL(PG_EINVAL, "null buffer");
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    const int blocks = (int)(g > cap ? cap : g);
+    void *scr = nullptr;
+    int rc = scratch_for(st, sizeof(double) * 5 * (size_t)blocks, &scr);
+    if (rc) return rc;
+    return launch_fit_metrics(y_true, y_pred, n, (double *)scr, blocks, sums_out, st);
+}
+
 int pg_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, void *stream) {
     if (!U || !out) PG_FAIL(PG_EINVAL, "null buffer");
     if (T < 1 || A0 < 1 || A1 < 1) PG_FAIL(PG_EINVAL, "bad shape");

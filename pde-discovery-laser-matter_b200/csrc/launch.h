@@ -90,6 +90,7 @@ int launch_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, in
                          int n_taps, double *out, cudaStream_t st);
 
 // rollout.cu
+int launch_fit_metrics(const double *y, const double *yh, int64_t n, double *partials, int blocks, double *out10, cudaStream_t st);
 int rollout_blocks(int64_t A0, int64_t A1, int n_sm);
 int launch_rollout(int lib, const double *U, int64_t A0, int64_t A1, const FdConsts &c, const double *coef, int n_steps,
                    double *work, double *partials, int blocks, double *rmse, cudaStream_t st);

@@ -74,6 +74,52 @@ static int rollout_t(const double *U, int64_t A0, int64_t A1, const FdConsts &c,
     return PG_OK;
 }
 
+// ----------------------------------------------------------------------------- fit metrics (ks2d:29-40, patch:47-65)
+// Two passes over (y_true, y_pred): raw sums, then sums centred on the means of the first pass (what np.std,
+// np.corrcoef and the reference's r2_score do).  Per-block partial sums, fixed-order reduction.
+//   pass 0 entries: sum r, sum r^2, sum |r|, sum y, sum yhat          (r = y - yhat)
+//   pass 1 entries: sum (y-my)^2, sum (yhat-mh)^2, sum (y-my)(yhat-mh), sum (r-mr)^2
+constexpr int FM_THREADS = 256;
+
+__global__ void __launch_bounds__(FM_THREADS) fit_metrics_kernel(const double *__restrict__ y, const double *__restrict__ yh,
+                                                                 int64_t n, int pass, const double *__restrict__ sums0,
+                                                                 double *__restrict__ partials) {
+    __shared__ double sh[FM_THREADS];
+    constexpr int NQ = 5;
+    double a[NQ] = {0, 0, 0, 0, 0};
+    double my = 0, mh = 0, mr = 0;
+    if (pass == 1) { my = sums0[3] / (double)n; mh = sums0[4] / (double)n; mr = sums0[0] / (double)n; }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double yt = y[i], yp = yh[i], r = __dsub_rn(yt, yp);
+        if (pass == 0) {
+            a[0] += r; a[1] = fma(r, r, a[1]); a[2] += fabs(r); a[3] += yt; a[4] += yp;
+        } else {
+            const double dy = yt - my, dh = yp - mh, dr = r - mr;
+            a[0] = fma(dy, dy, a[0]); a[1] = fma(dh, dh, a[1]); a[2] = fma(dy, dh, a[2]); a[3] = fma(dr, dr, a[3]);
+        }
+    }
+    for (int q = 0; q < NQ; ++q) {
+        sh[threadIdx.x] = a[q];
+        __syncthreads();
+        for (int w = FM_THREADS / 2; w > 0; w >>= 1) {
+            if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * NQ + q] = sh[0];
+        __syncthreads();
+    }
+}
+
+int launch_fit_metrics(const double *y, const double *yh, int64_t n, double *partials, int blocks, double *out10, cudaStream_t st) {
+    fit_metrics_kernel<<<blocks, FM_THREADS, 0, st>>>(y, yh, n, 0, nullptr, partials);
+    PG_LAUNCHED();
+    int rc = launch_reduce_partials(partials, blocks, 5, out10, 0, st);
+    if (rc) return rc;
+    fit_metrics_kernel<<<blocks, FM_THREADS, 0, st>>>(y, yh, n, 1, out10, partials);
+    PG_LAUNCHED();
+    return launch_reduce_partials(partials, blocks, 5, out10 + 5, 0, st);
+}
+
 int rollout_blocks(int64_t A0, int64_t A1, int n_sm) {
     int64_t g = (A0 * A1 + RO_THREADS - 1) / RO_THREADS;
     const int64_t cap = (int64_t)n_sm * 8;

@@ -11,11 +11,11 @@ patch:420-423), so replacing module attributes is a complete drop-in: no source 
 
 from __future__ import annotations
 
-_KS = ("gradients", "laplacian", "build_dictionary", "build_dictionary_true", "build_blockwise_dataset",
+_KS = ("rmse", "r2_score", "standardize_transform", "gradients", "laplacian", "build_dictionary", "build_dictionary_true", "build_blockwise_dataset",
        "standardize_fit", "ridge_fit", "stridge", "stridge_sign_constrained", "ensemble_stridge",
        "gaussian_smooth_periodic_2d", "time_smooth_moving_average")
 _BASIC = ("compute_derivatives", "build_library", "stridge_regression")
-_PATCH = ("stridge", "local_poly_derivatives", "build_dataset", "Library", "patch_grid")
+_PATCH = ("regression_metrics", "stridge", "local_poly_derivatives", "build_dataset", "Library", "patch_grid")
 
 
 def patch_reference(module, dialect: str | None = None):

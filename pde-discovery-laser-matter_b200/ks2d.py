@@ -37,6 +37,24 @@ def _frame(f2d):
     return f[None]
 
 
+# ------------------------------------------------------------------ fit metrics (ks2d:29-40)
+def rmse(y_true, y_pred) -> float:
+    """ks2d:29-32."""
+    s, n = ops.fit_metric_sums(y_true, y_pred)
+    return float(np.sqrt(s[1] / n)) if n else float("nan")
+
+
+def r2_score(y_true, y_pred) -> float:
+    """ks2d:35-40 (with its 1e-18 guard)."""
+    s, n = ops.fit_metric_sums(y_true, y_pred)
+    return float(1.0 - s[1] / (s[5] + 1e-18)) if n else float("nan")
+
+
+def standardize_transform(X, mean, scale):
+    """ks2d:51-52: (X - mean) / scale (elementwise; NumPy broadcasting on the host, nothing to accelerate)."""
+    return (np.asarray(X) - np.asarray(mean)) / np.asarray(scale)
+
+
 # ------------------------------------------------------------------ stencils (ks2d:63-73)
 def laplacian(f2d, dx: float, dy: float):
     """ks2d:63-67: periodic 5-point Laplacian of one frame."""

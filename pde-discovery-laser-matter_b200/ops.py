@@ -235,6 +235,21 @@ def ks_rollout(U, d0, d1, dt, coef, n_steps, *, library):
     return rmse
 
 
+def fit_metric_sums(y_true, y_pred):
+    """pg_fit_metrics: the ten sums behind rmse / r2 / mae / std / corr of (y_true, y_pred); NumPy array [10]."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    yt = _dev(np.asarray(y_true, dtype=np.float64).ravel() if not isinstance(y_true, torch.Tensor) else y_true.reshape(-1), torch.float64)
+    yp = _dev(np.asarray(y_pred, dtype=np.float64).ravel() if not isinstance(y_pred, torch.Tensor) else y_pred.reshape(-1), torch.float64)
+    if yt.numel() != yp.numel():
+        raise ValueError("y_true and y_pred must have the same number of elements")
+    out = torch.zeros(10, dtype=torch.float64, device=yt.device)
+    if yt.numel() == 0:
+        return out.cpu().numpy(), 0
+    L.check(lib.pg_fit_metrics(L.ptr(yt), L.ptr(yp), yt.numel(), L.ptr(out), L.stream_ptr()))
+    return out.cpu().numpy(), yt.numel()
+
+
 def time_moving_average(U, window):
     """pg_time_moving_average: reflect-padded moving average along t (ks2d:145-161)."""
     torch = L.torch_cuda()

@@ -112,6 +112,22 @@ def stridge(X, y, alpha: float = 0.01, threshold: float = 1e-5, max_iter: int = 
     return _np(out["coef"])[0, 0, 0]
 
 
+def regression_metrics(y_true, y_pred) -> dict:
+    """patch:47-65 from one two-pass reduction on the GPU (the median of |resid| via torch, on the device)."""
+    torch = L.torch_cuda()
+    yt = ops._dev(np.asarray(y_true, dtype=np.float64).ravel(), torch.float64)
+    yp = ops._dev(np.asarray(y_pred, dtype=np.float64).ravel(), torch.float64)
+    s, n = ops.fit_metric_sums(yt, yp)
+    rmse = float(np.sqrt(s[1] / n))
+    y_std = float(np.sqrt(s[5] / n))
+    corr = float(s[7] / np.sqrt(s[5] * s[6])) if n > 1 else float("nan")
+    # sklearn.metrics.r2_score (patch:38,57): no guard; a constant y_true scores 1 for a perfect fit, else 0
+    r2 = float(1.0 - s[1] / s[5]) if s[5] > 0 else (1.0 if s[1] == 0 else 0.0)
+    return {"r2": r2, "rmse": rmse, "mae": float(s[2] / n), "nrmse": float(rmse / (y_std + 1e-12)),
+            "corr": corr, "resid_mean": float(s[0] / n), "resid_std": float(np.sqrt(s[8] / n)),
+            "resid_med_abs": float(np.median((yt - yp).abs().cpu().numpy()))}
+
+
 # ------------------------------------------------------------------ fused per-patch ensemble (patch:351-443)
 def time_split(t_len: int, rt: int, train_frac: float):
     """patch:361-369."""

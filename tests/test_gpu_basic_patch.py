@@ -176,3 +176,24 @@ def test_patch_ensemble_larger_vs_oracle(P):
     assert np.array_equal(out["C"] != 0, ref["C"] != 0)
     np.testing.assert_allclose(out["C"], ref["C"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(out["agg"], ref["agg"], rtol=1e-6, atol=1e-9)
+
+
+def test_fit_metrics_on_gpu(P):
+    """rmse / r2_score (ks2d:29-40) and regression_metrics (patch:47-65) from the two-pass reduction kernel."""
+    from oracle import ks2d as OK
+    from pde_b200 import ks2d as K
+
+    rng = np.random.default_rng(8)
+    for n in (1, 7, 1000, 300_001):
+        y = 3.0 + rng.standard_normal(n)
+        yh = y + 0.1 * rng.standard_normal(n)
+        np.testing.assert_allclose(K.rmse(y, yh), OK.rmse(y, yh), rtol=1e-12)
+        if n > 1:
+            np.testing.assert_allclose(K.r2_score(y, yh), OK.r2_score(y, yh), rtol=1e-11)
+            ref, got = OP.regression_metrics(y, yh), P.regression_metrics(y, yh)
+            assert set(ref) == set(got)
+            for k in ref:
+                np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-13, err_msg=k)
+    assert K.r2_score(np.arange(5.0), np.arange(5.0)) == 1.0
+    X = rng.standard_normal((6, 3))
+    assert np.array_equal(K.standardize_transform(X, X.mean(0), X.std(0)), OK.standardize_transform(X, X.mean(0), X.std(0)))
