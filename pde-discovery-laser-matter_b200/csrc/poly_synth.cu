@@ -1,6 +1,7 @@
 // K2 -- local-polynomial derivative rows (patch:193-280) as a fixed (2rt+1)(2rs+1)^2-tap stencil,
 // and the synthetic-field generator used for the large benchmark stacks.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "launch.h"
@@ -88,8 +89,12 @@ __device__ __forceinline__ void reduce6(double (&a)[6], int lane) {
     a[3] = __shfl_sync(0xffffffffu, m, 16); a[4] = __shfl_sync(0xffffffffu, m, 20); a[5] = __shfl_sync(0xffffffffu, m, 24);
 }
 
-template <typename TIn>
-__global__ void __launch_bounds__(PW * 32) poly_rows_reg_kernel(const TIn *__restrict__ U, int64_t T, int64_t H, int64_t W,
+// WSMEM = false: weights in registers (8 warps per SM).  WSMEM = true: weights in shared memory, laid out
+// [tap][output][lane] so that a warp's read of one weight is one conflict-free 256-byte row; the kernel then
+// needs ~110 registers and two CTAs fit an SM, which matters because it is bound by the latency of its
+// scattered gathers (ncu: long_scoreboard 4.2 per issue at 8 warps per SM).
+template <typename TIn, bool WSMEM>
+__global__ void __launch_bounds__(PW * 32, WSMEM ? 3 : 1) poly_rows_reg_kernel(const TIn *__restrict__ U, int64_t T, int64_t H, int64_t W,
                                                                const int32_t *__restrict__ pts, int64_t n,
                                                                const double *__restrict__ W6, int rt, int rs, int mode,
                                                                double *__restrict__ X, double *__restrict__ y,
@@ -97,18 +102,25 @@ __global__ void __launch_bounds__(PW * 32) poly_rows_reg_kernel(const TIn *__res
     const int side = 2 * rs + 1, nnb = (2 * rt + 1) * side * side;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = mode == 1 ? 8 : 6;
-    int64_t off[PNE];
-    double w[6][PNE];
+    __shared__ double wsm[WSMEM ? PNE * 6 * 32 : 1];
+    constexpr int NP = WSMEM ? 3 : NPT;   // points in flight per warp
+    int off[PNE];                          // tap offsets in elements (the launcher checks that they fit 31 bits)
+    double w[WSMEM ? 1 : 6][WSMEM ? 1 : PNE];
 #pragma unroll
     for (int k = 0; k < PNE; ++k) {
         const int e = lane + 32 * k;
         const bool has = e < nnb;
         const int ee = has ? e : 0;
         const int ox = ee % side, oy = (ee / side) % side, ot = ee / (side * side);
-        off[k] = ((int64_t)ot * H + oy) * W + ox;
+        off[k] = (int)(((int64_t)ot * H + oy) * W + ox);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) w[q][k] = has ? W6[q * nnb + e] : 0.0;   // absent taps: a valid address, weight 0
+        for (int q = 0; q < 6; ++q) {
+            const double wv = has ? W6[q * nnb + e] : 0.0;   // absent taps: a valid address, weight 0
+            if constexpr (WSMEM) { if (warp == 0) wsm[(k * 6 + q) * 32 + lane] = wv; }
+            else w[q][k] = wv;
+        }
     }
+    if constexpr (WSMEM) __syncthreads();
     auto emit = [&](int64_t k, bool ok, double (&acc)[6]) {
         reduce6(acc, lane);
         if (lane != 0) return;
@@ -135,27 +147,30 @@ __global__ void __launch_bounds__(PW * 32) poly_rows_reg_kernel(const TIn *__res
         return ok ? ((t0 - rt) * H + (y0 - rs)) * W + (x0 - rs) : (int64_t)0;
     };
     const int64_t stride = (int64_t)gridDim.x * PW;
-    for (int64_t k = (int64_t)blockIdx.x * PW + warp; k < n; k += NPT * stride) {
-        bool ok[NPT];
-        int64_t kk[NPT], base[NPT];
-        double v[NPT][PNE];
+    for (int64_t k = (int64_t)blockIdx.x * PW + warp; k < n; k += NP * stride) {
+        bool ok[NP];
+        int64_t kk[NP], base[NP];
+        double v[NP][PNE];
 #pragma unroll
-        for (int j = 0; j < NPT; ++j) {
+        for (int j = 0; j < NP; ++j) {
             kk[j] = k + j * stride;
             ok[j] = false;
             base[j] = kk[j] < n ? base_of(kk[j], ok[j]) : 0;
         }
 #pragma unroll
-        for (int j = 0; j < NPT; ++j)
+        for (int j = 0; j < NP; ++j)
 #pragma unroll
             for (int e = 0; e < PNE; ++e) v[j][e] = ok[j] ? (double)U[base[j] + off[e]] : 0.0;
 #pragma unroll
-        for (int j = 0; j < NPT; ++j) {
+        for (int j = 0; j < NP; ++j) {
             double acc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int e = 0; e < PNE; ++e)
 #pragma unroll
-                for (int q = 0; q < 6; ++q) acc[q] = fma(w[q][e], v[j][e], acc[q]);
+                for (int q = 0; q < 6; ++q) {
+                    if constexpr (WSMEM) acc[q] = fma(wsm[(e * 6 + q) * 32 + lane], v[j][e], acc[q]);
+                    else acc[q] = fma(w[q][e], v[j][e], acc[q]);
+                }
             if (kk[j] < n) emit(kk[j], ok[j], acc);
         }
     }
@@ -170,12 +185,18 @@ int launch_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t W, 
     int64_t g = (n + PW - 1) / PW;
     if (g > 148 * 8) g = 148 * 8;
     if (nnb <= 32 * PNE) {   // taps fit the per-lane registers
-        int64_t gr = (n + NPT * PW - 1) / (NPT * PW);
-        if (gr > 148 * 2) gr = 148 * 2;
-        if (dtype == 0)
-            poly_rows_reg_kernel<float><<<(unsigned)gr, PW * 32, 0, st>>>((const float *)U, T, H, W, pts, n, W6, rt, rs, mode, X, y, counters);
-        else
-            poly_rows_reg_kernel<double><<<(unsigned)gr, PW * 32, 0, st>>>((const double *)U, T, H, W, pts, n, W6, rt, rs, mode, X, y, counters);
+        const bool wsmem = !getenv("PG_POLY_WREG") && (int64_t)(2 * rt + 1) * H * W < 0x7fffffff;
+        const int npt = wsmem ? 3 : NPT;
+        int64_t gr = (n + npt * PW - 1) / (npt * PW);
+        const int64_t cap = 148 * (wsmem ? 6 : 2);
+        if (gr > cap) gr = cap;
+        if (dtype == 0) {
+            if (wsmem) poly_rows_reg_kernel<float, true><<<(unsigned)gr, PW * 32, 0, st>>>((const float *)U, T, H, W, pts, n, W6, rt, rs, mode, X, y, counters);
+            else poly_rows_reg_kernel<float, false><<<(unsigned)gr, PW * 32, 0, st>>>((const float *)U, T, H, W, pts, n, W6, rt, rs, mode, X, y, counters);
+        } else {
+            if (wsmem) poly_rows_reg_kernel<double, true><<<(unsigned)gr, PW * 32, 0, st>>>((const double *)U, T, H, W, pts, n, W6, rt, rs, mode, X, y, counters);
+            else poly_rows_reg_kernel<double, false><<<(unsigned)gr, PW * 32, 0, st>>>((const double *)U, T, H, W, pts, n, W6, rt, rs, mode, X, y, counters);
+        }
         PG_LAUNCHED();
         return PG_OK;
     }
