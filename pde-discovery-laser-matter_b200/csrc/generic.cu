@@ -414,8 +414,72 @@ size_t rows_gram_smem(int p, int n_folds) {
     return sizeof(double) * (GW * n_folds * S + GW * 32 * (p + 2) + GW * n_folds * 2 * p) + 2 * S + 16;
 }
 
+// Many small problems (the per-patch fits: thousands of problems of ~100 rows): one WARP per problem, no shared
+// memory, no partials.  Lane j < p + 2 loads entry j of the extended row [1, y, x_0 - shift_0, ..]; every
+// statistics entry is a product of two of them, fetched by shuffle, with lane e owning entries e, e + 32, ..
+// (rows in order, one accumulator per entry: deterministic).
+constexpr int RS_NE = (PG_STATS_LEN(PG_MAX_P) + 31) / 32;
+
+__global__ void __launch_bounds__(256) rows_gram_small_kernel(RowsParams P, double *__restrict__ stats,
+                                                             double *__restrict__ colminmax) {
+    const int p = P.p, S = PG_STATS_LEN(p);
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= P.B) return;
+    int ea[RS_NE], eb[RS_NE];
+#pragma unroll
+    for (int k = 0; k < RS_NE; ++k) {
+        ea[k] = eb[k] = 0;
+        if (lane + 32 * k < S) stats_pair(lane + 32 * k, p, ea[k], eb[k]);
+    }
+    const double *Xb = P.X + b * P.n * P.ldx;
+    const double *yb = P.y + b * P.n;
+    const bool col = lane >= 2 && lane < p + 2;
+    const double sh = (P.shift && col) ? P.shift[b * p + lane - 2] : 0.0;
+    double acc[RS_NE];
+#pragma unroll
+    for (int k = 0; k < RS_NE; ++k) acc[k] = 0.0;
+    double vmin = INFINITY, vmax = -INFINITY;
+    constexpr int UN = 4;    // rows in flight per warp
+    for (int64_t r0 = 0; r0 < P.n; r0 += UN) {
+        double raw[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int64_t r = r0 + u;
+            raw[u] = 1.0;
+            if (r < P.n) {
+                if (lane == 1) raw[u] = yb[r];
+                else if (col) raw[u] = Xb[r * P.ldx + lane - 2];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (r0 + u >= P.n) break;
+            if (col) { vmin = fmin(vmin, raw[u]); vmax = fmax(vmax, raw[u]); }
+            const double ext = col ? __dsub_rn(raw[u], sh) : raw[u];
+#pragma unroll
+            for (int k = 0; k < RS_NE; ++k) {
+                if (32 * k >= S) break;
+                acc[k] = fma(__shfl_sync(0xffffffffu, ext, ea[k]), __shfl_sync(0xffffffffu, ext, eb[k]), acc[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RS_NE; ++k)
+        if (lane + 32 * k < S) stats[b * S + lane + 32 * k] = acc[k];
+    if (colminmax && col) {
+        colminmax[(b * 2 + 0) * p + lane - 2] = vmin;
+        colminmax[(b * 2 + 1) * p + lane - 2] = vmax;
+    }
+}
+
 int launch_rows_gram(const RowsParams &P, double *stats, double *colminmax, cudaStream_t st) {
     const int S = PG_STATS_LEN(P.p);
+    if (P.B >= 256 && P.n <= 4096 && P.n_folds == 1 && !P.fold_of_row && !P.weights) {
+        rows_gram_small_kernel<<<(unsigned)((P.B + 7) / 8), 256, 0, st>>>(P, stats, colminmax);
+        PG_LAUNCHED();
+        return PG_OK;
+    }
     const size_t smem = rows_gram_smem(P.p, P.n_folds);
     PG_CUDA(cudaFuncSetAttribute(rows_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rows_gram_kernel<<<(unsigned)(P.chunks * P.B), GW * 32, smem, st>>>(P);
