@@ -204,7 +204,8 @@ __device__ __forceinline__ double sum_frame_u(const double *__restrict__ st, con
 constexpr int DNW = 8;   // consumer warps
 
 template <int LIB, int NF, bool TIMEFOLD>
-__global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap, TiledParams P) {
+__global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap,
+                                                            const __grid_constant__ CUtensorMap tmap_last, TiledParams P) {
     constexpr int NW = DNW;
     using G_ = Geo<NW>;
     constexpr int TI = G_::TI, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES;
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
     auto geometry = [&](int64_t item, int &i0, int &j0, int64_t &tb0, int &nf) {
         const int tile = (int)(item % n_tiles), chunk = (int)(item / n_tiles);
         i0 = (tile / P.n_tiles1) * TI;
-        j0 = (tile % P.n_tiles1) * TJ;
+        j0 = min((tile % P.n_tiles1) * TJ, (int)P.A1 - TJ);   // a width that is not a multiple of 128: the last tile column is shifted left
         tb0 = (int64_t)chunk * P.chunk_tb;
         nf = (int)(min(P.n_row_frames, (tb0 + P.chunk_tb) * P.bt) - tb0 * P.bt);   // a ragged last t-block is shorter
     };
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         }
         fence_proxy_async();
         mbar_expect_tx(&full[s], G_::TMA_BYTES);
-        tma_load_4d(stages + s * STAGE_DOUBLES, &tmap, &full[s], 0, j0 >> 4, i0 - 2, t);
+        // the shifted tile column of a width with A1 % 16 == 8 starts inside a 16-column group: tmap_last views the field from column 8
+        tma_load_4d(stages + s * STAGE_DOUBLES, (j0 & 15) ? &tmap_last : &tmap, &full[s], 0, j0 >> 4, i0 - 2, t);
     };
     // coordinates of the load `ahead` frames after frame f of `item` (geometry i0, j0, t0, nf); walks into the
     // following items of this CTA; false when the CTA's stream of frames ends before that
@@ -391,6 +393,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         int fold = 0;
         double su_first = 0.0;
         const int64_t ib = (int64_t)(i0 >> 3) + warp, jb = (int64_t)(j0 >> 3) + (lm.g >> 1);
+        // blocks of a shifted last tile column that the tile column before it has already counted
+        const bool col_ok = (j0 & (TJ - 1)) == 0 || jb >= (int64_t)(P.n_tiles1 - 1) * (TJ / 8);
         int fb = 0;               // f % bt, kept incrementally (no integer division in the frame loop)
         int64_t tbs = tb0 - 1;    // t-block that starts at the latest frame with fb == 0
         for (int f = 0; f <= nf; ++f, ++G) {
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                 bool fin = isfinite(y_);
 #pragma unroll
                 for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
-                bool valid = (lane & 8) == 0;
+                bool valid = (lane & 8) == 0 && col_ok;
                 if (valid && !fin) { valid = false; ++bad_rows; }
                 else if (valid && (fold < 0 || fold >= P.n_folds)) { valid = false; ++bad_fold; }
                 if constexpr (TIMEFOLD) {
@@ -569,12 +573,14 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
         return false;
     if (P.b0 != 8 || P.b1 != 8) return false;
     if (P.n_folds > 2 && P.fold_of_row) return false;   // per-row folds: two masked accumulator sets; time folds: any number
-    if (P.A1 % 16 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // 4-D swizzled TMA view: whole 128-byte groups
+    // whole blocks along a1; 16-byte aligned rows for TMA / cp.async; at least one 128-column tile (a last tile column
+    // that does not start at a multiple of 128 is shifted left over its neighbour and skips the blocks already counted)
+    if (P.A1 % 8 != 0 || P.A1 < TJ || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;
     const int NW = DNW;
     const int TI = 8 * NW;
     const int workers = n_sm;
     // tile rows: a ragged last one is handled in-kernel when it still consists of whole blocks
-    const int64_t nt0 = P.A0 % 8 == 0 ? (P.A0 + TI - 1) / TI : P.A0 / TI, nt1 = P.A1 / TJ;
+    const int64_t nt0 = P.A0 % 8 == 0 ? (P.A0 + TI - 1) / TI : P.A0 / TI, nt1 = (P.A1 + TJ - 1) / TJ;
     const int64_t nbt = (P.T - 1 + P.bt - 1) / P.bt;   // a ragged last t-block (fewer frames) is handled in-kernel
     if (nt0 < 1 || nt1 < 1 || nbt < 1) return false;
     if (P.T > 0x7fffffff || P.A0 > 0x7fffffff || P.A1 > 0x7fffffff) return false;
@@ -592,7 +598,7 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
         if (cost < best_cost - 1e-9) { best_cost = cost; best_c = cc; }
     }
     const int64_t ctb = (nbt + best_c - 1) / best_c;
-    plan.nbt = nbt; plan.nb0 = P.A0 % 8 == 0 ? P.A0 / 8 : nt0 * (TI / 8); plan.nb1 = nt1 * (TJ / 8);
+    plan.nbt = nbt; plan.nb0 = P.A0 % 8 == 0 ? P.A0 / 8 : nt0 * (TI / 8); plan.nb1 = P.A1 / 8;
     plan.chunk_t = (int)ctb; plan.n_chunks = (nbt + ctb - 1) / ctb;
     plan.n_tiles0 = nt0; plan.n_tiles1 = nt1;
     const int64_t items = n_tiles * plan.n_chunks;
@@ -609,16 +615,16 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     return true;
 }
 
-template <int LIB, int NF, bool TIMEFOLD> static int launch_tiled_d(const CUtensorMap &map, const TiledParams &tp, int grid,
+template <int LIB, int NF, bool TIMEFOLD> static int launch_tiled_d(const CUtensorMap (&map)[2], const TiledParams &tp, int grid,
                                                                      cudaStream_t st) {
     const size_t smem = Geo<DNW>::smem(Lib<LIB>::P);
     PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, TIMEFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1_tiled_b88<LIB, NF, TIMEFOLD><<<grid, 32 * DNW, smem, st>>>(map, tp);
+    k1_tiled_b88<LIB, NF, TIMEFOLD><<<grid, 32 * DNW, smem, st>>>(map[0], map[1], tp);
     PG_LAUNCHED();
     return PG_OK;
 }
 
-template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const TiledParams &tp, int n_folds, int nw, int grid,
+template <int LIB> static int launch_tiled_t(const CUtensorMap (&map)[2], const TiledParams &tp, int n_folds, int nw, int grid,
                                              cudaStream_t st) {
     // time folds / no folds at the single-fold cost; per-row folds: two masked accumulator sets
     (void)n_folds; (void)nw;
@@ -628,10 +634,12 @@ template <int LIB> static int launch_tiled_t(const CUtensorMap &map, const Tiled
 
 int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st) {
     if (!encode_fn()) PG_FAIL(PG_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
-    CUtensorMap map;
+    CUtensorMap map[2];
     const int NW = plan.kernel_id;
-    const CUresult r = encode_field_map(&map, P.U, P.T, P.A0, P.A1, plan.tile0 + 4);
-    if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    for (int k = 0; k < 2; ++k) {
+        const CUresult r = encode_field_map(&map[k], P.U, P.T, P.A0, P.A1, plan.tile0 + 4, k ? P.A1 % 16 : 0);
+        if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    }
     TiledParams tp{};
     tp.U = P.U; tp.T = P.T; tp.A0 = P.A0; tp.A1 = P.A1;
     const double d0sq = P.c.d0sq, d1sq = P.c.d1sq;

@@ -134,12 +134,16 @@ inline int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-// 4-D tensor map over U[T][A0][A1] (fp64) viewed as (16, A1/16, A0, T), box (16, 8, box_rows, 1), 128-byte swizzle;
-// out-of-bounds elements are zero-filled.  Requires A1 % 16 == 0.
-inline CUresult encode_field_map(CUtensorMap *map, const double *U, int64_t T, int64_t A0, int64_t A1, int box_rows) {
+// 4-D tensor map over U[T][A0][A1] (fp64) viewed as (16, (A1 - col0)/16, A0, T) from column col0 on, box
+// (16, 8, box_rows, 1), 128-byte swizzle; out-of-bounds elements are zero-filled.  A box starts at a column
+// j0 with j0 % 16 == col0 (coordinate j0 >> 4); only the whole 16-column groups of a row are visible.
+// Requires A1 and col0 even (16-byte aligned rows) and A1 - col0 >= 16.
+inline CUresult encode_field_map(CUtensorMap *map, const double *U, int64_t T, int64_t A0, int64_t A1, int box_rows,
+                                 int64_t col0 = 0) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return CUDA_ERROR_NOT_SUPPORTED;
-    const cuuint64_t gdim[4] = {16, (cuuint64_t)(A1 / 16), (cuuint64_t)A0, (cuuint64_t)T};
+    U += col0;
+    const cuuint64_t gdim[4] = {16, (cuuint64_t)((A1 - col0) / 16), (cuuint64_t)A0, (cuuint64_t)T};
     const cuuint64_t gstr[3] = {128, (cuuint64_t)A1 * 8, (cuuint64_t)A0 * (cuuint64_t)A1 * 8};
     const cuuint32_t box[4] = {16, TJ / 16, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};

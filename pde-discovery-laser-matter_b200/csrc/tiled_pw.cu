@@ -183,9 +183,14 @@ __device__ __forceinline__ void march_pw(const double *__restrict__ st, const do
                         } else {
                             x[0] = Y; x[1] = uc; x[2] = uc * uc; x[3] = Lc; x[4] = B; x[5] = Gq; x[6] = uc * Lc;
                         }
+                        if constexpr (MASKED) {
+                            const bool ok = (colmask >> c) & 1u;
+#pragma unroll
+                            for (int k2 = 0; k2 < NX; ++k2) x[k2] = ok ? x[k2] : 0.0;
+                        }
                         pw_accumulate<NU, NACC>(acc, x);
                     }
-                    cnt += 4u;
+                    cnt += ncol;
                 }
             }
         }
@@ -282,7 +287,8 @@ __device__ __forceinline__ bool pw_flush(double (&acc)[Pw<LIB>::NACC], unsigned 
 // rows if they fall inside its window) with cp.async, one frame ahead, so they need warp-level visibility
 // only.
 template <int LIB, int R, int NW>
-__global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant__ CUtensorMap tmap, PwParams P) {
+__global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant__ CUtensorMap tmap,
+                                                          const __grid_constant__ CUtensorMap tmap_last, PwParams P) {
     using G_ = GeoPw<R, NW>;
     using X_ = Pw<LIB>;
     constexpr int TI = G_::TI, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES, NS = PW_NSTAGE;
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
     auto geometry = [&](int64_t item, int &i0, int &j0, int &t0, int &nf) {
         const int tile = (int)(item % n_tiles), chunk = (int)(item / n_tiles);
         i0 = (tile / P.n_tiles1) * TI;
-        j0 = (tile % P.n_tiles1) * TJ;
+        j0 = min((tile % P.n_tiles1) * TJ, (int)P.A1 - TJ);   // a width that is not a multiple of 128: the last tile column is shifted left
         t0 = chunk * P.chunk_frames;
         nf = (int)min((int64_t)P.chunk_frames, P.n_row_frames - t0);
     };
@@ -333,7 +339,8 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
     auto issue_load = [&](uint32_t s, int i0, int j0, int t) {
         fence_proxy_async();
         mbar_expect_tx(&full[s], G_::TMA_BYTES);
-        tma_load_4d(stages + s * STAGE_DOUBLES, &tmap, &full[s], 0, j0 >> 4, i0 - 2, t);
+        // a shifted tile column may start inside a 16-column group: tmap_last views the field from column A1 % 16
+        tma_load_4d(stages + s * STAGE_DOUBLES, (j0 & 15) ? &tmap_last : &tmap, &full[s], 0, j0 >> 4, i0 - 2, t);
     };
     // coordinates of the load `ahead` frames after frame f of `item`; walks into the following items of this
     // CTA; false when the CTA's stream of frames ends before that
@@ -366,6 +373,9 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
 
         // rows / columns of this warp / lane that are rows of the data set
         unsigned rowmask = 0, colmask = 0;
+        // a shifted last tile column skips the columns its left neighbour has already counted
+        const bool shifted = (j0 & (TJ - 1)) != 0;
+        const int64_t jmin = shifted ? (int64_t)(P.n_tiles1 - 1) * TJ : 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int64_t i = (int64_t)i0 + warp * R + r;
@@ -375,10 +385,10 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int64_t j = (int64_t)j0 + 4 * lm.g + c;
-            const bool ok = KS ? true : (j >= 2 && j < P.A1 - 2);
+            const bool ok = (KS ? true : (j >= 2 && j < P.A1 - 2)) && j >= jmin;
             colmask |= ok ? (1u << c) : 0u;
         }
-        const bool edge_cols = !KS && (j0 < 2 || (int64_t)j0 + TJ > P.A1 - 2);   // CTA-uniform
+        const bool edge_cols = shifted || (!KS && (j0 < 2 || (int64_t)j0 + TJ > P.A1 - 2));   // CTA-uniform
         const unsigned rows_per_frame = (unsigned)__popc(rowmask) * (unsigned)__popc(colmask);
 
         // Side cells of this warp's window (stage rows warp*R .. warp*R + R+3):
@@ -446,7 +456,8 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
                     }
                     const bool rows_all = rowmask == (1u << R) - 1u;   // warp-uniform
                     if constexpr (KS) {
-                        if (rows_all) march_pw<LIB, R, false, true>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                        if (edge_cols) march_pw<LIB, R, true, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                        else if (rows_all) march_pw<LIB, R, false, true>(st, stn, lm, P, rowmask, colmask, acc, cnt);
                         else march_pw<LIB, R, false, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
                     } else {
                         if (!edge_cols && rows_all) march_pw<LIB, R, false, true>(st, stn, lm, P, rowmask, colmask, acc, cnt);
@@ -479,7 +490,7 @@ bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     if (ks ? !(lib == PG_LIB_KS_TRUE || lib == PG_LIB_KS_TRUE_ADV || lib == PG_LIB_KS_RICH || lib == PG_LIB_KS_RICH_NOADV)
            : lib != PG_LIB_BASIC)
         return false;
-    if (P.A1 % 16 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // 4-D swizzled TMA view: whole 128-byte groups
+    if (P.A1 % 2 != 0 || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;   // 16-byte aligned rows for TMA / cp.async
     if (P.T < 2 || P.T > 0x7fffffff || P.A0 > 0x7fffffff || P.A1 > 0x7fffffff) return false;
     if (P.A0 < 4 || P.A1 < TJ) return false;
     if (!encode_fn()) return false;
@@ -487,7 +498,7 @@ bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     const int geo = pw_geo();
     const int NWg = geo == 1 ? 12 : 8;
     const int64_t nt0 = (P.A0 + TI - 1) / TI;
-    const int64_t nt1 = ks ? P.A1 / TJ : (P.A1 + TJ - 1) / TJ;
+    const int64_t nt1 = (P.A1 + TJ - 1) / TJ;   // a last tile column that is not whole is shifted left and masked
     const int64_t n_tiles = nt0 * nt1, nrf = P.T - 1;
     // number of frame chunks: balance the persistent CTAs; every item pays one extra frame + pipeline fill
     int64_t best_c = 1;
@@ -502,7 +513,7 @@ bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     plan = TiledPlan{};
     plan.nbt = nrf;
     plan.nb0 = P.R0;
-    plan.nb1 = ks ? nt1 * TJ : P.R1;
+    plan.nb1 = P.R1;
     plan.chunk_t = (int)cf;
     plan.n_chunks = (nrf + cf - 1) / cf;
     plan.n_tiles0 = nt0; plan.n_tiles1 = nt1;
@@ -515,21 +526,23 @@ bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     return true;
 }
 
-template <int LIB, int R, int NW> static int launch_pw_g(const CUtensorMap &map, const PwParams &pp, int grid, cudaStream_t st) {
+template <int LIB, int R, int NW> static int launch_pw_g(const CUtensorMap (&map)[2], const PwParams &pp, int grid, cudaStream_t st) {
     using G_ = GeoPw<R, NW>;
     PG_CUDA(cudaFuncSetAttribute(k1_tiled_pw<LIB, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
-    k1_tiled_pw<LIB, R, NW><<<grid, G_::THREADS, G_::SMEM, st>>>(map, pp);
+    k1_tiled_pw<LIB, R, NW><<<grid, G_::THREADS, G_::SMEM, st>>>(map[0], map[1], pp);
     PG_LAUNCHED();
     return PG_OK;
 }
-template <int LIB> static int launch_pw_t(const CUtensorMap &map, const PwParams &pp, int grid, int geo, cudaStream_t st) {
+template <int LIB> static int launch_pw_t(const CUtensorMap (&map)[2], const PwParams &pp, int grid, int geo, cudaStream_t st) {
     return geo == 1 ? launch_pw_g<LIB, 4, 12>(map, pp, grid, st) : launch_pw_g<LIB, 6, 8>(map, pp, grid, st);
 }
 
 int tiled_pw_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, cudaStream_t st) {
-    CUtensorMap map;
-    const CUresult r = encode_field_map(&map, P.U, P.T, P.A0, P.A1, 48 + 4);
-    if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    CUtensorMap map[2];
+    for (int k = 0; k < 2; ++k) {
+        const CUresult r = encode_field_map(&map[k], P.U, P.T, P.A0, P.A1, 48 + 4, k ? P.A1 % 16 : 0);
+        if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    }
     PwParams pp{};
     pp.U = P.U; pp.T = P.T; pp.A0 = P.A0; pp.A1 = P.A1;
     pp.rho = P.c.d1sq / P.c.d0sq;

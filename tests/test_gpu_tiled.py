@@ -31,7 +31,9 @@ def field(ops, shape, seed):
 @pytest.mark.parametrize("libname", list(LIBS))
 @pytest.mark.parametrize("shape,bt", [((7, 64, 128), 3),      # one tile: wraps on all four sides, two t-blocks
                                       ((10, 128, 256), 3),    # 2 x 2 tiles, three t-blocks
-                                      ((9, 72, 144), 3),      # remainder rows/cols + ragged t -> generic boxes
+                                      ((9, 72, 144), 3),      # ragged tile row, shifted last tile column (144 = 128 + 16), ragged t
+                                      ((7, 64, 136), 3),      # width % 16 == 8: the shifted column goes through the second tensor map
+                                      ((8, 76, 328), 2),      # rows that are not whole blocks -> generic box; 328 = 2 x 128 + 72
                                       ((6, 64, 384), 1),      # bt = 1, three tiles in a row
                                       ((12, 192, 128), 5),    # bt = 5, three tiles in a column, ragged t
                                       ((7, 88, 128), 3),      # ragged last tile row (88 = 64 + 24): wrap rows inside the box
@@ -159,3 +161,21 @@ def test_tiled_nonfinite_and_unsupported(env):
     with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
         ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 4, 8),
                         variant=L.VARIANT_TILED)
+    for shape in [(4, 64, 132), (4, 64, 120)]:      # ragged last block column; narrower than one tile
+        with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
+            ops.fd_lib_gram(field(ops, shape, seed=2), 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE,
+                            block=(3, 8, 8), variant=L.VARIANT_TILED)
+
+
+def test_shifted_tile_column_needs_no_generic_launch(env):
+    """A width that is a multiple of 8 but not of 128 is covered by the tiled kernel alone (last tile column shifted
+    left over its neighbour): the call launches exactly what a 128-multiple width launches."""
+    L, ops = env
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8), variant=L.VARIANT_AUTO)
+    counts = []
+    for A1 in (256, 200, 1000):
+        U = field(ops, (7, 64, A1), seed=3)
+        n0 = L.load().pg_launch_count()
+        ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, **kw)
+        counts.append(L.load().pg_launch_count() - n0)
+    assert counts[0] == counts[1] == counts[2]

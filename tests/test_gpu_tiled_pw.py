@@ -40,7 +40,8 @@ def basic_rows(U, d0, d1, dt):
                                    (4, 96, 256),      # 2 x 2 tiles
                                    (6, 64, 128),      # ragged last tile row (64 = 48 + 16): wrap rows inside the box
                                    (3, 20, 128),      # a single ragged tile: both wraps in one tile
-                                   (4, 100, 208)])    # ragged rows AND columns: remainder columns -> generic kernel
+                                   (4, 100, 208),     # ragged rows; shifted last tile column (208 = 128 + 80), masked columns
+                                   (3, 50, 330)])     # width % 16 == 10: the shifted column goes through the second tensor map
 def test_ks_pointwise_tiled(env, libname, shape):
     L, ops = env
     lib = getattr(L, libname)
@@ -172,7 +173,7 @@ def test_pointwise_unsupported_layouts_use_generic(env):
     with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
         ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, fold_of_row=fold,
                         variant=L.VARIANT_TILED)
-    odd = field(ops, (4, 48, 136), seed=7)      # the swizzled TMA view needs whole 128-byte column groups
+    odd = field(ops, (4, 48, 135), seed=7)      # TMA and the 16-byte side cells need 16-byte aligned rows: even widths
     with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
         ops.fd_lib_gram(odd, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, variant=L.VARIANT_TILED)
     narrow = field(ops, (4, 48, 64), seed=7)

@@ -25,6 +25,8 @@ BLOCK_CASES = [  # shape, bt, library, folds ("none" | "time3" | "row2")
     ((26, 512, 640), 5, "LIB_KS_RICH", "time3"),
     ((17, 200, 256), 2, "LIB_KS_RICH_NOADV", "row2"),
     ((300, 64, 128), 1, "LIB_KS_TRUE", "time3"),
+    ((31, 1000, 1000), 3, "LIB_KS_TRUE", "row2"),        # shifted last tile column, width % 16 == 8
+    ((22, 480, 720), 3, "LIB_KS_RICH", "time3"),         # 720 = 5 x 128 + 80
 ]
 
 
@@ -55,6 +57,9 @@ POINT_CASES = [  # shape, dialect, library, number of time folds
     ((30, 500, 768), "FD_KS_PERIODIC", "LIB_KS_RICH_NOADV", 1),
     ((30, 333, 640), "FD_BASIC_TRIM", "LIB_BASIC", 1),
     ((150, 96, 256), "FD_KS_PERIODIC", "LIB_KS_TRUE_ADV", 4),
+    ((21, 1000, 1000), "FD_KS_PERIODIC", "LIB_KS_TRUE", 2),     # shifted last tile column, width % 16 == 8
+    ((18, 250, 602), "FD_BASIC_TRIM", "LIB_BASIC", 2),          # basic_usage: shifted AND border-masked last column
+    ((16, 144, 170), "FD_KS_PERIODIC", "LIB_KS_RICH", 1),
 ]
 
 

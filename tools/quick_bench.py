@@ -77,6 +77,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--width", type=int, default=None, help="columns (default: --size)")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--generic", action="store_true")
     ap.add_argument("--sweep", action="store_true")
@@ -84,9 +85,10 @@ def main():
     ap.add_argument("--only", default=None, help="run a single named case")
     args = ap.parse_args()
     T, A = args.frames, args.size
-    U = ops.synth_field(T, A, A, seed=0, noise=0.05)
+    A1 = args.width or A
+    U = ops.synth_field(T, A, A1, seed=0, noise=0.05)
     torch.cuda.synchronize()
-    pts = T * A * A
+    pts = T * A * A1
     fof = (torch.arange(T - 1) >= int(0.7 * (T - 1))).to(torch.int32).cuda()  # on the device: no per-call copy
     out = []
     cases = [("true_b388_tiled", L.LIB_KS_TRUE, (3, 8, 8), L.VARIANT_TILED, 1),
