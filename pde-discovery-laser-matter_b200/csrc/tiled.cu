@@ -55,6 +55,7 @@ template <int NW> struct Geo {
 struct TiledParams {
     const double *U;
     int64_t T, A0, A1;
+    int A1c;                  // columns covered by tiles: the whole blocks, (A1 / 8) * 8
     double rho, kappa;        // L' = rho*(u[i+1]+u[i-1]) + (u[j+1]+u[j-1]) + kappa*u ; lap = r1*L'
     // Rows are accumulated UNSCALED (block sums without 1/h^k, 1/dt and 1/(64 bt)); sc[] holds the factor each
     // entry of the extended row [1, y, theta_0 ..] lacks, applied once per flush to the Gram products.
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
     auto geometry = [&](int64_t item, int &i0, int &j0, int64_t &tb0, int &nf) {
         const int tile = (int)(item % n_tiles), chunk = (int)(item / n_tiles);
         i0 = (tile / P.n_tiles1) * TI;
-        j0 = min((tile % P.n_tiles1) * TJ, (int)P.A1 - TJ);   // a width that is not a multiple of 128: the last tile column is shifted left
+        j0 = min((tile % P.n_tiles1) * TJ, P.A1c - TJ);   // a width that is not a multiple of 128: the last tile column is shifted left
         tb0 = (int64_t)chunk * P.chunk_tb;
         nf = (int)(min(P.n_row_frames, (tb0 + P.chunk_tb) * P.bt) - tb0 * P.bt);   // a ragged last t-block is shorter
     };
@@ -591,14 +592,16 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
         return false;
     if (P.b0 != 8 || P.b1 != 8) return false;
     if (P.n_folds > 2 && P.fold_of_row) return false;   // per-row folds: two masked accumulator sets; time folds: any number
-    // whole blocks along a1; 16-byte aligned rows for TMA / cp.async; at least one 128-column tile (a last tile column
-    // that does not start at a multiple of 128 is shifted left over its neighbour and skips the blocks already counted)
-    if (P.A1 % 8 != 0 || P.A1 < TJ || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;
+    // 16-byte aligned rows for TMA / cp.async; at least one 128-column tile.  The tiles cover the whole blocks along a1
+    // (a last tile column that does not start at a multiple of 128 is shifted left over its neighbour and skips the
+    // blocks already counted); a ragged last block column (A1 % 8 != 0) is left to the generic kernel.
+    if (P.A1 % 2 != 0 || P.A1 < TJ || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;
+    const int64_t A1c = P.A1 / 8 * 8;
     const int NW = DNW;
     const int TI = 8 * NW;
     const int workers = n_sm;
     // tile rows: a ragged last one is handled in-kernel when it still consists of whole blocks
-    const int64_t nt0 = P.A0 % 8 == 0 ? (P.A0 + TI - 1) / TI : P.A0 / TI, nt1 = (P.A1 + TJ - 1) / TJ;
+    const int64_t nt0 = P.A0 % 8 == 0 ? (P.A0 + TI - 1) / TI : P.A0 / TI, nt1 = (A1c + TJ - 1) / TJ;
     const int64_t nbt = (P.T - 1 + P.bt - 1) / P.bt;   // a ragged last t-block (fewer frames) is handled in-kernel
     if (nt0 < 1 || nt1 < 1 || nbt < 1) return false;
     if (P.T > 0x7fffffff || P.A0 > 0x7fffffff || P.A1 > 0x7fffffff) return false;
@@ -616,7 +619,7 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
         if (cost < best_cost - 1e-9) { best_cost = cost; best_c = cc; }
     }
     const int64_t ctb = (nbt + best_c - 1) / best_c;
-    plan.nbt = nbt; plan.nb0 = P.A0 % 8 == 0 ? P.A0 / 8 : nt0 * (TI / 8); plan.nb1 = P.A1 / 8;
+    plan.nbt = nbt; plan.nb0 = P.A0 % 8 == 0 ? P.A0 / 8 : nt0 * (TI / 8); plan.nb1 = A1c / 8;
     plan.chunk_t = (int)ctb; plan.n_chunks = (nbt + ctb - 1) / ctb;
     plan.n_tiles0 = nt0; plan.n_tiles1 = nt1;
     const int64_t items = n_tiles * plan.n_chunks;
@@ -655,11 +658,12 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     CUtensorMap map[2];
     const int NW = plan.kernel_id;
     for (int k = 0; k < 2; ++k) {
-        const CUresult r = encode_field_map(&map[k], P.U, P.T, P.A0, P.A1, plan.tile0 + 4, k ? P.A1 % 16 : 0);
+        const CUresult r = encode_field_map(&map[k], P.U, P.T, P.A0, P.A1, plan.tile0 + 4, k ? (P.A1 / 8 * 8) % 16 : 0);
         if (r != CUDA_SUCCESS) PG_FAIL(PG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     }
     TiledParams tp{};
     tp.U = P.U; tp.T = P.T; tp.A0 = P.A0; tp.A1 = P.A1;
+    tp.A1c = (int)(P.A1 / 8 * 8);
     const double d0sq = P.c.d0sq, d1sq = P.c.d1sq;
     tp.rho = d1sq / d0sq;
     tp.kappa = -2.0 * (1.0 + tp.rho);

@@ -34,6 +34,8 @@ def field(ops, shape, seed):
                                       ((9, 72, 144), 3),      # ragged tile row, shifted last tile column (144 = 128 + 16), ragged t
                                       ((7, 64, 136), 3),      # width % 16 == 8: the shifted column goes through the second tensor map
                                       ((8, 76, 328), 2),      # rows that are not whole blocks -> generic box; 328 = 2 x 128 + 72
+                                      ((7, 64, 132), 3),      # ragged last block column (4 columns) -> generic box
+                                      ((6, 72, 270), 2),      # 270 = 33 blocks + 6 columns: shifted tile at column 136 (second map)
                                       ((6, 64, 384), 1),      # bt = 1, three tiles in a row
                                       ((12, 192, 128), 5),    # bt = 5, three tiles in a column, ragged t
                                       ((7, 88, 128), 3),      # ragged last tile row (88 = 64 + 24): wrap rows inside the box
@@ -161,7 +163,7 @@ def test_tiled_nonfinite_and_unsupported(env):
     with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
         ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 4, 8),
                         variant=L.VARIANT_TILED)
-    for shape in [(4, 64, 132), (4, 64, 120)]:      # ragged last block column; narrower than one tile
+    for shape in [(4, 64, 131), (4, 64, 120)]:      # odd width (rows not 16-byte aligned); narrower than one tile
         with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
             ops.fd_lib_gram(field(ops, shape, seed=2), 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE,
                             block=(3, 8, 8), variant=L.VARIANT_TILED)
