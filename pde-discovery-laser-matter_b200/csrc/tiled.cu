@@ -370,7 +370,9 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         // periodic wrap rows then sit inside the TMA box, right below the last valid band
         const int vrows = (int)min((int64_t)TI, P.A0 - i0);
         const bool band_ok = warp * 8 < vrows;
-        const bool need_top = i0 == 0 && warp == 0, need_bot = i0 + TI >= P.A0 && warp == (vrows >> 3) - 1;
+        // (i0 + vrows + 2 > A0: one of the two halo rows below the tile lies beyond the frame -- also when the frame ends
+        // one row below a whole tile, A0 = 64 k + 1, whose remaining rows belong to the generic kernel)
+        const bool need_top = i0 == 0 && warp == 0, need_bot = (int64_t)i0 + vrows + 2 > P.A0 && warp == (vrows >> 3) - 1;
 
         // side cells of this warp's window (stage rows 8*warp .. 8*warp+11): lanes 0..23 one halo-column cell
         // each; the wrap rows TMA zero-filled (stage rows 0,1 / TI+2,TI+3) belong to the first / last band.

@@ -369,7 +369,9 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
         int i0, j0, t0, nf;
         geometry(item, i0, j0, t0, nf);
         const int vrows = (int)min((int64_t)TI, P.A0 - i0);      // tile rows inside the frame
-        const bool wt = KS && i0 == 0, wb = KS && i0 + TI >= P.A0;
+        // wb: one of the two halo rows below the tile lies beyond the frame (also A0 = 48 k + 1: the frame ends one row
+        // below a whole tile)
+        const bool wt = KS && i0 == 0, wb = KS && (int64_t)i0 + vrows + 2 > P.A0;
 
         // rows / columns of this warp / lane that are rows of the data set
         unsigned rowmask = 0, colmask = 0;

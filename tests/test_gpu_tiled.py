@@ -35,6 +35,8 @@ def field(ops, shape, seed):
                                       ((7, 64, 136), 3),      # width % 16 == 8: the shifted column goes through the second tensor map
                                       ((8, 76, 328), 2),      # rows that are not whole blocks -> generic box; 328 = 2 x 128 + 72
                                       ((7, 64, 132), 3),      # ragged last block column (4 columns) -> generic box
+                                      ((7, 65, 128), 3),      # the frame ends one row below a whole tile: its second halo row wraps
+                                      ((5, 129, 256), 2),
                                       ((6, 72, 270), 2),      # 270 = 33 blocks + 6 columns: shifted tile at column 136 (second map)
                                       ((6, 64, 384), 1),      # bt = 1, three tiles in a row
                                       ((12, 192, 128), 5),    # bt = 5, three tiles in a column, ragged t

@@ -41,7 +41,9 @@ def basic_rows(U, d0, d1, dt):
                                    (6, 64, 128),      # ragged last tile row (64 = 48 + 16): wrap rows inside the box
                                    (3, 20, 128),      # a single ragged tile: both wraps in one tile
                                    (4, 100, 208),     # ragged rows; shifted last tile column (208 = 128 + 80), masked columns
-                                   (3, 50, 330)])     # width % 16 == 10: the shifted column goes through the second tensor map
+                                   (3, 50, 330),      # width % 16 == 10: the shifted column goes through the second tensor map
+                                   (3, 49, 128),      # the frame ends one row below a whole tile: its second halo row wraps
+                                   (3, 97, 256)])
 def test_ks_pointwise_tiled(env, libname, shape):
     L, ops = env
     lib = getattr(L, libname)
