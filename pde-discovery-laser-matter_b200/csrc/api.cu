@@ -94,6 +94,53 @@ static int describe(K1Params &P, const double *U, int64_t T, int64_t A0, int64_t
     return PG_OK;
 }
 
+// KS dialect, (bt, 8m, 8n) blocks on a grid of whole (8, 8) sub-blocks: the tiled kernel writes the block-mean rows of
+// the (bt, 8, 8) sub-blocks (EMIT), the generic kernel averages the sub-block rows of each block (equal sizes, so the
+// mean of means is the block mean; ragged edge blocks hold fewer sub-blocks) and accumulates the statistics with the
+// caller's folds.  The rows are (p+1)/(64 bt) of the field's bytes.  Returns 1 when the layout does not qualify.
+static int two_stage_blocks(const K1Params &P, int lib, int64_t nBt, int64_t len, double *stats_out, int64_t *nonfinite_out,
+                            cudaStream_t st) {
+    if (P.dialect != PG_FD_KS_PERIODIC || P.b0 % 8 || P.b1 % 8 || P.A0 % 8 || P.A1 % 8) return 1;
+    // (bt, 8, 8) itself is fused in one kernel, except with more than two per-row folds (its masked accumulators hold two)
+    if (P.b0 == 8 && P.b1 == 8 && !(P.fold_of_row && P.n_folds > 2)) return 1;
+    K1Params Q = P;
+    Q.b0 = Q.b1 = 8; Q.nB0 = P.A0 / 8; Q.nB1 = P.A1 / 8;
+    Q.fold_of_row = nullptr; Q.fold_of_frame = nullptr; Q.n_folds = 1;
+    TiledPlan plan{};
+    if (!tiled_plan(Q, lib, nBt, sm_count(), plan)) return 1;
+    if (plan.nbt != nBt || plan.nb0 != Q.nB0 || plan.nb1 != Q.nB1) return 1;   // the tiles must cover the grid
+    const int p = library_width(lib), S = PG_STATS_LEN(p);
+    const int64_t items = nBt * P.nB0 * P.nB1;
+    int64_t g = (items + GW_THREADS - 1) / GW_THREADS;
+    const int ctas = (int)(g < 1 ? 1 : (g > sm_count() * 8 ? sm_count() * 8 : g));
+    const int64_t gen_parts = (int64_t)ctas * GW_WARPS;
+    const size_t b_parts = sizeof(double) * (size_t)(gen_parts * len + plan.n_parts * S);
+    const size_t b_extra = (plan.extra_scratch + 15) / 16 * 16;
+    const size_t b_rows = sizeof(double) * (size_t)(nBt * Q.nB0 * Q.nB1 * (p + 1));
+    void *scr = nullptr;
+    int rc = scratch_for(st, 64 + b_parts + b_extra + b_rows, &scr);
+    if (rc) return rc;
+    unsigned long long *counters = (unsigned long long *)scr;
+    double *partials = (double *)((char *)scr + 64);
+    char *extra = (char *)scr + 64 + b_parts;
+    double *rows8 = (double *)(extra + b_extra);
+    PG_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+    Q.counters = counters;
+    rc = tiled_launch(Q, lib, plan, partials + gen_parts * len, extra, st, rows8);
+    if (rc) return rc;
+    K1Params G = P;
+    G.counters = counters;
+    G.tb_lo = 0; G.tb_hi = nBt; G.i0_lo = 0; G.i0_hi = P.nB0; G.i1_lo = 0; G.i1_hi = P.nB1;
+    G.partials = partials; G.run_if = nullptr;
+    G.rows8 = rows8; G.sub0 = Q.nB0; G.sub1 = Q.nB1;
+    rc = launch_k1_generic(lib, G, ctas, st);
+    if (rc) return rc;
+    rc = launch_reduce_partials(partials, gen_parts, len, stats_out, 0, st);
+    if (rc) return rc;
+    if (nonfinite_out) PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    return PG_OK;
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -148,6 +195,10 @@ int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0
     const int64_t nBt = (Trows + bt - 1) / bt;
     P.nB0 = (P.R0 + b0 - 1) / b0; P.nB1 = (P.R1 + b1 - 1) / b1;
 
+    if (variant != PG_VARIANT_GENERIC) {
+        rc = two_stage_blocks(P, library_id, nBt, len, stats_out, nonfinite_out, st);
+        if (rc <= 0) return rc;
+    }
     // Tiled TMA kernels over the region they support; the generic kernel covers what is left.
     TiledPlan plan{};
     bool tiled = false, pointwise = false;

@@ -69,9 +69,22 @@ __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
             const int64_t jb = P.i1_lo + idx % n2;
             const int64_t ib = P.i0_lo + (idx / n2) % n1;
             const int64_t tb = P.tb_lo + idx / (n2 * n1);
-            const int64_t t0 = tb * P.bt, t1 = min(Trows, t0 + P.bt);
-            const int64_t i0 = ib * P.b0, i1 = min(P.R0, i0 + P.b0);
-            const int64_t j0 = jb * P.b1, j1 = min(P.R1, j0 + P.b1);
+            int64_t t0 = tb * P.bt, t1 = min(Trows, t0 + P.bt);
+            int64_t i0 = ib * P.b0, i1 = min(P.R0, i0 + P.b0);
+            int64_t j0 = jb * P.b1, j1 = min(P.R1, j0 + P.b1);
+            if (P.rows8) {
+                // second stage of the tiled path for (bt, 8m, 8n) blocks: the block mean is the mean of the equally
+                // sized (bt, 8, 8) sub-block means the tiled kernel wrote (ragged edge blocks hold fewer of them)
+                const int64_t s0 = i0 >> 3, s1 = (i1 + 7) >> 3, c0 = j0 >> 3, c1 = (j1 + 7) >> 3;
+                for (int64_t a = s0; a < s1; ++a)
+                    for (int64_t b = c0; b < c1; ++b) {
+                        const double *r = P.rows8 + ((tb * P.sub0 + a) * P.sub1 + b) * (p + 1);
+                        y = __dadd_rn(y, r[0]);
+#pragma unroll
+                        for (int k = 0; k < p; ++k) th[k] = __dadd_rn(th[k], r[1 + k]);
+                    }
+                t1 = t0 + 1; i0 = s0; i1 = s1; j0 = c0; j1 = c1;      // the divisor below: the number of sub-blocks
+            } else
             for (int64_t t = t0; t < t1; ++t) {
                 const double *F = P.U + t * frame;
                 const double *Fn = F + frame;

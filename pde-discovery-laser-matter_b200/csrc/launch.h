@@ -28,6 +28,10 @@ struct K1Params {
     unsigned long long *counters;   // [0] non-finite rows, [1] rows with an out-of-range fold id / index,
                                     // [2] set by the tiled pointwise kernel when a flushed accumulator was not finite
     const unsigned long long *run_if;  // nullable: the generic kernel only runs if *run_if != 0 (fallback launch)
+    // nullable: block-mean rows [nbt][sub0][sub1][p+1] (y first) of (bt, 8, 8) sub-blocks written by the tiled kernel; the
+    // generic kernel then averages the (b0/8) x (b1/8) sub-block rows of each block instead of evaluating grid points
+    const double *rows8;
+    int64_t sub0, sub1;
 };
 
 struct RowsParams {
@@ -101,6 +105,8 @@ int tiled_pw_launch(const K1Params &P, int lib, const TiledPlan &plan, double *p
 
 // tiled.cu ((bt,8,8) block means)
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan);
-int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st);
+// rows8 != null: write the block-mean rows [nbt][A0/8][A1/8][p+1] instead of accumulating statistics
+int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st,
+                 double *rows8 = nullptr);
 
 }  // namespace pg

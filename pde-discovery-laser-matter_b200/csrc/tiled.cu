@@ -75,6 +75,7 @@ struct TiledParams {
     int n_folds;
     double *partials;         // [gridDim.x*NW][n_folds][S]
     unsigned long long *counters;
+    double *rows8;            // EMIT kernels: block-mean rows [nbt][A0/8][A1c/8][p+1] (y first) instead of statistics
 };
 
 // ----------------------------------------------------------------------------- per-lane block sums
@@ -222,7 +223,9 @@ __device__ __forceinline__ double sum_frame_u(const double *__restrict__ st, con
 //     folds runs at the single-fold cost.  !TIMEFOLD: fold_of_row, NF <= 2 masked accumulators as before.
 constexpr int DNW = 8;   // consumer warps
 
-template <int LIB, int NF, bool TIMEFOLD>
+//   * EMIT: the (scaled) block-mean rows are written to P.rows8 instead of being accumulated: first stage of the path
+//     for (bt, 8m, 8n) blocks, whose rows are means of these sub-block rows (api.cu).
+template <int LIB, int NF, bool TIMEFOLD, bool EMIT = false>
 __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap,
                                                             const __grid_constant__ CUtensorMap tmap_last, TiledParams P) {
     constexpr int NW = DNW;
@@ -493,10 +496,18 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                     for (int k = 0; k < p; ++k)
                         if (!(kRich<LIB> && k == 0)) th[k] *= ratio;
                 }
+                if constexpr (EMIT) {
+                    if ((lane & 8) == 0 && col_ok) {
+                        double *r = P.rows8 + ((tbs * (P.A0 >> 3) + ib) * (int64_t)(P.A1c >> 3) + jb) * (p + 1);
+                        r[0] = y_ * P.sc[1];
+#pragma unroll
+                        for (int k = 0; k < p; ++k) r[1 + k] = th[k] * P.sc[2 + k];
+                    }
+                }
                 bool fin = isfinite(y_);
 #pragma unroll
                 for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
-                bool valid = (lane & 8) == 0 && col_ok;
+                bool valid = (lane & 8) == 0 && col_ok && !EMIT;
                 if (valid && !fin) { valid = false; ++bad_rows; }
                 else if (valid && (fold < 0 || fold >= P.n_folds)) { valid = false; ++bad_fold; }
                 if constexpr (TIMEFOLD) {
@@ -638,11 +649,11 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
     return true;
 }
 
-template <int LIB, int NF, bool TIMEFOLD> static int launch_tiled_d(const CUtensorMap (&map)[2], const TiledParams &tp, int grid,
-                                                                     cudaStream_t st) {
+template <int LIB, int NF, bool TIMEFOLD, bool EMIT = false>
+static int launch_tiled_d(const CUtensorMap (&map)[2], const TiledParams &tp, int grid, cudaStream_t st) {
     const size_t smem = Geo<DNW>::smem(Lib<LIB>::P);
-    PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, TIMEFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1_tiled_b88<LIB, NF, TIMEFOLD><<<grid, 32 * DNW, smem, st>>>(map[0], map[1], tp);
+    PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, TIMEFOLD, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_tiled_b88<LIB, NF, TIMEFOLD, EMIT><<<grid, 32 * DNW, smem, st>>>(map[0], map[1], tp);
     PG_LAUNCHED();
     return PG_OK;
 }
@@ -651,11 +662,13 @@ template <int LIB> static int launch_tiled_t(const CUtensorMap (&map)[2], const 
                                              cudaStream_t st) {
     // time folds / no folds at the single-fold cost; per-row folds: two masked accumulator sets
     (void)n_folds; (void)nw;
+    if (tp.rows8) return launch_tiled_d<LIB, 1, true, true>(map, tp, grid, st);
     if (!tp.fold_of_row) return launch_tiled_d<LIB, 1, true>(map, tp, grid, st);
     return launch_tiled_d<LIB, 2, false>(map, tp, grid, st);
 }
 
-int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st) {
+int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st,
+                 double *rows8) {
     if (!encode_fn()) PG_FAIL(PG_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
     CUtensorMap map[2];
     const int NW = plan.kernel_id;
@@ -706,6 +719,7 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     tp.nbt = plan.nbt; tp.n_row_frames = P.T - 1; tp.nB0 = P.nB0; tp.nB1 = P.nB1;
     tp.fold_of_row = P.fold_of_row; tp.fold_of_frame = P.fold_of_frame; tp.n_folds = P.n_folds;
     tp.partials = partials; tp.counters = P.counters;
+    tp.rows8 = rows8;
     switch (lib) {
         case PG_LIB_KS_TRUE: return launch_tiled_t<PG_LIB_KS_TRUE>(map, tp, P.n_folds, NW, plan.grid, st);
         case PG_LIB_KS_TRUE_ADV: return launch_tiled_t<PG_LIB_KS_TRUE_ADV>(map, tp, P.n_folds, NW, plan.grid, st);

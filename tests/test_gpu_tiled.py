@@ -183,3 +183,54 @@ def test_shifted_tile_column_needs_no_generic_launch(env):
         ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, **kw)
         counts.append(L.load().pg_launch_count() - n0)
     assert counts[0] == counts[1] == counts[2]
+
+
+@pytest.mark.parametrize("libname", ["LIB_KS_TRUE", "LIB_KS_RICH"])
+@pytest.mark.parametrize("shape,block", [((10, 128, 256), (3, 16, 16)),     # 2 x 2 sub-blocks per block
+                                         ((9, 72, 144), (2, 8, 32)),        # ragged edge blocks: 144 = 4 x 32 + 16
+                                         ((7, 192, 384), (3, 64, 128)),     # a block as large as a tile
+                                         ((8, 200, 272), (3, 24, 40))])     # multiples of 8 that do not divide the tile
+def test_blocks_of_whole_sub_blocks_two_stage(env, libname, shape, block):
+    """(bt, 8m, 8n) blocks: the tiled kernel writes the (bt, 8, 8) sub-block rows, the second stage averages them per
+    block (ks2d:358-401 keeps ragged edge blocks with their own divisor) -- against the generic kernel and the oracle."""
+    L, ops = env
+    lib = getattr(L, libname)
+    p = L.LIB_WIDTH[lib]
+    U = field(ops, shape, seed=shape[2] + block[1])
+    d0, d1, dt = 0.5, 0.4, 1e-3
+    nrows = -(-(shape[0] - 1) // block[0]) * -(-shape[1] // block[1]) * -(-shape[2] // block[2])
+    fold = np.random.default_rng(5).integers(0, 2, size=nrows).astype(np.uint8)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=block, fold_of_row=fold, n_folds=2)
+    n0 = L.load().pg_launch_count()
+    til = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    assert L.load().pg_launch_count() - n0 == 3          # tiled (rows), generic (combine), reduction
+    gen = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    for f in range(2):
+        assert_stats_close(til[f], gen[f], p)
+    dictionary, adv, _ = LIBS[libname]
+    _, X, y = ks_rows(U.cpu().numpy(), d0, d1, dt, dictionary, adv, block)
+    assert X.shape[0] == nrows
+    for f in range(2):
+        assert_stats_close(til[f], gram.pack_stats(X[fold == f], y[fold == f]), p)
+    # time folds and a NaN: the block that holds it is dropped and counted, like the generic kernel does
+    U[2, 5, 7] = float("nan")
+    fof = (np.arange(shape[0] - 1) >= (shape[0] - 1) // 2).astype(np.int32)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=block, fold_of_frame=fof, n_folds=2, return_nonfinite=True)
+    til, bad_t = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_TILED, **kw)
+    gen, bad_g = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_GENERIC, **kw)
+    assert int(bad_t.item()) == int(bad_g.item()) > 0
+    for f in range(2):
+        assert_stats_close(til.cpu().numpy()[f], gen.cpu().numpy()[f], p)
+
+
+def test_many_row_folds_go_through_the_sub_block_rows(env):
+    """More than two per-row folds with (bt, 8, 8) blocks: rows from the tiled kernel, folds applied by the second stage."""
+    L, ops = env
+    shape, bt = (10, 128, 256), 3
+    U = field(ops, shape, seed=11)
+    fold = np.random.default_rng(2).integers(0, 5, size=3 * 16 * 32).astype(np.uint8)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(bt, 8, 8), fold_of_row=fold, n_folds=5)
+    til = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
+    gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
+    for f in range(5):
+        assert_stats_close(til[f], gen[f], 3)
