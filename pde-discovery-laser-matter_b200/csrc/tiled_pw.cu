@@ -101,10 +101,21 @@ __host__ __device__ constexpr PwPair pw_entry(int e, int p, bool one) {
     return ua <= ub ? PwPair{ua, ub} : PwPair{ub, ua};
 }
 
-template <int NU, int NACC> __device__ __forceinline__ void pw_accumulate(double (&acc)[NACC], const double (&x)[NU - 1]) {
+// Columns that are products of two other columns make a linear sum equal to a pair sum: sum(u^2 * 1) == sum(u * u),
+// sum((u L') * 1) == sum(u * L').  pw_dup(b) = the pair (a1, a2) whose accumulator already holds the sum of unique
+// column b (a1 = 0: none); such linear sums are not accumulated and pw_emit reads the pair's accumulator instead.
+template <int LIB> __host__ __device__ constexpr PwPair pw_dup(int b) {
+    if (LIB == PG_LIB_BASIC) return b == 6 ? PwPair{2, 2} : PwPair{0, 0};                                  // u^2
+    if (LIB == PG_LIB_KS_RICH) return b == 3 ? PwPair{2, 2} : (b == 9 ? PwPair{2, 6} : PwPair{0, 0});       // u^2, u L'
+    if (LIB == PG_LIB_KS_RICH_NOADV) return b == 3 ? PwPair{2, 2} : (b == 7 ? PwPair{2, 4} : PwPair{0, 0});
+    return PwPair{0, 0};
+}
+
+template <int LIB, int NU, int NACC> __device__ __forceinline__ void pw_accumulate(double (&acc)[NACC], const double (&x)[NU - 1]) {
     int k = 0;
 #pragma unroll
-    for (int b = 1; b < NU; ++b) acc[k++] += x[b - 1];
+    for (int b = 1; b < NU; ++b, ++k)
+        if (pw_dup<LIB>(b).a == 0) acc[k] += x[b - 1];
 #pragma unroll
     for (int a = 1; a < NU; ++a)
 #pragma unroll
@@ -188,7 +199,7 @@ __device__ __forceinline__ void march_pw(const double *__restrict__ st, const do
 #pragma unroll
                             for (int k2 = 0; k2 < NX; ++k2) x[k2] = ok ? x[k2] : 0.0;
                         }
-                        pw_accumulate<NU, NACC>(acc, x);
+                        pw_accumulate<LIB, NU, NACC>(acc, x);
                     }
                     cnt += ncol;
                 }
@@ -225,7 +236,7 @@ __device__ __forceinline__ void march_pw(const double *__restrict__ st, const do
                             uc = ok ? uc : 0.0; Y = ok ? Y : 0.0; dxj = ok ? dxj : 0.0; dxi = ok ? dxi : 0.0; Lc = ok ? Lc : 0.0;
                         }
                         const double x[NX] = {Y, uc, dxj, dxi, Lc, uc * uc};
-                        pw_accumulate<NU, NACC>(acc, x);
+                        pw_accumulate<LIB, NU, NACC>(acc, x);
                     }
                     cnt += ncol;
                 }
@@ -242,6 +253,10 @@ template <int LIB, int E> __device__ __forceinline__ void pw_emit(const double (
     if (lane == (E & 31)) {
         double v;
         if constexpr (pr.a == 0 && pr.b == 0) v = n;
+        else if constexpr (pr.a == 0 && pw_dup<LIB>(pr.b).a != 0) {
+            constexpr PwPair d = pw_dup<LIB>(pr.b);     // linear sum of a product column: held by the pair's accumulator
+            v = acc[pw_slot(X_::NU, d.a, d.b)] * (sc[d.a] * sc[d.b]);
+        }
         else v = acc[pw_slot(X_::NU, pr.a, pr.b)] * (sc[pr.a] * sc[pr.b]);
         out[E] += v;
     }
