@@ -213,6 +213,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     halo = None
+    # PG_HALO: "peer" (default) = whole frame pulled through NVLink peer memory under K1, then a short tail launch;
+    # "means" = (8, 8) block means of the frame through peer memory, one K1 launch; "send_recv" / "send_recv_means" = the
+    # same two through NCCL point-to-point (A/B comparisons; profiles/README.md)
+    halo_kind = os.environ.get("PG_HALO", "peer")
+    halo_means = halo_kind.endswith("means")
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         with _StdoutToStderr():
@@ -244,13 +249,7 @@ def run_ours(args):
     fof_pass = []
     if world > 1:
         with _StdoutToStderr():
-            halo = slabs.PeerHalo((A, A)) if os.environ.get("PG_HALO", "peer") != "send_recv" else None
-        if halo is None:
-            class _SendRecv:   # NCCL point-to-point path (A/B comparison: PG_HALO=send_recv)
-                mode = "send_recv"
-                begin = staticmethod(lambda U_: slabs.exchange_halo_begin(U_) or None)
-                end = staticmethod(lambda tok: slabs.exchange_halo_end(tok))
-            halo = _SendRecv()
+            halo = slabs.PeerHalo((A, A), peer_memory=not halo_kind.startswith("send_recv"))
 
     def fill(ps):
         """(Re)generate sub-slab `ps` of this rank's slab; the trailing frame of the rank's LAST sub-slab comes
@@ -280,8 +279,26 @@ def run_ours(args):
                 fill(ps)
             # the halo frame is only read by the last t-block: start the exchange, run K1 on everything before
             # that block while the frame is in flight, then the small tail launch (statistics are additive)
-            token = halo.begin(U) if (world > 1 and ps == passes - 1) else None
             kw = dict(dialect=L.FD_KS_PERIODIC, library=library, block=block, n_folds=2, variant=variant)
+            if world > 1 and ps == passes - 1 and halo_means:
+                # default: the halo travels as (8, 8) block means of the neighbour's first frame (1/64 of its bytes) and
+                # K1 is ONE launch over the whole slab (pg_fd_lib_gram_tail)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if (record or passes > 1) else None
+                if ev:
+                    ev[2].record()
+                token, tail = halo.begin_block_means(U)
+                halo.end(token)
+                if ev:
+                    ev[0].record()
+                s = ops.fd_lib_gram(U, D0, D1, DT, fold_of_frame=fof_pass[ps], trailing_block_means=tail, **kw)
+                if ev:
+                    ev[1].record()
+                    if record:
+                        k1_ev.append([(ev[0], ev[1])])
+                    pass_ev.append((ev[2], ev[1]))
+                stats = s if stats is None else stats + s
+                continue
+            token = halo.begin(U) if (world > 1 and ps == passes - 1) else None
             cut = ((rows - 1) // block[0]) * block[0] if token is not None else rows
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if (record or passes > 1) else None
             if ev:
@@ -548,7 +565,7 @@ def run_ours(args):
                    f"c5: ONE synthetic {A}x{A}x{g_rows + 1} float64 stack in {world} time slab(s) of {rows_rank} row frames"
                    f"{' streamed through one buffer in %d passes (generator refill excluded)' % passes if passes > 1 else ''}, "
                    "KS periodic dialect, true dictionary p=3, block average (3,8,8), 2 time-holdout folds, 5x6 STRidge sweep", "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (pts_rank * 8 / 1e9),
-                   "parallelism": f"time slabs x{world}, 1-frame halo ({halo.mode}), all-reduce of 2x18 doubles" if world > 1 else "single GPU",
+                   "parallelism": (f"time slabs x{world}, 1-frame halo " + ("as 8x8 block means " if halo_means else "") + f"({halo.mode}), all-reduce of 2x18 doubles") if world > 1 else "single GPU",
                    "selected": {"alpha": float(alphas.cpu()[best // 6]), "threshold": float(thrs.cpu()[best % 6]),
                                 "coeffs": dict(zip(names, [float(c) for c in coef]))}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -115,6 +115,20 @@ PG_API int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, do
                    int variant, void *stream);
 
 /*
+ * pg_fd_lib_gram for a time slab whose trailing frame lives on another GPU (the forward u_t of
+ * ks2d:1511 is the only reader of frame T-1).  With (bt, 8m, 8n) blocks the time derivative of a block telescopes
+ * to a difference of block sums of u, so the (8, 8) block MEANS of the neighbour's first frame
+ * (`trailing_block_means`, [A0/8][A1/8], e.g. from pg_block_means on that frame: 1/64 of the frame's bytes) stand in
+ * for the frame itself: frame T-1 of U is then a placeholder whose values are ignored.  Needs a layout the tiled
+ * kernel covers completely (KS dialect, A0 % 8 == 0, A1 % 8 == 0, A1 >= 128, 16-byte aligned U), else
+ * PG_EUNSUPPORTED; trailing_block_means == NULL is pg_fd_lib_gram.
+ */
+PG_API int pg_fd_lib_gram_tail(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                   int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
+                   const int32_t *fold_of_frame, int n_folds, const double *trailing_block_means, double *stats_out,
+                   int64_t *nonfinite_out, int variant, void *stream);
+
+/*
  * Materialised term stacks, bit-identical to the reference's NumPy arithmetic (no FMA
  * contraction, true division).  PG_FD_KS_PERIODIC: terms_out [p][T][A0][A1] over ALL T
  * frames given (ks2d:63-73, 1017-1104).  PG_FD_BASIC_TRIM with PG_LIB_BASIC: terms_out is

@@ -47,6 +47,8 @@ _PROTOS = {
     "pg_library_width": (C.c_int, [_i32]),
     "pg_fd_lib_gram": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
                                  _i32, _ptr, _ptr, _i32, _ptr]),
+    "pg_fd_lib_gram_tail": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
+                                      _i32, _ptr, _ptr, _ptr, _i32, _ptr]),
     "pg_fd_terms": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _ptr, _ptr]),
     "pg_fd_gather_rows": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _ptr, _i64, _ptr, _ptr, _ptr]),
     "pg_block_means": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr]),

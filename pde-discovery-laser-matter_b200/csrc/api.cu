@@ -174,6 +174,14 @@ int pg_shutdown(void) {
 int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
                    int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
                    int n_folds, double *stats_out, int64_t *nonfinite_out, int variant, void *stream) {
+    return pg_fd_lib_gram_tail(U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
+                               nullptr, stats_out, nonfinite_out, variant, stream);
+}
+
+int pg_fd_lib_gram_tail(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+                        int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
+                        int n_folds, const double *trailing_block_means, double *stats_out, int64_t *nonfinite_out,
+                        int variant, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     K1Params P{};
     int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, true);
@@ -186,6 +194,9 @@ int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0
     const int64_t Trows = T - 1;
     P.bt = bt; P.b0 = b0; P.b1 = b1;
     P.fold_of_row = fold_of_row; P.fold_of_frame = fold_of_frame; P.n_folds = n_folds;
+    P.tail_means = trailing_block_means;
+    if (trailing_block_means && variant == PG_VARIANT_GENERIC)
+        PG_FAIL(PG_EUNSUPPORTED, "trailing_block_means is served by the tiled blockwise kernel only");
     const int64_t len = (int64_t)n_folds * S;
     if (Trows <= 0) {  // a single frame has no u_t: zero rows
         PG_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * len, st));
@@ -209,6 +220,9 @@ int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0
             PG_FAIL(PG_EUNSUPPORTED, "no tiled kernel for dialect %d library %d block (%d,%d,%d) shape (%lld,%lld,%lld)",
                     fd_dialect, library_id, bt, b0, b1, (long long)T, (long long)A0, (long long)A1);
     }
+    if (trailing_block_means && !(tiled && !pointwise && plan.nbt == nBt && plan.nb0 == P.nB0 && plan.nb1 == P.nB1))
+        PG_FAIL(PG_EUNSUPPORTED, "trailing_block_means needs a layout the tiled blockwise kernel covers completely "
+                "(KS dialect, (bt, 8m, 8n) blocks, A0 %% 8 == 0, A1 %% 8 == 0, A1 >= 128); send the whole frame instead");
     // generic launches: up to 4 boxes of block indices (the whole space when not tiled).  Box 0 of the
     // pointwise path is its conditional fallback: the tiled region again, run only if that kernel saw a
     // non-finite accumulator (the reference drops such rows; the generic kernel does it exactly).

@@ -32,6 +32,9 @@ struct K1Params {
     // generic kernel then averages the (b0/8) x (b1/8) sub-block rows of each block instead of evaluating grid points
     const double *rows8;
     int64_t sub0, sub1;
+    // nullable: (8, 8) block means [A0/8][A1/8] of the frame after the last row frame; frame T-1 of U is then a
+    // placeholder (tiled blockwise kernel only: pg_fd_lib_gram_tail)
+    const double *tail_means;
 };
 
 struct RowsParams {

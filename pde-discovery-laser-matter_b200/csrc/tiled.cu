@@ -76,6 +76,7 @@ struct TiledParams {
     double *partials;         // [gridDim.x*NW][n_folds][S]
     unsigned long long *counters;
     double *rows8;            // EMIT kernels: block-mean rows [nbt][A0/8][A1c/8][p+1] (y first) instead of statistics
+    const double *tail_means; // nullable: block means [A0/8][A1c/8] of the frame after the last row frame (it then is a placeholder)
 };
 
 // ----------------------------------------------------------------------------- per-lane block sums
@@ -448,6 +449,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             Sums F;
             if (band_ok) {
                 if (f < nf) march_frame<LIB>(st, lm, P, F);
+                else if (P.tail_means && t0 + nf == P.n_row_frames)   // the slab's trailing frame lives on another GPU
+                    F.SU = (lane & 8) ? 0.0 : 64.0 * P.tail_means[ib * (int64_t)(P.A1c >> 3) + jb];
                 else F.SU = sum_frame_u(st, lm);
             }
 
@@ -720,6 +723,7 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     tp.fold_of_row = P.fold_of_row; tp.fold_of_frame = P.fold_of_frame; tp.n_folds = P.n_folds;
     tp.partials = partials; tp.counters = P.counters;
     tp.rows8 = rows8;
+    tp.tail_means = P.tail_means;
     switch (lib) {
         case PG_LIB_KS_TRUE: return launch_tiled_t<PG_LIB_KS_TRUE>(map, tp, P.n_folds, NW, plan.grid, st);
         case PG_LIB_KS_TRUE_ADV: return launch_tiled_t<PG_LIB_KS_TRUE_ADV>(map, tp, P.n_folds, NW, plan.grid, st);

@@ -39,8 +39,12 @@ def field(U):
 
 
 def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row=None, fold_of_frame=None,
-                n_folds=1, variant=L.VARIANT_AUTO, return_nonfinite=False):
-    """K1: field -> statistics [n_folds][S(p)] without materialising Theta (pg_fd_lib_gram)."""
+                n_folds=1, variant=L.VARIANT_AUTO, return_nonfinite=False, trailing_block_means=None):
+    """K1: field -> statistics [n_folds][S(p)] without materialising Theta (pg_fd_lib_gram).
+
+    ``trailing_block_means`` ([A0/8][A1/8], see ``frame_block_means``): the (8, 8) block means of the frame that
+    follows U[-2]; U[-1] is then a placeholder whose values are ignored (pg_fd_lib_gram_tail: time slabs whose
+    trailing frame lives on another GPU)."""
     torch = L.torch_cuda()
     lib = L.load()
     U = field(U)
@@ -58,9 +62,32 @@ def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row
         raise ValueError(f"fold_of_frame must have T-1 = {T - 1} entries")
     stats = torch.empty((n_folds, L.stats_len(p)), dtype=torch.float64, device=U.device)
     bad = torch.zeros(1, dtype=torch.int64, device=U.device)
-    L.check(lib.pg_fd_lib_gram(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0, b1,
-                               L.ptr(fr), L.ptr(ff), n_folds, L.ptr(stats), L.ptr(bad), variant, L.stream_ptr()))
+    if trailing_block_means is not None:
+        tm = _dev(trailing_block_means, torch.float64)
+        if tm.numel() != (A0 // 8) * (A1 // 8):
+            raise ValueError(f"trailing_block_means must hold (A0/8) x (A1/8) = {(A0 // 8) * (A1 // 8)} block means")
+        L.check(lib.pg_fd_lib_gram_tail(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0,
+                                        b1, L.ptr(fr), L.ptr(ff), n_folds, L.ptr(tm), L.ptr(stats), L.ptr(bad), variant,
+                                        L.stream_ptr()))
+    else:
+        L.check(lib.pg_fd_lib_gram(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0, b1,
+                                   L.ptr(fr), L.ptr(ff), n_folds, L.ptr(stats), L.ptr(bad), variant, L.stream_ptr()))
     return (stats, bad) if return_nonfinite else stats
+
+
+def frame_block_means(frame, out=None):
+    """(8, 8) block means [A0/8][A1/8] of one (A0, A1) frame (pg_block_means): what a rank publishes of its first
+    frame instead of the frame itself (``fd_lib_gram(..., trailing_block_means=...)``)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    f = _dev(frame, torch.float64)
+    A0, A1 = f.shape
+    if A0 % 8 or A1 % 8:
+        raise ValueError("frame_block_means needs extents that are multiples of 8")
+    if out is None:
+        out = torch.empty((A0 // 8, A1 // 8), dtype=torch.float64, device=f.device)
+    L.check(lib.pg_block_means(L.ptr(f), 1, 1, A0, A1, 1, 8, 8, L.ptr(out), L.stream_ptr()))
+    return out
 
 
 def fd_terms(U, d0, d1, dt, *, dialect, library):

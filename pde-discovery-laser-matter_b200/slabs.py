@@ -44,7 +44,7 @@ class PeerHalo:
     (CPU tests, single GPU, unsupported platform); ``mode`` says which path is active.
     """
 
-    def __init__(self, frame_shape, group=None, device=None):
+    def __init__(self, frame_shape, group=None, device=None, peer_memory=True):
         import torch.distributed as dist
 
         self.group, self.mode, self.k = group, "send_recv", 0
@@ -53,6 +53,9 @@ class PeerHalo:
         self.done = None
         if self.world == 1:
             self.mode = "none"
+            return
+        if not peer_memory:          # A/B comparisons: NCCL / gloo point-to-point
+            self.why = "disabled by the caller"
             return
         try:
             torch = L.torch_cuda()
@@ -63,6 +66,14 @@ class PeerHalo:
             self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
             self.peer = self.hdl.get_buffer(self.rank + 1, shape, torch.float64) if self.rank < self.world - 1 else None
             self.stream = torch.cuda.Stream()
+            if shape[1] % 8 == 0 and shape[2] % 8 == 0:
+                # compressed exchange (begin_block_means): (8, 8) block means of the first frame, 1/64 of its bytes
+                mshape = (2, shape[1] // 8, shape[2] // 8)
+                self.bm = symm_mem.empty(mshape, dtype=torch.float64, device=self.buf.device)
+                self.bm_hdl = symm_mem.rendezvous(self.bm, group if group is not None else dist.group.WORLD)
+                self.bm_peer = (self.bm_hdl.get_buffer(self.rank + 1, mshape, torch.float64)
+                                if self.rank < self.world - 1 else None)
+                self.tail = torch.empty(mshape, dtype=torch.float64, device=self.buf.device)
             self.mode = "peer_memory"
         except Exception as exc:  # symmetric memory unavailable: keep the send/recv path
             self.why = repr(exc)
@@ -88,6 +99,48 @@ class PeerHalo:
             done = torch.cuda.Event()
             done.record(self.stream)
         return done
+
+    def begin_block_means(self, U_local, means_fn=None):
+        """Compressed exchange for (bt, 8m, 8n) blocks of the KS dialect: the forward time difference of a block
+        telescopes to a difference of block sums, so a rank only needs the (8, 8) block MEANS of its neighbour's first
+        frame (2 MB instead of 134 MB at 4096^2) and K1 runs as ONE launch over the whole slab
+        (``ops.fd_lib_gram(..., trailing_block_means=...)``) instead of bulk + a tail launch that waits for the frame.
+        Returns (token for end(), means or None on the last rank).  ``means_fn`` stands in for the CUDA kernel in
+        the CPU tests."""
+        if self.mode == "none":
+            return None, None
+        if means_fn is None:
+            from . import ops
+
+            means_fn = ops.frame_block_means
+        if self.mode == "send_recv":
+            import torch.distributed as dist
+
+            mine = means_fn(U_local[0])
+            out = mine.new_empty(mine.shape) if self.rank < self.world - 1 else None
+            ops_ = []
+            if self.rank > 0:
+                ops_.append(dist.P2POp(dist.isend, mine, self.rank - 1, self.group))
+            if out is not None:
+                ops_.append(dist.P2POp(dist.irecv, out, self.rank + 1, self.group))
+            reqs = dist.batch_isend_irecv(ops_) if ops_ else []
+            self._keep = mine                      # the send buffer must outlive the request
+            return reqs, out
+        torch = L.torch_cuda()
+        b = self.k & 1
+        self.k += 1
+        means_fn(U_local[0], out=self.bm[b])       # publish: the kernel writes into the symmetric buffer
+        self.bm_hdl.barrier(channel=0)
+        if self.bm_peer is None:
+            return None, None
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self.tail[b].copy_(self.bm_peer[b], non_blocking=True)   # copy engine over NVLink
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return done, self.tail[b]
 
     def end(self, token):
         """Make the current stream wait for the halo frame."""
@@ -142,14 +195,42 @@ def allreduce_stats(stats, group=None):
     return stats
 
 
+def block_means_halo_ok(shape, dialect, block) -> bool:
+    """Whether the trailing halo can travel as (8, 8) block means (pg_fd_lib_gram_tail's layout rule)."""
+    _, A0, A1 = (int(x) for x in shape)
+    return (dialect == L.FD_KS_PERIODIC and block[1] % 8 == 0 and block[2] % 8 == 0 and A0 % 8 == 0 and A1 % 8 == 0
+            and A1 >= 128)
+
+
 def sharded_stats(U_local, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_frame=None, fold_of_row=None,
-                  n_folds=1, variant=L.VARIANT_AUTO, group=None, halo=True, stats_fn=None, peer_halo=None):
+                  n_folds=1, variant=L.VARIANT_AUTO, group=None, halo=True, stats_fn=None, peer_halo=None,
+                  means_fn=None, block_means_halo=None):
     """Per-rank K1 over this rank's slab (own frames + trailing halo frame) followed by the
     all-reduce.  ``stats_fn`` lets the CPU tests stand in for the CUDA kernel.
 
     The halo frame is only read by the LAST t-block of the slab, so the exchange is started first,
     K1 runs on everything before that t-block while the frame is in flight, and only the small tail
     launch waits for it (the transfer is hidden; statistics are additive over time slabs)."""
+    if block_means_halo is None:
+        # Measured on B200 (bench.py, PG_HALO): with NVLink peer memory the whole frame is pulled by a copy engine under
+        # K1 and costs nothing, so the compressed form only saves the short tail launch and pays for a publish kernel
+        # before K1 (a wash); with NCCL / gloo send-recv the frame exchange serialises behind the persistent K1
+        # (+0.6 ms per step at 4096^2), so the 64x smaller message wins.
+        block_means_halo = peer_halo is not None and peer_halo.mode == "send_recv"
+    if block_means_halo and peer_halo is not None and halo and peer_halo.mode != "none" \
+            and (stats_fn is None or means_fn is not None) and block_means_halo_ok(U_local.shape, dialect, block) \
+            and variant != L.VARIANT_GENERIC:
+        # compressed halo: block means of the neighbour's first frame, ONE K1 launch over the whole slab
+        token, tail = peer_halo.begin_block_means(U_local, means_fn)
+        peer_halo.end(token)
+        if stats_fn is not None:
+            return allreduce_stats(stats_fn(U_local, tail), group)
+        from . import ops
+
+        stats = ops.fd_lib_gram(U_local, d0, d1, dt, dialect=dialect, library=library, block=block, n_folds=n_folds,
+                                variant=variant, fold_of_frame=fold_of_frame, fold_of_row=fold_of_row,
+                                trailing_block_means=tail)
+        return allreduce_stats(stats, group)
     if peer_halo is not None and halo:
         # NVLink peer-memory exchange (PeerHalo): same begin / end protocol
         token = peer_halo.begin(U_local)

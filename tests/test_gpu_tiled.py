@@ -234,3 +234,42 @@ def test_many_row_folds_go_through_the_sub_block_rows(env):
     gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
     for f in range(5):
         assert_stats_close(til[f], gen[f], 3)
+
+
+@pytest.mark.parametrize("libname,shape,block", [("LIB_KS_TRUE", (10, 128, 256), (3, 8, 8)),
+                                                 ("LIB_KS_RICH", (9, 72, 200), (2, 8, 8)),        # shifted tile column, ragged t
+                                                 ("LIB_KS_TRUE_ADV", (7, 64, 136), (3, 8, 8)),
+                                                 ("LIB_KS_TRUE", (8, 128, 256), (3, 16, 32))])    # two-stage blocks
+def test_trailing_block_means_stand_in_for_the_trailing_frame(env, libname, shape, block):
+    """pg_fd_lib_gram_tail: with the (8, 8) block means of the trailing frame the frame itself is a placeholder (time
+    slabs whose trailing frame lives on another GPU send 1/64 of its bytes)."""
+    import pde_b200
+
+    L, ops = env
+    lib = getattr(L, libname)
+    p = L.LIB_WIDTH[lib]
+    U = field(ops, shape, seed=21)
+    fof = (np.arange(shape[0] - 1) >= (shape[0] - 1) // 2).astype(np.int32)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=block, fold_of_frame=fof, n_folds=2)
+    ref = ops.fd_lib_gram(U, 0.5, 0.4, 1e-3, **kw).cpu().numpy()
+    means = ops.frame_block_means(U[-1])
+    np.testing.assert_allclose(means.cpu().numpy(),
+                               U[-1].cpu().numpy().reshape(shape[1] // 8, 8, shape[2] // 8, 8).mean(axis=(1, 3)), rtol=1e-13, atol=1e-15)
+    V = U.clone()
+    V[-1] = float("nan")                         # the placeholder must not be read for values
+    got, bad = ops.fd_lib_gram(V, 0.5, 0.4, 1e-3, trailing_block_means=means, return_nonfinite=True, **kw)
+    assert int(bad.item()) == 0
+    for f in range(2):
+        assert_stats_close(got.cpu().numpy()[f], ref[f], p, rtol=1e-12)
+    with pytest.raises(pde_b200.PdeGramError, match="trailing_block_means"):
+        ops.fd_lib_gram(V, 0.5, 0.4, 1e-3, trailing_block_means=means, variant=L.VARIANT_GENERIC, **kw)
+    if block == (3, 8, 8) and shape[2] == 256:
+        W = field(ops, (shape[0], shape[1], 132), seed=3)     # ragged block column: not covered by tiles alone
+        with pytest.raises(pde_b200.PdeGramError, match="trailing_block_means"):
+            ops.fd_lib_gram(W, 0.5, 0.4, 1e-3, trailing_block_means=torch_zeros(ops, (shape[1] // 8) * (132 // 8)), **kw)
+
+
+def torch_zeros(ops, n):
+    import torch
+
+    return torch.zeros(n, dtype=torch.float64, device="cuda")

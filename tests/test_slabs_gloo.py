@@ -31,6 +31,66 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _worker_means(rank, world, port, q):
+    """Compressed halo (block means of the neighbour's first frame) over gloo: the trailing frame stays a placeholder."""
+    import torch
+    import torch.distributed as dist
+
+    from pde_b200 import _lib as L
+    from pde_b200 import slabs
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        block = (3, 8, 8)
+        U = np.random.default_rng(1).standard_normal((13, 16, 128))
+        dx, dy, DT = 0.5, 0.25, 1e-2
+        lo, hi = slabs.slab_bounds(U.shape[0] - 1, block[0], world)[rank]
+        U_local = torch.from_numpy(U[lo:hi + 1].copy())
+        if rank < world - 1:
+            U_local[-1].zero_()
+
+        def means_fn(frame, out=None):
+            m = frame.reshape(frame.shape[0] // 8, 8, frame.shape[1] // 8, 8).mean(dim=(1, 3))
+            return m if out is None else out.copy_(m)
+
+        def stats_fn(Ul, tail=None):
+            a = Ul.numpy().copy()
+            if tail is not None:      # what the kernel does: only the block sums of the trailing frame enter (u_t telescopes)
+                a[-1] = np.kron(tail.numpy(), np.ones((8, 8)))
+            names, X, y = ks_rows(a, dx, dy, DT, "true", False, block)
+            return torch.from_numpy(gram.pack_stats(X, y))[None].clone()
+
+        peer = slabs.PeerHalo(U.shape[1:])
+        assert peer.mode == "send_recv"
+        s = slabs.sharded_stats(U_local, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=block,
+                                stats_fn=stats_fn, means_fn=means_fn, peer_halo=peer)
+        if rank < world - 1:
+            assert float(U_local[-1].abs().max()) == 0.0      # the frame itself never travelled
+        q.put((rank, s.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_block_means_halo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_means, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    U = np.random.default_rng(1).standard_normal((13, 16, 128))
+    names, X, y = ks_rows(U, 0.5, 0.25, 1e-2, "true", False, (3, 8, 8))
+    assert np.array_equal(res[0], res[1])
+    assert_stats_close(res[0][0], gram.pack_stats(X, y), 3, rtol=1e-12)
+
+
 def _worker(rank, world, port, block, q, use_peer=False):
     import torch
     import torch.distributed as dist
