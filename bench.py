@@ -531,6 +531,37 @@ def run_ours(args):
             patch["cpu_port_fits_per_s"] = n_cpu / (time.perf_counter() - t0c)
             patch["cpu_port_sample"] = f"first {n_cpu} patches, fixed-stencil NumPy port, 1 core (the reference's per-point lstsq is ~100x slower)"
 
+    # ---- BASELINE configs[0] / [1] (the reference's own CPU-runnable cases) through the drop-in API: a HOST NumPy stack
+    # of the script's default shape (2000 x 100 x 100) goes in, the fitted model comes out (host -> device copy,
+    # kernels, result read-back all inside the timed call); the CPU port of the same call beside it.
+    ref_cfgs = None
+    if not args.skip_variants and rank == 0 and args.frames >= 1024:
+        Uc = ops.synth_field(2000, 100, 100, seed=2, noise=0.05).cpu().numpy()
+        ref_cfgs = {"workload": "synthetic 2000x100x100 float64 HOST stack (the script's default grid), dx = dy = 0.5, DT = 1e-3; "
+                                "wall clock of one fit_from_field call incl. host<->device copies"}
+        cases = {"c1_pointwise_50k_true": dict(method="pointwise", dictionary="true"),
+                 "c2_blockwise388_true": dict(method="blockwise", dictionary="true"),
+                 "c2_blockwise388_rich_sweep": dict(method="blockwise", dictionary="rich", grid_search=True)}
+        for cname, ckw in cases.items():
+            K.fit_from_field(Uc, 0.5, 0.5, 1e-3, **ckw)
+            torch.cuda.synchronize()
+            t0c = time.perf_counter()
+            for _ in range(3):
+                mine = K.fit_from_field(Uc, 0.5, 0.5, 1e-3, **ckw)
+            torch.cuda.synchronize()
+            ref_cfgs[cname] = {"ours_ms": (time.perf_counter() - t0c) / 3 * 1e3}
+            if not args.no_cpu:
+                from oracle import ks2d as O
+
+                t0c = time.perf_counter()
+                theirs = O.run_config(Uc, 0.5, 0.5, 1e-3, **ckw)
+                ref_cfgs[cname]["cpu_port_ms"] = (time.perf_counter() - t0c) * 1e3
+                ref_cfgs[cname]["same_support"] = bool(np.array_equal(np.asarray(mine["coeffs"]) != 0,
+                                                                      np.asarray(theirs["coeffs"]) != 0))
+        if not args.no_cpu:
+            ref_cfgs["cpu_port_note"] = ("vectorised NumPy port, 1 process; the reference's build_blockwise_dataset loop "
+                                         "(ks2d:358-401) takes 18.7 s of C2's 23.5 s on 8 vCPUs (SURVEY section 6)")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -579,7 +610,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 30 * 3 * 8,
                 "sample": f"{e2e_frames} frames per GPU streamed from pinned host memory in 96-frame slabs (double-buffered), "
                           "through pde_b200.slabs.fit_streamed + stridge_batched"},
-        "gpu_launches": int(launches), "clocks": clocks, "variants": variants, "patch_ensemble": patch,
+        "gpu_launches": int(launches), "clocks": clocks, "variants": variants, "patch_ensemble": patch, "reference_configs": ref_cfgs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
