@@ -111,11 +111,23 @@ template <int LIB> __host__ __device__ constexpr PwPair pw_dup(int b) {
     return PwPair{0, 0};
 }
 
+// KS dialect: the grid is periodic and every time fold holds WHOLE frames, so the sum over a fold of a column that is
+// the output of a difference stencil (lap, bih = lap o lap, u_x, u_y) is identically zero: each grid value enters with
+// weights that add up to zero.  (The reference's own value is the rounding noise of that sum.)  Such linear sums are
+// not accumulated and are emitted as 0.  pw_zero(b): unique column b is one of them.
+template <int LIB> __host__ __device__ constexpr bool pw_zero(int b) {
+    if (LIB == PG_LIB_KS_TRUE) return b == 2 || b == 3;                    // lap, bih
+    if (LIB == PG_LIB_KS_TRUE_ADV) return b == 2 || b == 3 || b == 5 || b == 6;   // + u_x, u_y
+    if (LIB == PG_LIB_KS_RICH) return b >= 4 && b <= 7;                    // u_x, u_y, lap, bih
+    if (LIB == PG_LIB_KS_RICH_NOADV) return b == 4 || b == 5;              // lap, bih
+    return false;
+}
+
 template <int LIB, int NU, int NACC> __device__ __forceinline__ void pw_accumulate(double (&acc)[NACC], const double (&x)[NU - 1]) {
     int k = 0;
 #pragma unroll
     for (int b = 1; b < NU; ++b, ++k)
-        if (pw_dup<LIB>(b).a == 0) acc[k] += x[b - 1];
+        if (pw_dup<LIB>(b).a == 0 && !pw_zero<LIB>(b)) acc[k] += x[b - 1];
 #pragma unroll
     for (int a = 1; a < NU; ++a)
 #pragma unroll
@@ -142,7 +154,8 @@ template <int LIB> __device__ __forceinline__ void pw_scales(const PwParams &P, 
 // st = current frame's stage, stn = next frame's stage (u_t).  Band rows s = 0..R+3 are stage rows
 // band*R + s; the warp's own rows are s = 2..R+1 (bit r of rowmask = own row r is a row of the data set).
 // ROWS_ALL: every own row is a row of the data set (no per-row branch: the whole march is one basic block).
-template <int LIB, int R, bool MASKED, bool ROWS_ALL>
+// RHO1: square grid cells (d0 == d1, rho == 1): |grad u|^2 needs no multiplication by rho.
+template <int LIB, int R, bool MASKED, bool ROWS_ALL, bool RHO1 = false>
 __device__ __forceinline__ void march_pw(const double *__restrict__ st, const double *__restrict__ stn, const LaneMap &m,
                                          const PwParams &P, unsigned rowmask, unsigned colmask,
                                          double (&acc)[Pw<LIB>::NACC], unsigned &cnt) {
@@ -183,7 +196,7 @@ __device__ __forceinline__ void march_pw(const double *__restrict__ st, const do
                         const double Y = nx[c] - uc;
                         const double dx = u[r + 1][q] - u[r - 1][q];
                         const double dy = u[r][q + 1] - u[r][q - 1];
-                        const double Gq = fma(P.rho * dx, dx, dy * dy);
+                        const double Gq = RHO1 ? fma(dx, dx, dy * dy) : fma(P.rho * dx, dx, dy * dy);
                         const double Lc = L[r][k];
                         const double B = fma(P.kappa, Lc, fma(P.rho, L[r + 1][k] + L[r - 1][k], L[r][k + 1] + L[r][k - 1]));
                         double x[NX];
@@ -253,6 +266,7 @@ template <int LIB, int E> __device__ __forceinline__ void pw_emit(const double (
     if (lane == (E & 31)) {
         double v;
         if constexpr (pr.a == 0 && pr.b == 0) v = n;
+        else if constexpr (pr.a == 0 && pw_zero<LIB>(pr.b)) v = 0.0;      // periodic sum of a difference stencil
         else if constexpr (pr.a == 0 && pw_dup<LIB>(pr.b).a != 0) {
             constexpr PwPair d = pw_dup<LIB>(pr.b);     // linear sum of a product column: held by the pair's accumulator
             v = acc[pw_slot(X_::NU, d.a, d.b)] * (sc[d.a] * sc[d.b]);
@@ -474,6 +488,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
                     const bool rows_all = rowmask == (1u << R) - 1u;   // warp-uniform
                     if constexpr (KS) {
                         if (edge_cols) march_pw<LIB, R, true, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
+                        else if (rows_all && P.rho == 1.0) march_pw<LIB, R, false, true, true>(st, stn, lm, P, rowmask, colmask, acc, cnt);
                         else if (rows_all) march_pw<LIB, R, false, true>(st, stn, lm, P, rowmask, colmask, acc, cnt);
                         else march_pw<LIB, R, false, false>(st, stn, lm, P, rowmask, colmask, acc, cnt);
                     } else {

@@ -44,12 +44,13 @@ def basic_rows(U, d0, d1, dt):
                                    (3, 50, 330),      # width % 16 == 10: the shifted column goes through the second tensor map
                                    (3, 49, 128),      # the frame ends one row below a whole tile: its second halo row wraps
                                    (3, 97, 256)])
-def test_ks_pointwise_tiled(env, libname, shape):
+@pytest.mark.parametrize("d0,d1", [(0.5, 0.4), (0.5, 0.5)])      # square cells take the rho == 1 instantiation
+def test_ks_pointwise_tiled(env, libname, shape, d0, d1):
     L, ops = env
     lib = getattr(L, libname)
     p = L.LIB_WIDTH[lib]
     U = field(ops, shape, seed=shape[1])
-    d0, d1, dt = 0.5, 0.4, 1e-3
+    dt = 1e-3
     kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=(1, 1, 1))
     gen = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()[0]
     til = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_TILED, **kw).cpu().numpy()[0]
