@@ -605,6 +605,7 @@ def run_ours(args):
                      # fastest single step of the timed region (SM clocks still at their maximum: under a sustained loop
                      # this pool's GPUs report sw_power_cap after ~100 ms and drop to ~1.55-1.6 GHz, see `clocks`)
                      "k1_ms_best": k1_best, "frac_best": 8.0 * pts_rank / (k1_best * 1e-3) / 1e9 / peak,
+                     "k1_ms_steps": [round(x, 3) for x in k1_all],
                      "frac_of_nominal_8TBps": achieved / 8000.0},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 30 * 3 * 8,
