@@ -7,7 +7,8 @@
 // fetched separately as one 16-byte cell per row and side (a 32-byte sector instead of a 128/256-byte
 // line: this is what keeps DRAM traffic near the algorithmic 8 B/point), which also gives the periodic
 // wrap along a1 for free.  Wrap along a0: TMA zero-fills the out-of-bounds rows of a border tile and the
-// wrapped rows are copied over the zero fill after the load has landed.
+// wrapped rows are copied over the zero fill after the load has landed.  A width that is not a multiple of
+// 128: the last tile column is shifted left over its neighbour and skips the blocks already counted.
 //
 // The warps are DECOUPLED (no block-wide barrier per frame, no producer warp): see k1_tiled_b88 below.
 //

@@ -24,8 +24,10 @@
 //     region, and the reduction ignores this kernel's partials.
 //   * basic_usage rows are the interior [2:-2, 2:-2] of each frame: boundary tiles mask rows (warp-uniform)
 //     and columns (selects, only instantiated for tiles that touch the left / right border).  The KS
-//     dialect wraps periodically; a ragged last tile row (A0 not a multiple of 48) is handled here, ragged
-//     columns go to the generic kernel.
+//     dialect wraps periodically; a ragged last tile row (A0 not a multiple of 48) is handled here.
+//   * any even width >= 128: when the width is not a multiple of 128 the last tile column is shifted left so that
+//     it ends with the frame and masks the columns its neighbour has already counted (second tensor map for
+//     the box start inside a 16-column group); odd widths (rows not 16-byte aligned) use the generic kernel.
 #include <cuda.h>
 #include <math.h>
 
