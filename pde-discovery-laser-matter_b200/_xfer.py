@@ -1,0 +1,97 @@
+"""Host <-> device copies of large NumPy arrays for the drop-in signatures.
+
+The reference's functions take and return NumPy arrays, so the literal drop-ins (``build_dictionary``,
+``compute_derivatives``, ``fit_from_field`` on a host stack ...) are bounded by the copy of pageable memory, which
+the driver stages through a small internal buffer at ~10 GB/s.  Here arrays of at least ``MIN_BYTES`` go through two
+pinned staging buffers: a multi-threaded host copy (torch's CPU copy kernel, GIL released) fills one while the copy
+engine drains the other at PCIe rate.  Smaller arrays take the plain path.  Nothing here touches values.
+"""
+
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _lib as L
+
+MIN_BYTES = 16 << 20        # below this the plain pageable copy is as fast
+STAGE_BYTES = 32 << 20      # per staging buffer (two of them, allocated on first use)
+
+_stage = {}                 # device index -> (buffers, events)
+
+
+def _staging(torch):
+    dev = torch.cuda.current_device()
+    if dev not in _stage:
+        bufs = [torch.empty(STAGE_BYTES, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        _stage[dev] = (bufs, [None, None])
+    return _stage[dev]
+
+
+def _as_tensor(torch, a):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)     # read-only arrays: we only read
+        return torch.from_numpy(a)
+
+
+def to_device(a: np.ndarray):
+    """Contiguous NumPy array -> CUDA tensor of the same dtype and shape on the current device / stream."""
+    torch = L.torch_cuda()
+    a = np.ascontiguousarray(a)
+    src = _as_tensor(torch, a)
+    if a.nbytes < MIN_BYTES:
+        return src.cuda()
+    flat = src.reshape(-1)
+    dst = torch.empty(a.shape, dtype=src.dtype, device="cuda")
+    dflat = dst.view(-1)
+    bufs, evs = _staging(torch)
+    per = STAGE_BYTES // a.itemsize
+    stream = torch.cuda.current_stream()
+    for k, lo in enumerate(range(0, flat.numel(), per)):
+        hi = min(flat.numel(), lo + per)
+        b = k & 1
+        if evs[b] is not None:
+            evs[b].synchronize()                         # the copy engine has drained this buffer
+        pb = bufs[b][: (hi - lo) * a.itemsize].view(src.dtype)
+        pb.copy_(flat[lo:hi])                            # multi-threaded host copy into pinned memory
+        dflat[lo:hi].copy_(pb, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        evs[b] = ev
+    return dst
+
+
+def to_host(t) -> np.ndarray:
+    """CUDA tensor -> new NumPy array (synchronises the current stream)."""
+    torch = L.torch_cuda()
+    t = t.detach()
+    if not t.is_cuda or t.numel() * t.element_size() < MIN_BYTES:
+        return t.cpu().numpy()
+    t = t.contiguous()
+    out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+    oflat = _as_tensor(torch, out).reshape(-1)
+    tflat = t.view(-1)
+    bufs, evs = _staging(torch)
+    per = STAGE_BYTES // t.element_size()
+    stream = torch.cuda.current_stream()
+    pending = None                                       # (buffer index, lo, hi) whose device -> pinned copy is in flight
+    for k, lo in enumerate(range(0, tflat.numel(), per)):
+        hi = min(tflat.numel(), lo + per)
+        b = k & 1
+        if evs[b] is not None:
+            evs[b].synchronize()
+        pb = bufs[b][: (hi - lo) * t.element_size()].view(t.dtype)
+        pb.copy_(tflat[lo:hi], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        evs[b] = ev
+        if pending is not None:                          # drain the previous chunk while this one is in flight
+            pbuf, plo, phi, pev = pending
+            pev.synchronize()
+            oflat[plo:phi].copy_(pbuf)
+        pending = (pb, lo, hi, ev)
+    pbuf, plo, phi, pev = pending
+    pev.synchronize()
+    oflat[plo:phi].copy_(pbuf)
+    return out

@@ -15,7 +15,9 @@ TERM_NAMES = ["1", "u", "u_x", "u_y", "lap(u)", "u^2"]  # basic:99
 
 
 def _np(t):
-    return t.detach().cpu().numpy()
+    from . import _xfer
+
+    return _xfer.to_host(t)       # large results: pinned double-buffered staging
 
 
 def compute_derivatives(u, dx: float, dy: float, dt: float):

@@ -27,7 +27,9 @@ _LIB_OF = {"true": (L.LIB_KS_TRUE, TRUE_NAMES), "true_adv": (L.LIB_KS_TRUE_ADV, 
 
 
 def _np(t):
-    return t.detach().cpu().numpy()
+    from . import _xfer
+
+    return _xfer.to_host(t)       # large results: pinned double-buffered staging
 
 
 def _frame(f2d):

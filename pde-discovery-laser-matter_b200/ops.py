@@ -23,7 +23,9 @@ def _dev(a, dtype=None):
         if not t.is_cuda:
             t = t.cuda()
     else:
-        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        from . import _xfer
+
+        t = _xfer.to_device(np.asarray(a))     # large arrays: pinned double-buffered staging
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.contiguous()

@@ -22,7 +22,9 @@ MODEL4_NAMES = ["1", "u", "u_x", "u_y", "lap(u)", "u^2"]                   # pat
 
 
 def _np(t):
-    return t.detach().cpu().numpy()
+    from . import _xfer
+
+    return _xfer.to_host(t)       # large results: pinned double-buffered staging
 
 
 def _poly3d_exponents(deg: int):

@@ -419,3 +419,28 @@ def test_ensemble_stridge_weighted_grams(golden_ks2d):
     assert_stats_close(st, gram.pack_stats(X[idx], y[idx]), 9)
     with pytest.raises(NotImplementedError):
         K.ensemble_stridge(X, y, use_huber=True)
+
+
+def test_staged_host_device_copies_round_trip():
+    """Large NumPy arrays travel through pinned staging buffers (pde_b200._xfer): bit-identical both ways, for sizes
+    around the chunk boundaries, non-contiguous and read-only inputs and other dtypes."""
+    import torch
+
+    from pde_b200 import _xfer
+
+    rng = np.random.default_rng(0)
+    per = _xfer.STAGE_BYTES // 8
+    for n in (1000, _xfer.MIN_BYTES // 8, per - 1, per, per + 1, 2 * per + 12345, 5 * per // 2):
+        a = rng.standard_normal(n)
+        d = _xfer.to_device(a)
+        assert d.is_cuda and d.dtype == torch.float64 and tuple(d.shape) == a.shape
+        assert np.array_equal(d.cpu().numpy(), a)
+        assert np.array_equal(_xfer.to_host(d * 1.0), a)
+    a = rng.standard_normal((300, 200, 120)).astype(np.float32)      # 28.8 MB, fp32, 3-D
+    a.flags.writeable = False
+    assert np.array_equal(_xfer.to_host(_xfer.to_device(a)), a)
+    b = rng.standard_normal((64, 512, 512))[:, ::2, :]               # non-contiguous view, 67 MB
+    got = _xfer.to_host(_xfer.to_device(b))
+    assert got.shape == b.shape and np.array_equal(got, b)
+    i = rng.integers(0, 2 ** 40, size=3_000_000)                     # int64
+    assert np.array_equal(_xfer.to_host(_xfer.to_device(i)), i)
