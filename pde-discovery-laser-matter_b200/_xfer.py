@@ -35,15 +35,18 @@ def _as_tensor(torch, a):
         return torch.from_numpy(a)
 
 
-def to_device(a: np.ndarray):
-    """Contiguous NumPy array -> CUDA tensor of the same dtype and shape on the current device / stream."""
+def to_device(a: np.ndarray, out=None):
+    """NumPy array -> CUDA tensor of the same dtype and shape on the current device / stream (``out``: a contiguous
+    CUDA tensor of that dtype and size to fill instead of a new one)."""
     torch = L.torch_cuda()
     a = np.ascontiguousarray(a)
     src = _as_tensor(torch, a)
+    if out is not None and (not out.is_contiguous() or out.dtype != src.dtype or out.numel() != src.numel()):
+        raise ValueError("out must be a contiguous CUDA tensor of the array's dtype and size")
     if a.nbytes < MIN_BYTES:
-        return src.cuda()
+        return src.cuda() if out is None else out.view(-1).copy_(src.reshape(-1), non_blocking=True).view(out.shape)
     flat = src.reshape(-1)
-    dst = torch.empty(a.shape, dtype=src.dtype, device="cuda")
+    dst = torch.empty(a.shape, dtype=src.dtype, device="cuda") if out is None else out
     dflat = dst.view(-1)
     bufs, evs = _staging(torch)
     per = STAGE_BYTES // a.itemsize

@@ -265,14 +265,19 @@ def fit_streamed(U_host, d0, d1, dt, *, dialect=L.FD_KS_PERIODIC, library=L.LIB_
     are copied host->device on a copy stream into two device buffers while the compute stream
     runs K1 on the previous slab; per-slab statistics are summed on the device.
 
-    U_host: (T, A0, A1) float64 torch tensor in pinned memory (or a NumPy array, which is copied
-    through pageable memory and is slower).  Returns the [n_folds][S] statistics tensor (device).
+    U_host: (T, A0, A1) float64 torch tensor in pinned memory (DMA straight from it), or a NumPy array / pageable
+    tensor, whose slabs go through the pinned staging buffers of ``_xfer`` (multi-threaded host copy + DMA).
+    Returns the [n_folds][S] statistics tensor (device).
     """
     torch = L.torch_cuda()
-    from . import ops
+    from . import _xfer, ops
 
+    staged = None
     if isinstance(U_host, np.ndarray):
-        U_host = torch.from_numpy(np.ascontiguousarray(U_host, dtype=np.float64))
+        staged = np.ascontiguousarray(U_host, dtype=np.float64)
+        U_host = torch.from_numpy(staged)
+    elif not U_host.is_pinned():
+        staged = U_host.contiguous().numpy()
     T, A0, A1 = U_host.shape
     bt = int(block[0])
     slab_frames = max(bt, (slab_frames // bt) * bt)
@@ -292,7 +297,10 @@ def fit_streamed(U_host, d0, d1, dt, *, dialect=L.FD_KS_PERIODIC, library=L.LIB_
         with torch.cuda.stream(copy):
             if k >= 2:
                 copy.wait_event(freed[b])
-            buffers[b][: hi - lo + 1].copy_(U_host[lo:hi + 1], non_blocking=True)
+            if staged is None:
+                buffers[b][: hi - lo + 1].copy_(U_host[lo:hi + 1], non_blocking=True)
+            else:
+                _xfer.to_device(staged[lo:hi + 1], out=buffers[b][: hi - lo + 1])
             filled[b].record(copy)
         compute.wait_event(filled[b])
         s = ops.fd_lib_gram(buffers[b][: hi - lo + 1], d0, d1, dt, dialect=dialect, library=library, block=block,

@@ -444,3 +444,23 @@ def test_staged_host_device_copies_round_trip():
     assert got.shape == b.shape and np.array_equal(got, b)
     i = rng.integers(0, 2 ** 40, size=3_000_000)                     # int64
     assert np.array_equal(_xfer.to_host(_xfer.to_device(i)), i)
+
+
+def test_fit_streamed_from_host_stacks():
+    """slabs.fit_streamed: a HOST stack streamed in slabs (pinned tensor: DMA straight from it; NumPy array: pinned
+    staging) gives the statistics of the device-resident stack (slab additivity), folds included."""
+    import torch
+
+    from pde_b200 import _lib as L
+    from pde_b200 import ops, slabs
+
+    U = ops.synth_field(200, 256, 256, seed=4, noise=0.05)
+    fof = (np.arange(199) >= 138).astype(np.int32)
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8), n_folds=2)
+    ref = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, fold_of_frame=fof, **kw).cpu().numpy()
+    host_np = U.cpu().numpy()
+    pinned = torch.from_numpy(host_np).pin_memory()
+    for src in (host_np, pinned, torch.from_numpy(host_np)):
+        got = slabs.fit_streamed(src, 0.5, 0.5, 1e-3, fold_of_frame=fof, slab_frames=48, **kw).cpu().numpy()
+        for f in range(2):
+            assert_stats_close(got[f], ref[f], 3, rtol=1e-12)
