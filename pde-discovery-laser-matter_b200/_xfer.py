@@ -9,6 +9,7 @@ engine drains the other at PCIe rate.  Smaller arrays take the plain path.  Noth
 
 from __future__ import annotations
 
+import threading
 import warnings
 
 import numpy as np
@@ -19,6 +20,7 @@ MIN_BYTES = 16 << 20        # below this the plain pageable copy is as fast
 STAGE_BYTES = 32 << 20      # per staging buffer (two of them, allocated on first use)
 
 _stage = {}                 # device index -> (buffers, events)
+_lock = threading.Lock()    # the two staging buffers of a device serve one transfer at a time
 
 
 def _staging(torch):
@@ -48,20 +50,21 @@ def to_device(a: np.ndarray, out=None):
     flat = src.reshape(-1)
     dst = torch.empty(a.shape, dtype=src.dtype, device="cuda") if out is None else out
     dflat = dst.view(-1)
-    bufs, evs = _staging(torch)
     per = STAGE_BYTES // a.itemsize
     stream = torch.cuda.current_stream()
-    for k, lo in enumerate(range(0, flat.numel(), per)):
-        hi = min(flat.numel(), lo + per)
-        b = k & 1
-        if evs[b] is not None:
-            evs[b].synchronize()                         # the copy engine has drained this buffer
-        pb = bufs[b][: (hi - lo) * a.itemsize].view(src.dtype)
-        pb.copy_(flat[lo:hi])                            # multi-threaded host copy into pinned memory
-        dflat[lo:hi].copy_(pb, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(stream)
-        evs[b] = ev
+    with _lock:
+        bufs, evs = _staging(torch)
+        for k, lo in enumerate(range(0, flat.numel(), per)):
+            hi = min(flat.numel(), lo + per)
+            b = k & 1
+            if evs[b] is not None:
+                evs[b].synchronize()                         # the copy engine has drained this buffer
+            pb = bufs[b][: (hi - lo) * a.itemsize].view(src.dtype)
+            pb.copy_(flat[lo:hi])                            # multi-threaded host copy into pinned memory
+            dflat[lo:hi].copy_(pb, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            evs[b] = ev
     return dst
 
 
@@ -75,26 +78,27 @@ def to_host(t) -> np.ndarray:
     out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
     oflat = _as_tensor(torch, out).reshape(-1)
     tflat = t.view(-1)
-    bufs, evs = _staging(torch)
     per = STAGE_BYTES // t.element_size()
     stream = torch.cuda.current_stream()
-    pending = None                                       # (buffer index, lo, hi) whose device -> pinned copy is in flight
-    for k, lo in enumerate(range(0, tflat.numel(), per)):
-        hi = min(tflat.numel(), lo + per)
-        b = k & 1
-        if evs[b] is not None:
-            evs[b].synchronize()
-        pb = bufs[b][: (hi - lo) * t.element_size()].view(t.dtype)
-        pb.copy_(tflat[lo:hi], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(stream)
-        evs[b] = ev
-        if pending is not None:                          # drain the previous chunk while this one is in flight
-            pbuf, plo, phi, pev = pending
-            pev.synchronize()
-            oflat[plo:phi].copy_(pbuf)
-        pending = (pb, lo, hi, ev)
-    pbuf, plo, phi, pev = pending
-    pev.synchronize()
-    oflat[plo:phi].copy_(pbuf)
+    with _lock:
+        bufs, evs = _staging(torch)
+        pending = None                                   # (pinned chunk, lo, hi, event) whose device -> pinned copy is in flight
+        for k, lo in enumerate(range(0, tflat.numel(), per)):
+            hi = min(tflat.numel(), lo + per)
+            b = k & 1
+            if evs[b] is not None:
+                evs[b].synchronize()
+            pb = bufs[b][: (hi - lo) * t.element_size()].view(t.dtype)
+            pb.copy_(tflat[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            evs[b] = ev
+            if pending is not None:                      # drain the previous chunk while this one is in flight
+                pbuf, plo, phi, pev = pending
+                pev.synchronize()
+                oflat[plo:phi].copy_(pbuf)
+            pending = (pb, lo, hi, ev)
+        pbuf, plo, phi, pev = pending
+        pev.synchronize()
+        oflat[plo:phi].copy_(pbuf)
     return out
