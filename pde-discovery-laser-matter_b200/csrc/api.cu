@@ -2,6 +2,7 @@
 // management and kernel dispatch.  No exception crosses this boundary.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <map>
@@ -58,6 +59,11 @@ static int scratch_for(cudaStream_t st, size_t bytes, void **ptr) {
     return PG_OK;
 }
 
+static bool env_flag(const char *name) {
+    const char *v = getenv(name);
+    return v && *v && *v != '0';
+}
+
 static int sm_count() {
     static int n = 0;
     if (!n) {
@@ -102,7 +108,7 @@ static int two_stage_blocks(const K1Params &P, int lib, int64_t nBt, int64_t len
                             cudaStream_t st) {
     if (P.dialect != PG_FD_KS_PERIODIC || P.b0 % 8 || P.b1 % 8 || P.A0 % 8 || P.A1 % 8) return 1;
     // (bt, 8, 8) itself is fused in one kernel, except with more than two per-row folds (its masked accumulators hold two)
-    if (P.b0 == 8 && P.b1 == 8 && !(P.fold_of_row && P.n_folds > 2)) return 1;
+    if (P.b0 == 8 && P.b1 == 8 && !(P.fold_of_row && (P.n_folds > 2 || env_flag("PG_ROWFOLD_TWO_STAGE")))) return 1;
     K1Params Q = P;
     Q.b0 = Q.b1 = 8; Q.nB0 = P.A0 / 8; Q.nB1 = P.A1 / 8;
     Q.fold_of_row = nullptr; Q.fold_of_frame = nullptr; Q.n_folds = 1;
