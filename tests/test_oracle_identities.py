@@ -109,3 +109,31 @@ def test_block_sum_of_u_lap_from_neighbour_pair_products():
     hi = sum((w[2:10, q] * w[2:10, q + 1]).sum() for q in (2, 3, 4))
     pairs = kappa * (own ** 2).sum() + rho * (vb + 2 * vi) + (he + 2 * hi)
     np.testing.assert_allclose(pairs, direct, rtol=1e-12)
+
+
+def test_block_sums_of_linear_terms_from_boundary_scalars():
+    """Blockwise kernel (tiled.cu, march_frame): by the discrete divergence theorem the block sums of L' and of
+    L'(L') (the unscaled lap and bih) reduce to per-row scalars rsU, D, e of the lane's 12 x 8 window -- the formulas
+    of the kernel, transcribed, against the direct sums."""
+    rng = np.random.default_rng(6)
+    w = rng.standard_normal((12, 8))
+    rho = 0.64
+    kappa = -2.0 * (1.0 + rho)
+
+    def Lp(a):      # L' on the interior of a 2-D array
+        return rho * (a[2:, 1:-1] + a[:-2, 1:-1]) + (a[1:-1, 2:] + a[1:-1, :-2]) + kappa * a[1:-1, 1:-1]
+
+    L1 = Lp(w)                       # rows 1..10, columns 1..6
+    direct_SL = L1[1:9, 1:5].sum()   # own rows 2..9, own columns 2..5
+    direct_bih = Lp(L1)[0:8, 0:4].sum()   # L'(L') on rows 2..9, columns 2..5
+
+    rsU = w[:, 2:6].sum(axis=1)
+    D = (w[:, 1] - w[:, 2]) + (w[:, 6] - w[:, 5])
+    e = (w[:, 0] - w[:, 3]) + (w[:, 7] - w[:, 4])
+    sD, sE = D[2:10].sum(), e[2:10].sum()
+    rsL = lambda s: rho * ((rsU[s + 1] + rsU[s - 1]) - 2.0 * rsU[s]) + D[s]   # noqa: E731
+    SL = rho * ((rsU[10] - rsU[9]) - (rsU[2] - rsU[1])) + sD
+    SE1 = (rsL(1) - rsL(2)) + (rsL(10) - rsL(9))
+    SE2 = rho * ((D[10] + D[1]) - (D[2] + D[9])) + (-3.0 * sD + sE)
+    np.testing.assert_allclose(SL, direct_SL, rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(rho * SE1 + SE2, direct_bih, rtol=1e-11, atol=1e-11)
