@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
 }
 
 // ----------------------------------------------------------------------------- host side
-// warps per CTA (see Geo): 8 or 4; PG_TILED_WARPS overrides the default for experiments
+// eight consumer warps per CTA (DNW): one 64 x 128 tile, one CTA per SM
 
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan) {
     if (P.dialect != PG_FD_KS_PERIODIC) return false;

@@ -121,17 +121,16 @@ def main():
         print(json.dumps(rec), flush=True)
         out.append(rec)
     if args.sweep:
-        # tile geometry (warps per CTA) x TMA L2 promotion, read by the planner at every call
-        for nw in (8, 4):
-            for promo in (0, 1, 2, 3):
-                os.environ["PG_TILED_WARPS"], os.environ["PG_TMA_L2PROMO"] = str(nw), str(promo)
-                for name, lib, nf in (("true", L.LIB_KS_TRUE, 2), ("rich", L.LIB_KS_RICH, 2), ("true1f", L.LIB_KS_TRUE, 1)):
-                    kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=(3, 8, 8), variant=L.VARIANT_TILED, n_folds=nf)
-                    if nf == 2:
-                        kw["fold_of_frame"] = fof
-                    best, avg = time_call(lambda: ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, **kw), iters=args.iters)
-                    print(json.dumps(dict(case=f"{name}_nw{nw}_promo{promo}", ms_best=round(best, 3), ms_avg=round(avg, 3),
-                                          alg_GBps=round(8 * pts / best / 1e6, 1))), flush=True)
+        # TMA L2 promotion of the field's tensor map, read by the launcher at every call
+        for promo in (0, 1, 2, 3):
+            os.environ["PG_TMA_L2PROMO"] = str(promo)
+            for name, lib, nf in (("true", L.LIB_KS_TRUE, 2), ("rich", L.LIB_KS_RICH, 2), ("true1f", L.LIB_KS_TRUE, 1)):
+                kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=(3, 8, 8), variant=L.VARIANT_TILED, n_folds=nf)
+                if nf == 2:
+                    kw["fold_of_frame"] = fof
+                best, avg = time_call(lambda: ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, **kw), iters=args.iters)
+                print(json.dumps(dict(case=f"{name}_promo{promo}", ms_best=round(best, 3), ms_avg=round(avg, 3),
+                                      alg_GBps=round(8 * pts / best / 1e6, 1))), flush=True)
     # plain device copy of the same bytes for scale (read + write)
     V = torch.empty_like(U[: T // 2])
     best, _ = time_call(lambda: V.copy_(U[: T // 2]), iters=args.iters)
