@@ -26,13 +26,14 @@
 #ifndef PDEGRAM_H
 #define PDEGRAM_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define PG_VERSION 102
+#define PG_VERSION 103
 
 #if defined(__GNUC__)
 #define PG_API __attribute__((visibility("default")))
@@ -104,10 +105,15 @@ PG_API int pg_library_width(int library_id);
  *   fold_of_frame nullable, one fold id per frame 0..T-2; a block takes the fold of its first
  *                 frame (time-holdout folds); both NULL = a single fold 0
  *   stats_out     [n_folds][PG_STATS_LEN(p)]
- *   nonfinite_out nullable, 1 int64: number of block rows skipped because a mean was not
- *                 finite (ks2d:394-395).  If it is non-zero and fold_of_row was given, the
- *                 caller's row numbering no longer matches the reference's (which renumbers
- *                 after dropping) and must use pg_block_means + pg_rows_gram instead.
+ *   nonfinite_out nullable, 4 int64 counters of this call:
+ *                 [0] block rows skipped because a mean was not finite (ks2d:394-395).  If it is
+ *                     non-zero and fold_of_row was given, the caller's row numbering no longer matches
+ *                     the reference's (which renumbers after dropping): use pg_block_means +
+ *                     pg_rows_gram instead.
+ *                 [1] rows whose fold id was outside [0, n_folds): a caller error.  Such rows are NOT
+ *                     silently dropped: when this counter is non-zero every entry of stats_out is NaN.
+ *                 [2] internal (the pointwise fast path fell back to the exact non-finite handling)
+ *                 [3] halo waits that timed out (pg_fd_lib_gram_halo); non-zero => stats_out is NaN
  */
 PG_API int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
                    int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
@@ -127,6 +133,20 @@ PG_API int pg_fd_lib_gram_tail(const double *U, int64_t T, int64_t A0, int64_t A
                    int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
                    const int32_t *fold_of_frame, int n_folds, const double *trailing_block_means, double *stats_out,
                    int64_t *nonfinite_out, int variant, void *stream);
+
+/*
+ * pg_fd_lib_gram for a time slab whose trailing frame U[T-1] is STILL BEING WRITTEN when the call is made: a copy
+ * engine is pulling it from the next rank's slab over NVLink (pg_halo_exchange).  The persistent kernel starts at
+ * once and loads frame T-1 -- which only the last t-block of the slab reads -- after the 32-bit word *halo_flag
+ * (device memory, written behind the transfer by a stream memory operation) has reached halo_epoch (wrap-safe
+ * comparison).  One launch per slab instead of bulk + tail.  Same layout rule as pg_fd_lib_gram_tail with (bt, 8, 8)
+ * blocks, else PG_EUNSUPPORTED (then make `stream` wait for the transfer and call pg_fd_lib_gram).  A wait that
+ * exceeds ~4 s gives up: counter [3] is raised and the statistics are NaN.
+ */
+PG_API int pg_fd_lib_gram_halo(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                   int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
+                   const int32_t *fold_of_frame, int n_folds, const uint32_t *halo_flag, uint32_t halo_epoch,
+                   double *stats_out, int64_t *nonfinite_out, int variant, void *stream);
 
 /*
  * Materialised term stacks, bit-identical to the reference's NumPy arithmetic (no FMA
@@ -161,7 +181,8 @@ PG_API int pg_block_means(const double *stack, int k, int64_t T, int64_t A0, int
  * (ks2d:404, patch:78, basic:104) and the per-patch fits (patch:420-423).
  *   shift         nullable [B][p]: statistics are taken of (X - shift), which removes the
  *                 cancellation in G - n*mu*mu^T when mean^2 >> variance (use e.g. the first row)
- *   stats_out     [B][n_folds][PG_STATS_LEN(p)]
+ *   stats_out     [B][n_folds][PG_STATS_LEN(p)]; a fold id >= n_folds is a caller error and turns the
+ *                 statistics into NaN (general path; the small-problem fast path takes no folds)
  *   colminmax_out nullable [B][n_folds][2][p] = per-column min / max of the unshifted values; lets
  *                 the solver detect exactly-constant columns the way np.std()==0 does (ks2d:46-47)
  */
@@ -250,6 +271,43 @@ PG_API int pg_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1,
  */
 PG_API int pg_synth_field(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total,
                    uint64_t seed, int kind, double noise, void *stream);
+
+/*
+ * ---- Multi-GPU over NVLink peer memory (pg_comm_init, pg_halo_exchange, pg_allreduce_stats).
+ * The reference has no distributed code at all; these three calls are the whole exchange of the time-slab sharding:
+ * the trailing halo frame of the forward u_t (ks2d:1511) and the sum of the per-slab statistics.
+ *
+ * One process per GPU.  Each rank owns a zero-initialised WORKSPACE of pg_comm_workspace_bytes() bytes of device
+ * memory that every peer has mapped (CUDA VMM; pde_b200.slabs uses torch symmetric memory to allocate and exchange
+ * it).  peer_workspaces_host[q] is rank q's workspace AS MAPPED IN THIS PROCESS (q == rank: the local one).  Every
+ * rank must issue the same sequence of pg_comm_barrier / pg_allreduce_stats calls (epochs are counted per call).
+ * Device-side waits are bounded (~4 s); a wait that times out raises pg_comm_errors() and yields NaN statistics.
+ */
+#define PG_COMM_MAX_RANKS 16
+#define PG_COMM_MAX_LEN 1536 /* doubles per all-reduce: PG_MAX_FOLDS x PG_STATS_LEN(PG_MAX_P) = 1368 */
+PG_API size_t pg_comm_workspace_bytes(void);
+PG_API int pg_comm_init(int rank, int world, void *const *peer_workspaces_host, void **comm_out);
+PG_API int pg_comm_destroy(void *comm);
+/* number of device-side waits that timed out so far (synchronises the device), or -1 */
+PG_API int64_t pg_comm_errors(void *comm);
+/* all ranks have reached this point of `stream` and what they wrote before it is visible to peer reads (one warp) */
+PG_API int pg_comm_barrier(void *comm, void *stream);
+/*
+ * stats[len] <- sum over ranks, in place, in ONE launch: every rank stores its vector into every peer's workspace,
+ * flags it, waits for all flags and adds the world vectors in rank order, so all ranks hold the same bits and the
+ * result does not change from run to run (a ring / tree all-reduce promises neither).  len <= PG_COMM_MAX_LEN.
+ */
+PG_API int pg_allreduce_stats(void *comm, double *stats, int len, void *stream);
+/*
+ * Halo exchange without an SM: on `copy_stream`, a copy engine pulls `bytes` from peer_first_frame (the next rank's
+ * frame 0, mapped peer memory) into halo_dst (this rank's U[T-1]) and a stream memory operation then publishes a new
+ * epoch in the communicator's local flag word.  (*halo_flag_out, *halo_epoch_out) are what pg_fd_lib_gram_halo takes:
+ * K1 can be launched on another stream immediately.  The caller orders the transfer after the peers' data is ready
+ * (pg_comm_barrier on the compute stream + an event the copy stream waits for).  PG_EUNSUPPORTED when the driver has
+ * no stream memory operations: then copy with cudaMemcpyAsync and make the compute stream wait for it.
+ */
+PG_API int pg_halo_exchange(void *comm, double *halo_dst, const double *peer_first_frame, size_t bytes, void *copy_stream,
+                     const uint32_t **halo_flag_out, uint32_t *halo_epoch_out);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@ CSRC_DIR = PKG_DIR / "csrc"
 # ---- constants mirrored from include/pdegram.h
 PG_MAX_P = 16
 PG_MAX_FOLDS = 8
+PG_COMM_MAX_RANKS, PG_COMM_MAX_LEN = 16, 1536
 FD_KS_PERIODIC, FD_BASIC_TRIM = 0, 1
 LIB_KS_TRUE, LIB_KS_TRUE_ADV, LIB_KS_RICH, LIB_KS_RICH_NOADV, LIB_BASIC = 0, 1, 2, 3, 4
 LIB_KS_GRAD, LIB_KS_LAP, LIB_PATCH_MODEL4, LIB_PATCH_FULL, LIB_PATCH_DERIVS = 5, 6, 7, 8, 9
@@ -49,6 +50,15 @@ _PROTOS = {
                                  _i32, _ptr, _ptr, _i32, _ptr]),
     "pg_fd_lib_gram_tail": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
                                       _i32, _ptr, _ptr, _ptr, _i32, _ptr]),
+    "pg_fd_lib_gram_halo": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
+                                      _i32, _ptr, C.c_uint32, _ptr, _ptr, _i32, _ptr]),
+    "pg_comm_workspace_bytes": (C.c_size_t, []),
+    "pg_comm_init": (C.c_int, [_i32, _i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "pg_comm_destroy": (C.c_int, [_ptr]),
+    "pg_comm_errors": (C.c_int64, [_ptr]),
+    "pg_comm_barrier": (C.c_int, [_ptr, _ptr]),
+    "pg_allreduce_stats": (C.c_int, [_ptr, _ptr, _i32, _ptr]),
+    "pg_halo_exchange": (C.c_int, [_ptr, _ptr, _ptr, C.c_size_t, _ptr, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "pg_fd_terms": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _ptr, _ptr]),
     "pg_fd_gather_rows": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _ptr, _i64, _ptr, _ptr, _ptr]),
     "pg_block_means": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr]),

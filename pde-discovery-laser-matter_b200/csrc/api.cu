@@ -141,9 +141,9 @@ static int two_stage_blocks(const K1Params &P, int lib, int64_t nBt, int64_t len
     G.rows8 = rows8; G.sub0 = Q.nB0; G.sub1 = Q.nB1;
     rc = launch_k1_generic(lib, G, ctas, st);
     if (rc) return rc;
-    rc = launch_reduce_partials(partials, gen_parts, len, stats_out, 0, st);
+    rc = launch_reduce_partials(partials, gen_parts, len, stats_out, 0, st, nullptr, 0, 0, counters);
     if (rc) return rc;
-    if (nonfinite_out) PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (nonfinite_out) PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, 4 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     return PG_OK;
 }
 
@@ -177,17 +177,39 @@ int pg_shutdown(void) {
     return PG_OK;
 }
 
+static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+                            int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
+                            int n_folds, const double *trailing_block_means, const uint32_t *halo_flag, uint32_t halo_epoch,
+                            double *stats_out, int64_t *nonfinite_out, int variant, void *stream);
+
 int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
                    int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
                    int n_folds, double *stats_out, int64_t *nonfinite_out, int variant, void *stream) {
-    return pg_fd_lib_gram_tail(U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
-                               nullptr, stats_out, nonfinite_out, variant, stream);
+    return fd_lib_gram_impl(U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
+                            nullptr, nullptr, 0, stats_out, nonfinite_out, variant, stream);
 }
 
 int pg_fd_lib_gram_tail(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
                         int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
                         int n_folds, const double *trailing_block_means, double *stats_out, int64_t *nonfinite_out,
                         int variant, void *stream) {
+    return fd_lib_gram_impl(U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
+                            trailing_block_means, nullptr, 0, stats_out, nonfinite_out, variant, stream);
+}
+
+int pg_fd_lib_gram_halo(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+                        int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
+                        int n_folds, const uint32_t *halo_flag, uint32_t halo_epoch, double *stats_out,
+                        int64_t *nonfinite_out, int variant, void *stream) {
+    if (!halo_flag) PG_FAIL(PG_EINVAL, "halo_flag is null (use pg_fd_lib_gram)");
+    return fd_lib_gram_impl(U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
+                            nullptr, halo_flag, halo_epoch, stats_out, nonfinite_out, variant, stream);
+}
+
+static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+                            int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
+                            int n_folds, const double *trailing_block_means, const uint32_t *halo_flag, uint32_t halo_epoch,
+                            double *stats_out, int64_t *nonfinite_out, int variant, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     K1Params P{};
     int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, true);
@@ -201,18 +223,19 @@ int pg_fd_lib_gram_tail(const double *U, int64_t T, int64_t A0, int64_t A1, doub
     P.bt = bt; P.b0 = b0; P.b1 = b1;
     P.fold_of_row = fold_of_row; P.fold_of_frame = fold_of_frame; P.n_folds = n_folds;
     P.tail_means = trailing_block_means;
-    if (trailing_block_means && variant == PG_VARIANT_GENERIC)
-        PG_FAIL(PG_EUNSUPPORTED, "trailing_block_means is served by the tiled blockwise kernel only");
+    P.halo_flag = halo_flag; P.halo_epoch = halo_epoch;
+    if ((trailing_block_means || halo_flag) && variant == PG_VARIANT_GENERIC)
+        PG_FAIL(PG_EUNSUPPORTED, "trailing_block_means / halo_flag are served by the tiled blockwise kernel only");
     const int64_t len = (int64_t)n_folds * S;
     if (Trows <= 0) {  // a single frame has no u_t: zero rows
         PG_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * len, st));
-        if (nonfinite_out) PG_CUDA(cudaMemsetAsync(nonfinite_out, 0, sizeof(int64_t), st));
+        if (nonfinite_out) PG_CUDA(cudaMemsetAsync(nonfinite_out, 0, 4 * sizeof(int64_t), st));
         return PG_OK;
     }
     const int64_t nBt = (Trows + bt - 1) / bt;
     P.nB0 = (P.R0 + b0 - 1) / b0; P.nB1 = (P.R1 + b1 - 1) / b1;
 
-    if (variant != PG_VARIANT_GENERIC) {
+    if (variant != PG_VARIANT_GENERIC && !halo_flag) {
         rc = two_stage_blocks(P, library_id, nBt, len, stats_out, nonfinite_out, st);
         if (rc <= 0) return rc;
     }
@@ -226,9 +249,9 @@ int pg_fd_lib_gram_tail(const double *U, int64_t T, int64_t A0, int64_t A1, doub
             PG_FAIL(PG_EUNSUPPORTED, "no tiled kernel for dialect %d library %d block (%d,%d,%d) shape (%lld,%lld,%lld)",
                     fd_dialect, library_id, bt, b0, b1, (long long)T, (long long)A0, (long long)A1);
     }
-    if (trailing_block_means && !(tiled && !pointwise && plan.nbt == nBt && plan.nb0 == P.nB0 && plan.nb1 == P.nB1))
-        PG_FAIL(PG_EUNSUPPORTED, "trailing_block_means needs a layout the tiled blockwise kernel covers completely "
-                "(KS dialect, (bt, 8m, 8n) blocks, A0 %% 8 == 0, A1 %% 8 == 0, A1 >= 128); send the whole frame instead");
+    if ((trailing_block_means || halo_flag) && !(tiled && !pointwise && plan.nbt == nBt && plan.nb0 == P.nB0 && plan.nb1 == P.nB1))
+        PG_FAIL(PG_EUNSUPPORTED, "trailing_block_means / halo_flag need a layout the tiled blockwise kernel covers completely "
+                "(KS dialect, (bt, 8, 8) blocks, A0 %% 8 == 0, A1 %% 8 == 0, A1 >= 128); wait for the frame on the stream instead");
     // generic launches: up to 4 boxes of block indices (the whole space when not tiled).  Box 0 of the
     // pointwise path is its conditional fallback: the tiled region again, run only if that kernel saw a
     // non-finite accumulator (the reference drops such rows; the generic kernel does it exactly).
@@ -282,12 +305,12 @@ int pg_fd_lib_gram_tail(const double *U, int64_t T, int64_t A0, int64_t A1, doub
     }
     if (fallback)
         rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st, counters + 2, tiled_parts,
-                                    (int64_t)box_ctas[0] * GW_WARPS);
+                                    (int64_t)box_ctas[0] * GW_WARPS, counters);
     else
-        rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st);
+        rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st, nullptr, 0, 0, counters);
     if (rc) return rc;
     if (nonfinite_out)
-        PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, 4 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     return PG_OK;
 }
 

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__restrict__ partials, int64_t n_parts,
                                                               int64_t len, double *__restrict__ out, int accumulate,
                                                               const unsigned long long *__restrict__ flag, int64_t n_a,
-                                                              int64_t n_b) {
+                                                              int64_t n_b, const unsigned long long *__restrict__ poison) {
     __shared__ double sh[128];
     const int64_t e = blockIdx.x;
     double s = 0.0, comp = 0.0;
@@ -149,7 +149,13 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__re
         if (threadIdx.x < w) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + w]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[e] = accumulate ? __dadd_rn(out[e], sh[0]) : sh[0];
+    // rows with an out-of-range fold id (counters[1]) or a halo frame that never arrived (counters[3]) would silently
+    // shrink / corrupt the statistics: make them loud instead (no host synchronisation needed to notice)
+    if (threadIdx.x == 0) {
+        double v = sh[0];
+        if (poison && (poison[1] | poison[3])) v = nan("");
+        out[e] = accumulate ? __dadd_rn(out[e], v) : v;
+    }
 }
 
 // ----------------------------------------------------------------------------- term stacks
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(GW * 32) rows_gram_kernel(RowsParams P) {
 // per problem: stats[b][e] = sum_k partials[b][k][e];  colminmax likewise with min / max
 __global__ void rows_reduce_kernel(const double *__restrict__ partials, const double *__restrict__ mm_partials,
                                    int64_t B, int parts, int len, int mmlen, int p, double *__restrict__ stats,
-                                   double *__restrict__ colminmax) {
+                                   double *__restrict__ colminmax, const unsigned long long *__restrict__ poison) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < B * len) {
         const int64_t b = idx / len, e = idx % len;
@@ -323,7 +329,7 @@ __global__ void rows_reduce_kernel(const double *__restrict__ partials, const do
             comp = __dsub_rn(__dsub_rn(t, s), x);
             s = t;
         }
-        stats[idx] = s;
+        stats[idx] = (poison && poison[1]) ? nan("") : s;   // a fold id >= n_folds is a caller error: loud, not silent
     }
     if (colminmax && idx < B * mmlen) {
         const int64_t b = idx / mmlen, e = idx % mmlen;
@@ -367,9 +373,10 @@ int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st) {
 }
 
 int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate,
-                           cudaStream_t st, const unsigned long long *flag, int64_t n_a, int64_t n_b) {
+                           cudaStream_t st, const unsigned long long *flag, int64_t n_a, int64_t n_b,
+                           const unsigned long long *poison) {
     if (len <= 0) return PG_OK;
-    reduce_partials_kernel<<<(unsigned)len, 128, 0, st>>>(partials, n_parts, len, out, accumulate, flag, n_a, n_b);
+    reduce_partials_kernel<<<(unsigned)len, 128, 0, st>>>(partials, n_parts, len, out, accumulate, flag, n_a, n_b, poison);
     PG_LAUNCHED();
     return PG_OK;
 }
@@ -500,7 +507,7 @@ int launch_rows_gram(const RowsParams &P, double *stats, double *colminmax, cuda
     const int len = P.n_folds * S, mmlen = P.n_folds * 2 * P.p;
     const int64_t work = P.B * (int64_t)(len > mmlen ? len : mmlen);
     rows_reduce_kernel<<<(unsigned)((work + 127) / 128), 128, 0, st>>>(P.partials, P.mm_partials, P.B, P.chunks * GW,
-                                                                       len, mmlen, P.p, stats, colminmax);
+                                                                       len, mmlen, P.p, stats, colminmax, P.counters);
     PG_LAUNCHED();
     return PG_OK;
 }

@@ -35,6 +35,10 @@ struct K1Params {
     // nullable: (8, 8) block means [A0/8][A1/8] of the frame after the last row frame; frame T-1 of U is then a
     // placeholder (tiled blockwise kernel only: pg_fd_lib_gram_tail)
     const double *tail_means;
+    // nullable: frame T-1 of U is being filled by a copy engine; readable once *halo_flag >= halo_epoch
+    // (tiled blockwise kernel only: pg_fd_lib_gram_halo).  counters[3] counts waits that timed out.
+    const unsigned int *halo_flag;
+    unsigned int halo_epoch;
 };
 
 struct RowsParams {
@@ -81,8 +85,11 @@ struct TiledPlan {
 int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st);
 // Sum of partials[k][.] over k.  With `flag`: parts [0, n_a) are skipped if *flag != 0 and parts [n_a, n_a + n_b)
 // are skipped if *flag == 0 (fast path and its conditional fallback, see tiled_pw.cu).
+// `poison` (the launch's counters): the result is NaN when counters[1] (out-of-range fold ids) or counters[3] (halo
+// frame never arrived) is non-zero.
 int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate, cudaStream_t st,
-                           const unsigned long long *flag = nullptr, int64_t n_a = 0, int64_t n_b = 0);
+                           const unsigned long long *flag = nullptr, int64_t n_a = 0, int64_t n_b = 0,
+                           const unsigned long long *poison = nullptr);
 int launch_fd_terms(int dialect, int lib, const double *U, int64_t T, int64_t A0, int64_t A1, const FdConsts &c, double *out, cudaStream_t st);
 int launch_fd_gather(int lib, const K1Params &P, const int64_t *flat_idx, int64_t n, double *X, double *y, cudaStream_t st);
 int launch_block_means(const double *stack, int k, int64_t T, int64_t A0, int64_t A1, int bt, int b0, int b1, double *out, cudaStream_t st);

@@ -78,6 +78,10 @@ struct TiledParams {
     unsigned long long *counters;
     double *rows8;            // EMIT kernels: block-mean rows [nbt][A0/8][A1c/8][p+1] (y first) instead of statistics
     const double *tail_means; // nullable: block means [A0/8][A1c/8] of the frame after the last row frame (it then is a placeholder)
+    // nullable: frame T-1 of U is still being written (a copy engine pulling it from the next rank's slab);
+    // it may be loaded only once *halo_flag has reached halo_epoch (pg_fd_lib_gram_halo)
+    const unsigned int *halo_flag;
+    unsigned int halo_epoch;
 };
 
 // ----------------------------------------------------------------------------- per-lane block sums
@@ -279,6 +283,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                 if (tries >= (1 << 14)) *pace_off = 1;   // some CTA is not making progress (shared GPU?): stop pacing this CTA
             }
         }
+        if (P.halo_flag && t == (int)P.T - 1 && !wait_flag_reached(P.halo_flag, P.halo_epoch))
+            atomicAdd(&P.counters[3], 1ull);        // the frame never arrived: the API poisons the statistics
         fence_proxy_async();
         mbar_expect_tx(&full[s], G_::TMA_BYTES);
         // the shifted tile column of a width with A1 % 16 == 8 starts inside a 16-column group: tmap_last views the field from column 8
@@ -725,6 +731,7 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     tp.partials = partials; tp.counters = P.counters;
     tp.rows8 = rows8;
     tp.tail_means = P.tail_means;
+    tp.halo_flag = P.halo_flag; tp.halo_epoch = P.halo_epoch;
     switch (lib) {
         case PG_LIB_KS_TRUE: return launch_tiled_t<PG_LIB_KS_TRUE>(map, tp, P.n_folds, NW, plan.grid, st);
         case PG_LIB_KS_TRUE_ADV: return launch_tiled_t<PG_LIB_KS_TRUE_ADV>(map, tp, P.n_folds, NW, plan.grid, st);

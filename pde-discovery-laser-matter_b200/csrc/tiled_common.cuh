@@ -66,6 +66,25 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// Wait (one thread) until the 32-bit flag, written by a stream memory operation behind a copy-engine transfer, has
+// reached `epoch` (wrap-safe).  Bounded: ~4 s of polling, then false -- a kernel must never hang on a transfer
+// that was not queued.
+__device__ __forceinline__ bool wait_flag_reached(const unsigned int *flag, unsigned int epoch) {
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0;; ++spins) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - epoch) >= 0) return true;
+        if ((spins & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) return false;
+        }
+        __nanosleep(200);
+    }
+}
+
 // ----------------------------------------------------------------------------- swizzled tile layout
 // A stage holds a [rows][128] fp64 tile written by TMA through a 4-D view of the field
 // (16 doubles, A1/16 groups, A0, T) with CU_TENSOR_MAP_SWIZZLE_128B: inside every 128-byte segment the

@@ -339,7 +339,10 @@ def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", incl
         fold, _ = split_folds(n_rows, rng)
         stats, bad = ops.fd_lib_gram(Ud, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib, block=block,
                                      fold_of_row=fold, n_folds=2, variant=variant, return_nonfinite=True)
-        if int(bad.item()):
+        bad = bad.cpu()
+        if int(bad[1]):
+            raise ValueError(f"{int(bad[1])} block rows carry a fold id outside [0, 2)")
+        if int(bad[0]):
             # non-finite rows renumber the reference's permutation: redo through materialised block rows
             terms = ops.fd_terms(Ud[:-1], dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib)
             Ut = ((Ud[1:] - Ud[:-1]) / DT)[None]

@@ -41,8 +41,15 @@ def field(U):
 
 
 def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row=None, fold_of_frame=None,
-                n_folds=1, variant=L.VARIANT_AUTO, return_nonfinite=False, trailing_block_means=None):
+                n_folds=1, variant=L.VARIANT_AUTO, return_nonfinite=False, trailing_block_means=None, halo=None):
     """K1: field -> statistics [n_folds][S(p)] without materialising Theta (pg_fd_lib_gram).
+
+    ``return_nonfinite``: also return the call's four int64 counters (device tensor): [0] block rows dropped because a
+    mean was not finite, [1] rows with a fold id outside [0, n_folds) (a caller error: the statistics are then NaN),
+    [2] internal, [3] halo waits that timed out (statistics NaN).
+
+    ``halo`` = (flag_ptr, epoch) from ``slabs.PeerComm.pull_halo``: U[-1] is still being filled by a copy engine; the
+    kernel starts at once and reads that frame only after the flag has reached ``epoch`` (pg_fd_lib_gram_halo).
 
     ``trailing_block_means`` ([A0/8][A1/8], see ``frame_block_means``): the (8, 8) block means of the frame that
     follows U[-2]; U[-1] is then a placeholder whose values are ignored (pg_fd_lib_gram_tail: time slabs whose
@@ -63,8 +70,12 @@ def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row
     if ff is not None and ff.numel() != T - 1:
         raise ValueError(f"fold_of_frame must have T-1 = {T - 1} entries")
     stats = torch.empty((n_folds, L.stats_len(p)), dtype=torch.float64, device=U.device)
-    bad = torch.zeros(1, dtype=torch.int64, device=U.device)
-    if trailing_block_means is not None:
+    bad = torch.empty(4, dtype=torch.int64, device=U.device) if return_nonfinite else None
+    if halo is not None:
+        L.check(lib.pg_fd_lib_gram_halo(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0,
+                                        b1, L.ptr(fr), L.ptr(ff), n_folds, int(halo[0]), int(halo[1]), L.ptr(stats),
+                                        L.ptr(bad), variant, L.stream_ptr()))
+    elif trailing_block_means is not None:
         tm = _dev(trailing_block_means, torch.float64)
         if tm.numel() != (A0 // 8) * (A1 // 8):
             raise ValueError(f"trailing_block_means must hold (A0/8) x (A1/8) = {(A0 // 8) * (A1 // 8)} block means")

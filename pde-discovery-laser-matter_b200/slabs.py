@@ -15,10 +15,13 @@ import numpy as np
 from . import _lib as L
 
 
-def slab_bounds(n_row_frames: int, block_t: int, world: int):
+def slab_bounds(n_row_frames: int, block_t: int, world: int, allow_empty: bool = False):
     """Row-frame ranges [lo, hi) per rank: whole t-blocks, as even as possible; a ragged last
-    t-block (ks2d:384) stays with the last rank."""
+    t-block (ks2d:384) stays with the last rank.  More ranks than t-blocks is an error (an empty slab has no first
+    frame to hand to its left neighbour) unless ``allow_empty`` -- for callers that drop the empty ranges themselves."""
     n_tb = -(-n_row_frames // block_t)
+    if world > n_tb and not allow_empty:
+        raise ValueError(f"{world} ranks for {n_tb} t-block(s) of {block_t} frame(s): use at most {n_tb} ranks")
     base, extra = divmod(n_tb, world)
     out, tb = [], 0
     for r in range(world):
@@ -27,6 +30,137 @@ def slab_bounds(n_row_frames: int, block_t: int, world: int):
         out.append((lo, max(lo, hi)))
         tb += k
     return out
+
+
+class PeerComm:
+    """The C-ABI communicator (pg_comm_init / pg_comm_barrier / pg_allreduce_stats / pg_halo_exchange,
+    include/pdegram.h) over NVLink peer memory.
+
+    torch symmetric memory (CUDA VMM allocations mapped into every rank of the group) is only the ALLOCATOR and the
+    exchange of the mappings; what runs are the library's own kernels and copy-engine transfers on plain pointers:
+
+    * ``allreduce(stats)``: ONE launch; every rank stores its vector into every peer, waits for all flags and sums in
+      rank order, so the result is the same bits on every rank and from run to run (NCCL promises neither).
+    * ``slab(shape)``: a time slab allocated IN symmetric memory: the next rank's first frame can then be pulled
+      straight out of its slab, with no publishing copy.
+    * ``pull_halo(U_local)``: barrier (one warp, before K1), then on a side stream a copy engine pulls the next rank's
+      first frame into ``U_local[-1]`` and a stream memory operation raises a flag; returns ``(flag_ptr, epoch)`` for
+      ``ops.fd_lib_gram(..., halo=...)``: K1 is ONE launch that starts immediately and polls the flag only before it
+      loads the trailing frame (which the last t-block alone reads).
+
+    Raises when symmetric memory cannot be set up (CPU, one GPU, no peer access); callers keep ``PeerHalo``'s send/recv
+    path for that."""
+
+    def __init__(self, group=None, device=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        torch = L.torch_cuda()
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.lib = L.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > L.PG_COMM_MAX_RANKS:
+            raise L.PdeGramError(f"at most {L.PG_COMM_MAX_RANKS} ranks")
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self._symm = symm_mem
+        nbytes = int(self.lib.pg_comm_workspace_bytes())
+        self.ws = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.ws.zero_()
+        torch.cuda.synchronize()
+        self.ws_hdl = symm_mem.rendezvous(self.ws, self.group)
+        ptrs = self._peer_ptrs(self.ws_hdl, self.ws)
+        arr = (C.c_void_p * self.world)(*ptrs)
+        h = C.c_void_p()
+        L.check(self.lib.pg_comm_init(self.rank, self.world, arr, C.byref(h)))
+        self.h = h
+        dist.barrier(group)                 # every workspace is zeroed before anybody signals into it
+        torch.cuda.synchronize()
+        self.copy_stream = torch.cuda.Stream()
+        self._slabs = {}                    # data_ptr of a symmetric slab -> pointer of the NEXT rank's copy
+        self._pub = None                    # publish buffers for slabs that are not symmetric
+
+    def _peer_ptrs(self, hdl, t):
+        try:
+            return [int(x) for x in hdl.buffer_ptrs]
+        except Exception:
+            torch = L.torch_cuda()
+            return [int(hdl.get_buffer(q, tuple(t.shape), t.dtype).data_ptr()) for q in range(self.world)]
+
+    def slab(self, shape, dtype=None):
+        """A (T, A0, A1) stack in symmetric memory (collective: every rank calls it with the same shape)."""
+        import torch.distributed as dist
+
+        torch = L.torch_cuda()
+        shape = tuple(int(x) for x in shape)
+        numel = int(np.prod(shape))
+        # slabs of a ragged partition differ by a t-block: every rank allocates the largest one (symmetric allocations
+        # are matched by size) and works on a view of its own shape
+        n = torch.tensor([numel], dtype=torch.int64, device=self.device)
+        dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self.group)
+        base = self._symm.empty(int(n.item()), dtype=dtype or torch.float64, device=self.device)
+        hdl = self._symm.rendezvous(base, self.group)
+        ptrs = self._peer_ptrs(hdl, base)
+        t = base[:numel].view(shape)
+        self._slabs[int(t.data_ptr())] = (hdl, ptrs[self.rank + 1] if self.rank < self.world - 1 else None, base)
+        return t
+
+    def release(self, t):
+        self._slabs.pop(int(t.data_ptr()), None)
+
+    def barrier(self):
+        L.check(self.lib.pg_comm_barrier(self.h, L.stream_ptr()))
+
+    def allreduce(self, stats):
+        if not stats.is_contiguous():
+            raise L.PdeGramError("allreduce needs a contiguous statistics tensor")
+        L.check(self.lib.pg_allreduce_stats(self.h, L.ptr(stats), stats.numel(), L.stream_ptr()))
+        return stats
+
+    def errors(self) -> int:
+        return int(self.lib.pg_comm_errors(self.h))
+
+    def pull_halo(self, U_local):
+        """Start pulling the next rank's first frame into U_local[-1]; returns (flag_ptr, epoch) or None on the last
+        rank.  Stream-ordered: everything queued on the current stream before this call (e.g. the producer of
+        U_local) happens before the peers read it."""
+        import ctypes as C
+
+        torch = L.torch_cuda()
+        frame = U_local[0]
+        nbytes = frame.numel() * frame.element_size()
+        entry = self._slabs.get(int(U_local.data_ptr()))
+        if entry is None:
+            # not a symmetric slab: publish the first frame in a symmetric buffer (two alternate, so a slower
+            # neighbour may still be pulling the previous one)
+            if self._pub is None or self._pub[0].shape[1:] != frame.shape:
+                buf = self._symm.empty((2,) + tuple(frame.shape), dtype=frame.dtype, device=self.device)
+                hdl = self._symm.rendezvous(buf, self.group)
+                self._pub = (buf, hdl, self._peer_ptrs(hdl, buf), 0)
+            buf, hdl, ptrs, k = self._pub
+            self._pub = (buf, hdl, ptrs, k + 1)
+            b = k & 1
+            buf[b].copy_(frame)
+            src = ptrs[self.rank + 1] + b * nbytes if self.rank < self.world - 1 else None
+        else:
+            src = entry[1]
+        self.barrier()
+        if src is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record()
+        self.copy_stream.wait_event(ev)
+        flag, epoch = C.c_void_p(), C.c_uint32()
+        L.check(self.lib.pg_halo_exchange(self.h, L.ptr(U_local[-1]), src, nbytes, int(self.copy_stream.cuda_stream),
+                                          C.byref(flag), C.byref(epoch)))
+        return int(flag.value), int(epoch.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pg_comm_destroy(self.h)
+            self.h = None
 
 
 class PeerHalo:
@@ -202,15 +336,46 @@ def block_means_halo_ok(shape, dialect, block) -> bool:
             and A1 >= 128)
 
 
+def halo_flag_ok(shape, dialect, block) -> bool:
+    """Whether K1 can run as one launch that polls the halo flag (pg_fd_lib_gram_halo's layout rule)."""
+    _, A0, A1 = (int(x) for x in shape)
+    return (dialect == L.FD_KS_PERIODIC and int(block[1]) == 8 and int(block[2]) == 8 and A0 % 8 == 0 and A1 % 8 == 0
+            and A1 >= 128)
+
+
+def check_world(n_row_frames: int, block_t: int, world: int):
+    """Every rank must own at least one t-block: an empty slab would publish a first frame it does not have (its
+    U_local[0] is its own, not yet received, halo frame) and its left neighbour would difference against garbage."""
+    n_tb = -(-int(n_row_frames) // int(block_t))
+    if world > n_tb:
+        raise ValueError(f"{world} ranks for {n_tb} t-block(s): shrink the group to at most {n_tb} ranks "
+                         "(every rank needs at least one t-block)")
+
+
 def sharded_stats(U_local, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_frame=None, fold_of_row=None,
                   n_folds=1, variant=L.VARIANT_AUTO, group=None, halo=True, stats_fn=None, peer_halo=None,
-                  means_fn=None, block_means_halo=None):
+                  means_fn=None, block_means_halo=None, comm=None):
     """Per-rank K1 over this rank's slab (own frames + trailing halo frame) followed by the
     all-reduce.  ``stats_fn`` lets the CPU tests stand in for the CUDA kernel.
+
+    ``comm`` (a ``PeerComm``): the NVLink peer-memory path -- barrier, copy-engine pull of the halo frame behind a
+    flag, ONE K1 launch that polls the flag before its last t-block, one-launch rank-ordered all-reduce.
 
     The halo frame is only read by the LAST t-block of the slab, so the exchange is started first,
     K1 runs on everything before that t-block while the frame is in flight, and only the small tail
     launch waits for it (the transfer is hidden; statistics are additive over time slabs)."""
+    if U_local.shape[0] < 2:
+        raise ValueError("a slab needs at least one row frame and its trailing halo frame (world > number of t-blocks?)")
+    if comm is not None and stats_fn is None:
+        from . import ops
+
+        kw = dict(dialect=dialect, library=library, block=block, n_folds=n_folds, variant=variant,
+                  fold_of_frame=fold_of_frame, fold_of_row=fold_of_row)
+        tok = comm.pull_halo(U_local) if halo else None
+        if tok is not None and not (halo_flag_ok(U_local.shape, dialect, block) and variant != L.VARIANT_GENERIC):
+            L.torch_cuda().cuda.current_stream().wait_stream(comm.copy_stream)   # layout without the polling kernel
+            tok = None
+        return comm.allreduce(ops.fd_lib_gram(U_local, d0, d1, dt, halo=tok, **kw))
     if block_means_halo is None:
         # Measured on B200 (bench.py, PG_HALO): with NVLink peer memory the whole frame is pulled by a copy engine under
         # K1 and costs nothing, so the compressed form only saves the short tail launch and pays for a publish kernel

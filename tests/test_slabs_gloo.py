@@ -22,7 +22,57 @@ def test_slab_bounds():
     assert all(b[k][1] == b[k + 1][0] for k in range(7))
     assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 3
     assert slab_bounds(10, 3, 2) == [(0, 6), (6, 10)]            # ragged last t-block stays last
-    assert slab_bounds(4, 3, 4) == [(0, 3), (3, 4), (4, 4), (4, 4)]  # more ranks than t-blocks
+    assert slab_bounds(4, 3, 4, allow_empty=True) == [(0, 3), (3, 4), (4, 4), (4, 4)]  # more ranks than t-blocks
+    with pytest.raises(ValueError):      # ... is an error by default: an empty slab has no first frame to publish
+        slab_bounds(4, 3, 4)
+
+
+def _worker_too_many_ranks(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from pde_b200 import _lib as L
+    from pde_b200 import slabs
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 3 row frames in blocks of 3 = ONE t-block for two ranks: both the partition and the per-rank entry refuse
+        out = []
+        try:
+            slabs.slab_bounds(3, 3, world)
+        except ValueError as exc:
+            out.append("bounds:" + str(exc)[:20])
+        try:
+            slabs.check_world(3, 3, world)
+        except ValueError as exc:
+            out.append("check")
+        U_local = torch.zeros((1, 8, 128), dtype=torch.float64)       # an empty slab: only its halo frame
+        try:
+            slabs.sharded_stats(U_local, 0.5, 0.5, 1e-2, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8),
+                                stats_fn=lambda u: None)
+        except ValueError:
+            out.append("sharded")
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_more_ranks_than_t_blocks_is_rejected():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_too_many_ranks, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(2):
+        assert len(res[r]) == 3 and res[r][1:] == ["check", "sharded"], res
 
 
 def _free_port():
