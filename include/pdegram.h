@@ -103,9 +103,10 @@ PG_API int pg_library_width(int library_id);
  *   fold_of_row   nullable, one fold id per block row in reference row order (t-block major,
  *                 then a0-block, then a1-block); takes precedence over fold_of_frame
  *   fold_of_frame nullable, one fold id per frame 0..T-2; a block takes the fold of its first
- *                 frame (time-holdout folds); both NULL = a single fold 0
+ *                 frame (time-holdout folds); both NULL = a single fold 0.  A NEGATIVE id (255 in
+ *                 fold_of_row) excludes the row on purpose; an id >= n_folds is a caller error (counter [1])
  *   stats_out     [n_folds][PG_STATS_LEN(p)]
- *   nonfinite_out nullable, 4 int64 counters of this call:
+ *   nonfinite_out nullable, 8 int64 counters of this call:
  *                 [0] block rows skipped because a mean was not finite (ks2d:394-395).  If it is
  *                     non-zero and fold_of_row was given, the caller's row numbering no longer matches
  *                     the reference's (which renumbers after dropping): use pg_block_means +
@@ -114,6 +115,9 @@ PG_API int pg_library_width(int library_id);
  *                     silently dropped: when this counter is non-zero every entry of stats_out is NaN.
  *                 [2] internal (the pointwise fast path fell back to the exact non-finite handling)
  *                 [3] halo waits that timed out (pg_fd_lib_gram_halo); non-zero => stats_out is NaN
+ *                 [4..7] diagnostics of the tiled blockwise kernel: SM cycle counter and %globaltimer (ns) read by
+ *                     CTA 0 at its start ([4], [5]) and end ([6], [7]): ([6]-[4]) / ([7]-[5]) is the EFFECTIVE SM clock
+ *                     in GHz during the launch (what NVML reports is the requested clock); 0 for other kernels
  */
 PG_API int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
                    int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,

@@ -13,7 +13,7 @@ import subprocess
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libpdegram.so"
+LIB_PATH = Path(os.environ.get("PG_LIBPDEGRAM") or PKG_DIR / "libpdegram.so")   # env: experiment builds (tools/)
 CSRC_DIR = PKG_DIR / "csrc"
 
 # ---- constants mirrored from include/pdegram.h

@@ -143,7 +143,7 @@ static int two_stage_blocks(const K1Params &P, int lib, int64_t nBt, int64_t len
     if (rc) return rc;
     rc = launch_reduce_partials(partials, gen_parts, len, stats_out, 0, st, nullptr, 0, 0, counters);
     if (rc) return rc;
-    if (nonfinite_out) PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, 4 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (nonfinite_out) PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, 8 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     return PG_OK;
 }
 
@@ -229,7 +229,7 @@ static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, 
     const int64_t len = (int64_t)n_folds * S;
     if (Trows <= 0) {  // a single frame has no u_t: zero rows
         PG_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * len, st));
-        if (nonfinite_out) PG_CUDA(cudaMemsetAsync(nonfinite_out, 0, 4 * sizeof(int64_t), st));
+        if (nonfinite_out) PG_CUDA(cudaMemsetAsync(nonfinite_out, 0, 8 * sizeof(int64_t), st));
         return PG_OK;
     }
     const int64_t nBt = (Trows + bt - 1) / bt;
@@ -310,7 +310,7 @@ static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, 
         rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st, nullptr, 0, 0, counters);
     if (rc) return rc;
     if (nonfinite_out)
-        PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, 4 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        PG_CUDA(cudaMemcpyAsync(nonfinite_out, counters, 8 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     return PG_OK;
 }
 

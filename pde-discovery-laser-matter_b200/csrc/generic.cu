@@ -108,10 +108,11 @@ __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
                 th[k] = __ddiv_rn(th[k], cnt);
                 fin = fin && isfinite(th[k]);
             }
-            if (P.fold_of_row) fold = P.fold_of_row[(tb * P.nB0 + ib) * P.nB1 + jb];
+            if (P.fold_of_row) { fold = P.fold_of_row[(tb * P.nB0 + ib) * P.nB1 + jb]; if (fold == 255) fold = -1; }
             else if (P.fold_of_frame) fold = P.fold_of_frame[t0];
             if (!fin) { valid = false; ++bad_rows; }
-            else if (fold < 0 || fold >= P.n_folds) { valid = false; ++bad_fold; }
+            else if (fold < 0) valid = false;                         // excluded on purpose (-1 / 255): not an error
+            else if (fold >= P.n_folds) { valid = false; ++bad_fold; }
         }
         warp_accumulate_rows(wacc, ext, pa, pb, p, S, lane, valid, fold, th, y);
     }
@@ -284,7 +285,8 @@ __global__ void __launch_bounds__(GW * 32) rows_gram_kernel(RowsParams P) {
             ext[lane * W + 1] = yb[r];
             for (int j = 0; j < p; ++j) ext[lane * W + 2 + j] = sh ? __dsub_rn(Xb[r * P.ldx + j], sh[j]) : Xb[r * P.ldx + j];
             if (fb) fold = fb[r];
-            if (fold >= P.n_folds) { valid = false; ++bad_fold; }
+            if (fold == 255) valid = false;                           // excluded on purpose
+            else if (fold >= P.n_folds) { valid = false; ++bad_fold; }
         }
         __syncwarp();
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);

@@ -34,7 +34,10 @@
 
 namespace pg {
 
-constexpr int NSTAGE = 3;
+#ifndef PG_NSTAGE
+#define PG_NSTAGE 3
+#endif
+constexpr int NSTAGE = PG_NSTAGE;
 
 // Tile geometry: NW warps per CTA, one 8-row block band per warp (NW = 8: 64 x 128 tile, one CTA per SM).
 // Stage layout: swizzled tile [HR][TJ] written by TMA (tiled_common.cuh), then hcol [HR][4] = (left2, right2).
@@ -117,8 +120,8 @@ __device__ __forceinline__ int block_lane(int b) { return 8 * ((2 * b) & 3) + (b
 // rich library u^2 and u*L') cost per-point fp64 work.
 template <int LIB>
 __device__ __forceinline__ void march_frame(const double *__restrict__ st, const LaneMap &m, const TiledParams &P, Sums &F) {
-    double wp[4], wc[8], wn[8];              // own columns of row s-2; rows s-1 and s (all 8 columns)
-    double rsU[12], D[12];
+    double wp[4], wc[8], wn[8], nx[8];       // own columns of row s-2; rows s-1 and s (all 8 columns); row s+1 in flight
+    double rsU[12], D[12];                   // only rows 0-3, 8-11 (rsU) and 1, 2, 9, 10 (D) are ever formed
     // per-column partial sums of the nonlinear terms: four independent FMA chains per quantity
     double gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0}, u2[4] = {0, 0, 0, 0};
     // rich library, block sum of u*L': with the block sum of u^2 already at hand it needs only the products of
@@ -127,17 +130,29 @@ __device__ __forceinline__ void march_frame(const double *__restrict__ st, const
     //   SUL = kappa SU2 + rho (vb + 2 vi) + (he + 2 hi)
     // (same cancellation as u * lap itself: the terms are O(sum u^2), the result O((k h)^2 sum u^2)).
     double vi[2] = {0, 0}, hi[2] = {0, 0}, vb = 0, he = 0;
-    double sD = 0, sE = 0, sU = 0, sDy = 0;
+    // Column-pair sums over the output rows 2..9.  The row scalars D(s) and e(s) are only needed SUMMED over those
+    // rows (individually just at rows 1, 2, 9, 10), so the rows are added up per column pair first:
+    //   sum D = S16 - Sa,  sum e = S07 - Sb,  sum rsU = Sa + Sb      (8 additions per row instead of 12)
+    // (the advection libraries keep w1, w6, w2, w5 apart: sum (w6+w5) - (w2+w1) is their a1-difference column).
+    double S07 = 0, Sb = 0, S16 = 0, Sa = 0, S1 = 0, S6 = 0, S2 = 0, S5 = 0;
+    load_row8(st, m, 0, nx);
 #pragma unroll
     for (int s = 0; s < 12; ++s) {
-        load_row8(st, m, s, wn);
-        rsU[s] = (wn[2] + wn[3]) + (wn[4] + wn[5]);
-        D[s] = (wn[1] - wn[2]) + (wn[6] - wn[5]);
-        if (s >= 2 && s <= 9) {
-            sD += D[s];
-            sE += (wn[0] - wn[3]) + (wn[7] - wn[4]);
-            sU += rsU[s];
-            if constexpr (kNeedAdv<LIB>) sDy += (wn[6] + wn[5]) - (wn[2] + wn[1]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) wn[q] = nx[q];
+        if (s < 11) load_row8(st, m, s + 1, nx);          // one row ahead: the shared-memory latency hides under this row's arithmetic
+        const bool inner = s >= 2 && s <= 9, needU = s <= 3 || s >= 8, needD = s == 1 || s == 2 || s == 9 || s == 10;
+        const double b = wn[3] + wn[4];
+        double a = 0.0, o = 0.0;
+        if (needU || (inner && !kNeedAdv<LIB>)) a = wn[2] + wn[5];
+        if (needD || (inner && !kNeedAdv<LIB>)) o = wn[1] + wn[6];
+        if (needU) rsU[s] = a + b;
+        if (needD) D[s] = o - a;
+        if (inner) {
+            if constexpr (kNeedAdv<LIB>) { S1 += wn[1]; S6 += wn[6]; S2 += wn[2]; S5 += wn[5]; }
+            else { S16 += o; Sa += a; }
+            S07 += wn[0] + wn[7];
+            Sb += b;
         }
         if (s >= 3 && s <= 10) {
             // ---- nonlinear terms of output row s-1 (u in wc); rows s-2 (wp) and s (wn) are its a0-neighbours
@@ -173,6 +188,8 @@ __device__ __forceinline__ void march_frame(const double *__restrict__ st, const
 #pragma unroll
         for (int q = 0; q < 8; ++q) wc[q] = wn[q];
     }
+    if constexpr (kNeedAdv<LIB>) { S16 = S1 + S6; Sa = S2 + S5; }
+    const double sD = S16 - Sa, sE = S07 - Sb, sU = Sa + Sb;
     const double rsL1 = fma(P.rho, (rsU[2] + rsU[0]) - 2.0 * rsU[1], D[1]);
     const double rsL2 = fma(P.rho, (rsU[3] + rsU[1]) - 2.0 * rsU[2], D[2]);
     const double rsL9 = fma(P.rho, (rsU[10] + rsU[8]) - 2.0 * rsU[9], D[9]);
@@ -184,7 +201,7 @@ __device__ __forceinline__ void march_frame(const double *__restrict__ st, const
     F.SGx = (gx[0] + gx[1]) + (gx[2] + gx[3]);
     F.SGy = (gy[0] + gy[1]) + (gy[2] + gy[3]);
     if constexpr (kNeedAdv<LIB>) {
-        F.SDy = sDy;
+        F.SDy = (S6 + S5) - (S2 + S1);
         F.SDx = (rsU[10] + rsU[9]) - (rsU[2] + rsU[1]);   // sum_{2..9} (rsU(s+1) - rsU(s-1))
     }
     if constexpr (kRich<LIB>) {
@@ -227,7 +244,10 @@ __device__ __forceinline__ double sum_frame_u(const double *__restrict__ st, con
 //   * TIMEFOLD: folds given per frame (time-holdout folds) or no folds: a warp accumulates for ONE fold
 //     at a time in registers and flushes into its partial slot when the fold changes, so any number of
 //     folds runs at the single-fold cost.  !TIMEFOLD: fold_of_row, NF <= 2 masked accumulators as before.
-constexpr int DNW = 8;   // consumer warps
+#ifndef PG_DNW
+#define PG_DNW 8
+#endif
+constexpr int DNW = PG_DNW;   // consumer warps
 
 //   * EMIT: the (scaled) block-mean rows are written to P.rows8 instead of being accumulated: first stage of the path
 //     for (bt, 8m, 8n) blocks, whose rows are means of these sub-block rows (api.cu).
@@ -240,7 +260,12 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
     constexpr int p = Lib<LIB>::P;
     constexpr int S = PG_STATS_LEN(p);
     constexpr int W = p + 2;
-    constexpr int NE = (S + 31) / 32;   // lane-owned statistics entries
+    constexpr bool PRIV = S * NF <= 36;   // every lane keeps the whole statistics vector in registers
+    // Lane-owned statistics entries (the path that spreads the vector over the lanes).  The rich libraries' first
+    // column is the constant 1, so the p + 2 entries it takes part in (sum theta_0 = G_00 = n, sum theta_0 y = sum y,
+    // G_0j = sum theta_j) duplicate other entries: they are not accumulated, the flush copies them.
+    constexpr bool SKIPDUP = kRich<LIB> && !PRIV;
+    constexpr int NE = ((SKIPDUP ? S - (p + 2) : S) + 31) / 32;
     constexpr int SB = G_::slots(p);    // block rows per staging batch
     static_assert(!TIMEFOLD || NF == 1, "time folds accumulate one fold at a time");
     extern __shared__ unsigned char smem_dyn[];
@@ -252,6 +277,10 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
     double *ext_all = reinterpret_cast<double *>(smem_raw + NSTAGE * G_::STAGE_BYTES + 64);  // [NW][SB][W]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0 && blockIdx.x == 0) {   // diagnostics: SM cycle counter / wall clock at the start of CTA 0 (effective SM clock)
+        P.counters[4] = (unsigned long long)clock64();
+        P.counters[5] = global_ns();
+    }
     if (tid == 0) {
         *pace_off = 0;
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
@@ -317,21 +346,27 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
 
     const LaneMap lm = make_lane_map(warp * 8, HOFF, lane);
     double *ext = ext_all + warp * SB * W;
-    int ea[NE], eb[NE];
+    int ea[NE], eb[NE], ee[NE];
     bool ev[NE];
 #pragma unroll
     for (int k = 0; k < NE; ++k) {
-        const int e = lane + 32 * k;
-        ev[k] = e < S;
-        ea[k] = eb[k] = 0;
-        if (ev[k]) stats_pair(e, p, ea[k], eb[k]);
+        // the (lane + 32 k)-th entry that is accumulated (static register indices: one scan per k, once per kernel)
+        const int want = lane + 32 * k;
+        int cnt = 0, fe = -1, fa = 0, fb = 0;
+        for (int e = 0; e < S; ++e) {
+            int a, b;
+            stats_pair(e, p, a, b);
+            if (SKIPDUP && (a == 2 || b == 2)) continue;       // an entry with theta_0 = 1: duplicate
+            if (cnt == want) { fe = e; fa = a; fb = b; }
+            ++cnt;
+        }
+        ev[k] = fe >= 0; ee[k] = fe < 0 ? 0 : fe; ea[k] = fa; eb[k] = fb;
     }
     double acc[NF][NE];
 #pragma unroll
     for (int f = 0; f < NF; ++f)
 #pragma unroll
         for (int k = 0; k < NE; ++k) acc[f][k] = 0.0;
-    constexpr bool PRIV = S * NF <= 36;   // every lane keeps the whole statistics vector in registers
     constexpr int SP = PRIV ? S : 1;
     double pacc[NF][SP];
 #pragma unroll
@@ -360,8 +395,15 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         } else {
 #pragma unroll
             for (int k = 0; k < NE; ++k) {
-                if (ev[k]) out[lane + 32 * k] = fma(acc[f][k], P.sc[ea[k]] * P.sc[eb[k]], out[lane + 32 * k]);
+                if (ev[k]) out[ee[k]] = fma(acc[f][k], P.sc[ea[k]] * P.sc[eb[k]], out[ee[k]]);
                 acc[f][k] = 0.0;
+            }
+            if constexpr (SKIPDUP) {
+                // entries of the constant column: sum theta_0 = n, sum theta_0 y = sum y, G_0j = (j == 0 ? n : sum theta_j)
+                __syncwarp();
+                if (lane == 0) out[3] = out[0];
+                else if (lane == 1) out[3 + p] = out[1];
+                else if (lane - 2 < p) out[3 + 2 * p + (lane - 2)] = lane == 2 ? out[0] : out[3 + (lane - 2)];
             }
         }
         __syncwarp();
@@ -519,7 +561,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                 for (int k = 0; k < p; ++k) fin = fin && isfinite(th[k]);
                 bool valid = (lane & 8) == 0 && col_ok && !EMIT;
                 if (valid && !fin) { valid = false; ++bad_rows; }
-                else if (valid && (fold < 0 || fold >= P.n_folds)) { valid = false; ++bad_fold; }
+                else if (valid && fold < 0) valid = false;            // excluded on purpose (-1 / 255): not an error
+                else if (valid && fold >= P.n_folds) { valid = false; ++bad_fold; }
                 if constexpr (TIMEFOLD) {
                     // fold is warp-uniform (one id per t-block): switch the accumulation target when it changes
                     if (fold >= 0 && fold < P.n_folds && fold != cur_fold) {
@@ -583,7 +626,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                     su_first = F.SU;
                     ++tbs;
                     if constexpr (TIMEFOLD) fold = P.fold_of_frame ? P.fold_of_frame[t0 + f] : 0;
-                    else fold = P.fold_of_row[(tbs * P.nB0 + ib) * P.nB1 + jb];
+                    else { fold = P.fold_of_row[(tbs * P.nB0 + ib) * P.nB1 + jb]; if (fold == 255) fold = -1; }
                 }
                 A.SL += F.SL; A.SE1 += F.SE1; A.SE2 += F.SE2; A.SGx += F.SGx; A.SGy += F.SGy;
                 if constexpr (kNeedAdv<LIB>) { A.SDx += F.SDx; A.SDy += F.SDy; }
@@ -593,6 +636,10 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         }
     }
     cp_async_wait<0>();
+    if (tid == 0 && blockIdx.x == 0) {
+        P.counters[6] = (unsigned long long)clock64();
+        P.counters[7] = global_ns();
+    }
     if (P.epoch_done && warp == 0 && lane == 0)
         for (int k = (int)(G >> P.epoch_shift); k < P.n_epochs; ++k) atomicAdd(P.epoch_done + k, 1u);
     if (bad_rows) atomicAdd(&P.counters[0], bad_rows);

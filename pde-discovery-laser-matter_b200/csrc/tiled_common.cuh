@@ -66,6 +66,12 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Wait (one thread) until the 32-bit flag, written by a stream memory operation behind a copy-engine transfer, has
 // reached `epoch` (wrap-safe).  Bounded: ~4 s of polling, then false -- a kernel must never hang on a transfer
 // that was not queued.

@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
                 const int fold = fold_next;
                 if (f + 1 < nf && P.fold_of_frame) fold_next = __ldg(P.fold_of_frame + t0 + f + 1);
                 if (fold < 0 || fold >= P.n_folds) {
-                    bad_fold += rows_per_frame;
+                    if (fold >= 0) bad_fold += rows_per_frame;          // a negative id excludes the frame on purpose
                 } else {
                     if (fold != cur_fold) {
                         if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);

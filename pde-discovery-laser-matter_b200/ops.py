@@ -46,7 +46,8 @@ def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row
 
     ``return_nonfinite``: also return the call's four int64 counters (device tensor): [0] block rows dropped because a
     mean was not finite, [1] rows with a fold id outside [0, n_folds) (a caller error: the statistics are then NaN),
-    [2] internal, [3] halo waits that timed out (statistics NaN).
+    [2] internal, [3] halo waits that timed out (statistics NaN), [4..7] SM cycle counter / globaltimer ns at the start
+    and end of the tiled blockwise kernel's CTA 0 (effective SM clock of the launch).
 
     ``halo`` = (flag_ptr, epoch) from ``slabs.PeerComm.pull_halo``: U[-1] is still being filled by a copy engine; the
     kernel starts at once and reads that frame only after the flag has reached ``epoch`` (pg_fd_lib_gram_halo).
@@ -70,7 +71,7 @@ def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row
     if ff is not None and ff.numel() != T - 1:
         raise ValueError(f"fold_of_frame must have T-1 = {T - 1} entries")
     stats = torch.empty((n_folds, L.stats_len(p)), dtype=torch.float64, device=U.device)
-    bad = torch.empty(4, dtype=torch.int64, device=U.device) if return_nonfinite else None
+    bad = torch.zeros(8, dtype=torch.int64, device=U.device) if return_nonfinite else None
     if halo is not None:
         L.check(lib.pg_fd_lib_gram_halo(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0,
                                         b1, L.ptr(fr), L.ptr(ff), n_folds, int(halo[0]), int(halo[1]), L.ptr(stats),

@@ -105,13 +105,21 @@ def test_tiled_many_time_folds(env):
     for f in range(5):
         assert til[f][0] == gen[f][0] == 3 * 8 * 32
         assert_stats_close(til[f], gen[f], 3)
-    fof[6:9] = 9                                             # one t-block with an id outside [0, 5): skipped
+    fof[6:9] = -1                                            # one t-block excluded on purpose (negative id): skipped
     kw["fold_of_frame"] = fof
     gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
     til = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw).cpu().numpy()
     assert til[0][0] == 2 * 8 * 32
     for f in range(5):
         assert_stats_close(til[f], gen[f], 3)
+    fof[6:9] = 9                                             # an id >= n_folds is a caller error: loud (NaN + counter [1])
+    kw["fold_of_frame"] = fof
+    for variant in (L.VARIANT_GENERIC, L.VARIANT_TILED):
+        st, ctr = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=variant, return_nonfinite=True, **kw)
+        assert np.isnan(st.cpu().numpy()).all() and int(ctr[1].item()) == 8 * 32
+    bad_pw = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(1, 1, 1),
+                             fold_of_frame=fof, n_folds=5)
+    assert np.isnan(bad_pw.cpu().numpy()).all()
     # the rich library keeps its statistics spread over the lanes (no private copy): same flush path
     kw.update(library=L.LIB_KS_RICH, fold_of_frame=(np.arange(T - 1) // 9).astype(np.int32))
     gen = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw).cpu().numpy()
@@ -160,7 +168,7 @@ def test_tiled_nonfinite_and_unsupported(env):
     kw = dict(dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8), return_nonfinite=True)
     gen, bad_g = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_GENERIC, **kw)
     til, bad_t = ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, variant=L.VARIANT_TILED, **kw)
-    assert int(bad_g.item()) == int(bad_t.item()) > 0
+    assert int(bad_g[0].item()) == int(bad_t[0].item()) > 0
     assert_stats_close(til.cpu().numpy()[0], gen.cpu().numpy()[0], 3)
     with pytest.raises(pde_b200.PdeGramError, match="no tiled kernel"):
         ops.fd_lib_gram(U, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 4, 8),
@@ -218,7 +226,7 @@ def test_blocks_of_whole_sub_blocks_two_stage(env, libname, shape, block):
     kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=block, fold_of_frame=fof, n_folds=2, return_nonfinite=True)
     til, bad_t = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_TILED, **kw)
     gen, bad_g = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_GENERIC, **kw)
-    assert int(bad_t.item()) == int(bad_g.item()) > 0
+    assert int(bad_t[0].item()) == int(bad_g[0].item()) > 0
     for f in range(2):
         assert_stats_close(til.cpu().numpy()[f], gen.cpu().numpy()[f], p)
 
