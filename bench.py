@@ -467,7 +467,7 @@ def run_ours(args):
                 self.halo.end(token)
                 if ev:
                     ev[2].record()
-                s = s + ops.fd_lib_gram(V[cut:], D0, D1, DT, fold_of_frame=fof[cut:], **kw)
+                ops.stats_accumulate(s, ops.fd_lib_gram(V[cut:], D0, D1, DT, fold_of_frame=fof[cut:], **kw))
                 if ev:
                     ev[3].record()
             if ev:
@@ -490,7 +490,7 @@ def run_ours(args):
                 if self.passes > 1:
                     self.fill(ps)
                 s = self.k1(ps, library, block, variant, record)
-                stats = s if stats is None else stats.add_(s)
+                stats = s if stats is None else ops.stats_accumulate(stats, s)
             stats = self.reduce(stats)
             p = L.LIB_WIDTH[library]
             self.last_stats = stats

@@ -229,11 +229,51 @@ PG_API int pg_poly_rows(const void *U, int dtype, int64_t T, int64_t H, int64_t 
  *                [B][na][nt][2] = (r2, rmse) (ks2d:29-40) and best_out [B] = flat index
  *                a*nt+t maximising (r2, -n_active, -rmse), first maximum wins (ks2d:1731-1741)
  *   coef_out     [B][na][nt][p] coefficients in the units of the given columns
+ *   relres_out   nullable [B][na][nt] (needs eval_stats): held-out ss_res / sum y^2 as the statistics give it, BEFORE
+ *                the clamp at 0.  ss_res = yy - 2 c.b + c.G.c cancels when the fit is exact: below ~1e-9 the metrics
+ *                are rounding noise (r2 is still 1 to ~1e-9, rmse and the sweep's tie-break are not reliable) and
+ *                the caller should evaluate residuals from the rows: pg_rows_residual_ss / pg_fd_residual_ss.
  */
 PG_API int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect, int flags, const double *alphas,
                        int na, const double *thrs, int nt, int max_iter, const uint8_t *const_mask,
                        const int8_t *signs, const double *colminmax, const double *shift, const double *eval_stats,
-                       double *coef_out, double *metrics_out, int32_t *best_out, void *stream);
+                       double *coef_out, double *metrics_out, int32_t *best_out, double *relres_out, void *stream);
+
+/*
+ * build_library of basic_usage (basic:75-101) for the literal signature: four flat arrays of n values (u, u_x, u_y,
+ * lap_u as compute_derivatives returned them) -> Theta_out [n][6] = [1, u, u_x, u_y, lap, u*u].
+ */
+PG_API int pg_basic_library_rows(const double *u, const double *u_x, const double *u_y, const double *lap_u, int64_t n,
+                          double *Theta_out, void *stream);
+
+/* dst[i] += src[i], i < n: statistics are additive over sub-slabs, passes and folds (fit_streamed, K-fold train sets) */
+PG_API int pg_stats_accumulate(double *dst, const double *src, int64_t n, void *stream);
+
+/*
+ * The block-mean rows of pg_fd_lib_gram materialised: rows_out [nrows][p + 1] = (mean u_t, mean theta_0 ..) per block
+ * in reference row order (t-block major), NOTHING dropped (a non-finite mean stays in its row).  Serves the rare
+ * case in which rows must be renumbered after the reference drops non-finite ones (ks2d:394-395) before its random
+ * row split (ks2d:1638-1641).  Generic kernel, reference arithmetic.
+ */
+PG_API int pg_fd_block_rows(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                     int fd_dialect, int library_id, int bt, int b0, int b1, double *rows_out, void *stream);
+
+/*
+ * Exact held-out residual sums of n_coef <= 32 fitted models (r2_score / rmse, ks2d:29-40, on the test rows; the
+ * sweep's arg-max key of ks2d:1731-1741 compares them): ss_out [n_coef + 1] = sum over the rows of fold `eval_fold`
+ * (-1: all rows) of (y - theta . coef_j)^2, and the row count in the last entry.
+ *   pg_rows_residual_ss   rows X [n][ldx], y [n] on the device (sampled pointwise rows, literal stridge(X, y) calls)
+ *   pg_fd_residual_ss     straight from the field: the block rows are re-formed on the fly by the generic kernel
+ *                         (same arguments as pg_fd_lib_gram), a second pass that is only needed when relres_out of
+ *                         pg_stridge_batched signals cancellation (fits exact to ~1e-8: clean synthetic data)
+ * coef [n_coef][p] in the units of the library columns.
+ */
+PG_API int pg_rows_residual_ss(const double *X, const double *y, int64_t n, int p, int64_t ldx, const uint8_t *fold_of_row,
+                        int eval_fold, const double *coef, int n_coef, double *ss_out, void *stream);
+PG_API int pg_fd_residual_ss(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                      int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
+                      const int32_t *fold_of_frame, int n_folds, int eval_fold, const double *coef, int n_coef,
+                      double *ss_out, void *stream);
 
 /*
  * Rollout check of a discovered KS-dialect PDE (ks2d:1804-1838): explicit Euler from frame 0,

@@ -66,7 +66,13 @@ _PROTOS = {
     "pg_rows_gram_weighted": (C.c_int, [_ptr, _ptr, _i64, _i32, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
     "pg_poly_rows": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _ptr, _i64, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "pg_stridge_batched": (C.c_int, [_ptr, _i64, _i32, _i32, _i32, _ptr, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr,
-                                     _ptr, _ptr, _ptr, _ptr, _ptr]),
+                                     _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "pg_basic_library_rows": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
+    "pg_stats_accumulate": (C.c_int, [_ptr, _ptr, _i64, _ptr]),
+    "pg_fd_block_rows": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr]),
+    "pg_rows_residual_ss": (C.c_int, [_ptr, _ptr, _i64, _i32, _i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr]),
+    "pg_fd_residual_ss": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
+                                    _i32, _i32, _ptr, _i32, _ptr, _ptr]),
     "pg_ks_rollout": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _ptr, _i32, _ptr, _ptr, _ptr]),
     "pg_fit_metrics": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr]),
     "pg_time_moving_average": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr]),

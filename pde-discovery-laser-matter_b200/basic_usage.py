@@ -36,12 +36,8 @@ def compute_derivatives(u, dx: float, dy: float, dt: float):
 
 
 def build_library(u, u_x, u_y, lap_u):
-    """basic:75-101: Theta (N,6) = [1, u, u_x, u_y, lap, u^2] (C-order flatten).  Pure data
-    movement plus one product; done on the device with torch as the buffer manager."""
-    torch = L.torch_cuda()
-    f = [ops._dev(np.asarray(a, dtype=np.float64).reshape(-1), torch.float64) for a in (u, u_x, u_y, lap_u)]
-    Theta = torch.stack([torch.ones_like(f[0]), f[0], f[1], f[2], f[3], f[0] * f[0]], dim=1)
-    return _np(Theta), list(TERM_NAMES)
+    """basic:75-101: Theta (N,6) = [1, u, u_x, u_y, lap, u^2] (C-order flatten): pg_basic_library_rows."""
+    return _np(ops.basic_library_rows(u, u_x, u_y, lap_u)), list(TERM_NAMES)
 
 
 def stridge_regression(Theta, u_t, alpha: float = 0.01, threshold: float = 0.01, max_iter: int = 10):

@@ -314,6 +314,98 @@ static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, 
     return PG_OK;
 }
 
+int pg_fd_residual_ss(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+                      int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
+                      int n_folds, int eval_fold, const double *coef, int n_coef, double *ss_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    K1Params P{};
+    int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, true);
+    if (rc) return rc;
+    if (bt <= 0 || b0 <= 0 || b1 <= 0) PG_FAIL(PG_EINVAL, "block sizes must be > 0");
+    if (n_folds < 1 || n_folds > PG_MAX_FOLDS) PG_FAIL(PG_EINVAL, "n_folds must be in 1..%d", PG_MAX_FOLDS);
+    if (eval_fold < -1 || eval_fold >= n_folds) PG_FAIL(PG_EINVAL, "eval_fold must be -1 (all rows) or a fold id");
+    if (n_coef < 1 || n_coef > 32) PG_FAIL(PG_EINVAL, "n_coef must be in 1..32 (call again for more)");
+    if (!coef || !ss_out) PG_FAIL(PG_EINVAL, "null buffer");
+    const int64_t Trows = T - 1;
+    if (Trows <= 0) {
+        PG_CUDA(cudaMemsetAsync(ss_out, 0, sizeof(double) * (n_coef + 1), st));
+        return PG_OK;
+    }
+    P.bt = bt; P.b0 = b0; P.b1 = b1;
+    P.fold_of_row = fold_of_row; P.fold_of_frame = fold_of_frame; P.n_folds = n_folds;
+    const int64_t nBt = (Trows + bt - 1) / bt;
+    P.nB0 = (P.R0 + b0 - 1) / b0; P.nB1 = (P.R1 + b1 - 1) / b1;
+    P.tb_lo = 0; P.tb_hi = nBt; P.i0_lo = 0; P.i0_hi = P.nB0; P.i1_lo = 0; P.i1_hi = P.nB1;
+    const int64_t items = nBt * P.nB0 * P.nB1;
+    int64_t g = (items + GW_THREADS - 1) / GW_THREADS;
+    const int ctas = (int)(g < 1 ? 1 : (g > sm_count() * 8 ? sm_count() * 8 : g));
+    void *scr = nullptr;
+    rc = scratch_for(st, 64 + sizeof(double) * (size_t)ctas * (n_coef + 1), &scr);
+    if (rc) return rc;
+    PG_CUDA(cudaMemsetAsync(scr, 0, 64, st));
+    P.counters = (unsigned long long *)scr;
+    double *partials = (double *)((char *)scr + 64);
+    rc = launch_k1_generic_resid(library_id, P, coef, n_coef, eval_fold, partials, ctas, st);
+    if (rc) return rc;
+    return launch_reduce_partials(partials, ctas, n_coef + 1, ss_out, 0, st, nullptr, 0, 0, P.counters);
+}
+
+int pg_basic_library_rows(const double *u, const double *u_x, const double *u_y, const double *lap_u, int64_t n,
+                          double *Theta_out, void *stream) {
+    if (n < 0) PG_FAIL(PG_EINVAL, "n < 0");
+    if (n == 0) return PG_OK;
+    if (!u || !u_x || !u_y || !lap_u || !Theta_out) PG_FAIL(PG_EINVAL, "null buffer");
+    return launch_basic_library_rows(u, u_x, u_y, lap_u, n, Theta_out, (cudaStream_t)stream);
+}
+
+int pg_stats_accumulate(double *dst, const double *src, int64_t n, void *stream) {
+    if (n < 0) PG_FAIL(PG_EINVAL, "n < 0");
+    if (n == 0) return PG_OK;
+    if (!dst || !src) PG_FAIL(PG_EINVAL, "null buffer");
+    return launch_stats_accumulate(dst, src, n, (cudaStream_t)stream);
+}
+
+int pg_fd_block_rows(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+                     int library_id, int bt, int b0, int b1, double *rows_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    K1Params P{};
+    int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, true);
+    if (rc) return rc;
+    if (bt <= 0 || b0 <= 0 || b1 <= 0) PG_FAIL(PG_EINVAL, "block sizes must be > 0");
+    if (!rows_out) PG_FAIL(PG_EINVAL, "rows_out is null");
+    const int64_t Trows = T - 1;
+    if (Trows <= 0) return PG_OK;
+    P.bt = bt; P.b0 = b0; P.b1 = b1; P.n_folds = 1;
+    const int64_t nBt = (Trows + bt - 1) / bt;
+    P.nB0 = (P.R0 + b0 - 1) / b0; P.nB1 = (P.R1 + b1 - 1) / b1;
+    P.tb_lo = 0; P.tb_hi = nBt; P.i0_lo = 0; P.i0_hi = P.nB0; P.i1_lo = 0; P.i1_hi = P.nB1;
+    const int64_t items = nBt * P.nB0 * P.nB1;
+    int64_t g = (items + GW_THREADS - 1) / GW_THREADS;
+    const int ctas = (int)(g < 1 ? 1 : (g > sm_count() * 8 ? sm_count() * 8 : g));
+    return launch_k1_generic_rows(library_id, P, rows_out, ctas, st);
+}
+
+int pg_rows_residual_ss(const double *X, const double *y, int64_t n, int p, int64_t ldx, const uint8_t *fold_of_row,
+                        int eval_fold, const double *coef, int n_coef, double *ss_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p < 1 || p > PG_MAX_P) PG_FAIL(PG_EINVAL, "p must be in 1..%d", PG_MAX_P);
+    if (n < 0 || ldx < p) PG_FAIL(PG_EINVAL, "bad shape n=%lld ldx=%lld", (long long)n, (long long)ldx);
+    if (n_coef < 1 || n_coef > 32) PG_FAIL(PG_EINVAL, "n_coef must be in 1..32 (call again for more)");
+    if (!coef || !ss_out || (n > 0 && (!X || !y))) PG_FAIL(PG_EINVAL, "null buffer");
+    if (n == 0) {
+        PG_CUDA(cudaMemsetAsync(ss_out, 0, sizeof(double) * (n_coef + 1), st));
+        return PG_OK;
+    }
+    int64_t g = (n + GW_THREADS * 8 - 1) / (GW_THREADS * 8);
+    const int ctas = (int)(g < 1 ? 1 : (g > sm_count() * 8 ? sm_count() * 8 : g));
+    void *scr = nullptr;
+    int rc = scratch_for(st, sizeof(double) * (size_t)ctas * (n_coef + 1), &scr);
+    if (rc) return rc;
+    rc = launch_rows_resid(X, y, n, p, ldx, fold_of_row, eval_fold, coef, n_coef, (double *)scr, ctas, st);
+    if (rc) return rc;
+    return launch_reduce_partials((double *)scr, ctas, n_coef + 1, ss_out, 0, st);
+}
+
 int pg_fd_terms(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
                 int library_id, double *terms_out, void *stream) {
     K1Params P{};
@@ -434,7 +526,7 @@ int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect, int f
                        const double *thrs, int nt, int max_iter, const uint8_t *const_mask, const int8_t *signs,
                        const double *colminmax,
                        const double *shift, const double *eval_stats, double *coef_out, double *metrics_out,
-                       int32_t *best_out, void *stream) {
+                       int32_t *best_out, double *relres_out, void *stream) {
     if (p < 1 || p > PG_MAX_P) PG_FAIL(PG_EINVAL, "p must be in 1..%d", PG_MAX_P);
     if (dialect < PG_STRIDGE_KS || dialect > PG_STRIDGE_BASIC) PG_FAIL(PG_EINVAL, "unknown STRidge dialect %d", dialect);
     if (B < 0 || na < 1 || nt < 1 || max_iter < 0) PG_FAIL(PG_EINVAL, "bad sizes");
@@ -443,10 +535,12 @@ int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect, int f
     if (dialect == PG_STRIDGE_BASIC && shift) PG_FAIL(PG_EINVAL, "the basic_usage dialect works on the raw Gram; shift must be null");
     if ((eval_stats != nullptr) != (metrics_out != nullptr)) PG_FAIL(PG_EINVAL, "eval_stats and metrics_out go together");
     if (best_out && !metrics_out) PG_FAIL(PG_EINVAL, "best_out needs eval_stats/metrics_out");
+    if (relres_out && !metrics_out) PG_FAIL(PG_EINVAL, "relres_out needs eval_stats/metrics_out");
     StridgeParams P{};
     P.stats = stats; P.B = B; P.p = p; P.dialect = dialect; P.flags = flags; P.alphas = alphas; P.na = na;
     P.thrs = thrs; P.nt = nt; P.max_iter = max_iter; P.const_mask = const_mask; P.signs = signs; P.colminmax = colminmax;
     P.shift = shift; P.eval_stats = eval_stats; P.coef_out = coef_out; P.metrics_out = metrics_out;
+    P.relres_out = relres_out;
     return launch_stridge(P, best_out, (cudaStream_t)stream);
 }
 

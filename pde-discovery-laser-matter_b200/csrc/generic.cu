@@ -34,6 +34,65 @@ __device__ __forceinline__ void fill_pairs(uint8_t *pa, uint8_t *pb, int p, int 
     }
 }
 
+// One block row (reference arithmetic): the block means th[0..p), y of block `idx` of the launch's index box, its
+// fold id and whether it is a row at all (finite, fold in range).  Shared by the statistics kernel and the
+// held-out-residual kernel.
+template <int LIB>
+__device__ __forceinline__ bool generic_block_row(const K1Params &P, int64_t idx, int64_t n1, int64_t n2, double *th, double &y,
+                                                  int &fold, unsigned long long &bad_rows, unsigned long long &bad_fold) {
+    constexpr int p = Lib<LIB>::P;
+    const int64_t frame = P.A0 * P.A1;
+    const int64_t Trows = P.T - 1;
+    const int64_t jb = P.i1_lo + idx % n2;
+    const int64_t ib = P.i0_lo + (idx / n2) % n1;
+    const int64_t tb = P.tb_lo + idx / (n2 * n1);
+    int64_t t0 = tb * P.bt, t1 = min(Trows, t0 + P.bt);
+    int64_t i0 = ib * P.b0, i1 = min(P.R0, i0 + P.b0);
+    int64_t j0 = jb * P.b1, j1 = min(P.R1, j0 + P.b1);
+    if (P.rows8) {
+        // second stage of the tiled path for (bt, 8m, 8n) blocks: the block mean is the mean of the equally
+        // sized (bt, 8, 8) sub-block means the tiled kernel wrote (ragged edge blocks hold fewer of them)
+        const int64_t s0 = i0 >> 3, s1 = (i1 + 7) >> 3, c0 = j0 >> 3, c1 = (j1 + 7) >> 3;
+        for (int64_t a = s0; a < s1; ++a)
+            for (int64_t b = c0; b < c1; ++b) {
+                const double *r = P.rows8 + ((tb * P.sub0 + a) * P.sub1 + b) * (p + 1);
+                y = __dadd_rn(y, r[0]);
+#pragma unroll
+                for (int k = 0; k < p; ++k) th[k] = __dadd_rn(th[k], r[1 + k]);
+            }
+        t1 = t0 + 1; i0 = s0; i1 = s1; j0 = c0; j1 = c1;      // the divisor below: the number of sub-blocks
+    } else
+    for (int64_t t = t0; t < t1; ++t) {
+        const double *F = P.U + t * frame;
+        const double *Fn = F + frame;
+        for (int64_t i = i0; i < i1; ++i)
+            for (int64_t j = j0; j < j1; ++j) {
+                PointVals v;
+                eval_point<LIB>(P, F, i, j, v);
+                double row[p];
+                lib_row<LIB>(v, row);
+                const int64_t o = (i + P.off) * P.A1 + (j + P.off);
+                y = __dadd_rn(y, __ddiv_rn(__dsub_rn(Fn[o], F[o]), P.c.dt));
+#pragma unroll
+                for (int k = 0; k < p; ++k) th[k] = __dadd_rn(th[k], row[k]);
+            }
+    }
+    const double cnt = (double)((t1 - t0) * (i1 - i0) * (j1 - j0));
+    y = __ddiv_rn(y, cnt);
+    bool fin = isfinite(y);
+#pragma unroll
+    for (int k = 0; k < p; ++k) {
+        th[k] = __ddiv_rn(th[k], cnt);
+        fin = fin && isfinite(th[k]);
+    }
+    if (P.fold_of_row) { fold = P.fold_of_row[(tb * P.nB0 + ib) * P.nB1 + jb]; if (fold == 255) fold = -1; }
+    else if (P.fold_of_frame) fold = P.fold_of_frame[t0];
+    if (!fin) { ++bad_rows; return false; }
+    if (fold < 0) return false;                         // excluded on purpose (-1 / 255): not an error
+    if (fold >= P.n_folds) { ++bad_fold; return false; }
+    return true;
+}
+
 template <int LIB>
 __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
     constexpr int p = Lib<LIB>::P;
@@ -54,8 +113,6 @@ __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
     const int64_t n0 = P.tb_hi - P.tb_lo, n1 = P.i0_hi - P.i0_lo, n2 = P.i1_hi - P.i1_lo;
     const int64_t total = n0 * n1 * n2;
     const int64_t stride = (int64_t)gridDim.x * GW * 32;
-    const int64_t frame = P.A0 * P.A1;
-    const int64_t Trows = P.T - 1;
     unsigned long long bad_rows = 0, bad_fold = 0;
 
     for (int64_t base = ((int64_t)blockIdx.x * GW + warp) * 32; base < total; base += stride) {
@@ -65,61 +122,135 @@ __global__ void __launch_bounds__(GW * 32) k1_generic_kernel(K1Params P) {
         int fold = 0;
 #pragma unroll
         for (int k = 0; k < p; ++k) th[k] = 0.0;
-        if (valid) {
-            const int64_t jb = P.i1_lo + idx % n2;
-            const int64_t ib = P.i0_lo + (idx / n2) % n1;
-            const int64_t tb = P.tb_lo + idx / (n2 * n1);
-            int64_t t0 = tb * P.bt, t1 = min(Trows, t0 + P.bt);
-            int64_t i0 = ib * P.b0, i1 = min(P.R0, i0 + P.b0);
-            int64_t j0 = jb * P.b1, j1 = min(P.R1, j0 + P.b1);
-            if (P.rows8) {
-                // second stage of the tiled path for (bt, 8m, 8n) blocks: the block mean is the mean of the equally
-                // sized (bt, 8, 8) sub-block means the tiled kernel wrote (ragged edge blocks hold fewer of them)
-                const int64_t s0 = i0 >> 3, s1 = (i1 + 7) >> 3, c0 = j0 >> 3, c1 = (j1 + 7) >> 3;
-                for (int64_t a = s0; a < s1; ++a)
-                    for (int64_t b = c0; b < c1; ++b) {
-                        const double *r = P.rows8 + ((tb * P.sub0 + a) * P.sub1 + b) * (p + 1);
-                        y = __dadd_rn(y, r[0]);
-#pragma unroll
-                        for (int k = 0; k < p; ++k) th[k] = __dadd_rn(th[k], r[1 + k]);
-                    }
-                t1 = t0 + 1; i0 = s0; i1 = s1; j0 = c0; j1 = c1;      // the divisor below: the number of sub-blocks
-            } else
-            for (int64_t t = t0; t < t1; ++t) {
-                const double *F = P.U + t * frame;
-                const double *Fn = F + frame;
-                for (int64_t i = i0; i < i1; ++i)
-                    for (int64_t j = j0; j < j1; ++j) {
-                        PointVals v;
-                        eval_point<LIB>(P, F, i, j, v);
-                        double row[p];
-                        lib_row<LIB>(v, row);
-                        const int64_t o = (i + P.off) * P.A1 + (j + P.off);
-                        y = __dadd_rn(y, __ddiv_rn(__dsub_rn(Fn[o], F[o]), P.c.dt));
-#pragma unroll
-                        for (int k = 0; k < p; ++k) th[k] = __dadd_rn(th[k], row[k]);
-                    }
-            }
-            const double cnt = (double)((t1 - t0) * (i1 - i0) * (j1 - j0));
-            y = __ddiv_rn(y, cnt);
-            bool fin = isfinite(y);
-#pragma unroll
-            for (int k = 0; k < p; ++k) {
-                th[k] = __ddiv_rn(th[k], cnt);
-                fin = fin && isfinite(th[k]);
-            }
-            if (P.fold_of_row) { fold = P.fold_of_row[(tb * P.nB0 + ib) * P.nB1 + jb]; if (fold == 255) fold = -1; }
-            else if (P.fold_of_frame) fold = P.fold_of_frame[t0];
-            if (!fin) { valid = false; ++bad_rows; }
-            else if (fold < 0) valid = false;                         // excluded on purpose (-1 / 255): not an error
-            else if (fold >= P.n_folds) { valid = false; ++bad_fold; }
-        }
+        if (valid) valid = generic_block_row<LIB>(P, idx, n1, n2, th, y, fold, bad_rows, bad_fold);
         warp_accumulate_rows(wacc, ext, pa, pb, p, S, lane, valid, fold, th, y);
     }
     if (bad_rows) atomicAdd(&P.counters[0], bad_rows);
     if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
     double *out = P.partials + ((int64_t)blockIdx.x * GW + warp) * P.n_folds * S;
     for (int e = lane; e < P.n_folds * S; e += 32) out[e] = wacc[e];
+}
+
+// The block-mean rows themselves, [nrows][p + 1] (y first) in reference row order, nothing dropped: the rare path on
+// which the caller has to renumber rows after dropping non-finite ones (ks2d:394-395 followed by ks2d:1638-1641).
+template <int LIB>
+__global__ void __launch_bounds__(GW * 32) k1_generic_rows_kernel(K1Params P, double *__restrict__ rows_out) {
+    constexpr int p = Lib<LIB>::P;
+    const int64_t n0 = P.tb_hi - P.tb_lo, n1 = P.i0_hi - P.i0_lo, n2 = P.i1_hi - P.i1_lo;
+    const int64_t total = n0 * n1 * n2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        double th[p], y = 0.0;
+        int fold = 0;
+        unsigned long long b0 = 0, b1 = 0;
+#pragma unroll
+        for (int k = 0; k < p; ++k) th[k] = 0.0;
+        generic_block_row<LIB>(P, idx, n1, n2, th, y, fold, b0, b1);
+        double *r = rows_out + idx * (p + 1);
+        r[0] = y;
+#pragma unroll
+        for (int k = 0; k < p; ++k) r[1 + k] = th[k];
+    }
+}
+
+// Held-out residuals of fitted models straight from the field (second pass; SURVEY 8a21: r2 / rmse of ks2d:29-40 need
+// sum (y - theta.c)^2, which the statistics only give up to cancellation when the fit is exact to ~1e-8).  Every
+// thread forms its block row like the statistics kernel and adds r_j^2 for each of the J <= 32 coefficient vectors
+// when the row belongs to fold `eval_fold` (-1: every row).  partials [gridDim.x][J + 1] (last entry: row count).
+constexpr int RESID_MAX_J = 32;
+
+template <int LIB>
+__global__ void __launch_bounds__(GW * 32) k1_generic_resid_kernel(K1Params P, const double *__restrict__ coef, int J,
+                                                                    int eval_fold, double *__restrict__ partials) {
+    constexpr int p = Lib<LIB>::P;
+    __shared__ double cs[RESID_MAX_J * PG_MAX_P];
+    __shared__ double red[GW][RESID_MAX_J + 1];
+    for (int e = threadIdx.x; e < J * p; e += blockDim.x) cs[e] = coef[e];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n0 = P.tb_hi - P.tb_lo, n1 = P.i0_hi - P.i0_lo, n2 = P.i1_hi - P.i1_lo;
+    const int64_t total = n0 * n1 * n2;
+    const int64_t stride = (int64_t)gridDim.x * GW * 32;
+    unsigned long long bad_rows = 0, bad_fold = 0;
+    double acc[RESID_MAX_J + 1];
+#pragma unroll
+    for (int j = 0; j <= RESID_MAX_J; ++j) acc[j] = 0.0;
+    for (int64_t idx = ((int64_t)blockIdx.x * GW + warp) * 32 + lane; idx < total; idx += stride) {
+        double th[p], y = 0.0;
+        int fold = 0;
+#pragma unroll
+        for (int k = 0; k < p; ++k) th[k] = 0.0;
+        if (!generic_block_row<LIB>(P, idx, n1, n2, th, y, fold, bad_rows, bad_fold)) continue;
+        if (eval_fold >= 0 && fold != eval_fold) continue;
+        acc[RESID_MAX_J] += 1.0;
+#pragma unroll
+        for (int j = 0; j < RESID_MAX_J; ++j) {
+            if (j >= J) break;
+            double pred = 0.0;
+#pragma unroll
+            for (int k = 0; k < p; ++k) pred = fma(th[k], cs[j * p + k], pred);
+            const double r = y - pred;
+            acc[j] = fma(r, r, acc[j]);
+        }
+    }
+    if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
+    // fixed-order reduction: lanes by butterfly, warps in order
+#pragma unroll
+    for (int j = 0; j <= RESID_MAX_J; ++j) {
+        double v = acc[j];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= RESID_MAX_J) {
+        double v = 0.0;
+        for (int w = 0; w < GW; ++w) v += red[w][threadIdx.x];
+        if (threadIdx.x < J) partials[(int64_t)blockIdx.x * (J + 1) + threadIdx.x] = v;
+        else if (threadIdx.x == RESID_MAX_J) partials[(int64_t)blockIdx.x * (J + 1) + J] = v;
+    }
+}
+
+// Rows form of the same: X [n][ldx], y [n], optional fold byte per row.
+__global__ void __launch_bounds__(GW * 32) rows_resid_kernel(const double *__restrict__ X, const double *__restrict__ y,
+                                                             int64_t n, int p, int64_t ldx, const uint8_t *__restrict__ fold_of_row,
+                                                             int eval_fold, const double *__restrict__ coef, int J,
+                                                             double *__restrict__ partials) {
+    __shared__ double cs[RESID_MAX_J * PG_MAX_P];
+    __shared__ double red[GW][RESID_MAX_J + 1];
+    for (int e = threadIdx.x; e < J * p; e += blockDim.x) cs[e] = coef[e];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc[RESID_MAX_J + 1];
+#pragma unroll
+    for (int j = 0; j <= RESID_MAX_J; ++j) acc[j] = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        if (fold_of_row && eval_fold >= 0 && fold_of_row[r] != eval_fold) continue;
+        acc[RESID_MAX_J] += 1.0;
+        const double *x = X + r * ldx;
+        const double yr = y[r];
+#pragma unroll
+        for (int j = 0; j < RESID_MAX_J; ++j) {
+            if (j >= J) break;
+            double pred = 0.0;
+            for (int k = 0; k < p; ++k) pred = fma(x[k], cs[j * p + k], pred);
+            const double d = yr - pred;
+            acc[j] = fma(d, d, acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j <= RESID_MAX_J; ++j) {
+        double v = acc[j];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= RESID_MAX_J) {
+        double v = 0.0;
+        for (int w = 0; w < GW; ++w) v += red[w][threadIdx.x];
+        if (threadIdx.x < J) partials[(int64_t)blockIdx.x * (J + 1) + threadIdx.x] = v;
+        else if (threadIdx.x == RESID_MAX_J) partials[(int64_t)blockIdx.x * (J + 1) + J] = v;
+    }
 }
 
 // out[e] (+)= sum over parts of partials[part][e].  One CTA per entry: thread k adds parts
@@ -345,6 +476,23 @@ __global__ void rows_reduce_kernel(const double *__restrict__ partials, const do
     }
 }
 
+// build_library of basic_usage (basic:75-101): Theta [N][6] = [1, u, u_x, u_y, lap, u*u] from four flat arrays
+__global__ void basic_library_rows_kernel(const double *__restrict__ u, const double *__restrict__ ux,
+                                          const double *__restrict__ uy, const double *__restrict__ lap, int64_t n,
+                                          double *__restrict__ Theta) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = u[i];
+        double *r = Theta + i * 6;
+        r[0] = 1.0; r[1] = v; r[2] = ux[i]; r[3] = uy[i]; r[4] = lap[i]; r[5] = __dmul_rn(v, v);
+    }
+}
+
+// dst[i] += src[i] (statistics of sub-slabs / folds are additive)
+__global__ void stats_accumulate_kernel(double *__restrict__ dst, const double *__restrict__ src, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __dadd_rn(dst[i], src[i]);
+}
+
 // ----------------------------------------------------------------------------- host launchers
 static int grid_for(int64_t work_items, int per_cta, int max_ctas) {
     int64_t g = (work_items + per_cta - 1) / per_cta;
@@ -372,6 +520,59 @@ int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st) {
         case PG_LIB_BASIC: return launch_k1_generic_t<PG_LIB_BASIC>(P, ctas, st);
         default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_lib_gram", lib);
     }
+}
+
+template <int LIB> static int launch_k1_resid_t(const K1Params &P, const double *coef, int J, int eval_fold, double *partials,
+                                                int ctas, cudaStream_t st) {
+    k1_generic_resid_kernel<LIB><<<ctas, GW * 32, 0, st>>>(P, coef, J, eval_fold, partials);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
+int launch_k1_generic_resid(int lib, const K1Params &P, const double *coef, int J, int eval_fold, double *partials, int ctas,
+                            cudaStream_t st) {
+    switch (lib) {
+        case PG_LIB_KS_TRUE: return launch_k1_resid_t<PG_LIB_KS_TRUE>(P, coef, J, eval_fold, partials, ctas, st);
+        case PG_LIB_KS_TRUE_ADV: return launch_k1_resid_t<PG_LIB_KS_TRUE_ADV>(P, coef, J, eval_fold, partials, ctas, st);
+        case PG_LIB_KS_RICH: return launch_k1_resid_t<PG_LIB_KS_RICH>(P, coef, J, eval_fold, partials, ctas, st);
+        case PG_LIB_KS_RICH_NOADV: return launch_k1_resid_t<PG_LIB_KS_RICH_NOADV>(P, coef, J, eval_fold, partials, ctas, st);
+        case PG_LIB_BASIC: return launch_k1_resid_t<PG_LIB_BASIC>(P, coef, J, eval_fold, partials, ctas, st);
+        default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_residual_ss", lib);
+    }
+}
+
+int launch_basic_library_rows(const double *u, const double *ux, const double *uy, const double *lap, int64_t n, double *Theta,
+                              cudaStream_t st) {
+    if (n <= 0) return PG_OK;
+    basic_library_rows_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(u, ux, uy, lap, n, Theta);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
+int launch_stats_accumulate(double *dst, const double *src, int64_t n, cudaStream_t st) {
+    if (n <= 0) return PG_OK;
+    stats_accumulate_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, st>>>(dst, src, n);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
+int launch_k1_generic_rows(int lib, const K1Params &P, double *rows_out, int ctas, cudaStream_t st) {
+    switch (lib) {
+#define PG_CASE(L) case L: k1_generic_rows_kernel<L><<<ctas, GW * 32, 0, st>>>(P, rows_out); break;
+        PG_CASE(PG_LIB_KS_TRUE) PG_CASE(PG_LIB_KS_TRUE_ADV) PG_CASE(PG_LIB_KS_RICH) PG_CASE(PG_LIB_KS_RICH_NOADV)
+        PG_CASE(PG_LIB_BASIC)
+#undef PG_CASE
+        default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_block_rows", lib);
+    }
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
+int launch_rows_resid(const double *X, const double *y, int64_t n, int p, int64_t ldx, const uint8_t *fold_of_row,
+                      int eval_fold, const double *coef, int J, double *partials, int ctas, cudaStream_t st) {
+    rows_resid_kernel<<<ctas, GW * 32, 0, st>>>(X, y, n, p, ldx, fold_of_row, eval_fold, coef, J, partials);
+    PG_LAUNCHED();
+    return PG_OK;
 }
 
 int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate,

@@ -69,6 +69,7 @@ struct StridgeParams {
     const double *eval_stats;    // [B][S] or null
     double *coef_out;            // [B][na][nt][p]
     double *metrics_out;         // [B][na][nt][2] or null
+    double *relres_out;          // [B][na][nt] or null: held-out ss_res / sum y^2 BEFORE clamping (cancellation indicator)
 };
 
 // What the tiled kernel covers: block indices [0,nbt) x [0,nb0) x [0,nb1) of the row space.
@@ -90,6 +91,14 @@ int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st);
 int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len, double *out, int accumulate, cudaStream_t st,
                            const unsigned long long *flag = nullptr, int64_t n_a = 0, int64_t n_b = 0,
                            const unsigned long long *poison = nullptr);
+// held-out residual sums (second pass): partials [ctas][J + 1] (sum r_j^2 ..., row count)
+int launch_k1_generic_resid(int lib, const K1Params &P, const double *coef, int J, int eval_fold, double *partials, int ctas,
+                            cudaStream_t st);
+int launch_basic_library_rows(const double *u, const double *ux, const double *uy, const double *lap, int64_t n, double *Theta, cudaStream_t st);
+int launch_stats_accumulate(double *dst, const double *src, int64_t n, cudaStream_t st);
+int launch_k1_generic_rows(int lib, const K1Params &P, double *rows_out, int ctas, cudaStream_t st);
+int launch_rows_resid(const double *X, const double *y, int64_t n, int p, int64_t ldx, const uint8_t *fold_of_row, int eval_fold,
+                      const double *coef, int J, double *partials, int ctas, cudaStream_t st);
 int launch_fd_terms(int dialect, int lib, const double *U, int64_t T, int64_t A0, int64_t A1, const FdConsts &c, double *out, cudaStream_t st);
 int launch_fd_gather(int lib, const K1Params &P, const int64_t *flat_idx, int64_t n, double *X, double *y, cudaStream_t st);
 int launch_block_means(const double *stack, int k, int64_t T, int64_t A0, int64_t A1, int bt, int b0, int b1, double *out, cudaStream_t st);

@@ -264,6 +264,10 @@ __global__ void __launch_bounds__(SW * 32) stridge_kernel(StridgeParams P) {
         quad = warp_sum(quad);
         const double yy = esyy - 2.0 * hc * esy + en * hc * hc;
         double ss_res = yy - 2.0 * lin + quad;
+        // Three O(yy) terms: for a fit that is exact to ~1e-8 the difference is rounding noise (|ss_res| <~ 1e-15 yy).
+        // relres_out hands the caller the ratio so that it can take the residuals from the rows instead
+        // (pg_rows_residual_ss / pg_fd_residual_ss); the clamp only keeps sqrt() defined.
+        if (P.relres_out && lane == 0) P.relres_out[job] = ss_res / (yy > 0.0 ? yy : 1.0);
         if (ss_res < 0.0) ss_res = 0.0;
         const double ss_tot = esyy - esy * esy / en;
         if (lane == 0) {

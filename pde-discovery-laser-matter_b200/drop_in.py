@@ -38,6 +38,23 @@ def patch_reference(module, dialect: str | None = None):
     done = []
     for n in names:
         if hasattr(module, n):
-            setattr(module, n, getattr(src, n))
+            new = getattr(src, n)
+            if n == "ensemble_stridge":
+                new = _ensemble_wrapper(getattr(module, n), new)
+            setattr(module, n, new)
             done.append(n)
     return done
+
+
+def _ensemble_wrapper(original, gpu):
+    """The script's main() always calls ensemble_stridge(..., use_huber=True, huber_delta=...) for
+    ``--regression ensemble`` (ks2d:1707-1715).  The Huber inner solve iterates on raw residuals (IRLS with a
+    median scale), which is not Gram-reducible and is out of scope: that call keeps running the
+    module's own function, so the rebound script never crashes; the ridge ensemble (use_huber=False) runs on the GPU."""
+    def ensemble_stridge(X, y, *args, use_huber=False, **kw):
+        if use_huber:
+            return original(X, y, *args, use_huber=True, **kw)
+        return gpu(X, y, *args, use_huber=False, **kw)
+
+    ensemble_stridge.__wrapped__ = original
+    return ensemble_stridge

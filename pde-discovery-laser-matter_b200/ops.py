@@ -253,10 +253,95 @@ def stridge_batched(stats, p, *, dialect, alphas, thresholds, max_iter, flags=0,
     coef = torch.empty((B, na, nt, p), dtype=torch.float64, device=stats.device)
     metrics = torch.empty((B, na, nt, 2), dtype=torch.float64, device=stats.device) if ev is not None else None
     best = torch.empty((B,), dtype=torch.int32, device=stats.device) if ev is not None else None
+    relres = torch.empty((B, na, nt), dtype=torch.float64, device=stats.device) if ev is not None else None
     L.check(lib.pg_stridge_batched(L.ptr(stats), B, p, dialect, flags, L.ptr(al), na, L.ptr(th), nt, int(max_iter),
                                    L.ptr(cm), L.ptr(sg), L.ptr(mm), L.ptr(sh), L.ptr(ev), L.ptr(coef), L.ptr(metrics), L.ptr(best),
-                                   L.stream_ptr()))
-    return dict(coef=coef, metrics=metrics, best=best)
+                                   L.ptr(relres), L.stream_ptr()))
+    return dict(coef=coef, metrics=metrics, best=best, relres=relres)
+
+
+def stats_accumulate(dst, src):
+    """pg_stats_accumulate: dst += src in place (contiguous float64 CUDA tensors of one size); returns dst."""
+    lib = L.load()
+    if dst.numel() != src.numel():
+        raise ValueError("dst and src must have the same number of entries")
+    L.check(lib.pg_stats_accumulate(L.ptr(dst), L.ptr(src.contiguous()), dst.numel(), L.stream_ptr()))
+    return dst
+
+
+def basic_library_rows(u, u_x, u_y, lap_u):
+    """pg_basic_library_rows: Theta [N][6] = [1, u, u_x, u_y, lap, u^2] (basic:75-101) from four arrays of N values."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    f = [_dev(np.asarray(a, dtype=np.float64).reshape(-1), torch.float64) for a in (u, u_x, u_y, lap_u)]
+    n = f[0].numel()
+    if any(x.numel() != n for x in f):
+        raise ValueError("u, u_x, u_y, lap_u must have the same number of values")
+    Theta = torch.empty((n, 6), dtype=torch.float64, device=f[0].device)
+    L.check(lib.pg_basic_library_rows(L.ptr(f[0]), L.ptr(f[1]), L.ptr(f[2]), L.ptr(f[3]), n, L.ptr(Theta), L.stream_ptr()))
+    return Theta
+
+
+def fd_block_rows(U, d0, d1, dt, *, dialect, library, block):
+    """pg_fd_block_rows: the block-mean rows [nrows][p + 1] (y first), nothing dropped."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, A0, A1 = U.shape
+    p = L.LIB_WIDTH[library]
+    bt, b0, b1 = (int(b) for b in block)
+    R0, R1 = (A0, A1) if dialect == L.FD_KS_PERIODIC else (A0 - 4, A1 - 4)
+    nrows = -(-max(T - 1, 0) // bt) * -(-R0 // b0) * -(-R1 // b1)
+    rows = torch.empty((nrows, p + 1), dtype=torch.float64, device=U.device)
+    L.check(lib.pg_fd_block_rows(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0, b1,
+                                 L.ptr(rows), L.stream_ptr()))
+    return rows
+
+
+def rows_residual_ss(X, y, coef, *, fold_of_row=None, eval_fold=-1):
+    """pg_rows_residual_ss: exact held-out residual sums of J fitted models from rows on the device.
+    X [n][p], y [n], coef [J][p] -> (ss [J] NumPy, n_rows)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    X = _dev(X, torch.float64)
+    y = _dev(y, torch.float64)
+    n, p = X.shape
+    coef = _dev(np.asarray(coef, dtype=np.float64) if not isinstance(coef, torch.Tensor) else coef, torch.float64).reshape(-1, p).contiguous()
+    fr = _dev(fold_of_row, torch.uint8)
+    out = []
+    for j0 in range(0, coef.shape[0], 32):
+        c = coef[j0:j0 + 32].contiguous()
+        ss = torch.empty(c.shape[0] + 1, dtype=torch.float64, device=X.device)
+        L.check(lib.pg_rows_residual_ss(L.ptr(X), L.ptr(y), n, p, p, L.ptr(fr), int(eval_fold), L.ptr(c), c.shape[0], L.ptr(ss),
+                                        L.stream_ptr()))
+        out.append(ss)
+    host = [o.cpu().numpy() for o in out]
+    return np.concatenate([h[:-1] for h in host]), int(host[0][-1])
+
+
+def fd_residual_ss(U, d0, d1, dt, coef, *, dialect, library, block=(1, 1, 1), fold_of_row=None, fold_of_frame=None,
+                   n_folds=1, eval_fold=-1):
+    """pg_fd_residual_ss: the same straight from the field (the block rows are re-formed on the fly; a second pass
+    used only when the statistics-derived residual cancels).  coef [J][p] -> (ss [J] NumPy, n_rows)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, A0, A1 = U.shape
+    p = L.LIB_WIDTH[library]
+    bt, b0, b1 = (int(b) for b in block)
+    coef = _dev(np.asarray(coef, dtype=np.float64) if not isinstance(coef, torch.Tensor) else coef, torch.float64).reshape(-1, p).contiguous()
+    fr = _dev(fold_of_row, torch.uint8)
+    ff = _dev(fold_of_frame, torch.int32)
+    out = []
+    for j0 in range(0, coef.shape[0], 32):
+        c = coef[j0:j0 + 32].contiguous()
+        ss = torch.empty(c.shape[0] + 1, dtype=torch.float64, device=U.device)
+        L.check(lib.pg_fd_residual_ss(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0, b1,
+                                      L.ptr(fr), L.ptr(ff), n_folds, int(eval_fold), L.ptr(c), c.shape[0], L.ptr(ss),
+                                      L.stream_ptr()))
+        out.append(ss)
+    host = [o.cpu().numpy() for o in out]
+    return np.concatenate([h[:-1] for h in host]), int(host[0][-1])
 
 
 def ks_rollout(U, d0, d1, dt, coef, n_steps, *, library):

@@ -420,7 +420,7 @@ def sharded_stats(U_local, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fol
         fof = None if fold_of_frame is None else ops._dev(fold_of_frame)
         stats = ops.fd_lib_gram(U_local[:cut + 1], d0, d1, dt, fold_of_frame=None if fof is None else fof[:cut], **kw)
         finish(reqs)
-        stats = stats + ops.fd_lib_gram(U_local[cut:], d0, d1, dt, fold_of_frame=None if fof is None else fof[cut:], **kw)
+        ops.stats_accumulate(stats, ops.fd_lib_gram(U_local[cut:], d0, d1, dt, fold_of_frame=None if fof is None else fof[cut:], **kw))
     return allreduce_stats(stats, group)
 
 
@@ -470,6 +470,6 @@ def fit_streamed(U_host, d0, d1, dt, *, dialect=L.FD_KS_PERIODIC, library=L.LIB_
         compute.wait_event(filled[b])
         s = ops.fd_lib_gram(buffers[b][: hi - lo + 1], d0, d1, dt, dialect=dialect, library=library, block=block,
                             fold_of_frame=None if fof is None else fof[lo:hi], n_folds=n_folds, variant=variant)
-        total += s
+        ops.stats_accumulate(total, s)
         freed[b].record(compute)
     return total

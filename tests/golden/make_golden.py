@@ -198,9 +198,12 @@ def golden_ks2d_rollout(ks):
 
 
 def golden_ks2d_configs(ks):
-    """C1 / C2 / C2+rich+sweep exactly as main() runs them."""
+    """C1 / C2 / C2+rich+sweep exactly as main() runs them; C1 + sweep: the clean config with
+    the 5 x 6 sweep, where every cell scores r2 == 1.0 and the reference's tie-break (n_active, then rmse ~ 2e-11)
+    decides -- the case that needs held-out residuals from the rows, not from the statistics."""
     runs = {
         "c1": [],
+        "c1_sweep": ["--grid-search"],
         "c2": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05"],
         "c2_rich_sweep": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05",
                           "--dictionary", "rich", "--grid-search"],
@@ -214,6 +217,7 @@ def golden_ks2d_configs(ks):
     full = {}
     for tag, (noise, method, dictionary, sweep) in {
         "c1": (0.0, "pointwise", "true", False),
+        "c1_sweep": (0.0, "pointwise", "true", True),
         "c2": (0.05, "blockwise", "true", False),
         "c2_rich_sweep": (0.05, "blockwise", "rich", True),
     }.items():

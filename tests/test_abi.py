@@ -57,7 +57,7 @@ def test_argument_validation_needs_no_gpu(lib):
     """PG_EINVAL paths return before any CUDA call, so they can be exercised on the CPU box."""
     rc = lib.pg_fd_lib_gram(None, 4, 8, 8, 1.0, 1.0, 1.0, 0, 0, 1, 1, 1, None, None, 1, None, None, 0, None)
     assert rc == -1 and b"U is null" in lib.pg_last_error()
-    rc = lib.pg_stridge_batched(None, 1, 99, 0, 0, None, 1, None, 1, 25, None, None, None, None, None, None, None, None, None)
+    rc = lib.pg_stridge_batched(None, 1, 99, 0, 0, None, 1, None, 1, 25, None, None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"p must be" in lib.pg_last_error()
     rc = lib.pg_block_means(1, 1, 2, 2, 2, 0, 1, 1, 1, None)  # dummy non-null pointers, block_t = 0
     assert rc == -1 and b"block sizes" in lib.pg_last_error()

@@ -201,6 +201,7 @@ def test_c_abi_error_codes(L):
 
 @pytest.mark.parametrize("tag,kw", [
     ("c1", dict(method="pointwise", dictionary="true")),
+    ("c1_sweep", dict(method="pointwise", dictionary="true", grid_search=True)),
     ("c2", dict(method="blockwise", dictionary="true")),
     ("c2_rich_sweep", dict(method="blockwise", dictionary="rich", grid_search=True)),
 ])
@@ -208,7 +209,7 @@ def test_reference_configs_fused(K, ks_default_stack, golden_configs, tag, kw):
     """BASELINE configs[0] and [1] end to end on the GPU (field -> K1 -> K3), against the numbers
     the unmodified reference main() printed and its full-precision replay."""
     U, dx, dy, DT = ks_default_stack
-    if tag != "c1":
+    if not tag.startswith("c1"):
         U = O.add_noise(U, 0.05, seed=999)
     out = K.fit_from_field(U, dx, dy, DT, **kw)
     gold, full = golden_configs[tag], golden_configs["full_precision"][tag]
@@ -217,18 +218,66 @@ def test_reference_configs_fused(K, ks_default_stack, golden_configs, tag, kw):
     assert (out["alpha"], out["threshold"], out["n_active"]) == (hyper["alpha"], hyper["threshold"], hyper["n_active"])
     best_row = [r for r in full["table"] if (r["alpha"], r["threshold"]) == (out["alpha"], out["threshold"])][0]
     assert_coef_close(out["coeffs"], np.array(best_row["coeffs"]), what=tag)
-    if tag == "c1":
-        # exact fit: r2 == 1 to rounding; ss_res from statistics cancels (documented), so only r2 is pinned
-        assert abs(out["r2_test"] - 1.0) < 1e-9
+    if tag.startswith("c1"):
+        # exact fit (rmse 2e-11 on |y| ~ 0.4): the statistics-derived residual cancels, K3 says so (relres) and the
+        # held-out metrics come from the rows (pg_rows_residual_ss).  The reference's sweep then ties on r2 == 1.0
+        # and n_active and picks the smallest rmse (ks2d:1731-1741): same cell, same numbers.
+        assert out["metrics_source"] == "residuals" and out["metrics_reliable"] and out["relres_min"] < 1e-9
+        assert out["r2_test"] == hyper["r2_test"] == 1.0
+        np.testing.assert_allclose(out["rmse_test"], hyper["rmse_test"], rtol=1e-4)
     else:
+        assert out["metrics_source"] == "statistics"
         np.testing.assert_allclose(out["r2_test"], hyper["r2_test"], rtol=1e-7)
         np.testing.assert_allclose(out["rmse_test"], hyper["rmse_test"], rtol=1e-7)
     if "table" in out and kw.get("grid_search"):
         for (a, thr, r2, err, na), row in zip(out["table"], full["table"]):
             assert (a, thr, na) == (row["alpha"], row["threshold"], row["n_active"])
             np.testing.assert_allclose(r2, row["r2_test"], rtol=1e-7)
+            if tag.startswith("c1"):
+                np.testing.assert_allclose(err, row["rmse_test"], rtol=1e-4)
             assert_coef_close(out["coef_grid"][O.GRID_ALPHAS.index(a), O.GRID_THRESHOLDS.index(thr)],
                               np.array(row["coeffs"]), what=f"{tag} sweep {a} {thr}")
+
+
+def test_exact_residuals_from_the_field_on_a_clean_blockwise_fit(K, ks_default_stack):
+    """Clean data, blockwise rows (never materialised): the held-out residuals come from a second pass over the field
+    (pg_fd_residual_ss) and agree with the oracle's row-based metrics; the selection equals the oracle's."""
+    U, dx, dy, DT = ks_default_stack
+    U = U[:400]
+    out = K.fit_from_field(U, dx, dy, DT, method="blockwise", dictionary="true", grid_search=True)
+    ref = O.run_config(U, dx, dy, DT, method="blockwise", dictionary="true", grid_search=True)
+    assert out["metrics_source"] == "residuals"
+    assert (out["alpha"], out["threshold"]) == (ref["alpha"], ref["threshold"])
+    assert_coef_close(out["coeffs"], ref["coeffs"], what="clean blockwise")
+    np.testing.assert_allclose(out["rmse_test"], ref["rmse_test"], rtol=1e-3)
+    # the residual kernels against explicit rows
+    from pde_b200 import _lib as L
+    from pde_b200 import ops
+
+    names, X, y = ks_rows(U, dx, dy, DT, "true", False, (3, 8, 8))
+    C = np.array([ref["coeffs"], [-1.0, -1.0, -0.5], [0.0, 0.0, 0.0]])
+    fold = (np.arange(len(y)) % 3 == 0).astype(np.uint8)
+    want = np.array([np.sum((y[fold == 1] - X[fold == 1] @ c) ** 2) for c in C])
+    got_rows, n_rows = ops.rows_residual_ss(X, y, C, fold_of_row=fold, eval_fold=1)
+    got_fd, n_fd = ops.fd_residual_ss(U, dx, dy, DT, C, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8),
+                                      fold_of_row=fold, n_folds=2, eval_fold=1)
+    assert n_rows == n_fd == int(fold.sum())
+    np.testing.assert_allclose(got_rows, want, rtol=1e-9)
+    np.testing.assert_allclose(got_fd, want, rtol=1e-6)      # the zero-coefficient and the exact rows agree far better
+    np.testing.assert_allclose(got_fd[2], want[2], rtol=1e-12)
+
+
+def test_statistics_only_fit_flags_unreliable_metrics(K, ks_default_stack):
+    """fit_from_stats without an evaluator on an exact fit: no silent clamp, the result says the metrics are noise."""
+    from pde_b200 import _lib as L
+    from pde_b200 import ops
+
+    U, dx, dy, DT = ks_default_stack
+    fof = (np.arange(299) >= 210).astype(np.int32)
+    st = ops.fd_lib_gram(U[:300], dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8),
+                         fold_of_frame=fof, n_folds=2)
+    out = K.fit_from_stats(st[0], st[1], K.TRUE_NAMES)
+    assert out["metrics_reliable"] is False and out["metrics_source"] == "statistics" and abs(out["r2_test"] - 1) < 1e-9
 
 
 def test_reference_script_runs_with_rebound_functions(K, ks_default_stack, golden_configs):
