@@ -55,6 +55,10 @@ extern "C" {
 /* finite-difference dialect */
 #define PG_FD_KS_PERIODIC 0 /* ks2d:63-73   periodic np.roll stencils, rows = all points of U[:-1] */
 #define PG_FD_BASIC_TRIM 1  /* basic:32-72  interior stencils, rows = U[:-1, 2:-2, 2:-2]           */
+#define PG_FD_SLICE_CENTRAL 2 /* analyze_results:257-274: every difference is a pair / triple of SLICES cropped to a
+                               common origin, so row (t,i,j) holds u = U[t,i,j], u_x = (U[t,i,j+2]-U[t,i,j])/(2 d1),
+                               u_y = (U[t,i+2,j]-U[t,i,j])/(2 d0), u_xx, u_yy from (j, j+1, j+2) / (i, i+1, i+2) and the
+                               CENTRAL-time u_t = (U[t+2,i,j]-U[t,i,j])/(2 dt); rows = U[:-2, :-2, :-2] (x = a1)      */
 
 /* candidate library (column order is the reference's) */
 #define PG_LIB_KS_TRUE 0       /* p=3  lap, bih, |grad|^2                         ks2d:1095-1099 */
@@ -67,6 +71,9 @@ extern "C" {
 #define PG_LIB_PATCH_MODEL4 7  /* p=6  1,u,u_x,u_y,lap,u^2      (pg_poly_rows)    patch:160-162  */
 #define PG_LIB_PATCH_FULL 8    /* p=8  + u*u_x, u*u_y           (pg_poly_rows)    patch:163-172  */
 #define PG_LIB_PATCH_DERIVS 9  /* p=6  u,u_t,u_x,u_y,u_xx,u_yy  (pg_poly_rows)    patch:240-246  */
+#define PG_LIB_AR_FULL 10      /* p=13 1,u,u_x,u_y,u_xx,u_yy,lap,u^2,u*u_x,u*u_y,u^3,u_x^2,u_y^2  "Model 6" of
+                                  analyze_results:618-623; Models 1-5 (:598-617) are column subsets of it, so one pass
+                                  serves all six (the statistics of a subset are entries of this one)             */
 
 /* STRidge dialect */
 #define PG_STRIDGE_KS 0      /* ks2d:404-428   centre+scale X, LU solve, 1+max_iter fits      */
@@ -75,6 +82,7 @@ extern "C" {
 /* STRidge flags */
 #define PG_STRIDGE_RMS_PRESCALE 1 /* ks2d:1647-1655: divide columns by sqrt(G_jj/n)+1e-12 first
                                      ('1' columns keep scale 1) and unscale the coefficients  */
+#define PG_STRIDGE_NO_EPS 2       /* analyze_results:578 unscales with c / scale_ (no + 1e-12; patch:98 and ks2d:428 add it) */
 
 /* kernel variant for pg_fd_lib_gram */
 #define PG_VARIANT_AUTO 0    /* tiled TMA kernel where it applies, generic kernel for the rest */
@@ -97,7 +105,8 @@ PG_API int pg_library_width(int library_id);
  * (ks2d:358-401) and X.T@X / X.T@y (ks2d:55-58); or compute_derivatives + build_library +
  * Theta.T@Theta (basic:32-101,123-124).
  *
- *   U             [T][A0][A1]; rows come from frames 0..T-2 (frame T-1 only feeds u_t)
+ *   U             [T][A0][A1]; rows come from frames 0..T-2 (frame T-1 only feeds u_t); PG_FD_SLICE_CENTRAL: frames
+ *                 0..T-3 (two trailing frames), fold_of_frame then has T-2 entries
  *   bt,b0,b1      block sizes along t,a0,a1 (1,1,1 = pointwise); ragged trailing blocks
  *                 are kept with their own divisor (ks2d:384-389)
  *   fold_of_row   nullable, one fold id per block row in reference row order (t-block major,
@@ -284,6 +293,23 @@ PG_API int pg_fd_residual_ss(const double *U, int64_t T, int64_t A0, int64_t A1,
  */
 PG_API int pg_ks_rollout(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
                   int library_id, const double *coef, int n_steps, double *work, double *rmse_out, void *stream);
+
+/*
+ * Validation of the analyze_results dialect, the step after its solve.
+ * pg_ar_rollout: rollout_k_rmse (analyze_results:348-395).  From every start frame t in [t0, t1 - k_steps) the model
+ *   u_t = sum_k coef[k] * term(term_ids[k]) is advanced k_steps explicit-Euler steps with derivs_2d's stencils (same-grid
+ *   central differences through np.pad(mode="reflect"), analyze_results:300-313; x = a1) and compared with frame
+ *   t + k_steps.  term_ids index PG_LIB_AR_FULL's 13 columns; terms are added in the given order, |coef| < 1e-12
+ *   skipped.  mask nullable [H][W] bytes (spatial hold-out region).  work: DEVICE scratch [2][t1-k_steps-t0][H][W].
+ *   sums_out DEVICE [4] = sum e^2, sum y, sum y^2, count over the targets: rmse = sqrt([0]/[3]), nrmse = rmse / (std + 1e-12).
+ * pg_one_step_ss: one_step_prediction_rmse (analyze_results:150-187): sums_out [2] = sum over t < t_max and the
+ *   (masked) frame of (u[t+1] - (u[t] + dt * ut_pred[t]))^2, and the count.  u_field [t_max + 1][frame], ut_pred [t_max][frame].
+ */
+PG_API int pg_ar_rollout(const double *U, int64_t T, int64_t H, int64_t W, double d0, double d1, double dt,
+                  const int32_t *term_ids, const double *coef, int n_terms, int k_steps, int64_t t0, int64_t t1,
+                  const uint8_t *mask, double *work, double *sums_out, void *stream);
+PG_API int pg_one_step_ss(const double *u_field, const double *ut_pred, int64_t t_max, int64_t frame, double dt,
+                   const uint8_t *mask, double *sums_out, void *stream);
 
 /*
  * Sums behind the reference's fit metrics (rmse / r2_score ks2d:29-40; regression_metrics patch:47-65) of

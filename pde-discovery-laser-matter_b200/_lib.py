@@ -20,14 +20,14 @@ CSRC_DIR = PKG_DIR / "csrc"
 PG_MAX_P = 16
 PG_MAX_FOLDS = 8
 PG_COMM_MAX_RANKS, PG_COMM_MAX_LEN = 16, 1536
-FD_KS_PERIODIC, FD_BASIC_TRIM = 0, 1
+FD_KS_PERIODIC, FD_BASIC_TRIM, FD_SLICE_CENTRAL = 0, 1, 2
 LIB_KS_TRUE, LIB_KS_TRUE_ADV, LIB_KS_RICH, LIB_KS_RICH_NOADV, LIB_BASIC = 0, 1, 2, 3, 4
-LIB_KS_GRAD, LIB_KS_LAP, LIB_PATCH_MODEL4, LIB_PATCH_FULL, LIB_PATCH_DERIVS = 5, 6, 7, 8, 9
+LIB_KS_GRAD, LIB_KS_LAP, LIB_PATCH_MODEL4, LIB_PATCH_FULL, LIB_PATCH_DERIVS, LIB_AR_FULL = 5, 6, 7, 8, 9, 10
 STRIDGE_KS, STRIDGE_SKLEARN, STRIDGE_BASIC = 0, 1, 2
-STRIDGE_RMS_PRESCALE = 1
+STRIDGE_RMS_PRESCALE, STRIDGE_NO_EPS = 1, 2
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TILED = 0, 1, 2
 LIB_WIDTH = {LIB_KS_TRUE: 3, LIB_KS_TRUE_ADV: 5, LIB_KS_RICH: 9, LIB_KS_RICH_NOADV: 7, LIB_BASIC: 6,
-             LIB_KS_GRAD: 2, LIB_KS_LAP: 1, LIB_PATCH_MODEL4: 6, LIB_PATCH_FULL: 8, LIB_PATCH_DERIVS: 6}
+             LIB_KS_GRAD: 2, LIB_KS_LAP: 1, LIB_PATCH_MODEL4: 6, LIB_PATCH_FULL: 8, LIB_PATCH_DERIVS: 6, LIB_AR_FULL: 13}
 
 
 def stats_len(p: int) -> int:
@@ -74,6 +74,8 @@ _PROTOS = {
     "pg_fd_residual_ss": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
                                     _i32, _i32, _ptr, _i32, _ptr, _ptr]),
     "pg_ks_rollout": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _ptr, _i32, _ptr, _ptr, _ptr]),
+    "pg_ar_rollout": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _ptr, _ptr, _i32, _i32, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "pg_one_step_ss": (C.c_int, [_ptr, _ptr, _i64, _i64, _dbl, _ptr, _ptr, _ptr]),
     "pg_fit_metrics": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr]),
     "pg_time_moving_average": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr]),
     "pg_periodic_conv": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr, _i32, _ptr, _ptr]),

@@ -87,7 +87,12 @@ static int describe(K1Params &P, const double *U, int64_t T, int64_t A0, int64_t
     P.U = U; P.T = T; P.A0 = A0; P.A1 = A1;
     P.c = make_consts(d0, d1, dt);
     P.dialect = dialect;
-    if (dialect == PG_FD_KS_PERIODIC) {
+    P.t_halo = 1;
+    if (dialect == PG_FD_SLICE_CENTRAL) {
+        if (lib != PG_LIB_AR_FULL) PG_FAIL(PG_EINVAL, "the analyze_results dialect has library PG_LIB_AR_FULL (its Models 1-5 are column subsets)");
+        if (A0 < 3 || A1 < 3) PG_FAIL(PG_EINVAL, "the analyze_results dialect needs A0, A1 >= 3 (rows are U[:-2, :-2, :-2])");
+        P.R0 = A0 - 2; P.R1 = A1 - 2; P.off = 0; P.t_halo = 2;
+    } else if (dialect == PG_FD_KS_PERIODIC) {
         if (fused && !ks_lib(lib)) PG_FAIL(PG_EINVAL, "library %d does not belong to the KS dialect", lib);
         P.R0 = A0; P.R1 = A1; P.off = 0;
     } else if (dialect == PG_FD_BASIC_TRIM) {
@@ -219,7 +224,7 @@ static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, 
     if (!stats_out) PG_FAIL(PG_EINVAL, "stats_out is null");
     if (variant < PG_VARIANT_AUTO || variant > PG_VARIANT_TILED) PG_FAIL(PG_EINVAL, "unknown variant %d", variant);
     const int p = library_width(library_id), S = PG_STATS_LEN(p);
-    const int64_t Trows = T - 1;
+    const int64_t Trows = T - P.t_halo;
     P.bt = bt; P.b0 = b0; P.b1 = b1;
     P.fold_of_row = fold_of_row; P.fold_of_frame = fold_of_frame; P.n_folds = n_folds;
     P.tail_means = trailing_block_means;
@@ -326,7 +331,7 @@ int pg_fd_residual_ss(const double *U, int64_t T, int64_t A0, int64_t A1, double
     if (eval_fold < -1 || eval_fold >= n_folds) PG_FAIL(PG_EINVAL, "eval_fold must be -1 (all rows) or a fold id");
     if (n_coef < 1 || n_coef > 32) PG_FAIL(PG_EINVAL, "n_coef must be in 1..32 (call again for more)");
     if (!coef || !ss_out) PG_FAIL(PG_EINVAL, "null buffer");
-    const int64_t Trows = T - 1;
+    const int64_t Trows = T - P.t_halo;
     if (Trows <= 0) {
         PG_CUDA(cudaMemsetAsync(ss_out, 0, sizeof(double) * (n_coef + 1), st));
         return PG_OK;
@@ -373,7 +378,7 @@ int pg_fd_block_rows(const double *U, int64_t T, int64_t A0, int64_t A1, double 
     if (rc) return rc;
     if (bt <= 0 || b0 <= 0 || b1 <= 0) PG_FAIL(PG_EINVAL, "block sizes must be > 0");
     if (!rows_out) PG_FAIL(PG_EINVAL, "rows_out is null");
-    const int64_t Trows = T - 1;
+    const int64_t Trows = T - P.t_halo;
     if (Trows <= 0) return PG_OK;
     P.bt = bt; P.b0 = b0; P.b1 = b1; P.n_folds = 1;
     const int64_t nBt = (Trows + bt - 1) / bt;
@@ -427,7 +432,7 @@ int pg_fd_gather_rows(const double *U, int64_t T, int64_t A0, int64_t A1, double
     if (n < 0) PG_FAIL(PG_EINVAL, "n < 0");
     if (n == 0) return PG_OK;
     if (!flat_idx || !X_out || !y_out) PG_FAIL(PG_EINVAL, "null buffer");
-    if (T < 2) PG_FAIL(PG_EINVAL, "need at least 2 frames for u_t");
+    if (T < 1 + P.t_halo) PG_FAIL(PG_EINVAL, "need at least %d frames for u_t", 1 + P.t_halo);
     void *scr = nullptr;
     rc = scratch_for(st, 64, &scr);
     if (rc) return rc;
@@ -558,6 +563,37 @@ int pg_ks_rollout(const double *U, int64_t T, int64_t A0, int64_t A1, double d0,
     rc = scratch_for(st, sizeof(double) * (size_t)blocks * (size_t)n_steps, &scr);
     if (rc) return rc;
     return launch_rollout(library_id, U, A0, A1, P.c, coef, n_steps, work, (double *)scr, blocks, rmse_out, st);
+}
+
+int pg_ar_rollout(const double *U, int64_t T, int64_t H, int64_t W, double d0, double d1, double dt, const int32_t *term_ids,
+                  const double *coef, int n_terms, int k_steps, int64_t t0, int64_t t1, const uint8_t *mask, double *work,
+                  double *sums_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!U || !term_ids || !coef || !work || !sums_out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (T < 1 || H < 2 || W < 2) PG_FAIL(PG_EINVAL, "bad shape (reflect padding needs H, W >= 2)");
+    if (!(d0 > 0) || !(d1 > 0) || !(dt > 0)) PG_FAIL(PG_EINVAL, "grid spacings must be positive");
+    if (n_terms < 1 || n_terms > PG_MAX_P) PG_FAIL(PG_EINVAL, "n_terms must be in 1..%d", PG_MAX_P);
+    if (k_steps < 1) PG_FAIL(PG_EINVAL, "k_steps must be >= 1");
+    if (t0 < 0 || t1 > T || t1 - t0 <= k_steps) PG_FAIL(PG_EINVAL, "the slice [t0, t1) must lie inside the stack and hold more than k_steps frames");
+    const int64_t n_start = t1 - k_steps - t0;
+    const int blocks = rollout_blocks(n_start * H, W, sm_count());
+    void *scr = nullptr;
+    int rc = scratch_for(st, sizeof(double) * 4 * (size_t)blocks, &scr);
+    if (rc) return rc;
+    return launch_ar_rollout(U, H, W, make_consts(d0, d1, dt), term_ids, coef, n_terms, k_steps, t0, n_start, mask, work,
+                             (double *)scr, blocks, sums_out, st);
+}
+
+int pg_one_step_ss(const double *u_field, const double *ut_pred, int64_t t_max, int64_t frame, double dt, const uint8_t *mask,
+                   double *sums_out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!u_field || !ut_pred || !sums_out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (t_max < 1 || frame < 1) PG_FAIL(PG_EINVAL, "t_max and frame must be >= 1");
+    const int blocks = rollout_blocks(t_max, frame, sm_count());
+    void *scr = nullptr;
+    int rc = scratch_for(st, sizeof(double) * 2 * (size_t)blocks, &scr);
+    if (rc) return rc;
+    return launch_one_step(u_field, ut_pred, t_max, frame, dt, mask, (double *)scr, blocks, sums_out, st);
 }
 
 int pg_fit_metrics(const double *y_true, const double *y_pred, int64_t n, double *sums_out, void *stream) {

@@ -38,6 +38,7 @@ template <> struct Lib<PG_LIB_KS_RICH_NOADV> { static constexpr int P = 7; stati
 template <> struct Lib<PG_LIB_BASIC>         { static constexpr int P = 6; static constexpr bool BIH = false; };
 template <> struct Lib<PG_LIB_KS_GRAD>       { static constexpr int P = 2; static constexpr bool BIH = false; };
 template <> struct Lib<PG_LIB_KS_LAP>        { static constexpr int P = 1; static constexpr bool BIH = false; };
+template <> struct Lib<PG_LIB_AR_FULL>       { static constexpr int P = 13; static constexpr bool BIH = false; };
 
 inline int library_width(int lib) {
     switch (lib) {
@@ -51,6 +52,7 @@ inline int library_width(int lib) {
         case PG_LIB_PATCH_MODEL4: return 6;
         case PG_LIB_PATCH_FULL: return 8;
         case PG_LIB_PATCH_DERIVS: return 6;
+        case PG_LIB_AR_FULL: return 13;
         default: return -1;
     }
 }
@@ -59,6 +61,7 @@ inline int library_width(int lib) {
 // differences along a0/a1.
 struct PointVals {
     double u, g0, g1, lap, bih;
+    double d00, d11;   // second differences along a0 / a1 (slice-central dialect only)
 };
 
 // Library row from point values.  Products use explicit _rn intrinsics so the compiler cannot
@@ -79,6 +82,11 @@ template <int LIB> __device__ __forceinline__ void lib_row(const PointVals &v, d
     } else if constexpr (LIB == PG_LIB_BASIC) {
         // basic_usage calls the LAST axis "x": u_x = g1, u_y = g0 (basic:58-59)
         th[0] = 1.0; th[1] = v.u; th[2] = v.g1; th[3] = v.g0; th[4] = v.lap; th[5] = __dmul_rn(v.u, v.u);
+    } else if constexpr (LIB == PG_LIB_AR_FULL) {
+        // analyze_results:618-623; x = a1.  u**3 is np.power(u, 3) there: u*u*u differs from it by <= 1 ulp
+        th[0] = 1.0; th[1] = v.u; th[2] = v.g1; th[3] = v.g0; th[4] = v.d11; th[5] = v.d00; th[6] = v.lap;
+        th[7] = __dmul_rn(v.u, v.u); th[8] = __dmul_rn(v.u, v.g1); th[9] = __dmul_rn(v.u, v.g0);
+        th[10] = __dmul_rn(__dmul_rn(v.u, v.u), v.u); th[11] = __dmul_rn(v.g1, v.g1); th[12] = __dmul_rn(v.g0, v.g0);
     } else if constexpr (LIB == PG_LIB_KS_GRAD) {
         th[0] = v.g0; th[1] = v.g1;
     } else if constexpr (LIB == PG_LIB_KS_LAP) {
@@ -142,6 +150,22 @@ __device__ __forceinline__ void basic_point(const double *__restrict__ F, int64_
     v.g1 = central_diff(ue, uw, c.two_d1);
     // lap = u_xx + u_yy with x = a1 (basic:69); addition commutes, so operand order is free
     v.lap = __dadd_rn(second_diff(ue, uc, uw, c.d1sq), second_diff(un, uc, us, c.d0sq));
+    v.bih = 0.0;
+}
+
+// Slice-aligned point of the analyze_results dialect (analyze_results:257-274): the reference differences slices
+// that it then crops to a common ORIGIN, so the "central" differences of row (i, j) reach forward only:
+// (i, j), (i+1, j), (i+2, j), (i, j+1), (i, j+2); valid for i < A0-2, j < A1-2.
+__device__ __forceinline__ void slice_point(const double *__restrict__ F, int64_t A1, int64_t i, int64_t j,
+                                            const FdConsts &c, PointVals &v) {
+    const double uc = F[i * A1 + j];
+    const double e1 = F[i * A1 + j + 1], e2 = F[i * A1 + j + 2], n1 = F[(i + 1) * A1 + j], n2 = F[(i + 2) * A1 + j];
+    v.u = uc;
+    v.g1 = central_diff(e2, uc, c.two_d1);             // u_x  (:257)
+    v.g0 = central_diff(n2, uc, c.two_d0);             // u_y  (:258)
+    v.d11 = second_diff(e2, e1, uc, c.d1sq);           // u_xx (:259)
+    v.d00 = second_diff(n2, n1, uc, c.d0sq);           // u_yy (:260)
+    v.lap = __dadd_rn(v.d11, v.d00);                   // laplacian = u_xx + u_yy (:274)
     v.bih = 0.0;
 }
 

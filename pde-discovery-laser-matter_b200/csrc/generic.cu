@@ -20,6 +20,8 @@ template <int LIB>
 __device__ __forceinline__ void eval_point(const K1Params &P, const double *F, int64_t i, int64_t j, PointVals &v) {
     if constexpr (LIB == PG_LIB_BASIC) {
         basic_point(F, P.A1, i + P.off, j + P.off, P.c, v);
+    } else if constexpr (LIB == PG_LIB_AR_FULL) {
+        slice_point(F, P.A1, i, j, P.c, v);
     } else {
         ks_point<Lib<LIB>::BIH>(F, P.A0, P.A1, i, j, P.c, v);
     }
@@ -42,7 +44,7 @@ __device__ __forceinline__ bool generic_block_row(const K1Params &P, int64_t idx
                                                   int &fold, unsigned long long &bad_rows, unsigned long long &bad_fold) {
     constexpr int p = Lib<LIB>::P;
     const int64_t frame = P.A0 * P.A1;
-    const int64_t Trows = P.T - 1;
+    const int64_t Trows = P.T - P.t_halo;
     const int64_t jb = P.i1_lo + idx % n2;
     const int64_t ib = P.i0_lo + (idx / n2) % n1;
     const int64_t tb = P.tb_lo + idx / (n2 * n1);
@@ -64,7 +66,9 @@ __device__ __forceinline__ bool generic_block_row(const K1Params &P, int64_t idx
     } else
     for (int64_t t = t0; t < t1; ++t) {
         const double *F = P.U + t * frame;
-        const double *Fn = F + frame;
+        // forward u_t = (U[t+1] - U[t]) / dt (ks2d:1511, basic:46-48); central (U[t+2] - U[t]) / (2 dt) (analyze_results:261)
+        const double *Fn = F + P.t_halo * frame;
+        const double tdiv = P.t_halo == 2 ? __dmul_rn(2.0, P.c.dt) : P.c.dt;
         for (int64_t i = i0; i < i1; ++i)
             for (int64_t j = j0; j < j1; ++j) {
                 PointVals v;
@@ -72,7 +76,7 @@ __device__ __forceinline__ bool generic_block_row(const K1Params &P, int64_t idx
                 double row[p];
                 lib_row<LIB>(v, row);
                 const int64_t o = (i + P.off) * P.A1 + (j + P.off);
-                y = __dadd_rn(y, __ddiv_rn(__dsub_rn(Fn[o], F[o]), P.c.dt));
+                y = __dadd_rn(y, __ddiv_rn(__dsub_rn(Fn[o], F[o]), tdiv));
 #pragma unroll
                 for (int k = 0; k < p; ++k) th[k] = __dadd_rn(th[k], row[k]);
             }
@@ -331,7 +335,7 @@ template <int LIB>
 __global__ void fd_gather_kernel(K1Params P, const int64_t *__restrict__ flat_idx, int64_t n, double *__restrict__ X,
                                  double *__restrict__ y) {
     constexpr int p = Lib<LIB>::P;
-    const int64_t frame = P.A0 * P.A1, rs = P.R0 * P.R1, nrows = (P.T - 1) * rs;
+    const int64_t frame = P.A0 * P.A1, rs = P.R0 * P.R1, nrows = (P.T - P.t_halo) * rs;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t idx = flat_idx[k];
         if (idx < 0 || idx >= nrows) {  // caller error; poison the row so it cannot pass silently
@@ -349,7 +353,7 @@ __global__ void fd_gather_kernel(K1Params P, const int64_t *__restrict__ flat_id
 #pragma unroll
         for (int c = 0; c < p; ++c) X[k * p + c] = row[c];
         const int64_t o = (i + P.off) * P.A1 + (j + P.off);
-        y[k] = __ddiv_rn(__dsub_rn(F[frame + o], F[o]), P.c.dt);
+        y[k] = __ddiv_rn(__dsub_rn(F[P.t_halo * frame + o], F[o]), P.t_halo == 2 ? __dmul_rn(2.0, P.c.dt) : P.c.dt);
     }
 }
 
@@ -518,6 +522,7 @@ int launch_k1_generic(int lib, const K1Params &P, int ctas, cudaStream_t st) {
         case PG_LIB_KS_RICH: return launch_k1_generic_t<PG_LIB_KS_RICH>(P, ctas, st);
         case PG_LIB_KS_RICH_NOADV: return launch_k1_generic_t<PG_LIB_KS_RICH_NOADV>(P, ctas, st);
         case PG_LIB_BASIC: return launch_k1_generic_t<PG_LIB_BASIC>(P, ctas, st);
+        case PG_LIB_AR_FULL: return launch_k1_generic_t<PG_LIB_AR_FULL>(P, ctas, st);
         default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_lib_gram", lib);
     }
 }
@@ -537,6 +542,7 @@ int launch_k1_generic_resid(int lib, const K1Params &P, const double *coef, int 
         case PG_LIB_KS_RICH: return launch_k1_resid_t<PG_LIB_KS_RICH>(P, coef, J, eval_fold, partials, ctas, st);
         case PG_LIB_KS_RICH_NOADV: return launch_k1_resid_t<PG_LIB_KS_RICH_NOADV>(P, coef, J, eval_fold, partials, ctas, st);
         case PG_LIB_BASIC: return launch_k1_resid_t<PG_LIB_BASIC>(P, coef, J, eval_fold, partials, ctas, st);
+        case PG_LIB_AR_FULL: return launch_k1_resid_t<PG_LIB_AR_FULL>(P, coef, J, eval_fold, partials, ctas, st);
         default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_residual_ss", lib);
     }
 }
@@ -560,7 +566,7 @@ int launch_k1_generic_rows(int lib, const K1Params &P, double *rows_out, int cta
     switch (lib) {
 #define PG_CASE(L) case L: k1_generic_rows_kernel<L><<<ctas, GW * 32, 0, st>>>(P, rows_out); break;
         PG_CASE(PG_LIB_KS_TRUE) PG_CASE(PG_LIB_KS_TRUE_ADV) PG_CASE(PG_LIB_KS_RICH) PG_CASE(PG_LIB_KS_RICH_NOADV)
-        PG_CASE(PG_LIB_BASIC)
+        PG_CASE(PG_LIB_BASIC) PG_CASE(PG_LIB_AR_FULL)
 #undef PG_CASE
         default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_block_rows", lib);
     }
@@ -613,7 +619,7 @@ int launch_fd_gather(int lib, const K1Params &P, const int64_t *flat_idx, int64_
     switch (lib) {
 #define PG_CASE(L) case L: fd_gather_kernel<L><<<g, 128, 0, st>>>(P, flat_idx, n, X, y); break;
         PG_CASE(PG_LIB_KS_TRUE) PG_CASE(PG_LIB_KS_TRUE_ADV) PG_CASE(PG_LIB_KS_RICH) PG_CASE(PG_LIB_KS_RICH_NOADV)
-        PG_CASE(PG_LIB_BASIC)
+        PG_CASE(PG_LIB_BASIC) PG_CASE(PG_LIB_AR_FULL)
 #undef PG_CASE
         default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_gather_rows", lib);
     }

@@ -19,6 +19,7 @@ struct K1Params {
     int bt, b0, b1;
     int64_t R0, R1;        // row-space extents along a0/a1 (A0,A1 for KS; A0-4,A1-4 for BASIC)
     int64_t off;           // index offset of the row space inside a frame (0 for KS, 2 for BASIC)
+    int t_halo;            // trailing frames that only feed u_t: 1 (forward difference), 2 (central, PG_FD_SLICE_CENTRAL)
     int64_t nB0, nB1;      // number of blocks along a0/a1 (ceil)
     int64_t tb_lo, tb_hi, i0_lo, i0_hi, i1_lo, i1_hi;  // block-index ranges this launch covers
     const uint8_t *fold_of_row;
@@ -113,6 +114,11 @@ int launch_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, in
                          int n_taps, double *out, cudaStream_t st);
 
 // rollout.cu
+int launch_ar_rollout(const double *U, int64_t H, int64_t W, const FdConsts &c, const int32_t *term_ids, const double *coef,
+                      int n_terms, int k_steps, int64_t t0, int64_t n_start, const uint8_t *mask, double *work, double *partials,
+                      int blocks, double *out4, cudaStream_t st);
+int launch_one_step(const double *u, const double *ut, int64_t t_max, int64_t frame, double dt, const uint8_t *mask,
+                    double *partials, int blocks, double *out2, cudaStream_t st);
 int launch_fit_metrics(const double *y, const double *yh, int64_t n, double *partials, int blocks, double *out10, cudaStream_t st);
 int rollout_blocks(int64_t A0, int64_t A1, int n_sm);
 int launch_rollout(int lib, const double *U, int64_t A0, int64_t A1, const FdConsts &c, const double *coef, int n_steps,

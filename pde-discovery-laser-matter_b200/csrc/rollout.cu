@@ -74,6 +74,120 @@ static int rollout_t(const double *U, int64_t A0, int64_t A1, const FdConsts &c,
     return PG_OK;
 }
 
+// ----------------------------------------------------------------------------- analyze_results rollout (ar:300-395)
+// rollout_k_rmse: from EVERY start frame t of a time slice, k explicit-Euler steps u <- u + dt * f(u) with the model's
+// terms evaluated by derivs_2d (same-grid central differences through np.pad(mode="reflect"), NOT the fit's
+// slice-aligned stencils), then the error against frame t + k.  The start frames are independent: one launch per
+// Euler step advances all of them ([n_start][H][W] state, ping-pong), the last step also accumulates
+// sum e^2, sum y, sum y^2 and the count over the (optionally masked) targets.
+// Terms are added in the caller's order, |c| < 1e-12 skipped, products not contracted (ar:316-345).
+__device__ __forceinline__ int64_t reflect1(int64_t i, int64_t n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
+
+__global__ void __launch_bounds__(RO_THREADS) ar_rollout_step_kernel(const double *__restrict__ in, int64_t in_stride,
+                                                                     double *__restrict__ out, const double *__restrict__ target,
+                                                                     int64_t n_start, int64_t H, int64_t W, FdConsts c,
+                                                                     const int32_t *__restrict__ term_ids,
+                                                                     const double *__restrict__ coef, int n_terms, int last,
+                                                                     const uint8_t *__restrict__ mask, double *__restrict__ partials) {
+    __shared__ double sh[RO_THREADS];
+    const int64_t frame = H * W, total = n_start * frame;
+    double a[4] = {0, 0, 0, 0};
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = idx / frame, r = idx % frame, i = r / W, j = r % W;
+        const double *F = in + s * in_stride;
+        const double uc = F[i * W + j];
+        const double ue = F[i * W + reflect1(j + 1, W)], uw = F[i * W + reflect1(j - 1, W)];
+        const double un = F[reflect1(i + 1, H) * W + j], us = F[reflect1(i - 1, H) * W + j];
+        const double ux = central_diff(ue, uw, c.two_d1), uy = central_diff(un, us, c.two_d0);
+        const double uxx = second_diff(ue, uc, uw, c.d1sq), uyy = second_diff(un, uc, us, c.d0sq);
+        double rhs = 0.0;
+        for (int k = 0; k < n_terms; ++k) {
+            const double cf = coef[k];
+            if (fabs(cf) < 1e-12) continue;
+            double v;
+            switch (term_ids[k]) {
+                case 0: v = 1.0; break;
+                case 1: v = uc; break;
+                case 2: v = ux; break;
+                case 3: v = uy; break;
+                case 4: v = uxx; break;
+                case 5: v = uyy; break;
+                case 6: v = __dadd_rn(uxx, uyy); break;
+                case 7: v = __dmul_rn(uc, uc); break;
+                case 8: v = __dmul_rn(uc, ux); break;
+                case 9: v = __dmul_rn(uc, uy); break;
+                case 10: v = __dmul_rn(__dmul_rn(uc, uc), uc); break;
+                case 11: v = __dmul_rn(ux, ux); break;
+                default: v = __dmul_rn(uy, uy); break;
+            }
+            rhs = __dadd_rn(rhs, __dmul_rn(cf, v));
+        }
+        const double unew = __dadd_rn(uc, __dmul_rn(c.dt, rhs));
+        out[idx] = unew;
+        if (last && (!mask || mask[r])) {
+            const double y = target[s * frame + r], d = __dsub_rn(y, unew);
+            a[0] = fma(d, d, a[0]); a[1] += y; a[2] = fma(y, y, a[2]); a[3] += 1.0;
+        }
+    }
+    if (!last) return;
+    for (int q = 0; q < 4; ++q) {
+        sh[threadIdx.x] = a[q];
+        __syncthreads();
+        for (int w = RO_THREADS / 2; w > 0; w >>= 1) {
+            if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * 4 + q] = sh[0];
+        __syncthreads();
+    }
+}
+
+int launch_ar_rollout(const double *U, int64_t H, int64_t W, const FdConsts &c, const int32_t *term_ids, const double *coef,
+                      int n_terms, int k_steps, int64_t t0, int64_t n_start, const uint8_t *mask, double *work, double *partials,
+                      int blocks, double *out4, cudaStream_t st) {
+    const int64_t frame = H * W, vol = n_start * frame;
+    for (int k = 0; k < k_steps; ++k) {
+        const double *in = k == 0 ? U + t0 * frame : work + (int64_t)((k - 1) & 1) * vol;
+        double *out = work + (int64_t)(k & 1) * vol;
+        ar_rollout_step_kernel<<<blocks, RO_THREADS, 0, st>>>(in, frame, out, U + (t0 + k_steps) * frame, n_start, H, W, c, term_ids,
+                                                              coef, n_terms, k == k_steps - 1, mask, partials);
+        PG_LAUNCHED();
+    }
+    return launch_reduce_partials(partials, blocks, 4, out4, 0, st);
+}
+
+// one_step_prediction_rmse (ar:150-187): sum over t < t_max of (u[t+1] - (u[t] + dt * ut_pred[t]))^2 (+ count)
+__global__ void __launch_bounds__(RO_THREADS) one_step_kernel(const double *__restrict__ u, const double *__restrict__ ut,
+                                                              int64_t t_max, int64_t frame, double dt,
+                                                              const uint8_t *__restrict__ mask, double *__restrict__ partials) {
+    __shared__ double sh[RO_THREADS];
+    double a[2] = {0, 0};
+    const int64_t total = t_max * frame;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[idx % frame]) continue;
+        const double pred = __dadd_rn(u[idx], __dmul_rn(dt, ut[idx]));
+        const double d = __dsub_rn(u[idx + frame], pred);
+        a[0] = fma(d, d, a[0]); a[1] += 1.0;
+    }
+    for (int q = 0; q < 2; ++q) {
+        sh[threadIdx.x] = a[q];
+        __syncthreads();
+        for (int w = RO_THREADS / 2; w > 0; w >>= 1) {
+            if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * 2 + q] = sh[0];
+        __syncthreads();
+    }
+}
+
+int launch_one_step(const double *u, const double *ut, int64_t t_max, int64_t frame, double dt, const uint8_t *mask,
+                    double *partials, int blocks, double *out2, cudaStream_t st) {
+    one_step_kernel<<<blocks, RO_THREADS, 0, st>>>(u, ut, t_max, frame, dt, mask, partials);
+    PG_LAUNCHED();
+    return launch_reduce_partials(partials, blocks, 2, out2, 0, st);
+}
+
 // ----------------------------------------------------------------------------- fit metrics (ks2d:29-40, patch:47-65)
 // Two passes over (y_true, y_pred): raw sums, then sums centred on the means of the first pass (what np.std,
 // np.corrcoef and the reference's r2_score do).  Per-block partial sums, fixed-order reduction.

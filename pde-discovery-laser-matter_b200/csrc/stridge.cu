@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(SW * 32) stridge_kernel(StridgeParams P) {
     double cj = 0.0;
     if (lane < p) {
         cj = w.c[lane];
-        if (P.dialect != PG_STRIDGE_BASIC) cj = cj / (w.s[lane] + 1e-12);
+        if (P.dialect != PG_STRIDGE_BASIC) cj = (P.flags & PG_STRIDGE_NO_EPS) ? cj / w.s[lane] : cj / (w.s[lane] + 1e-12);
         if (P.flags & PG_STRIDGE_RMS_PRESCALE) cj = cj / w.d[lane];
         P.coef_out[job * p + lane] = cj;
     }

@@ -31,6 +31,19 @@ def _dev(a, dtype=None):
     return t.contiguous()
 
 
+def row_space(shape, dialect):
+    """(row frames, R0, R1) of a (T, A0, A1) stack: KS every point of U[:-1]; basic_usage U[:-1, 2:-2, 2:-2];
+    analyze_results U[:-2, :-2, :-2] (central time difference, slice-aligned stencils)."""
+    T, A0, A1 = (int(x) for x in shape)
+    if dialect == L.FD_KS_PERIODIC:
+        return max(T - 1, 0), A0, A1
+    if dialect == L.FD_BASIC_TRIM:
+        return max(T - 1, 0), A0 - 4, A1 - 4
+    if dialect == L.FD_SLICE_CENTRAL:
+        return max(T - 2, 0), A0 - 2, A1 - 2
+    raise ValueError(f"unknown finite-difference dialect {dialect}")
+
+
 def field(U):
     """A (T, A0, A1) float64 stack on the device."""
     torch = L.torch_cuda()
@@ -63,13 +76,13 @@ def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row
     bt, b0, b1 = (int(b) for b in block)
     fr = _dev(fold_of_row, torch.uint8)
     ff = _dev(fold_of_frame, torch.int32)
+    Tr, R0, R1 = row_space(U.shape, dialect)
     if fr is not None:
-        R0, R1 = (A0, A1) if dialect == L.FD_KS_PERIODIC else (A0 - 4, A1 - 4)
-        nrows = -(-(T - 1) // bt) * -(-R0 // b0) * -(-R1 // b1)
+        nrows = -(-Tr // bt) * -(-R0 // b0) * -(-R1 // b1)
         if fr.numel() != nrows:
             raise ValueError(f"fold_of_row has {fr.numel()} entries, the block grid has {nrows} rows")
-    if ff is not None and ff.numel() != T - 1:
-        raise ValueError(f"fold_of_frame must have T-1 = {T - 1} entries")
+    if ff is not None and ff.numel() != Tr:
+        raise ValueError(f"fold_of_frame must have one entry per row frame = {Tr} entries")
     stats = torch.empty((n_folds, L.stats_len(p)), dtype=torch.float64, device=U.device)
     bad = torch.zeros(8, dtype=torch.int64, device=U.device) if return_nonfinite else None
     if halo is not None:
@@ -290,8 +303,8 @@ def fd_block_rows(U, d0, d1, dt, *, dialect, library, block):
     T, A0, A1 = U.shape
     p = L.LIB_WIDTH[library]
     bt, b0, b1 = (int(b) for b in block)
-    R0, R1 = (A0, A1) if dialect == L.FD_KS_PERIODIC else (A0 - 4, A1 - 4)
-    nrows = -(-max(T - 1, 0) // bt) * -(-R0 // b0) * -(-R1 // b1)
+    Tr, R0, R1 = row_space(U.shape, dialect)
+    nrows = -(-Tr // bt) * -(-R0 // b0) * -(-R1 // b1)
     rows = torch.empty((nrows, p + 1), dtype=torch.float64, device=U.device)
     L.check(lib.pg_fd_block_rows(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0, b1,
                                  L.ptr(rows), L.stream_ptr()))
@@ -359,6 +372,45 @@ def ks_rollout(U, d0, d1, dt, coef, n_steps, *, library):
     L.check(lib.pg_ks_rollout(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), library, L.ptr(coef), n_steps,
                               L.ptr(work), L.ptr(rmse) if n_steps > 0 else None, L.stream_ptr()))
     return rmse
+
+
+def ar_rollout_sums(U, d0, d1, dt, term_ids, coef, k_steps, t0, t1, mask=None):
+    """pg_ar_rollout: (sum e^2, sum y, sum y^2, count) of the k-step Euler rollouts from every start frame of [t0, t1)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    U = field(U)
+    T, H, W = U.shape
+    ids = _dev(np.asarray(term_ids, dtype=np.int32))
+    cf = _dev(np.asarray(coef, dtype=np.float64).reshape(-1))
+    if ids.numel() != cf.numel():
+        raise ValueError("one coefficient per term")
+    m = None if mask is None else _dev(np.ascontiguousarray(np.asarray(mask, dtype=bool)).astype(np.uint8))
+    if m is not None and tuple(m.shape) != (H, W):
+        raise ValueError(f"spatial_mask shape {tuple(m.shape)} does not match field shape {(H, W)}")
+    n_start = int(t1) - int(k_steps) - int(t0)
+    work = torch.empty((2, max(n_start, 1), H, W), dtype=torch.float64, device=U.device)
+    out = torch.empty(4, dtype=torch.float64, device=U.device)
+    L.check(lib.pg_ar_rollout(L.ptr(U), T, H, W, float(d0), float(d1), float(dt), L.ptr(ids), L.ptr(cf), ids.numel(),
+                              int(k_steps), int(t0), int(t1), L.ptr(m), L.ptr(work), L.ptr(out), L.stream_ptr()))
+    return out.cpu().numpy()
+
+
+def one_step_sums(u_field, ut_pred, dt, mask=None):
+    """pg_one_step_ss: (sum (u[t+1] - (u[t] + dt ut_pred[t]))^2, count) over t < min(len(u) - 1, len(ut_pred))."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    u = _dev(np.asarray(u_field, dtype=np.float64) if not isinstance(u_field, torch.Tensor) else u_field, torch.float64)
+    ut = _dev(np.asarray(ut_pred, dtype=np.float64) if not isinstance(ut_pred, torch.Tensor) else ut_pred, torch.float64)
+    t_max = min(u.shape[0] - 1, ut.shape[0])
+    if t_max <= 0:
+        return None
+    frame = int(np.prod(u.shape[1:]))
+    if int(np.prod(ut.shape[1:])) != frame:
+        raise ValueError("u_field and ut_pred must have the same frame shape")
+    m = None if mask is None else _dev(np.ascontiguousarray(np.asarray(mask, dtype=bool)).astype(np.uint8))
+    out = torch.empty(2, dtype=torch.float64, device=u.device)
+    L.check(lib.pg_one_step_ss(L.ptr(u), L.ptr(ut), t_max, frame, float(dt), L.ptr(m), L.ptr(out), L.stream_ptr()))
+    return out.cpu().numpy()
 
 
 def fit_metric_sums(y_true, y_pred):

