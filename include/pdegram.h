@@ -319,6 +319,13 @@ PG_API int pg_one_step_ss(const double *u_field, const double *ut_pred, int64_t 
  *   [8] sum (r - mean r)^2  [9] unused (0)
  */
 PG_API int pg_fit_metrics(const double *y_true, const double *y_pred, int64_t n, double *sums_out, void *stream);
+/*
+ * The same sums for B problems at once, y_pred = X @ coef formed on the fly (patch:425-429: regression_metrics of every
+ * patch's train / test rows): X [B][n][ldx], y [B][n], coef [B][p]; sums_out [B][10]; resid_out nullable [B][n] = y - X @ c
+ * (the caller takes the median of |resid|).
+ */
+PG_API int pg_rows_metrics_batched(const double *X, const double *y, const double *coef, int64_t B, int64_t n, int p,
+                            int64_t ldx, double *sums_out, double *resid_out, void *stream);
 
 /*
  * Optional denoising prologue of the ks2d script (ks2d:1448-1468), the step before the hot path.
@@ -328,6 +335,15 @@ PG_API int pg_fit_metrics(const double *y_true, const double *y_pred, int64_t n,
  *   (periodic); two calls with the taps of the periodic Gaussian ifft(exp(-sigma^2 k^2 / 2)) reproduce
  *   gaussian_smooth_periodic_2d (ks2d:125-142) without an FFT.  offsets / weights are DEVICE arrays.
  */
+/*
+ * pg_reflect_conv: one axis of scipy.ndimage.gaussian_filter (patch:335,343; analyze_results:222,250), the smoothing
+ *   step before the patch / analyze_results paths: correlation with the symmetric taps weights [2 radius + 1] (DEVICE,
+ *   centre at [radius]) under mode="reflect" (half-sample symmetric), accumulated in double in scipy's order (centre,
+ *   then the pairs (in[l-j] + in[l+j]) * w from the outermost inwards) and rounded to the stack's dtype (0 = float32,
+ *   1 = float64) once per axis: bit-identical to scipy for both dtypes.  Two calls (axis 0, then 1) filter every frame.
+ */
+PG_API int pg_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, int axis, const double *weights,
+                    int radius, void *out, void *stream);
 PG_API int pg_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, void *stream);
 PG_API int pg_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int axis, const int32_t *offsets,
                      const double *weights, int n_taps, double *out, void *stream);

@@ -77,6 +77,8 @@ _PROTOS = {
     "pg_ar_rollout": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _ptr, _ptr, _i32, _i32, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "pg_one_step_ss": (C.c_int, [_ptr, _ptr, _i64, _i64, _dbl, _ptr, _ptr, _ptr]),
     "pg_fit_metrics": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr]),
+    "pg_rows_metrics_batched": (C.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i32, _i64, _ptr, _ptr, _ptr]),
+    "pg_reflect_conv": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _i32, _ptr, _i32, _ptr, _ptr]),
     "pg_time_moving_average": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr]),
     "pg_periodic_conv": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr, _i32, _ptr, _ptr]),
     "pg_synth_field": (C.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _u64, _i32, _dbl, _ptr]),

@@ -609,6 +609,25 @@ int pg_fit_metrics(const double *y_true, const double *y_pred, int64_t n, double
     return launch_fit_metrics(y_true, y_pred, n, (double *)scr, blocks, sums_out, st);
 }
 
+int pg_rows_metrics_batched(const double *X, const double *y, const double *coef, int64_t B, int64_t n, int p, int64_t ldx,
+                            double *sums_out, double *resid_out, void *stream) {
+    if (p < 1 || p > PG_MAX_P) PG_FAIL(PG_EINVAL, "p must be in 1..%d", PG_MAX_P);
+    if (B < 0 || n < 1 || ldx < p) PG_FAIL(PG_EINVAL, "bad shape B=%lld n=%lld ldx=%lld", (long long)B, (long long)n, (long long)ldx);
+    if (B == 0) return PG_OK;
+    if (!X || !y || !coef || !sums_out) PG_FAIL(PG_EINVAL, "null buffer");
+    return launch_rows_metrics_batched(X, y, coef, B, n, p, ldx, sums_out, resid_out, (cudaStream_t)stream);
+}
+
+int pg_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, int axis, const double *weights, int radius,
+                    void *out, void *stream) {
+    if (!in || !out || !weights) PG_FAIL(PG_EINVAL, "null buffer");
+    if (dtype != 0 && dtype != 1) PG_FAIL(PG_EINVAL, "dtype must be 0 (float32) or 1 (float64)");
+    if (T < 1 || A0 < 1 || A1 < 1 || radius < 0) PG_FAIL(PG_EINVAL, "bad shape");
+    if (axis != 0 && axis != 1) PG_FAIL(PG_EINVAL, "axis must be 0 or 1");
+    if (in == out) PG_FAIL(PG_EINVAL, "in-place filtering is not supported");
+    return launch_reflect_conv(in, dtype, T, A0, A1, axis, weights, radius, out, (cudaStream_t)stream);
+}
+
 int pg_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, void *stream) {
     if (!U || !out) PG_FAIL(PG_EINVAL, "null buffer");
     if (T < 1 || A0 < 1 || A1 < 1) PG_FAIL(PG_EINVAL, "bad shape");

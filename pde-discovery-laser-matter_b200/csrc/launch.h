@@ -113,12 +113,17 @@ int launch_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A
 int launch_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int axis, const int32_t *off, const double *w,
                          int n_taps, double *out, cudaStream_t st);
 
+int launch_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, int axis, const double *w, int radius,
+                        void *out, cudaStream_t st);
+
 // rollout.cu
 int launch_ar_rollout(const double *U, int64_t H, int64_t W, const FdConsts &c, const int32_t *term_ids, const double *coef,
                       int n_terms, int k_steps, int64_t t0, int64_t n_start, const uint8_t *mask, double *work, double *partials,
                       int blocks, double *out4, cudaStream_t st);
 int launch_one_step(const double *u, const double *ut, int64_t t_max, int64_t frame, double dt, const uint8_t *mask,
                     double *partials, int blocks, double *out2, cudaStream_t st);
+int launch_rows_metrics_batched(const double *X, const double *y, const double *coef, int64_t B, int64_t n, int p, int64_t ldx,
+                                double *sums_out, double *resid_out, cudaStream_t st);
 int launch_fit_metrics(const double *y, const double *yh, int64_t n, double *partials, int blocks, double *out10, cudaStream_t st);
 int rollout_blocks(int64_t A0, int64_t A1, int n_sm);
 int launch_rollout(int lib, const double *U, int64_t A0, int64_t A1, const FdConsts &c, const double *coef, int n_steps,

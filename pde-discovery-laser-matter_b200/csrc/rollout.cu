@@ -224,6 +224,57 @@ __global__ void __launch_bounds__(FM_THREADS) fit_metrics_kernel(const double *_
     }
 }
 
+// Batched form for the per-patch fits (patch:425-429: regression_metrics of X @ c on every patch's train and test
+// rows): one warp per problem, the same two passes; sums_out [B][10] as pg_fit_metrics, resid_out [B][n] optional
+// (|resid| medians are taken by the caller).
+__global__ void __launch_bounds__(128) rows_metrics_batched_kernel(const double *__restrict__ X, const double *__restrict__ y,
+                                                                   const double *__restrict__ coef, int64_t B, int64_t n, int p,
+                                                                   int64_t ldx, double *__restrict__ sums, double *__restrict__ resid) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const double *Xb = X + b * n * ldx, *yb = y + b * n, *cb = coef + b * p;
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int64_t r = lane; r < n; r += 32) {
+        double pred = 0.0;     // X @ c: a dot product per row, in column order
+        for (int k = 0; k < p; ++k) pred = fma(Xb[r * ldx + k], cb[k], pred);
+        const double yt = yb[r], d = __dsub_rn(yt, pred);
+        if (resid) resid[b * n + r] = d;
+        a[0] += d; a[1] = fma(d, d, a[1]); a[2] += fabs(d); a[3] += yt; a[4] += pred;
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+    const double nn = (double)n, my = a[3] / nn, mh = a[4] / nn, mr = a[0] / nn;
+    double c2[4] = {0, 0, 0, 0};
+    for (int64_t r = lane; r < n; r += 32) {
+        double pred = 0.0;
+        for (int k = 0; k < p; ++k) pred = fma(Xb[r * ldx + k], cb[k], pred);
+        const double yt = yb[r], d = __dsub_rn(yt, pred);
+        const double dy = yt - my, dh = pred - mh, dr = d - mr;
+        c2[0] = fma(dy, dy, c2[0]); c2[1] = fma(dh, dh, c2[1]); c2[2] = fma(dy, dh, c2[2]); c2[3] = fma(dr, dr, c2[3]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c2[q] += __shfl_xor_sync(0xffffffffu, c2[q], o);
+    if (lane == 0) {
+        double *s = sums + b * 10;
+        for (int q = 0; q < 5; ++q) s[q] = a[q];
+        for (int q = 0; q < 4; ++q) s[5 + q] = c2[q];
+        s[9] = 0.0;
+    }
+}
+
+int launch_rows_metrics_batched(const double *X, const double *y, const double *coef, int64_t B, int64_t n, int p, int64_t ldx,
+                                double *sums_out, double *resid_out, cudaStream_t st) {
+    if (B <= 0) return PG_OK;
+    rows_metrics_batched_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(X, y, coef, B, n, p, ldx, sums_out, resid_out);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
 int launch_fit_metrics(const double *y, const double *yh, int64_t n, double *partials, int blocks, double *out10, cudaStream_t st) {
     fit_metrics_kernel<<<blocks, FM_THREADS, 0, st>>>(y, yh, n, 0, nullptr, partials);
     PG_LAUNCHED();

@@ -56,6 +56,39 @@ __global__ void periodic_conv_kernel(const double *__restrict__ in, int64_t T, i
     }
 }
 
+// scipy.ndimage.gaussian_filter (patch:335,343; analyze_results:222,250): one axis of the separable filter with
+// mode="reflect" (half-sample symmetric: d c b a | a b c d | d c b a).  scipy's correlate1d accumulates in double,
+// centre tap first, then the symmetric pairs from the outermost inwards, (in[l+j] + in[l-j]) * w[j]; this kernel adds
+// in the same order without contraction and rounds to the array's dtype once per axis, so the result is bit-identical
+// to scipy for float64 and for float32 stacks.  w [2 r + 1] are scipy's normalised taps (w[r] the centre).
+__device__ __forceinline__ int64_t symmetric_index(int64_t i, int64_t n) {
+    while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - i - 1;
+    return i;
+}
+
+template <typename T_>
+__global__ void reflect_conv_kernel(const T_ *__restrict__ in, int64_t T, int64_t A0, int64_t A1, int axis,
+                                    const double *__restrict__ w, int radius, T_ *__restrict__ out) {
+    const int64_t frame = A0 * A1, total = T * frame;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = idx / frame, r = idx % frame, i = r / A1, j = r % A1;
+        const T_ *F = in + t * frame;
+        double acc = __dmul_rn((double)F[r], w[radius]);
+        for (int jj = -radius; jj < 0; ++jj) {
+            double a, b;
+            if (axis == 0) {
+                a = (double)F[symmetric_index(i + jj, A0) * A1 + j];
+                b = (double)F[symmetric_index(i - jj, A0) * A1 + j];
+            } else {
+                a = (double)F[i * A1 + symmetric_index(j + jj, A1)];
+                b = (double)F[i * A1 + symmetric_index(j - jj, A1)];
+            }
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), w[radius + jj]));
+        }
+        out[idx] = (T_)acc;
+    }
+}
+
 static unsigned grid_of(int64_t items) {
     int64_t g = (items + 255) / 256;
     return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -63,6 +96,16 @@ static unsigned grid_of(int64_t items) {
 
 int launch_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, cudaStream_t st) {
     time_moving_average_kernel<<<grid_of(A0 * A1), 256, 0, st>>>(U, T, A0 * A1, window, out);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
+int launch_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, int axis, const double *w, int radius,
+                        void *out, cudaStream_t st) {
+    if (dtype == 0)
+        reflect_conv_kernel<float><<<grid_of(T * A0 * A1), 256, 0, st>>>((const float *)in, T, A0, A1, axis, w, radius, (float *)out);
+    else
+        reflect_conv_kernel<double><<<grid_of(T * A0 * A1), 256, 0, st>>>((const double *)in, T, A0, A1, axis, w, radius, (double *)out);
     PG_LAUNCHED();
     return PG_OK;
 }

@@ -15,7 +15,10 @@ _KS = ("rmse", "r2_score", "standardize_transform", "gradients", "laplacian", "b
        "standardize_fit", "ridge_fit", "stridge", "stridge_sign_constrained", "ensemble_stridge",
        "gaussian_smooth_periodic_2d", "time_smooth_moving_average")
 _BASIC = ("compute_derivatives", "build_library", "stridge_regression")
-_PATCH = ("regression_metrics", "stridge", "local_poly_derivatives", "build_dataset", "Library", "patch_grid")
+_PATCH = ("regression_metrics", "stridge", "local_poly_derivatives", "build_dataset", "Library", "patch_grid",
+          "safe_sample_points")
+# gaussian_filter is scipy's (imported by name into patch / analyze_results): pde_b200.patch.gaussian_filter takes the
+# whole stack at once, the scripts call it per frame, so it is offered but not rebound.
 
 
 def patch_reference(module, dialect: str | None = None):

@@ -428,6 +428,54 @@ def fit_metric_sums(y_true, y_pred):
     return out.cpu().numpy(), yt.numel()
 
 
+def rows_metrics_batched(X, y, coef, want_resid=False):
+    """pg_rows_metrics_batched: X [B][n][p], y [B][n], coef [B][p] -> sums [B][10] (as fit_metric_sums) (+ resid [B][n])."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    X = _dev(X, torch.float64)
+    y = _dev(y, torch.float64)
+    B, n, p = X.shape
+    coef = _dev(coef, torch.float64).reshape(B, p).contiguous()
+    sums = torch.empty((B, 10), dtype=torch.float64, device=X.device)
+    resid = torch.empty((B, n), dtype=torch.float64, device=X.device) if want_resid else None
+    L.check(lib.pg_rows_metrics_batched(L.ptr(X), L.ptr(y), L.ptr(coef), B, n, p, p, L.ptr(sums), L.ptr(resid), L.stream_ptr()))
+    return (sums, resid) if want_resid else sums
+
+
+def gaussian_taps(sigma, truncate=4.0):
+    """scipy.ndimage's normalised Gaussian taps (_gaussian_kernel1d, order 0): (radius, weights [2 r + 1])."""
+    sigma = float(sigma)
+    r = int(truncate * sigma + 0.5)
+    x = np.arange(-r, r + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return r, np.ascontiguousarray(phi[::-1])
+
+
+def gaussian_filter_frames(U, sigma, truncate=4.0):
+    """scipy.ndimage.gaussian_filter(frame, sigma) (mode="reflect") of every frame of a float32 / float64 stack:
+    two pg_reflect_conv passes (rows, then columns, rounding to the stack's dtype in between, as scipy does)."""
+    torch = L.torch_cuda()
+    lib = L.load()
+    if isinstance(U, np.ndarray):
+        if U.dtype not in (np.float32, np.float64):
+            U = U.astype(np.float64)
+        U = _dev(U)
+    if U.dtype not in (torch.float32, torch.float64):
+        U = U.to(torch.float64)
+    U = U.contiguous()
+    T, A0, A1 = U.shape
+    if float(sigma) <= 0:
+        return U.clone()
+    r, w = gaussian_taps(sigma, truncate)
+    w_d = _dev(w)
+    tmp, out = torch.empty_like(U), torch.empty_like(U)
+    dt = 0 if U.dtype == torch.float32 else 1
+    L.check(lib.pg_reflect_conv(L.ptr(U), dt, T, A0, A1, 0, L.ptr(w_d), r, L.ptr(tmp), L.stream_ptr()))
+    L.check(lib.pg_reflect_conv(L.ptr(tmp), dt, T, A0, A1, 1, L.ptr(w_d), r, L.ptr(out), L.stream_ptr()))
+    return out
+
+
 def time_moving_average(U, window):
     """pg_time_moving_average: reflect-padded moving average along t (ks2d:145-161)."""
     torch = L.torch_cuda()

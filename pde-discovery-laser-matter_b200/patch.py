@@ -130,6 +130,58 @@ def regression_metrics(y_true, y_pred) -> dict:
             "resid_med_abs": float(np.median((yt - yp).abs().cpu().numpy()))}
 
 
+def _metrics_from_sums(s, n, resid_abs_median):
+    """patch:47-65 from the sums of pg_fit_metrics / pg_rows_metrics_batched (arrays over a leading batch axis)."""
+    s = np.asarray(s, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rmse = np.sqrt(s[..., 1] / n)
+        y_std = np.sqrt(s[..., 5] / n)
+        r2 = np.where(s[..., 5] > 0, 1.0 - s[..., 1] / s[..., 5], np.where(s[..., 1] == 0, 1.0, 0.0))
+        corr = s[..., 7] / np.sqrt(s[..., 5] * s[..., 6]) if n > 1 else np.full(s.shape[:-1], np.nan)
+    return {"r2": r2, "rmse": rmse, "mae": s[..., 2] / n, "nrmse": rmse / (y_std + 1e-12), "corr": corr,
+            "resid_mean": s[..., 0] / n, "resid_std": np.sqrt(s[..., 8] / n), "resid_med_abs": resid_abs_median}
+
+
+def gaussian_filter(stack, sigma):
+    """``np.array([gaussian_filter(img, sigma=sigma) for img in stack])`` of patch:335,343 (scipy.ndimage, reflect
+    boundary): bit-identical for float32 and float64 stacks (pg_reflect_conv).  A single 2-D frame works too."""
+    a = np.asarray(stack)
+    if a.ndim == 2:
+        return _np(ops.gaussian_filter_frames(a[None], sigma))[0]
+    return _np(ops.gaussian_filter_frames(a, sigma))
+
+
+def safe_sample_points(rng, t_indices, h, w, rs, n):
+    """patch:248-260 (host RNG, draw order kept)."""
+    ys = rng.integers(rs, h - rs, size=n)
+    xs = rng.integers(rs, w - rs, size=n)
+    ts = rng.choice(t_indices, size=n, replace=True)
+    return list(zip(ts.tolist(), ys.tolist(), xs.tolist()))
+
+
+def global_checks(U, agg, rng, *, rt=2, rs=3, deg=3, dt=1.0, dx=0.1, dy=0.1, model="full", train_frac=0.7,
+                  n_global=800, n_step=1200):
+    """patch:446-465 with the aggregated model: (a) regression_metrics on 800 points sampled over the held-out
+    frames, (b) the one-step check on 1200 sampled points, sqrt(mean((u(t+1) - u(t) - dt * u_t_pred)^2)).  ``rng`` is
+    the generator the per-patch loop has already advanced (the draws continue its stream, as in main())."""
+    t_len, h, w = U.shape
+    lib = Library(names=MODEL4_NAMES if model == "model4" else FULL_NAMES)
+    t_valid, _, t_test = time_split(t_len, rt, train_frac)
+    agg = np.asarray(agg, dtype=np.float64)
+    pts_g = safe_sample_points(rng, t_test, h, w, rs, n_global)
+    Xg, yg = build_dataset(U, pts_g, rt, rs, deg, dt, dx, dy, lib)
+    m_test = regression_metrics(yg, Xg @ agg)
+    pts_s = safe_sample_points(rng, t_valid[:-1], h, w, rs, n_step)
+    Xs, _ = build_dataset(U, pts_s, rt, rs, deg, dt, dx, dy, lib)
+    ut_pred = Xs @ agg
+    P = np.asarray(pts_s, dtype=np.int64)
+    ok = P[:, 0] + 1 < t_len
+    Uh = np.asarray(U)
+    du = (Uh[P[ok, 0] + 1, P[ok, 1], P[ok, 2]] - Uh[P[ok, 0], P[ok, 1], P[ok, 2]]).astype(np.float64)   # float32 difference, like float(U[..] - U[..])
+    one_step = float(np.sqrt(np.mean((du - dt * ut_pred[ok]) ** 2))) if ok.any() else float("nan")
+    return dict(test_metrics=m_test, one_step_rmse=one_step, global_points=pts_g, step_points=pts_s)
+
+
 # ------------------------------------------------------------------ fused per-patch ensemble (patch:351-443)
 def time_split(t_len: int, rt: int, train_frac: float):
     """patch:361-369."""
@@ -173,18 +225,22 @@ def stability_aggregate(C, threshold: float, stability_freq: float = 0.6):
 
 
 def fit_patches(U, *, rt=2, rs=3, deg=3, patch=21, overlap=10, samples_per_patch=120, train_frac=0.7, alpha=0.01,
-                threshold=1e-5, seed=0, model="full", dx=0.1, dy=0.1, dt=1.0, max_iter=25, train_pts=None):
-    """The per-patch loop of main() (patch:351-443) as three batched launches: K2 over every
-    sampled point of every patch, rows -> per-patch statistics, K3 over all patches."""
+                threshold=1e-5, seed=0, model="full", dx=0.1, dy=0.1, dt=1.0, max_iter=25, train_pts=None, test_pts=None,
+                with_metrics=True):
+    """The per-patch loop of main() (patch:351-443) as batched launches: K2 over every sampled point of every patch,
+    rows -> per-patch statistics, K3 over all patches, and (``with_metrics``) the per-patch train / test
+    regression_metrics of patch:425-429 from one more K2 launch over the test points.  ``rng`` in the result is the
+    generator after the loop's draws (global_checks continues its stream)."""
     torch = L.torch_cuda()
     t_len, h, w = U.shape
     lib = Library(names=MODEL4_NAMES if model == "model4" else FULL_NAMES)
     p = len(lib.names)
+    rng = None
     if train_pts is None:
         _, t_train, t_test = time_split(t_len, rt, train_frac)
         coords = patch_grid(h, w, patch, overlap)
         rng = np.random.default_rng(seed)
-        train_pts, _test_pts = sample_patch_points(rng, coords, h, w, patch, rs, t_train, t_test, int(samples_per_patch))
+        train_pts, test_pts = sample_patch_points(rng, coords, h, w, patch, rs, t_train, t_test, int(samples_per_patch))
     B, n_s = train_pts.shape[:2]
     W6 = poly_stencil(rt, rs, deg, float(dt), float(dx), float(dy))
     X, y = ops.poly_rows(U, _check_points(U, train_pts, rt, rs), W6, rt, rs, library=lib.library_id)
@@ -196,5 +252,14 @@ def fit_patches(U, *, rt=2, rs=3, deg=3, patch=21, overlap=10, samples_per_patch
                               max_iter=int(max_iter), colminmax=mm[:, 0], shift=shift)
     C = _np(out["coef"])[:, 0, 0, :]
     res = stability_aggregate(C, threshold)
-    res.update(C=C, train_pts=train_pts, names=list(lib.names))
+    res.update(C=C, train_pts=train_pts, test_pts=test_pts, names=list(lib.names), rng=rng)
+    if with_metrics and B:
+        coef_d = out["coef"][:, 0, 0, :].contiguous()
+        s_tr, r_tr = ops.rows_metrics_batched(X, y, coef_d, want_resid=True)
+        res["train_metrics"] = _metrics_from_sums(_np(s_tr), n_s, np.median(np.abs(_np(r_tr)), axis=1))
+        if test_pts is not None and len(test_pts):
+            n_te = test_pts.shape[1]
+            Xt, yt = ops.poly_rows(U, _check_points(U, test_pts, rt, rs), W6, rt, rs, library=lib.library_id)
+            s_te, r_te = ops.rows_metrics_batched(Xt.reshape(B, n_te, p), yt.reshape(B, n_te), coef_d, want_resid=True)
+            res["test_metrics"] = _metrics_from_sums(_np(s_te), n_te, np.median(np.abs(_np(r_te)), axis=1))
     return res

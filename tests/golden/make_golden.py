@@ -318,7 +318,8 @@ def golden_patch(pa):
     coords = pa.patch_grid(h, w, 11, 5)
     rng = np.random.default_rng(0)
     n_s = 40
-    C, tr_all, te_all = [], [], []
+    C, tr_all, te_all, m_tr_all, m_te_all = [], [], [], [], []
+    mkeys = ("r2", "rmse", "mae", "nrmse", "corr", "resid_mean", "resid_std", "resid_med_abs")
     for (y0, x0) in coords:
         ys_low, ys_high = max(rs, y0 + rs), min(h - rs, y0 + 11 - rs)
         xs_low, xs_high = max(rs, x0 + rs), min(w - rs, x0 + 11 - rs)
@@ -335,6 +336,12 @@ def golden_patch(pa):
         C.append(pa.stridge(Xtr, ytr, alpha=0.01, threshold=1e-5))
         tr_all.append(np.array(tr_pts))
         te_all.append(np.stack([ts2, ys2, xs2], 1))
+        # patch:421-429: the held-out points of the patch and both sets of regression_metrics
+        te_pts = list(zip(ts2.tolist(), ys2.tolist(), xs2.tolist()))
+        Xte, yte = pa.build_dataset(U, te_pts, rt=rt, rs=rs, deg=deg, dt=dt, dx=dx, dy=dy, lib=lib8)
+        m_tr, m_te = pa.regression_metrics(ytr, Xtr @ C[-1]), pa.regression_metrics(yte, Xte @ C[-1])
+        m_tr_all.append([m_tr[k] for k in mkeys])
+        m_te_all.append([m_te[k] for k in mkeys])
     C = np.stack(C)
     out.update(loop_C=C, loop_train_pts=np.stack(tr_all), loop_test_pts=np.stack(te_all), loop_coords=np.array(coords))
     nonzero = np.abs(C) > 1e-5
@@ -345,6 +352,31 @@ def golden_patch(pa):
     out["loop_q75"] = np.percentile(C, 75, axis=0)
     out["loop_sign_stability"] = np.mean(np.sign(C) == np.sign(med + 1e-12), axis=0)
     out["loop_agg"] = np.where(out["loop_freq"] >= 0.6, med, 0.0)
+    out["loop_train_metrics"], out["loop_test_metrics"] = np.array(m_tr_all), np.array(m_te_all)
+    # patch:446-465 with the same generator: global held-out test and the one-step check of the aggregated model
+    agg = out["loop_agg"]
+    pts_g = pa.safe_sample_points(rng, t_indices=t_test, h=h, w=w, rs=rs, n=90)
+    Xg, yg = pa.build_dataset(U, pts_g, rt=rt, rs=rs, deg=deg, dt=dt, dx=dx, dy=dy, lib=lib8)
+    m_g = pa.regression_metrics(yg, Xg @ agg)
+    out["global_test_metrics"] = np.array([m_g[k] for k in mkeys])
+    step_pts = pa.safe_sample_points(rng, t_indices=t_valid[:-1], h=h, w=w, rs=rs, n=130)
+    Xs, _ = pa.build_dataset(U, step_pts, rt=rt, rs=rs, deg=deg, dt=dt, dx=dx, dy=dy, lib=lib8)
+    ut_pred = Xs @ agg
+    errs = []
+    for (t0, y0, x0), utp in zip(step_pts, ut_pred.tolist()):
+        if t0 + 1 >= t_len:
+            continue
+        du = float(U[t0 + 1, y0, x0] - U[t0, y0, x0])
+        errs.append((du - dt * utp) ** 2)
+    out["one_step_rmse"] = np.array([float(np.sqrt(np.mean(errs)))])
+    out["global_pts"], out["step_pts"] = np.array(pts_g), np.array(step_pts)
+    # the smoothing step before the path (patch:335,343): scipy's gaussian_filter per frame, float32 and float64
+    from scipy.ndimage import gaussian_filter
+    raw = np.random.default_rng(8).random((3, 19, 23)).astype(np.float32)
+    out["gf_raw"] = raw
+    out["gf_f32_1.0"] = np.array([gaussian_filter(img, sigma=1.0) for img in raw])
+    out["gf_f32_1.2"] = np.array([gaussian_filter(img, sigma=1.2) for img in raw])
+    out["gf_f64_1.5"] = np.array([gaussian_filter(img, sigma=1.5) for img in raw.astype(np.float64)])
     # sklearn-dialect STRidge on assorted small problems (incl. a constant column)
     rng2 = np.random.default_rng(21)
     Xs_, ys_, cs_, grid_ = [], [], [], []

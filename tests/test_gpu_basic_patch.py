@@ -199,3 +199,29 @@ def test_fit_metrics_on_gpu(P):
     assert K.r2_score(np.arange(5.0), np.arange(5.0)) == 1.0
     X = rng.standard_normal((6, 3))
     assert np.array_equal(K.standardize_transform(X, X.mean(0), X.std(0)), OK.standardize_transform(X, X.mean(0), X.std(0)))
+
+
+def test_patch_metrics_global_checks_and_gaussian_filter(P, golden_patch):
+    """patch:425-429 per-patch train / test regression_metrics, patch:446-465 global held-out test and one-step check
+    (continuing the loop's RNG stream), patch:335,343 scipy gaussian_filter: all against outputs of the reference."""
+    g = golden_patch
+    keys = ("r2", "rmse", "mae", "nrmse", "corr", "resid_mean", "resid_std", "resid_med_abs")
+    out = P.fit_patches(g["U"], patch=11, overlap=5, samples_per_patch=40, seed=0)
+    assert np.array_equal(out["test_pts"], g["loop_test_pts"])
+    for tag in ("train", "test"):
+        got = np.stack([out[f"{tag}_metrics"][k] for k in keys], axis=1)
+        np.testing.assert_allclose(got, g[f"loop_{tag}_metrics"], rtol=2e-7, atol=1e-10)      # metrics of a 1e-8 coefficient match
+    chk = P.global_checks(g["U"], out["agg"], out["rng"], n_global=90, n_step=130)
+    assert np.array_equal(np.array(chk["global_points"]), g["global_pts"]) and np.array_equal(np.array(chk["step_points"]), g["step_pts"])
+    np.testing.assert_allclose([chk["test_metrics"][k] for k in keys], g["global_test_metrics"], rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(chk["one_step_rmse"], g["one_step_rmse"][0], rtol=1e-8)
+    raw = g["gf_raw"]
+    for tag, sigma, src in (("gf_f32_1.0", 1.0, raw), ("gf_f32_1.2", 1.2, raw), ("gf_f64_1.5", 1.5, raw.astype(np.float64))):
+        got = P.gaussian_filter(src, sigma)
+        assert got.dtype == g[tag].dtype and np.array_equal(got, g[tag]), tag          # bit-identical to scipy
+    assert np.array_equal(P.gaussian_filter(raw[0], 1.0), g["gf_f32_1.0"][0])
+    # a radius larger than the frame: scipy reflects repeatedly
+    from scipy.ndimage import gaussian_filter
+
+    small = np.random.default_rng(2).random((2, 5, 4))
+    assert np.array_equal(P.gaussian_filter(small, 2.0), np.array([gaussian_filter(f, sigma=2.0) for f in small]))
