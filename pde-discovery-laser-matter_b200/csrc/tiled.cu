@@ -50,7 +50,7 @@ template <int NW> struct Geo {
     static constexpr int TMA_BYTES = HR * TJ * 8;
     static constexpr int THREADS = 32 * NW;
     // block rows staged per Gram-update batch
-    __host__ __device__ static constexpr int slots(int p) { return 8; }
+    __host__ __device__ static constexpr int slots(int p) { return 16; }   // all 16 blocks of a band in one batch
     __host__ __device__ static constexpr size_t smem(int p) {
         return (size_t)NSTAGE * STAGE_BYTES + 64 + sizeof(double) * NW * slots(p) * (p + 2) + 1024;   // + alignment slack
     }
@@ -65,7 +65,6 @@ struct TiledParams {
     // entry of the extended row [1, y, theta_0 ..] lacks, applied once per flush to the Gram products.
     double sc[PG_MAX_P + 2];
     int bt;
-    int flags;                // experiments: bit 0 = issue the next frame's side cells after this frame has landed
     // Pacing (see k1_tiled_b88): epoch_done[k] counts the CTAs that have consumed their k-th group of 2^epoch_shift
     // frames; a CTA loads frames of epoch k only once every CTA is through epoch k - epoch_lead.
     unsigned int *epoch_done;
@@ -440,8 +439,12 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         const int64_t top_src1 = wrap((int64_t)i0 - 1, P.A0) * P.A1 + j0;
         const int64_t bot_src = wrap((int64_t)i0 + vrows, P.A0) * P.A1 + j0;
         const int64_t bot_src1 = wrap((int64_t)i0 + vrows + 1, P.A0) * P.A1 + j0;
-        auto issue_halo = [&](double *stage, int64_t t) {
-            if (h_off >= 0) cp_async16(stage + h_off, P.U + t * frame + h_src);
+        // the side cell of this lane in the frame whose copy is issued next: a running pointer (one 64-bit add per
+        // frame instead of t * frame + h_src every time)
+        const double *hp = P.U + t0 * frame + h_src;
+        auto issue_halo = [&](double *stage) {
+            if (h_off >= 0) cp_async16(stage + h_off, hp);
+            hp += frame;
         };
         auto issue_wrap = [&](double *stage, int64_t t) {
             const double *Ft = P.U + t * frame;
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         };
         // first frame of the item: its stage has landed => every warp released the stage's previous frame
         mbar_wait(&full[cs], cph);
-        issue_halo(stages + cs * STAGE_DOUBLES, t0);
+        issue_halo(stages + cs * STAGE_DOUBLES);
         issue_wrap(stages + cs * STAGE_DOUBLES, t0);
         cp_async_commit();
 
@@ -478,13 +481,12 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             int n_i0 = i0, n_j0 = j0, n_t = (int)t0 + f + NSTAGE;
             bool n_ok = true;
             if (f + NSTAGE > nf) n_ok = ahead_coords(item, i0, j0, (int)t0, nf, f, NSTAGE, n_i0, n_j0, n_t);
-            if (P.flags & 1) mbar_wait(&full[cs], cph);
             if (f + 1 < nf) {
                 // side cells of the next frame, one frame ahead.  Its stage may still hold the frame two back:
                 // wait until every warp released that one (what the producer waits for as well).
                 const uint32_t g1 = G + 1, s1 = cs + 1 == NSTAGE ? 0 : cs + 1, ph1 = s1 == 0 ? cph ^ 1 : cph;
                 if (g1 >= NSTAGE) mbar_wait(&empty[s1], ph1 ^ 1);
-                issue_halo(stages + s1 * STAGE_DOUBLES, t0 + f + 1);
+                issue_halo(stages + s1 * STAGE_DOUBLES);
                 if (need_top || need_bot) {
                     mbar_wait(&full[s1], ph1);     // the wrap rows lie inside the TMA box
                     issue_wrap(stages + s1 * STAGE_DOUBLES, t0 + f + 1);
@@ -594,27 +596,31 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
                 } else {
 #pragma unroll
                     for (int h = 0; h < 16 / SB; ++h) {
-                        const bool mine = valid && (lm.g >> 1) / SB == h;
-                        if (mine) {
+                        // The lane that holds the row of block h * SB + slot stages it; a row that does not count (not
+                        // finite, excluded fold, already counted by the neighbouring tile column) is staged as ZEROS, so
+                        // the product loop below has no branches: the compiler issues its loads together instead of one
+                        // LDS -> DFMA dependency per product (ncu: that serialisation was a quarter of the rich kernel).
+                        if ((lane & 8) == 0 && (lm.g >> 1) / SB == h) {
                             double *r = ext + ((lm.g >> 1) % SB) * W;
-                            r[0] = 1.0; r[1] = y_;
+                            r[0] = valid ? 1.0 : 0.0; r[1] = valid ? y_ : 0.0;
 #pragma unroll
-                            for (int k = 0; k < p; ++k) r[2 + k] = th[k];
+                            for (int k = 0; k < p; ++k) r[2 + k] = valid ? th[k] : 0.0;
                         }
                         __syncwarp();
-                        const unsigned vm = __ballot_sync(0xffffffffu, mine);
 #pragma unroll
                         for (int slot_i = 0; slot_i < SB; ++slot_i) {
-                            const int src = block_lane(h * SB + slot_i);
-                            if (!((vm >> src) & 1u)) continue;
-                            const int fr = TIMEFOLD ? 0 : __shfl_sync(0xffffffffu, fold, src);
                             const double *r = ext + slot_i * W;
+                            if constexpr (NF == 1) {
 #pragma unroll
-                            for (int k = 0; k < NE; ++k) {
-                                if (!ev[k]) continue;
-                                const double prod = r[ea[k]] * r[eb[k]];
+                                for (int k = 0; k < NE; ++k) acc[0][k] = fma(r[ea[k]], r[eb[k]], acc[0][k]);
+                            } else {
+                                const int fr = __shfl_sync(0xffffffffu, fold, block_lane(h * SB + slot_i));
 #pragma unroll
-                                for (int ff = 0; ff < NF; ++ff) acc[ff][k] += (NF == 1 || fr == ff) ? prod : 0.0;
+                                for (int k = 0; k < NE; ++k) {
+                                    const double prod = r[ea[k]] * r[eb[k]];
+#pragma unroll
+                                    for (int ff = 0; ff < NF; ++ff) acc[ff][k] = fma(prod, fr == ff ? 1.0 : 0.0, acc[ff][k]);
+                                }
                             }
                         }
                         __syncwarp();
@@ -758,7 +764,6 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
         }
     }
     tp.bt = P.bt;
-    tp.flags = env_int("PG_TILED_FLAGS", 0);
     tp.epoch_shift = 2;                                   // epochs of 4 frames
     // a CTA may run this many epochs ahead of the slowest (PG_TILED_LEAD < 0: no pacing).  Measured at C4: DRAM traffic
     // 1.11x the algorithmic bytes without pacing, 1.01x with lead 2 (but the waits cost more than they save), lead 4
