@@ -249,6 +249,21 @@ PG_API int pg_stridge_batched(const double *stats, int64_t B, int p, int dialect
                        double *coef_out, double *metrics_out, int32_t *best_out, double *relres_out, void *stream);
 
 /*
+ * scripts/patch_based_sindy.py: the regression rows of discover_pde_for_patch (sindy:300-340) for B
+ * patches at once.  U [T][H][W] float64 images, origins [B][2] = (y, x) of each patch_size^2 patch; per patch the rows
+ * run over frames 1..T-2 and the pixels with skip_boundary <= r, c < patch_size - skip_boundary that are multiples of
+ * `subsample`, in np.where order; periodic np.roll differences INSIDE the patch (sindy:226-234), central time
+ * difference (sindy:236-245).  X_out [B][n][11], y_out [B][n], n = (T-2) * n_side^2 (returned through
+ * rows_per_patch_out_host, a HOST pointer, also when the output buffers are not yet known: pass B = 0).
+ * scramble = 1 reproduces the reference's feature layout: it column_stacks the eleven (h, w) term arrays into (h, 11 w)
+ * and views that as (h, w, 11) (sindy:269, 327-329), so feature k of pixel (r, c) is term (11 c + k) / w at column
+ * (11 c + k) % w.  scramble = 0 gives the eleven terms at the pixel (what the code presumably meant).
+ */
+PG_API int pg_sindy_rows(const double *U, int64_t T, int64_t H, int64_t W, const int32_t *origins, int64_t B, int patch_size,
+                  int skip_boundary, int subsample, double d0, double d1, double dt, int scramble, double *X_out,
+                  double *y_out, int64_t *rows_per_patch_out_host, void *stream);
+
+/*
  * build_library of basic_usage (basic:75-101) for the literal signature: four flat arrays of n values (u, u_x, u_y,
  * lap_u as compute_derivatives returned them) -> Theta_out [n][6] = [1, u, u_x, u_y, lap, u*u].
  */

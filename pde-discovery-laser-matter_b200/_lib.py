@@ -67,6 +67,8 @@ _PROTOS = {
     "pg_poly_rows": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _ptr, _i64, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr]),
     "pg_stridge_batched": (C.c_int, [_ptr, _i64, _i32, _i32, _i32, _ptr, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr,
                                      _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "pg_sindy_rows": (C.c_int, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i32, _i32, _i32, _dbl, _dbl, _dbl, _i32, _ptr, _ptr,
+                                C.POINTER(C.c_int64), _ptr]),
     "pg_basic_library_rows": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
     "pg_stats_accumulate": (C.c_int, [_ptr, _ptr, _i64, _ptr]),
     "pg_fd_block_rows": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr]),

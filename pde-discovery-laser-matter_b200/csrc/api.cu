@@ -355,6 +355,23 @@ int pg_fd_residual_ss(const double *U, int64_t T, int64_t A0, int64_t A1, double
     return launch_reduce_partials(partials, ctas, n_coef + 1, ss_out, 0, st, nullptr, 0, 0, P.counters);
 }
 
+int pg_sindy_rows(const double *U, int64_t T, int64_t H, int64_t W, const int32_t *origins, int64_t B, int patch_size,
+                  int skip_boundary, int subsample, double d0, double d1, double dt, int scramble, double *X_out, double *y_out,
+                  int64_t *rows_per_patch_out_host, void *stream) {
+    if (!U || !origins || !X_out || !y_out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (T < 3 || patch_size < 3 || patch_size > H || patch_size > W) PG_FAIL(PG_EINVAL, "need T >= 3 and 3 <= patch_size <= H, W");
+    if (skip_boundary < 0 || subsample < 1 || B < 0) PG_FAIL(PG_EINVAL, "bad skip_boundary / subsample / B");
+    if (!(d0 > 0) || !(d1 > 0) || !(dt > 0)) PG_FAIL(PG_EINVAL, "grid spacings must be positive");
+    // mask (sindy:308-320): rows / columns skip .. ps-skip-1 that are multiples of `subsample`
+    const int first = ((skip_boundary + subsample - 1) / subsample) * subsample;
+    const int last = patch_size - skip_boundary - 1;
+    const int n_side = last >= first ? (last - first) / subsample + 1 : 0;
+    if (rows_per_patch_out_host) *rows_per_patch_out_host = (int64_t)(T - 2) * n_side * n_side;
+    if (B == 0 || n_side == 0) return PG_OK;
+    return launch_sindy_rows(U, T, H, W, origins, B, patch_size, skip_boundary, subsample, make_consts(d0, d1, dt), scramble ? 1 : 0,
+                             n_side, first, X_out, y_out, (cudaStream_t)stream);
+}
+
 int pg_basic_library_rows(const double *u, const double *u_x, const double *u_y, const double *lap_u, int64_t n,
                           double *Theta_out, void *stream) {
     if (n < 0) PG_FAIL(PG_EINVAL, "n < 0");

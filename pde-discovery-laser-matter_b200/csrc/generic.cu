@@ -480,6 +480,57 @@ __global__ void rows_reduce_kernel(const double *__restrict__ partials, const do
     }
 }
 
+// patch_based_sindy.py: per-patch periodic-roll differences and the 11-term library
+//   1, u, u_x, u_y, u_xx, u_yy, lap, u^2, u u_x, u u_y, u lap      (sindy:226-270; x = a1, np.roll wraps INSIDE the patch)
+// The reference column_stacks the eleven (h, w) term arrays into an (h, 11 w) array and then views it as (h, w, 11)
+// (sindy:269, 327-329): the "feature k of pixel (r, c)" it regresses on is therefore element c*11 + k of row r of the
+// concatenation, i.e. term (c*11 + k) / w at column (c*11 + k) % w -- eleven consecutive samples of one or two terms,
+// not the eleven terms at the pixel.  A faithful port has to reproduce that index map; sindy_term() below is the one
+// place where it lives.
+__device__ __forceinline__ double sindy_term(const double *__restrict__ F, int64_t ld, int ps, int r, int c, int tid,
+                                             const FdConsts &k) {
+    const int rm = r == 0 ? ps - 1 : r - 1, rp = r == ps - 1 ? 0 : r + 1, cm = c == 0 ? ps - 1 : c - 1, cp = c == ps - 1 ? 0 : c + 1;
+    const double u = F[r * ld + c];
+    if (tid == 0) return 1.0;
+    if (tid == 1) return u;
+    if (tid == 7) return __dmul_rn(u, u);
+    const double ue = F[r * ld + cp], uw = F[r * ld + cm], un = F[rp * ld + c], us = F[rm * ld + c];
+    const double ux = central_diff(ue, uw, k.two_d1), uy = central_diff(un, us, k.two_d0);
+    const double uxx = second_diff(ue, u, uw, k.d1sq), uyy = second_diff(un, u, us, k.d0sq);
+    switch (tid) {
+        case 2: return ux;
+        case 3: return uy;
+        case 4: return uxx;
+        case 5: return uyy;
+        case 6: return __dadd_rn(uxx, uyy);
+        case 8: return __dmul_rn(u, ux);
+        case 9: return __dmul_rn(u, uy);
+        default: return __dmul_rn(u, __dadd_rn(uxx, uyy));
+    }
+}
+
+// rows of discover_pde_for_patch (sindy:300-340): patch b at origin (oy, ox), frames 1 .. T-2, the masked / subsampled
+// pixels in np.where order; X [B][n][11] with the reference's scrambled features (scramble = 1) or the eleven terms
+// at the pixel (scramble = 0), y [B][n] = (p[i+1] - p[i-1]) / (2 dt).
+__global__ void sindy_rows_kernel(const double *__restrict__ U, int64_t T, int64_t H, int64_t W, const int32_t *__restrict__ origins,
+                                  int64_t B, int ps, int skip, int sub, FdConsts k, int scramble, int n_side, int first,
+                                  double *__restrict__ X, double *__restrict__ y) {
+    const int64_t per_frame = (int64_t)n_side * n_side, n = (T - 2) * per_frame, total = B * n;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = idx / n, q = idx % n, fi = q / per_frame + 1, m = q % per_frame;
+        const int r = first + (int)(m / n_side) * sub, c = first + (int)(m % n_side) * sub;
+        const double *F = U + fi * H * W + (int64_t)origins[2 * b] * W + origins[2 * b + 1];
+        double *xr = X + idx * 11;
+#pragma unroll 1
+        for (int t = 0; t < 11; ++t) {
+            const int f = c * 11 + t;
+            xr[t] = scramble ? sindy_term(F, W, ps, r, f % ps, f / ps, k) : sindy_term(F, W, ps, r, c, t, k);
+        }
+        const int64_t o = (int64_t)r * W + c;
+        y[idx] = __ddiv_rn(__dsub_rn(F[H * W + o], F[o - H * W]), __dmul_rn(2.0, k.dt));
+    }
+}
+
 // build_library of basic_usage (basic:75-101): Theta [N][6] = [1, u, u_x, u_y, lap, u*u] from four flat arrays
 __global__ void basic_library_rows_kernel(const double *__restrict__ u, const double *__restrict__ ux,
                                           const double *__restrict__ uy, const double *__restrict__ lap, int64_t n,
@@ -545,6 +596,16 @@ int launch_k1_generic_resid(int lib, const K1Params &P, const double *coef, int 
         case PG_LIB_AR_FULL: return launch_k1_resid_t<PG_LIB_AR_FULL>(P, coef, J, eval_fold, partials, ctas, st);
         default: PG_FAIL(PG_EINVAL, "library %d cannot be used with pg_fd_residual_ss", lib);
     }
+}
+
+int launch_sindy_rows(const double *U, int64_t T, int64_t H, int64_t W, const int32_t *origins, int64_t B, int ps, int skip, int sub,
+                      const FdConsts &k, int scramble, int n_side, int first, double *X, double *y, cudaStream_t st) {
+    const int64_t total = B * (T - 2) * n_side * n_side;
+    if (total <= 0) return PG_OK;
+    sindy_rows_kernel<<<grid_for(total, 128, 148 * 16), 128, 0, st>>>(U, T, H, W, origins, B, ps, skip, sub, k, scramble, n_side, first,
+                                                                     X, y);
+    PG_LAUNCHED();
+    return PG_OK;
 }
 
 int launch_basic_library_rows(const double *u, const double *ux, const double *uy, const double *lap, int64_t n, double *Theta,

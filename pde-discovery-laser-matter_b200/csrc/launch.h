@@ -95,6 +95,8 @@ int launch_reduce_partials(const double *partials, int64_t n_parts, int64_t len,
 // held-out residual sums (second pass): partials [ctas][J + 1] (sum r_j^2 ..., row count)
 int launch_k1_generic_resid(int lib, const K1Params &P, const double *coef, int J, int eval_fold, double *partials, int ctas,
                             cudaStream_t st);
+int launch_sindy_rows(const double *U, int64_t T, int64_t H, int64_t W, const int32_t *origins, int64_t B, int ps, int skip, int sub,
+                      const FdConsts &k, int scramble, int n_side, int first, double *X, double *y, cudaStream_t st);
 int launch_basic_library_rows(const double *u, const double *ux, const double *uy, const double *lap, int64_t n, double *Theta, cudaStream_t st);
 int launch_stats_accumulate(double *dst, const double *src, int64_t n, cudaStream_t st);
 int launch_k1_generic_rows(int lib, const K1Params &P, double *rows_out, int ctas, cudaStream_t st);

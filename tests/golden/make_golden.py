@@ -460,9 +460,44 @@ def golden_analyze():
     np.savez_compressed(OUT / "analyze.npz", **out)
 
 
+# --------------------------------------------------------------------------- patch_based_sindy
+def golden_sindy():
+    """The unmodified PatchBasedSINDy class (scripts/patch_based_sindy.py) on synthetic float64 images: rows and fit of
+    one patch sequence (discover_pde_for_patch) and the whole quality-weighted ensemble."""
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, mock.MagicMock())
+    with mock.patch.object(Path, "mkdir", lambda *a, **k: None):
+        sd = _load("ref_sindy", REF / "scripts" / "patch_based_sindy.py")
+    rng = np.random.default_rng(23)
+    T, H, W = 8, 72, 88
+    t, y, x = np.meshgrid(np.arange(T), np.arange(H), np.arange(W), indexing="ij")
+    imgs = (0.5 + 0.25 * np.sin(0.21 * x + 0.13 * y - 0.3 * t) + 0.15 * np.cos(0.09 * x - 0.19 * y + 0.17 * t)
+            + 0.01 * rng.standard_normal((T, H, W)))
+    model = sd.PatchBasedSINDy(dt=1.0, dx=0.1, dy=0.1, patch_size=32, overlap=8)
+    model.images = [imgs[k] for k in range(T)]
+    out = dict(images=imgs, params=np.array([1.0, 0.1, 0.1, 32, 8]))
+    seq = [f[24:56, 48:80].copy() for f in imgs]
+    with contextlib.redirect_stdout(io.StringIO()):
+        c, q = model.discover_pde_for_patch(seq, alpha=0.01)
+        ens, names, info = model.discover_pde_patch_ensemble(alpha=0.01, min_patches=3)
+        per = [model.discover_pde_for_patch([fp[k][0] for fp in [model.extract_patches(im) for im in model.images]], alpha=0.01)
+               for k in range(len(model.extract_patches(model.images[0])))]
+    out.update(one_coeffs=c, one_quality=np.array([q]), ens_coeffs=ens, names=np.array(names),
+               ens_patch_coeffs=np.array([p_[0] for p_ in per]), ens_patch_qualities=np.array([p_[1] for p_ in per]),
+               ens_std=info["coeffs_std"], ens_n_patches=np.array([info["n_patches"]]),
+               ens_quality=np.array([info["avg_quality"], info["quality_std"]]))
+    # the rows the reference regresses on (its scrambled library view), first interior frame of that patch
+    u = seq[1]
+    lib, _ = model.build_library(u, *model.compute_derivatives(u))
+    out["lib_shape"] = np.array(lib.shape)
+    out["lib_view_sample"] = lib.reshape(32, 32, -1)[8:28:4, 8:28:4]
+    np.savez_compressed(OUT / "sindy.npz", **out)
+
+
 def main():
     ks, ba, pa = load_reference()
     golden_analyze()
+    golden_sindy()
     golden_ks2d_small(ks)
     golden_ks2d_signed(ks)
     golden_basic(ba)

@@ -1,5 +1,6 @@
-"""Parity at BASELINE.json's full single-GPU size (configs[3]: 2048 x 2048 x 1024 float64, 34.4 GB), through
-properties that do not need the NumPy oracle at that size: the tiled TMA kernels against the generic
+"""Parity at BASELINE.json's full single-GPU size (configs[3]: 2048 x 2048 x 1024 float64, 34.4 GB): a full-width
+sub-range of the stack against the NumPy oracle, and the whole stack through properties that do not need the oracle
+at that size: the tiled TMA kernels against the generic
 reference-arithmetic kernel on the same stack (statistics to 1e-10), additivity over time slabs (what the
 multi-GPU path relies on), run-to-run bit identity, and the selected model of the 5 x 6 sweep."""
 
@@ -55,6 +56,29 @@ def test_c4_blockwise_tiled_vs_generic_and_slabs(env):
     b = K.fit_from_stats(gen[0], gen[1], K.TRUE_NAMES, grid_search=True)
     assert (a["alpha"], a["threshold"]) == (b["alpha"], b["threshold"])
     assert_coef_close(a["coeffs"], b["coeffs"], what="c4 sweep")
+
+
+@pytest.mark.parametrize("lib,p,dictionary", [("LIB_KS_TRUE", 3, "true"), ("LIB_KS_RICH", 9, "rich")])
+def test_c4_tiled_sub_range_against_the_oracle(env, lib, p, dictionary):
+    """The tiled kernel at the full C4 width against the NumPy ORACLE (not against another kernel of this library): a
+    time range in the middle of the stack, every one of the 2048 columns, 512 rows; the rows wrap periodically, so
+    the sub-stack is compared as a periodic field of its own, which is what both sides compute."""
+    from helpers import ks_rows
+    from oracle import gram
+
+    L, ops, U, fof = env
+    sub = U[400:425, 768:1280, :].contiguous()
+    got = ops.fd_lib_gram(sub, 0.5, 0.5, 1e-3, dialect=L.FD_KS_PERIODIC, library=getattr(L, lib), block=(3, 8, 8),
+                          variant=L.VARIANT_TILED).cpu().numpy()[0]
+    names, X, y = ks_rows(sub.cpu().numpy(), 0.5, 0.5, 1e-3, dictionary, False, (3, 8, 8))
+    ref = gram.pack_stats(X, y)
+    assert got[0] == ref[0] == 8 * 64 * 256
+    assert_stats_close(got, ref, p)
+    # the north star's wording taken literally: entrywise relative error of every entry that is not a cancelling sum
+    from bench import stats_rel_err
+
+    cs, ew = stats_rel_err(got, ref, p)
+    assert cs <= 1e-10 and ew <= 1e-9, (cs, ew)
 
 
 @pytest.mark.parametrize("dialect,lib,p", [("FD_KS_PERIODIC", "LIB_KS_TRUE", 3), ("FD_BASIC_TRIM", "LIB_BASIC", 6)])

@@ -412,3 +412,30 @@ def test_analyze_statistics_formulation_selects_the_same_support():
         c = c * (scale + 1e-12) / scale            # the patch dialect's unscaling adds 1e-12 (patch:98); ar:578 does not
         assert np.array_equal(c != 0, g[f"m{idx}_coeffs"] != 0), name
         np.testing.assert_allclose(c, g[f"m{idx}_coeffs"], rtol=1e-8)
+
+
+# --------------------------------------------------------------------------- patch_based_sindy
+def test_sindy_oracle_matches_the_reference_class():
+    """oracle/sindy.py against tests/golden/sindy.npz (the unmodified PatchBasedSINDy class on synthetic images), the
+    scrambled feature view included."""
+    from conftest import GOLDEN
+    from oracle import sindy as OS
+
+    g = np.load(GOLDEN / "sindy.npz")
+    dt, dx, dy, ps, ov = g["params"]
+    ps, ov = int(ps), int(ov)
+    assert tuple(g["lib_shape"]) == (ps, 11 * ps)                       # column_stack of 2-D arrays concatenates columns
+    seq = [f[24:56, 48:80].copy() for f in g["images"]]
+    X, y = OS.patch_rows(seq, dx, dy, dt)
+    assert np.array_equal(X.reshape(6, 5, 5, 11)[0], g["lib_view_sample"])
+    c, q = OS.fit_rows(X, y, 0.01)
+    np.testing.assert_allclose(c, g["one_coeffs"], rtol=1e-10)
+    np.testing.assert_allclose(q, g["one_quality"][0], rtol=1e-10)
+    ens, info = OS.ensemble(g["images"], ps, ov, dx, dy, dt, min_patches=3)
+    np.testing.assert_allclose(info["patch_coeffs"], g["ens_patch_coeffs"], rtol=1e-10)
+    np.testing.assert_allclose(info["patch_qualities"], g["ens_patch_qualities"], rtol=1e-10, atol=1e-15)
+    assert np.array_equal(ens != 0, g["ens_coeffs"] != 0)
+    np.testing.assert_allclose(ens, g["ens_coeffs"], rtol=1e-10)
+    # the unscrambled variant differs (it is what the code presumably meant, not what it does)
+    Xu, _ = OS.patch_rows(seq, dx, dy, dt, scramble=False)
+    assert not np.array_equal(Xu, X) and np.array_equal(Xu[:, 0], np.ones(len(Xu)))
