@@ -125,7 +125,15 @@ __device__ __forceinline__ LaneMap make_lane_map(int row0, int hoff, int lane) {
 __device__ __forceinline__ void load_row8(const double *__restrict__ st, const LaneMap &m, int s, double (&w)[8]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double2 x = *reinterpret_cast<const double2 *>(st + m.a[k] + s * m.s[k]);
+        int off = m.a[k] + s * m.s[k];
+#ifndef PG_NO_OPAQUE_ROW_OFFSET
+        // cells -1 / 64 of the two edge lanes live in the halo-column array, so the row stride of k = 0 and k = 3 is a
+        // per-lane value.  Left alone, the compiler strength-reduces a[k] + s * stride into ONE register that it
+        // increments in place row after row -- and every increment then waits (short scoreboard, write-after-read) for
+        // the LDS that is still reading the register.  Making each row's offset opaque forces a fresh IMAD per row.
+        if (k == 0 || k == 3) asm("" : "+r"(off));
+#endif
+        const double2 x = *reinterpret_cast<const double2 *>(st + off);
         w[2 * k] = x.x; w[2 * k + 1] = x.y;
     }
 }
