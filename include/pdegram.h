@@ -162,6 +162,18 @@ PG_API int pg_fd_lib_gram_halo(const double *U, int64_t T, int64_t A0, int64_t A
                    double *stats_out, int64_t *nonfinite_out, int variant, void *stream);
 
 /*
+ * The same with TWO stacks: the library columns come from U, the time derivative from Uy (same shape).  This is the
+ * ks2d script's optional denoising with --denoise-space-on features (ks2d:1448-1468, 1510-1511): u_t is taken of the
+ * time-smoothed stack, the features of the additionally space-smoothed one.  Generic kernel (reference arithmetic).
+ */
+PG_API int pg_fd_lib_gram_two(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1,
+                       double dt, int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
+                       const int32_t *fold_of_frame, int n_folds, double *stats_out, int64_t *nonfinite_out, void *stream);
+PG_API int pg_fd_gather_rows_two(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1,
+                          double dt, int fd_dialect, int library_id, const int64_t *flat_idx, int64_t n, double *X_out,
+                          double *y_out, void *stream);
+
+/*
  * Materialised term stacks, bit-identical to the reference's NumPy arithmetic (no FMA
  * contraction, true division).  PG_FD_KS_PERIODIC: terms_out [p][T][A0][A1] over ALL T
  * frames given (ks2d:63-73, 1017-1104).  PG_FD_BASIC_TRIM with PG_LIB_BASIC: terms_out is

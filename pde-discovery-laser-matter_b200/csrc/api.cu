@@ -182,7 +182,7 @@ int pg_shutdown(void) {
     return PG_OK;
 }
 
-static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
                             int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
                             int n_folds, const double *trailing_block_means, const uint32_t *halo_flag, uint32_t halo_epoch,
                             double *stats_out, int64_t *nonfinite_out, int variant, void *stream);
@@ -190,7 +190,7 @@ static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, 
 int pg_fd_lib_gram(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
                    int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
                    int n_folds, double *stats_out, int64_t *nonfinite_out, int variant, void *stream) {
-    return fd_lib_gram_impl(U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
+    return fd_lib_gram_impl(U, nullptr, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
                             nullptr, nullptr, 0, stats_out, nonfinite_out, variant, stream);
 }
 
@@ -198,7 +198,7 @@ int pg_fd_lib_gram_tail(const double *U, int64_t T, int64_t A0, int64_t A1, doub
                         int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
                         int n_folds, const double *trailing_block_means, double *stats_out, int64_t *nonfinite_out,
                         int variant, void *stream) {
-    return fd_lib_gram_impl(U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
+    return fd_lib_gram_impl(U, nullptr, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
                             trailing_block_means, nullptr, 0, stats_out, nonfinite_out, variant, stream);
 }
 
@@ -207,11 +207,19 @@ int pg_fd_lib_gram_halo(const double *U, int64_t T, int64_t A0, int64_t A1, doub
                         int n_folds, const uint32_t *halo_flag, uint32_t halo_epoch, double *stats_out,
                         int64_t *nonfinite_out, int variant, void *stream) {
     if (!halo_flag) PG_FAIL(PG_EINVAL, "halo_flag is null (use pg_fd_lib_gram)");
-    return fd_lib_gram_impl(U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
+    return fd_lib_gram_impl(U, nullptr, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
                             nullptr, halo_flag, halo_epoch, stats_out, nonfinite_out, variant, stream);
 }
 
-static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
+int pg_fd_lib_gram_two(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                       int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
+                       const int32_t *fold_of_frame, int n_folds, double *stats_out, int64_t *nonfinite_out, void *stream) {
+    if (!Uy) PG_FAIL(PG_EINVAL, "Uy is null (use pg_fd_lib_gram)");
+    return fd_lib_gram_impl(U, Uy, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
+                            nullptr, nullptr, 0, stats_out, nonfinite_out, PG_VARIANT_GENERIC, stream);
+}
+
+static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
                             int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row, const int32_t *fold_of_frame,
                             int n_folds, const double *trailing_block_means, const uint32_t *halo_flag, uint32_t halo_epoch,
                             double *stats_out, int64_t *nonfinite_out, int variant, void *stream) {
@@ -219,6 +227,7 @@ static int fd_lib_gram_impl(const double *U, int64_t T, int64_t A0, int64_t A1, 
     K1Params P{};
     int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, true);
     if (rc) return rc;
+    P.Uy = Uy;
     if (bt <= 0 || b0 <= 0 || b1 <= 0) PG_FAIL(PG_EINVAL, "block sizes must be > 0");  // ks2d:378-379
     if (n_folds < 1 || n_folds > PG_MAX_FOLDS) PG_FAIL(PG_EINVAL, "n_folds must be in 1..%d", PG_MAX_FOLDS);
     if (!stats_out) PG_FAIL(PG_EINVAL, "stats_out is null");
@@ -439,13 +448,31 @@ int pg_fd_terms(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, d
     return launch_fd_terms(fd_dialect, library_id, U, T, A0, A1, P.c, terms_out, (cudaStream_t)stream);
 }
 
+static int fd_gather_impl(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                          int fd_dialect, int library_id, const int64_t *flat_idx, int64_t n, double *X_out, double *y_out,
+                          void *stream);
+
+int pg_fd_gather_rows_two(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                          int fd_dialect, int library_id, const int64_t *flat_idx, int64_t n, double *X_out, double *y_out,
+                          void *stream) {
+    if (!Uy) PG_FAIL(PG_EINVAL, "Uy is null (use pg_fd_gather_rows)");
+    return fd_gather_impl(U, Uy, T, A0, A1, d0, d1, dt, fd_dialect, library_id, flat_idx, n, X_out, y_out, stream);
+}
+
 int pg_fd_gather_rows(const double *U, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
                       int fd_dialect, int library_id, const int64_t *flat_idx, int64_t n, double *X_out, double *y_out,
                       void *stream) {
+    return fd_gather_impl(U, nullptr, T, A0, A1, d0, d1, dt, fd_dialect, library_id, flat_idx, n, X_out, y_out, stream);
+}
+
+static int fd_gather_impl(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
+                          int fd_dialect, int library_id, const int64_t *flat_idx, int64_t n, double *X_out, double *y_out,
+                          void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     K1Params P{};
     int rc = describe(P, U, T, A0, A1, d0, d1, dt, fd_dialect, library_id, true);
     if (rc) return rc;
+    P.Uy = Uy;
     if (n < 0) PG_FAIL(PG_EINVAL, "n < 0");
     if (n == 0) return PG_OK;
     if (!flat_idx || !X_out || !y_out) PG_FAIL(PG_EINVAL, "null buffer");

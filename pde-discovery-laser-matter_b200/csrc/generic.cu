@@ -67,7 +67,8 @@ __device__ __forceinline__ bool generic_block_row(const K1Params &P, int64_t idx
     for (int64_t t = t0; t < t1; ++t) {
         const double *F = P.U + t * frame;
         // forward u_t = (U[t+1] - U[t]) / dt (ks2d:1511, basic:46-48); central (U[t+2] - U[t]) / (2 dt) (analyze_results:261)
-        const double *Fn = F + P.t_halo * frame;
+        const double *Fy = P.Uy ? P.Uy + t * frame : F;          // the stack u_t is taken of (the same one unless Uy is given)
+        const double *Fn = Fy + P.t_halo * frame;
         const double tdiv = P.t_halo == 2 ? __dmul_rn(2.0, P.c.dt) : P.c.dt;
         for (int64_t i = i0; i < i1; ++i)
             for (int64_t j = j0; j < j1; ++j) {
@@ -76,7 +77,7 @@ __device__ __forceinline__ bool generic_block_row(const K1Params &P, int64_t idx
                 double row[p];
                 lib_row<LIB>(v, row);
                 const int64_t o = (i + P.off) * P.A1 + (j + P.off);
-                y = __dadd_rn(y, __ddiv_rn(__dsub_rn(Fn[o], F[o]), tdiv));
+                y = __dadd_rn(y, __ddiv_rn(__dsub_rn(Fn[o], Fy[o]), tdiv));
 #pragma unroll
                 for (int k = 0; k < p; ++k) th[k] = __dadd_rn(th[k], row[k]);
             }
@@ -353,7 +354,8 @@ __global__ void fd_gather_kernel(K1Params P, const int64_t *__restrict__ flat_id
 #pragma unroll
         for (int c = 0; c < p; ++c) X[k * p + c] = row[c];
         const int64_t o = (i + P.off) * P.A1 + (j + P.off);
-        y[k] = __ddiv_rn(__dsub_rn(F[P.t_halo * frame + o], F[o]), P.t_halo == 2 ? __dmul_rn(2.0, P.c.dt) : P.c.dt);
+        const double *Fy = P.Uy ? P.Uy + t * frame : F;
+        y[k] = __ddiv_rn(__dsub_rn(Fy[P.t_halo * frame + o], Fy[o]), P.t_halo == 2 ? __dmul_rn(2.0, P.c.dt) : P.c.dt);
     }
 }
 

@@ -13,6 +13,10 @@ constexpr int GW_THREADS = GW_WARPS * 32;
 
 struct K1Params {
     const double *U;
+    // nullable: a second stack of the same shape that the time derivative is taken of (ks2d:1448-1468 with
+    // --denoise-space-on features: u_t comes from the time-smoothed stack, the library from the space-smoothed one);
+    // generic kernels only
+    const double *Uy;
     int64_t T, A0, A1;
     FdConsts c;
     int dialect;

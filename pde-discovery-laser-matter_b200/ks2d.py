@@ -357,8 +357,15 @@ def fit_time_cv(U, dx, dy, DT, *, n_folds=5, dictionary="true", include_advectio
 
 def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", include_advection=False,
                    enforce_no_advection=False, block=(3, 8, 8), n_sample=50_000, alpha=1e-6, threshold=1e-10,
-                   grid_search=False, fold_of_frame=None, seed=0, variant=L.VARIANT_AUTO, signs=None):
+                   grid_search=False, fold_of_frame=None, seed=0, variant=L.VARIANT_AUTO, signs=None,
+                   denoise_time_window=1, denoise_space_sigma=0.0, denoise_space_on="features"):
     """The reference's main() hot path for one config, fused on the GPU.
+
+    ``denoise_*``: the script's optional smoothing before the path (ks2d:1448-1468): a reflect-padded moving average
+    along t, then a periodic Gaussian per frame applied to the stack the library is built from ("features": u_t still
+    comes from the time-smoothed stack, so K1 reads two stacks, generic kernel) or to both ("all": one smoothed stack,
+    the tiled kernels).  The smoothing runs as its own kernels before K1 (a separate pass over HBM; see DESIGN.md on
+    why it is not fused into K1's shared-memory tiles).
 
     method="blockwise": K1 forms block means and both folds' Grams in one pass over U; the
         70/30 row permutation (ks2d:1638-1641) stays on the host RNG and is passed as one fold
@@ -374,22 +381,38 @@ def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", incl
     torch = L.torch_cuda()
     Ud = ops.field(U)
     T, A0, A1 = Ud.shape
+    Uy = None                                   # the stack u_t is taken of, when it differs from the library's
+    if int(denoise_time_window) > 1:
+        if int(denoise_time_window) % 2 == 0:
+            raise ValueError("time smoothing window must be odd")
+        Ud = ops.time_moving_average(Ud, int(denoise_time_window))
+    if float(denoise_space_sigma) > 0.0:
+        if denoise_space_on == "all":
+            Ud = ops.gaussian_smooth_periodic(Ud, float(denoise_space_sigma))
+        elif denoise_space_on == "features":
+            Uy, Ud = Ud, ops.gaussian_smooth_periodic(Ud, float(denoise_space_sigma))
+        else:
+            raise ValueError("denoise_space_on must be 'features' or 'all'")
     rng = np.random.default_rng(seed)  # ks2d:1470
     info = {}
     exact = None
     kd = dict(dialect=L.FD_KS_PERIODIC, library=lib)
+    if Uy is not None and method not in ("blockwise", "pointwise"):
+        raise NotImplementedError("two-stack denoising is served for method='blockwise' and 'pointwise'")
     if method == "blockwise":
         bt, b0, b1 = block
         n_rows = -(-(T - 1) // bt) * -(-A0 // b0) * -(-A1 // b1)
         fold, _ = split_folds(n_rows, rng)
         stats, bad = ops.fd_lib_gram(Ud, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib, block=block,
-                                     fold_of_row=fold, n_folds=2, variant=variant, return_nonfinite=True)
+                                     fold_of_row=fold, n_folds=2, variant=variant, return_nonfinite=True, Uy=Uy)
         bad = bad.cpu()
         if int(bad[1]):
             raise ValueError(f"{int(bad[1])} block rows carry a fold id outside [0, 2)")
         if int(bad[0]):
             # non-finite rows renumber the reference's permutation: redo through materialised block rows
             # (pg_fd_block_rows; the rows are 1 / (bt b0 b1) of the field, the drop is host NumPy like the split itself)
+            if Uy is not None:
+                raise NotImplementedError("non-finite rows together with two-stack denoising")
             rows = _np(ops.fd_block_rows(Ud, dx, dy, DT, dialect=L.FD_KS_PERIODIC, library=lib, block=block))
             rows = rows[np.isfinite(rows).all(axis=1)]
             rng = np.random.default_rng(seed)
@@ -398,7 +421,7 @@ def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", incl
             stats = ops.rows_gram(Xr, yr, fold_of_row=fold, n_folds=2)[0]
             n_rows = rows.shape[0]
             exact = lambda C: ops.rows_residual_ss(Xr, yr, C, fold_of_row=fold_r, eval_fold=1)   # noqa: E731
-        else:
+        elif Uy is None:
             exact = lambda C: ops.fd_residual_ss(Ud, dx, dy, DT, C, block=block, fold_of_row=fold, n_folds=2,  # noqa: E731
                                                  eval_fold=1, **kd)
         info["X_shape"] = (n_rows, len(names))
@@ -411,7 +434,7 @@ def fit_from_field(U, dx, dy, DT, *, method="blockwise", dictionary="true", incl
     elif method == "pointwise":
         n_total = (T - 1) * A0 * A1
         flat_idx = rng.choice(n_total, size=int(min(n_sample, n_total)), replace=False)
-        X, y = ops.fd_gather_rows(Ud, dx, dy, DT, flat_idx, dialect=L.FD_KS_PERIODIC, library=lib)
+        X, y = ops.fd_gather_rows(Ud, dx, dy, DT, flat_idx, dialect=L.FD_KS_PERIODIC, library=lib, Uy=Uy)
         # ks2d:1633-1636 drops non-finite rows BEFORE the split: rows_gram's statistics turn non-finite when one is
         # present, which is the only case that needs the (host-side, 50 000 x p) filter
         probe = _np(ops.rows_gram(X, y))[0, 0]

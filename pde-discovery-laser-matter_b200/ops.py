@@ -54,13 +54,16 @@ def field(U):
 
 
 def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row=None, fold_of_frame=None,
-                n_folds=1, variant=L.VARIANT_AUTO, return_nonfinite=False, trailing_block_means=None, halo=None):
+                n_folds=1, variant=L.VARIANT_AUTO, return_nonfinite=False, trailing_block_means=None, halo=None, Uy=None):
     """K1: field -> statistics [n_folds][S(p)] without materialising Theta (pg_fd_lib_gram).
 
     ``return_nonfinite``: also return the call's four int64 counters (device tensor): [0] block rows dropped because a
     mean was not finite, [1] rows with a fold id outside [0, n_folds) (a caller error: the statistics are then NaN),
     [2] internal, [3] halo waits that timed out (statistics NaN), [4..7] SM cycle counter / globaltimer ns at the start
     and end of the tiled blockwise kernel's CTA 0 (effective SM clock of the launch).
+
+    ``Uy``: a second stack of U's shape that the time derivative is taken of (the library still comes from U):
+    pg_fd_lib_gram_two, the ks2d script's ``--denoise-space-on features`` (generic kernel).
 
     ``halo`` = (flag_ptr, epoch) from ``slabs.PeerComm.pull_halo``: U[-1] is still being filled by a copy engine; the
     kernel starts at once and reads that frame only after the flag has reached ``epoch`` (pg_fd_lib_gram_halo).
@@ -85,7 +88,13 @@ def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row
         raise ValueError(f"fold_of_frame must have one entry per row frame = {Tr} entries")
     stats = torch.empty((n_folds, L.stats_len(p)), dtype=torch.float64, device=U.device)
     bad = torch.zeros(8, dtype=torch.int64, device=U.device) if return_nonfinite else None
-    if halo is not None:
+    if Uy is not None:
+        Uy = field(Uy)
+        if Uy.shape != U.shape:
+            raise ValueError("Uy must have the shape of U")
+        L.check(lib.pg_fd_lib_gram_two(L.ptr(U), L.ptr(Uy), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0,
+                                       b1, L.ptr(fr), L.ptr(ff), n_folds, L.ptr(stats), L.ptr(bad), L.stream_ptr()))
+    elif halo is not None:
         L.check(lib.pg_fd_lib_gram_halo(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0,
                                         b1, L.ptr(fr), L.ptr(ff), n_folds, int(halo[0]), int(halo[1]), L.ptr(stats),
                                         L.ptr(bad), variant, L.stream_ptr()))
@@ -133,8 +142,9 @@ def fd_terms(U, d0, d1, dt, *, dialect, library):
     return out
 
 
-def fd_gather_rows(U, d0, d1, dt, flat_idx, *, dialect, library):
-    """K1c: sampled pointwise rows (pg_fd_gather_rows) -> (X [n][p], y [n])."""
+def fd_gather_rows(U, d0, d1, dt, flat_idx, *, dialect, library, Uy=None):
+    """K1c: sampled pointwise rows (pg_fd_gather_rows) -> (X [n][p], y [n]).  ``Uy``: the stack u_t is taken of, when
+    it is not U (pg_fd_gather_rows_two)."""
     torch = L.torch_cuda()
     lib = L.load()
     U = field(U)
@@ -143,8 +153,15 @@ def fd_gather_rows(U, d0, d1, dt, flat_idx, *, dialect, library):
     n, p = idx.numel(), L.LIB_WIDTH[library]
     X = torch.empty((n, p), dtype=torch.float64, device=U.device)
     y = torch.empty((n,), dtype=torch.float64, device=U.device)
-    L.check(lib.pg_fd_gather_rows(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, L.ptr(idx), n,
-                                  L.ptr(X), L.ptr(y), L.stream_ptr()))
+    if Uy is not None:
+        Uy = field(Uy)
+        if Uy.shape != U.shape:
+            raise ValueError("Uy must have the shape of U")
+        L.check(lib.pg_fd_gather_rows_two(L.ptr(U), L.ptr(Uy), T, A0, A1, float(d0), float(d1), float(dt), dialect, library,
+                                          L.ptr(idx), n, L.ptr(X), L.ptr(y), L.stream_ptr()))
+    else:
+        L.check(lib.pg_fd_gather_rows(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, L.ptr(idx), n,
+                                      L.ptr(X), L.ptr(y), L.stream_ptr()))
     return X, y
 
 

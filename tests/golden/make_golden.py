@@ -204,6 +204,11 @@ def golden_ks2d_configs(ks):
     runs = {
         "c1": [],
         "c1_sweep": ["--grid-search"],
+        # the optional smoothing before the path (ks2d:1448-1468), both placements of the spatial Gaussian
+        "c2_denoise_features": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05",
+                                "--denoise-time-window", "5", "--denoise-space-sigma", "1.5"],
+        "c2_denoise_all_pointwise": ["--perturbation", "N2_noise", "--noise-rel", "0.05", "--denoise-time-window", "3",
+                                     "--denoise-space-sigma", "3.0", "--denoise-space-on", "all"],
         "c2": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05"],
         "c2_rich_sweep": ["--method", "blockwise", "--perturbation", "N2_noise", "--noise-rel", "0.05",
                           "--dictionary", "rich", "--grid-search"],

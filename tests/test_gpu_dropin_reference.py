@@ -45,7 +45,7 @@ def _parse_ks(text):
 
 
 @needs_ref
-@pytest.mark.parametrize("tag", ["c1", "c1_sweep", "c2", "c2_rich_sweep"])
+@pytest.mark.parametrize("tag", ["c1", "c1_sweep", "c2", "c2_rich_sweep", "c2_denoise_features", "c2_denoise_all_pointwise"])
 def test_ks2d_main_runs_on_the_gpu_functions(tag, golden_configs):
     import pde_b200
 
@@ -64,8 +64,10 @@ def test_ks2d_main_runs_on_the_gpu_functions(tag, golden_configs):
         assert h["r2_test"] == g["r2_test"] == 1.0
         np.testing.assert_allclose(h["rmse_test"], g["rmse_test"], rtol=1e-3)    # 2e-11: the rounding noise of an exact fit
     else:
-        np.testing.assert_allclose(h["r2_test"], g["r2_test"], rtol=1e-8)
-        np.testing.assert_allclose(h["rmse_test"], g["rmse_test"], rtol=1e-8)
+        # (the denoise runs go through the periodic Gaussian, a circular convolution here and an FFT product there)
+        tol = 1e-6 if "denoise" in tag else 1e-8
+        np.testing.assert_allclose(h["r2_test"], g["r2_test"], rtol=tol)
+        np.testing.assert_allclose(h["rmse_test"], g["rmse_test"], rtol=tol)
 
 
 @needs_ref

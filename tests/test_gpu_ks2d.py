@@ -272,6 +272,24 @@ def test_exact_residuals_from_the_field_on_a_clean_blockwise_fit(K, ks_default_s
     np.testing.assert_allclose(got_fd[2], want[2], rtol=1e-12)
 
 
+@pytest.mark.parametrize("tag,kw", [
+    ("c2_denoise_features", dict(method="blockwise", denoise_time_window=5, denoise_space_sigma=1.5)),
+    ("c2_denoise_all_pointwise", dict(method="pointwise", denoise_time_window=3, denoise_space_sigma=3.0, denoise_space_on="all")),
+])
+def test_fused_path_with_the_denoising_prologue(K, ks_default_stack, golden_configs, tag, kw):
+    """ks2d:1448-1468 before the fused path: time moving average, then the periodic Gaussian on the library's stack only
+    (u_t from the other stack: pg_fd_lib_gram_two) or on both; against what the reference main() printed."""
+    U, dx, dy, DT = ks_default_stack
+    U = O.add_noise(U, 0.05, seed=999)
+    out = K.fit_from_field(U, dx, dy, DT, dictionary="true", **kw)
+    gold = golden_configs[tag]
+    assert list(out["X_shape"]) == gold["X_shape"]
+    for n, c in zip(out["names"], out["coeffs"]):
+        assert abs(c - gold["coeffs_printed"][n]) <= 1.5e-6, (n, c, gold["coeffs_printed"][n])
+    np.testing.assert_allclose(out["r2_test"], gold["hyper"]["r2_test"], rtol=1e-6)
+    np.testing.assert_allclose(out["rmse_test"], gold["hyper"]["rmse_test"], rtol=1e-6)
+
+
 def test_statistics_only_fit_flags_unreliable_metrics(K, ks_default_stack):
     """fit_from_stats without an evaluator on an exact fit: no silent clamp, the result says the metrics are noise."""
     from pde_b200 import _lib as L
