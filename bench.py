@@ -45,11 +45,14 @@ DT = 1e-3
 BLOCK = (3, 8, 8)
 C5_SIZE, C5_FRAMES = 4096, 2048      # BASELINE configs[4]
 
-# fp64 instructions per grid point of the K1 specialisations, counted per opcode (DFMA/DADD/DMUL) on the ncu source
-# pages committed under profiles/ (r01_k1_pointwise_ncu_summary.txt, r02_k1_rich_ncu_summary.txt); the fp64 roofline
-# of a variant is points/s x this / (SMs x 64 per clock x SM clock)
-FP64_PER_POINT = {"true_p3_block388": 8.2, "rich_p9_block388": 14.9, "true_adv_p5_block388": 8.6,
-                  "ks_true_p3_pointwise": 28.3, "basic_usage_p6_pointwise": 34.0}
+def fp64_per_point():
+    """fp64 instructions per grid point of the K1 specialisations, counted per opcode (DADD/DFMA/DMUL) on the ncu source
+    pages and committed as profiles/fp64_per_point.json (tools/summarize_profiles.py).  The fp64 roofline of a variant
+    is points/s x this / (SMs x 64 per clock x SM clock)."""
+    f = ROOT / "profiles" / "fp64_per_point.json"
+    if not f.exists():
+        return {}
+    return {k: v["fp64_per_point"] for k, v in json.loads(f.read_text())["kernels"].items()}
 
 
 def workload_text(args, world):
@@ -727,6 +730,8 @@ def run_ours(args):
     variants = {}
     sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
     fp64_peak = 148 * 64 * sm_hz * 1e6
+
+    FP64_PER_POINT = fp64_per_point()
 
     def variant_entry(name, ms, steps_):
         v = world * pts_k1 * steps_ / (ms * 1e-3)

@@ -1,11 +1,14 @@
 """Turn the scratch ncu outputs under gpurun_out/ into the tracked summaries under profiles/.
 
-    python tools/summarize_profiles.py r01
+    python tools/summarize_profiles.py r02
 
-Reads gpurun_out/launches_r1.csv (ncu --metrics gpu__time_duration.sum launch list of bench.py) and
-gpurun_out/prof_k1_r1.ncu-rep (ncu --set full capture of the K1 kernel), writes
-profiles/<tag>_launches_summary.csv, <tag>_launches_full.csv, <tag>_k1_tiled_ncu_summary.txt and
-profiles/k1_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic)."""
+Reads gpurun_out/launches_<tag>.csv (ncu --metrics gpu__time_duration.sum launch list of bench.py),
+gpurun_out/prof_k1_<tag>.ncu-rep (ncu --set full capture of the K1 kernel inside bench.py) and the quick_bench captures
+prof_rich_<tag>, prof_adv_<tag>, prof_pw_ks_<tag>, prof_pw_basic_<tag> (.ncu-rep); writes
+profiles/<tag>_launches_summary.csv, <tag>_launches_full.csv, <tag>_k1_tiled_ncu_summary.txt,
+<tag>_k1_variants_ncu_summary.txt, profiles/k1_traffic.json (DRAM bytes per launch, read by bench.py for
+roofline.traffic) and profiles/fp64_per_point.json (fp64 instructions per grid point of every K1 specialisation,
+counted per opcode on the ncu source pages; read by bench.py for the fp64 roofline of the variants)."""
 
 import collections
 import csv
@@ -18,7 +21,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "profiles"
 SRC = ROOT / "gpurun_out"
-CMD = "python bench.py --steps 2 --warmup 3 --no-cpu --skip-e2e --skip-variants"
+CMD = "python bench.py --steps 2 --warmup 3 --no-cpu --skip-e2e --skip-variants --skip-c5"
 ALG = 8 * 1024 * 2048 * 2048
 
 WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -39,7 +42,7 @@ TIME = {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3, "msecond": 1.0, "usecond": 
 
 
 def launches(tag):
-    rows = [r for r in csv.reader(open(SRC / "launches_r1.csv")) if r and not r[0].startswith("==")]
+    rows = [r for r in csv.reader(open(SRC / f"launches_{tag}.csv")) if r and not r[0].startswith("==")]
     hdr = rows[0]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     tot, cnt = collections.Counter(), collections.Counter()
@@ -58,12 +61,12 @@ def launches(tag):
     for k, v in tot.most_common():
         out.append(f"\"{k}\",{cnt[k]},{v:.1f},{v / T:.4f},{(v / Tt if k in timed else 0):.4f}")
     (OUT / f"{tag}_launches_summary.csv").write_text("\n".join(out) + "\n")
-    (OUT / f"{tag}_launches_full.csv").write_text((SRC / "launches_r1.csv").read_text())
+    (OUT / f"{tag}_launches_full.csv").write_text((SRC / f"launches_{tag}.csv").read_text())
     print("\n".join(out[:10]))
 
 
 def full(tag):
-    raw = subprocess.run(["ncu", "-i", str(SRC / "prof_k1_r1.ncu-rep"), "--page", "raw", "--csv"], capture_output=True,
+    raw = subprocess.run(["ncu", "-i", str(SRC / f"prof_k1_{tag}.ncu-rep"), "--page", "raw", "--csv"], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -91,14 +94,49 @@ def full(tag):
     print("\n".join(lines[-28:]))
 
 
-def pointwise(tag):
-    """ncu --set full captures of the tiled pointwise kernel (tools/quick_bench.py --pointwise --frames 256)."""
+def fp64_per_point(rep, points):
+    """fp64 thread-instructions (DADD / DFMA / DMUL) per grid point and per-opcode shares, from the ncu source page."""
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    si = ti = wi = None
+    fp = tot = warp_fp = warp_tot = 0.0
+    sections = 0
+    for r in rows:
+        if r and r[0] == "Address":                      # one header per section (ncu prints one or more per captured launch)
+            si, ti, wi = r.index("Source"), r.index("Thread Instructions Executed"), r.index("Instructions Executed")
+            sections += 1
+            continue
+        if si is None or len(r) <= max(si, ti, wi):
+            continue
+        ops = [o for o in r[si].split() if not o.startswith("@")]
+        if not ops:
+            continue
+        n, w = float(r[ti] or 0), float(r[wi] or 0)
+        tot += n
+        warp_tot += w
+        if ops[0].split(".")[0] in ("DADD", "DFMA", "DMUL"):
+            fp += n
+            warp_fp += w
+    points = points * max(sections, 1)                   # `points` = grid points of ONE launch
+    return {"fp64_per_point": fp / points, "instr_per_point": tot / points, "fp64_share_of_warp_instr": warp_fp / max(warp_tot, 1.0)}
+
+
+def variants(tag):
+    """ncu --set full captures of the other K1 specialisations (tools/quick_bench.py --frames 256 --only <case>)."""
     alg = 8 * 256 * 2048 * 2048
-    lines = ["# ncu --set full --clock-control none --import-source on -k regex:k1_tiled_pw -s 2 -c 1  "
-             "python tools/quick_bench.py --pointwise --frames 256 --only <case>",
-             f"# {tag}, B200, 2048x2048x256 fp64, every grid point a row; algorithmic bytes per launch = {alg / 1e9:.2f} GB",
-             "# bound: fp64 issue (64 DFMA/clk/SM), see sm__pipe_fp64_cycles_active"]
-    for rep, what in (("prof_pw_ks.ncu-rep", "KS dialect, true library p = 3"), ("prof_pw_basic.ncu-rep", "basic_usage dialect p = 6")):
+    pts = 256 * 2048 * 2048
+    lines = ["# ncu --set full --clock-control none --import-source on -k regex:k1_tiled -s 2 -c 1  "
+             "python tools/quick_bench.py [--pointwise] --frames 256 --only <case>",
+             f"# {tag}, B200, 2048x2048x256 fp64; algorithmic bytes per launch = {alg / 1e9:.2f} GB",
+             "# pointwise kernels are bound by fp64 issue (64 DFMA/clk/SM), see sm__pipe_fp64_cycles_active"]
+    counts = {}
+    k1 = SRC / f"prof_k1_{tag}.ncu-rep"
+    if k1.exists():
+        counts["true_p3_block388"] = fp64_per_point(k1, 1024 * 2048 * 2048)
+    for rep, what, key in ((f"prof_rich_{tag}.ncu-rep", "blockwise (3,8,8), KS rich library p = 9", "rich_p9_block388"),
+                           (f"prof_adv_{tag}.ncu-rep", "blockwise (3,8,8), KS true + advection p = 5", "true_adv_p5_block388"),
+                           (f"prof_pw_ks_{tag}.ncu-rep", "pointwise, KS dialect, true library p = 3", "ks_true_p3_pointwise"),
+                           (f"prof_pw_basic_{tag}.ncu-rep", "pointwise, basic_usage dialect p = 6", "basic_usage_p6_pointwise")):
         f = SRC / rep
         if not f.exists():
             continue
@@ -112,9 +150,17 @@ def pointwise(tag):
                     i = hdr.index(w)
                     lines.append(f"{w} = {r[i]} {units[i]}")
             ms = float(r[hdr.index("gpu__time_duration.sum")]) * TIME[units[hdr.index("gpu__time_duration.sum")]]
-            pts = 256 * 2048 * 2048
-            lines.append(f"derived: {pts / (ms / 1e3) / 1e9:.1f} G points/s; algorithmic GB/s = {alg / 1e9 / (ms / 1e3):.1f}")
-    (OUT / f"{tag}_k1_pointwise_ncu_summary.txt").write_text("\n".join(lines) + "\n")
+            g = lambda n: float(r[hdr.index(n)]) * UNIT[units[hdr.index(n)]]
+            dram = g("dram__bytes_read.sum") + g("dram__bytes_write.sum")
+            counts[key] = fp64_per_point(f, pts)
+            lines.append(f"derived: {pts / (ms / 1e3) / 1e9:.1f} G points/s; algorithmic GB/s = {alg / 1e9 / (ms / 1e3):.1f}; "
+                         f"DRAM traffic / algorithmic = {dram / alg:.4f}; fp64 instructions per point = {counts[key]['fp64_per_point']:.2f} "
+                         f"of {counts[key]['instr_per_point']:.2f} thread instructions per point")
+    (OUT / f"{tag}_k1_variants_ncu_summary.txt").write_text("\n".join(lines) + "\n")
+    if counts:
+        json.dump({"source": f"ncu source pages of the {tag} captures (tools/summarize_profiles.py): DADD + DFMA + DMUL thread "
+                             "instructions / grid points of the launch", "kernels": counts},
+                  open(OUT / "fp64_per_point.json", "w"), indent=1)
     print("\n".join(lines[-8:]))
 
 
@@ -123,4 +169,4 @@ if __name__ == "__main__":
     OUT.mkdir(exist_ok=True)
     launches(tag)
     full(tag)
-    pointwise(tag)
+    variants(tag)
