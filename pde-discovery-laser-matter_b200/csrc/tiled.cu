@@ -246,13 +246,26 @@ __device__ __forceinline__ double sum_frame_u(const double *__restrict__ st, con
 #ifndef PG_DNW
 #define PG_DNW 8
 #endif
+#ifndef PG_TILED_WS_DEFAULT
+#define PG_TILED_WS_DEFAULT 1
+#endif
 constexpr int DNW = PG_DNW;   // consumer warps
+// warp-specialised kernels: 12 warps are launched at <= 168 registers; the producer warpgroup shrinks to 72 and the two
+// consumer warpgroups grow to 216 (2 x 128 x 216 + 128 x 72 = 64512 <= 65536)
+constexpr int WS_PRODUCER_REGS = 72, WS_CONSUMER_REGS = 216;
 
 //   * EMIT: the (scaled) block-mean rows are written to P.rows8 instead of being accumulated: first stage of the path
 //     for (bt, 8m, 8n) blocks, whose rows are means of these sub-block rows (api.cu).
-template <int LIB, int NF, bool TIMEFOLD, bool EMIT = false>
-__global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap,
-                                                            const __grid_constant__ CUtensorMap tmap_last, TiledParams P) {
+//   * WS (warp-specialised): a third warpgroup is launched whose first warp is the PRODUCER: it walks the CTA's frame
+//     stream, waits for a stage to be released, paces, issues the TMA load and copies the halo-column cells of ALL
+//     bands (completion of those copies is tied to the same `full` barrier with cp.async.mbarrier.arrive), so the
+//     consumer warps no longer execute any of that control code (ncu: it was a quarter of their non-waiting time,
+//     low-IPC branches and address arithmetic repeated by all eight warps).  setmaxnreg hands the producer
+//     warpgroup's registers to the consumers, which keep their ~230 registers although 12 warps are resident.
+template <int LIB, int NF, bool TIMEFOLD, bool EMIT = false, bool WS = false>
+__global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(const __grid_constant__ CUtensorMap tmap,
+                                                                             const __grid_constant__ CUtensorMap tmap_last,
+                                                                             TiledParams P) {
     constexpr int NW = DNW;
     using G_ = Geo<NW>;
     constexpr int TI = G_::TI, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES;
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
     }
     if (tid == 0) {
         *pace_off = 0;
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], WS ? 33 : 1); mbar_init(&empty[s], NW); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -301,7 +314,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
 
     // load index g of this CTA -> (tile origin, frame); g counts every frame of every item in order
     // gl = CTA-local index of the load (pacing); one lane calls this
-    auto issue_load = [&](uint32_t s, int i0, int j0, int t, uint32_t gl) {
+    // what a load may have to wait for besides its stage: the pacing epoch and the arrival of the halo frame
+    auto load_gate = [&](int t, uint32_t gl) {
         if (P.epoch_done && (gl & ((1u << P.epoch_shift) - 1u)) == 0 && *pace_off == 0) {
             const int k = (int)(gl >> P.epoch_shift) - P.epoch_lead;
             if (k >= 0 && k < P.n_epochs) {
@@ -313,10 +327,16 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         }
         if (P.halo_flag && t == (int)P.T - 1 && !wait_flag_reached(P.halo_flag, P.halo_epoch))
             atomicAdd(&P.counters[3], 1ull);        // the frame never arrived: the API poisons the statistics
+    };
+    auto issue_tma = [&](uint32_t s, int i0, int j0, int t) {
         fence_proxy_async();
         mbar_expect_tx(&full[s], G_::TMA_BYTES);
         // the shifted tile column of a width with A1 % 16 == 8 starts inside a 16-column group: tmap_last views the field from column 8
         tma_load_4d(stages + s * STAGE_DOUBLES, (j0 & 15) ? &tmap_last : &tmap, &full[s], 0, j0 >> 4, i0 - 2, t);
+    };
+    auto issue_load = [&](uint32_t s, int i0, int j0, int t, uint32_t gl) {
+        load_gate(t, gl);
+        issue_tma(s, i0, j0, t);
     };
     // coordinates of the load `ahead` frames after frame f of `item` (geometry i0, j0, t0, nf); walks into the
     // following items of this CTA; false when the CTA's stream of frames ends before that
@@ -333,7 +353,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         ai0 = i0; aj0 = j0; at = t0 + rem;
         return true;
     };
-    if (tid == 0 && (int64_t)blockIdx.x < n_items) {
+    if (!WS && tid == 0 && (int64_t)blockIdx.x < n_items) {
         int i0, j0, nf;
         int64_t tb0;
         geometry(blockIdx.x, i0, j0, tb0, nf);
@@ -341,6 +361,63 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             int ai0, aj0, at;
             if (ahead_coords(blockIdx.x, i0, j0, (int)(tb0 * P.bt), nf, 0, a, ai0, aj0, at)) issue_load(a, ai0, aj0, at, (uint32_t)a);
         }
+    }
+    if constexpr (WS) {
+        if (warp >= NW) {
+            // ---- producer warpgroup: give the registers back, one warp feeds the ring
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_PRODUCER_REGS));
+            if (warp > NW) return;
+            auto count_epoch = [&](uint32_t g) {     // load g has been consumed by every warp
+                if (P.epoch_done && ((g + 1) & ((1u << P.epoch_shift) - 1u)) == 0 && (int)(g >> P.epoch_shift) < P.n_epochs)
+                    atomicAdd(P.epoch_done + (g >> P.epoch_shift), 1u);
+            };
+            constexpr int NC = (2 * G_::HR + 31) / 32;     // halo-column cells per lane and frame
+            uint32_t Gp = 0, s = 0, ph = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int i0, j0, nf;
+                int64_t tb0;
+                geometry(item, i0, j0, tb0, nf);
+                int hoff[NC];
+                int64_t hsrc[NC];
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    const int c = lane + 32 * k, Rr = c >> 1, side = c & 1;
+                    hoff[k] = c < 2 * G_::HR ? HOFF + Rr * 4 + side * 2 : -1;
+                    hsrc[k] = wrap((int64_t)i0 - 2 + Rr, P.A0) * P.A1 + wrap((int64_t)(side ? j0 + TJ : j0 - 2), P.A1);
+                }
+                const int t0 = (int)(tb0 * P.bt);
+                const double *Ft = P.U + (int64_t)t0 * frame;
+                for (int f = 0; f <= nf; ++f, ++Gp, Ft += frame) {
+                    // the pacing poll (a global load) and the halo-frame flag come BEFORE the wait for the stage: the
+                    // producer idles there anyway, so their latency never delays a load
+                    if (lane == 0) load_gate(t0 + f, Gp);
+                    __syncwarp();
+                    if (Gp >= NSTAGE) mbar_wait(&empty[s], ph ^ 1);   // every consumer warp has released load Gp - NSTAGE
+                    if (lane == 0) issue_tma(s, i0, j0, t0 + f);
+                    if (f < nf) {                                // the frame after a chunk only feeds u_t: own columns
+                        double *stg = stages + s * STAGE_DOUBLES;
+#pragma unroll
+                        for (int k = 0; k < NC; ++k)
+                            if (hoff[k] >= 0) cp_async16(stg + hoff[k], Ft + hsrc[k]);
+                    }
+                    cp_async_mbar_arrive_noinc(&full[s]);
+                    if (lane == 0 && Gp >= NSTAGE) count_epoch(Gp - NSTAGE);
+                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
+            cp_async_wait_all();
+            if (lane == 0 && P.epoch_done) {
+                // the last loads are still being consumed: count their epochs as they are released, then every epoch
+                // this CTA will never reach
+                for (uint32_t g = Gp > NSTAGE ? Gp - NSTAGE : 0; g < Gp; ++g) {
+                    mbar_wait(&empty[g % NSTAGE], (g / NSTAGE) & 1);
+                    count_epoch(g);
+                }
+                for (int k = (int)(Gp >> P.epoch_shift); k < P.n_epochs; ++k) atomicAdd(P.epoch_done + k, 1u);
+            }
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_CONSUMER_REGS));
     }
 
     const LaneMap lm = make_lane_map(warp * 8, HOFF, lane);
@@ -462,8 +539,8 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             }
         };
         // first frame of the item: its stage has landed => every warp released the stage's previous frame
-        mbar_wait(&full[cs], cph);
-        issue_halo(stages + cs * STAGE_DOUBLES);
+        if (!WS || need_top || need_bot) mbar_wait(&full[cs], cph);
+        if constexpr (!WS) issue_halo(stages + cs * STAGE_DOUBLES);
         issue_wrap(stages + cs * STAGE_DOUBLES, t0);
         cp_async_commit();
 
@@ -480,21 +557,36 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             // that releases it last can re-arm it without any arithmetic in between)
             int n_i0 = i0, n_j0 = j0, n_t = (int)t0 + f + NSTAGE;
             bool n_ok = true;
-            if (f + NSTAGE > nf) n_ok = ahead_coords(item, i0, j0, (int)t0, nf, f, NSTAGE, n_i0, n_j0, n_t);
-            if (f + 1 < nf) {
-                // side cells of the next frame, one frame ahead.  Its stage may still hold the frame two back:
-                // wait until every warp released that one (what the producer waits for as well).
-                const uint32_t g1 = G + 1, s1 = cs + 1 == NSTAGE ? 0 : cs + 1, ph1 = s1 == 0 ? cph ^ 1 : cph;
-                if (g1 >= NSTAGE) mbar_wait(&empty[s1], ph1 ^ 1);
-                issue_halo(stages + s1 * STAGE_DOUBLES);
-                if (need_top || need_bot) {
-                    mbar_wait(&full[s1], ph1);     // the wrap rows lie inside the TMA box
+            if constexpr (!WS) {
+                if (f + NSTAGE > nf) n_ok = ahead_coords(item, i0, j0, (int)t0, nf, f, NSTAGE, n_i0, n_j0, n_t);
+                if (f + 1 < nf) {
+                    // side cells of the next frame, one frame ahead.  Its stage may still hold the frame two back:
+                    // wait until every warp released that one (what the producer waits for as well).
+                    const uint32_t g1 = G + 1, s1 = cs + 1 == NSTAGE ? 0 : cs + 1, ph1 = s1 == 0 ? cph ^ 1 : cph;
+                    if (g1 >= NSTAGE) mbar_wait(&empty[s1], ph1 ^ 1);
+                    issue_halo(stages + s1 * STAGE_DOUBLES);
+                    if (need_top || need_bot) {
+                        mbar_wait(&full[s1], ph1);     // the wrap rows lie inside the TMA box
+                        issue_wrap(stages + s1 * STAGE_DOUBLES, t0 + f + 1);
+                    }
+                }
+                cp_async_commit();
+                mbar_wait(&full[cs], cph);
+                cp_async_wait<1>();
+            } else if (need_top || need_bot) {
+                // only the wrap rows of a border tile are still copied by the band that reads them, one frame ahead,
+                // once the TMA box they lie in has landed (the producer warp has loaded it: its stage was free)
+                if (f + 1 < nf) {
+                    const uint32_t s1 = cs + 1 == NSTAGE ? 0 : cs + 1, ph1 = s1 == 0 ? cph ^ 1 : cph;
+                    mbar_wait(&full[s1], ph1);
                     issue_wrap(stages + s1 * STAGE_DOUBLES, t0 + f + 1);
                 }
+                cp_async_commit();
+                mbar_wait(&full[cs], cph);
+                cp_async_wait<1>();
+            } else {
+                mbar_wait(&full[cs], cph);
             }
-            cp_async_commit();
-            mbar_wait(&full[cs], cph);
-            cp_async_wait<1>();
             __syncwarp();
 
             Sums F;
@@ -510,7 +602,9 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
             // writes inside the TMA box, so only their writers need the cross-proxy fence.
             if (need_top || need_bot) fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && mbar_arrive_pending(&empty[cs]) == 1) {
+            if constexpr (WS) {
+                if (lane == 0) mbar_arrive(&empty[cs]);
+            } else if (lane == 0 && mbar_arrive_pending(&empty[cs]) == 1) {
                 // every warp has consumed load G: count the epoch it closes, then re-arm the stage
                 if (P.epoch_done && ((G + 1) & ((1u << P.epoch_shift) - 1u)) == 0 && (int)(G >> P.epoch_shift) < P.n_epochs)
                     atomicAdd(P.epoch_done + (G >> P.epoch_shift), 1u);
@@ -646,7 +740,7 @@ __global__ void __launch_bounds__(32 * DNW, 1) k1_tiled_b88(const __grid_constan
         P.counters[6] = (unsigned long long)clock64();
         P.counters[7] = global_ns();
     }
-    if (P.epoch_done && warp == 0 && lane == 0)
+    if (!WS && P.epoch_done && warp == 0 && lane == 0)
         for (int k = (int)(G >> P.epoch_shift); k < P.n_epochs; ++k) atomicAdd(P.epoch_done + k, 1u);
     if (bad_rows) atomicAdd(&P.counters[0], bad_rows);
     if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
@@ -715,8 +809,13 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
 template <int LIB, int NF, bool TIMEFOLD, bool EMIT = false>
 static int launch_tiled_d(const CUtensorMap (&map)[2], const TiledParams &tp, int grid, cudaStream_t st) {
     const size_t smem = Geo<DNW>::smem(Lib<LIB>::P);
-    PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, TIMEFOLD, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1_tiled_b88<LIB, NF, TIMEFOLD, EMIT><<<grid, 32 * DNW, smem, st>>>(map[0], map[1], tp);
+    if (env_int("PG_TILED_WS", PG_TILED_WS_DEFAULT)) {
+        PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, TIMEFOLD, EMIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_tiled_b88<LIB, NF, TIMEFOLD, EMIT, true><<<grid, 32 * (DNW + 4), smem, st>>>(map[0], map[1], tp);
+    } else {
+        PG_CUDA(cudaFuncSetAttribute(k1_tiled_b88<LIB, NF, TIMEFOLD, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_tiled_b88<LIB, NF, TIMEFOLD, EMIT><<<grid, 32 * DNW, smem, st>>>(map[0], map[1], tp);
+    }
     PG_LAUNCHED();
     return PG_OK;
 }
@@ -764,11 +863,17 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
         }
     }
     tp.bt = P.bt;
-    tp.epoch_shift = 2;                                   // epochs of 4 frames
-    // a CTA may run this many epochs ahead of the slowest (PG_TILED_LEAD < 0: no pacing).  Measured at C4: DRAM traffic
-    // 1.11x the algorithmic bytes without pacing, 1.01x with lead 2 (but the waits cost more than they save), lead 4
-    // is the fastest.  The lead must cover the ring depth (a CTA waits for its own epochs too): >= 2.
-    tp.epoch_lead = env_int("PG_TILED_LEAD", 4);
+    // Pacing: epochs of 2^shift frames; a CTA may run `lead` epochs ahead of the slowest (PG_TILED_LEAD < 0: no pacing).
+    // Measured at C4 with the decoupled kernel: DRAM traffic 1.11x the algorithmic bytes without pacing, 1.01x with
+    // epochs of 4 frames and lead 2 (but the waits cost more than they save), lead 4 is the fastest.  The
+    // warp-specialised kernel is faster on the SM side, its CTAs stay closer together by themselves (1.06x without
+    // pacing) and it is the WAITS that cost: epochs of 8 frames with a lead of 16-24 are its optimum (5.10-5.15 ms
+    // against 5.27 for (4 frames, lead 16), 5.44 without pacing, 5.5-5.7 for (4 frames, lead 4); tools/k1_ab.py).
+    // The lead must cover the ring depth (a CTA waits for its own epochs too): >= 2.
+    const bool ws = env_int("PG_TILED_WS", PG_TILED_WS_DEFAULT) != 0;
+    tp.epoch_shift = env_int("PG_TILED_ESHIFT", ws ? 3 : 2);
+    if (tp.epoch_shift < 2) tp.epoch_shift = 2;           // the counters are sized for epochs of >= 4 frames
+    tp.epoch_lead = env_int("PG_TILED_LEAD", ws ? 20 : 4);
     if (tp.epoch_lead >= 0 && tp.epoch_lead < 2) tp.epoch_lead = 2;
     tp.n_epochs = (int)(plan.extra_scratch / sizeof(unsigned int)) - 1;
     tp.epoch_done = nullptr;

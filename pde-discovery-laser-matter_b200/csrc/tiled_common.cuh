@@ -61,6 +61,15 @@ __device__ __forceinline__ uint32_t mbar_arrive_pending(uint64_t *bar) {
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool zero = false) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(zero ? 0 : 16) : "memory");
 }
+// arrive on `bar` once every cp.async this thread has issued so far has completed (the barrier's expected count
+// includes this arrival: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
