@@ -317,9 +317,15 @@ __device__ __forceinline__ bool pw_flush(double (&acc)[Pw<LIB>::NACC], unsigned 
 // copies the 16-byte side cells its own window needs (halo columns of its R+4 rows; the periodic wrap
 // rows if they fall inside its window) with cp.async, one frame ahead, so they need warp-level visibility
 // only.
-template <int LIB, int R, int NW>
-__global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant__ CUtensorMap tmap,
-                                                          const __grid_constant__ CUtensorMap tmap_last, PwParams P) {
+// WS (warp-specialised, see k1_tiled_b88): a third warpgroup is launched; its first warp is the producer (stage wait,
+// TMA load, the halo-column cells of all bands, tied to the `full` barrier), the band warps keep only the wrap rows of
+// border tiles and the march.  setmaxnreg moves the producer warpgroup's registers to the consumers.
+constexpr int PW_WS_PRODUCER_REGS = 56, PW_WS_CONSUMER_REGS = 224;   // 2 x 128 x 224 + 128 x 56 = 64512 <= 65536
+
+template <int LIB, int R, int NW, bool WS = false>
+__global__ void __launch_bounds__(32 * (NW + (WS ? 4 : 0)), 1) k1_tiled_pw(const __grid_constant__ CUtensorMap tmap,
+                                                                           const __grid_constant__ CUtensorMap tmap_last,
+                                                                           PwParams P) {
     using G_ = GeoPw<R, NW>;
     using X_ = Pw<LIB>;
     constexpr int TI = G_::TI, HOFF = G_::HOFF, STAGE_DOUBLES = G_::STAGE_DOUBLES, NS = PW_NSTAGE;
@@ -332,22 +338,9 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
     uint64_t *empty = full + NS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const LaneMap lm = make_lane_map(warp * R, HOFF, lane);
-
-    double acc[X_::NACC];
-#pragma unroll
-    for (int k = 0; k < X_::NACC; ++k) acc[k] = 0.0;
-    unsigned cnt = 0;           // rows accumulated by this lane since the last flush
-    int cur_fold = -1;
-    bool poisoned = false;
-    unsigned long long bad_fold = 0;
-
-    double *slot = P.partials + ((int64_t)blockIdx.x * NW + warp) * P.n_folds * S;
-    for (int e = lane; e < P.n_folds * S; e += 32) slot[e] = 0.0;
-    __syncwarp();
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], WS ? 33 : 1); mbar_init(&empty[s], NW); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -386,7 +379,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
         ai0 = i0; aj0 = j0; at = t0 + rem;
         return true;
     };
-    if (tid == 0 && (int64_t)blockIdx.x < n_items) {
+    if (!WS && tid == 0 && (int64_t)blockIdx.x < n_items) {
         int i0, j0, t0, nf;
         geometry(blockIdx.x, i0, j0, t0, nf);
         for (int a = 0; a < NS; ++a) {
@@ -394,6 +387,60 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
             if (ahead_coords(blockIdx.x, i0, j0, t0, nf, 0, a, ai0, aj0, at)) issue_load(a, ai0, aj0, at);
         }
     }
+    if constexpr (WS) {
+        if (warp >= NW) {
+            // ---- producer warpgroup: give the registers back, one warp feeds the ring
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PW_WS_PRODUCER_REGS));
+            if (warp > NW) return;
+            constexpr int NC = (2 * G_::HR + 31) / 32;     // halo-column cells per lane and frame
+            uint32_t Gp = 0, s = 0, ph = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int i0, j0, t0, nf;
+                geometry(item, i0, j0, t0, nf);
+                int hoff[NC];
+                int64_t hsrc[NC];          // < 0: outside the frame (basic_usage) -> zero-filled
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    const int c = lane + 32 * k, Rr = c >> 1, side = c & 1;
+                    const int C = side ? j0 + TJ : j0 - 2;
+                    const int64_t gi = (int64_t)i0 - 2 + Rr;
+                    hoff[k] = c < 2 * G_::HR ? HOFF + Rr * 4 + side * 2 : -1;
+                    if constexpr (KS) hsrc[k] = wrap(gi, P.A0) * P.A1 + wrap((int64_t)C, P.A1);
+                    else hsrc[k] = (gi >= 0 && gi < P.A0 && C >= 0 && C < P.A1) ? gi * P.A1 + C : -1;
+                }
+                const double *Ft = P.U + (int64_t)t0 * frame;
+                for (int f = 0; f <= nf; ++f, ++Gp, Ft += frame) {
+                    if (Gp >= NS) mbar_wait(&empty[s], ph ^ 1);   // every band warp has released load Gp - NS
+                    if (lane == 0) issue_load(s, i0, j0, t0 + f);
+                    if (f < nf) {                                // the frame after a chunk only feeds u_t: own columns
+                        double *stg = stages + s * STAGE_DOUBLES;
+#pragma unroll
+                        for (int k = 0; k < NC; ++k)
+                            if (hoff[k] >= 0) cp_async16(stg + hoff[k], hsrc[k] >= 0 ? Ft + hsrc[k] : P.U, hsrc[k] < 0);
+                    }
+                    cp_async_mbar_arrive_noinc(&full[s]);
+                    if (++s == NS) { s = 0; ph ^= 1; }
+                }
+            }
+            cp_async_wait_all();
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PW_WS_CONSUMER_REGS));
+    }
+
+    const LaneMap lm = make_lane_map(warp * R, HOFF, lane);
+
+    double acc[X_::NACC];
+#pragma unroll
+    for (int k = 0; k < X_::NACC; ++k) acc[k] = 0.0;
+    unsigned cnt = 0;           // rows accumulated by this lane since the last flush
+    int cur_fold = -1;
+    bool poisoned = false;
+    unsigned long long bad_fold = 0;
+
+    double *slot = P.partials + ((int64_t)blockIdx.x * NW + warp) * P.n_folds * S;
+    for (int e = lane; e < P.n_folds * S; e += 32) slot[e] = 0.0;
+    __syncwarp();
 
     uint32_t G = 0;  // consumer load index (stage = G % NS, parity = (G / NS) & 1)
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -447,9 +494,10 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
             w_row[k] = need ? Rr : -1;
             w_src[k] = wrap((int64_t)i0 - 2 + Rr, P.A0) * P.A1 + j0;
         }
+        const bool has_wrap = KS && (w_row[0] >= 0 || w_row[1] >= 0 || w_row[2] >= 0 || w_row[3] >= 0);   // warp-uniform
         auto issue_cells = [&](double *stage, int64_t t) {
             const double *Ft = P.U + t * frame;
-            if (h_off >= 0) cp_async16(stage + h_off, h_src >= 0 ? Ft + h_src : P.U, h_src < 0);
+            if (!WS && h_off >= 0) cp_async16(stage + h_off, h_src >= 0 ? Ft + h_src : P.U, h_src < 0);
             if constexpr (KS) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -463,20 +511,23 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
 
         int fold_next = P.fold_of_frame ? __ldg(P.fold_of_frame + t0) : 0;
         mbar_wait(&full[G % NS], (G / NS) & 1);
-        issue_cells(stages + (G % NS) * STAGE_DOUBLES, t0);
+        if (!WS || has_wrap) issue_cells(stages + (G % NS) * STAGE_DOUBLES, t0);
 
         for (int f = 0; f <= nf; ++f, ++G) {
             const double *st = stages + (G % NS) * STAGE_DOUBLES;
             // where this frame's stage goes next, known up front so that re-arming it costs no arithmetic
             int n_i0 = i0, n_j0 = j0, n_t = t0 + f + NS;
             bool n_ok = true;
-            if (f + NS > nf) n_ok = ahead_coords(item, i0, j0, t0, nf, f, NS, n_i0, n_j0, n_t);
+            if constexpr (!WS)
+                if (f + NS > nf) n_ok = ahead_coords(item, i0, j0, t0, nf, f, NS, n_i0, n_j0, n_t);
             if (f < nf) {
                 double *stn = stages + ((G + 1) % NS) * STAGE_DOUBLES;
                 mbar_wait(&full[(G + 1) % NS], ((G + 1) / NS) & 1);   // frame t+1: u_t now, differentiated next
-                if (f + 1 < nf) issue_cells(stn, (int64_t)t0 + f + 1);
-                else cp_async_commit();
-                cp_async_wait<1>();                                    // this frame's cells have landed
+                if (!WS || has_wrap) {
+                    if (f + 1 < nf) issue_cells(stn, (int64_t)t0 + f + 1);
+                    else cp_async_commit();
+                    cp_async_wait<1>();                                // this frame's cells have landed
+                }
                 __syncwarp();
                 const int fold = fold_next;
                 if (f + 1 < nf && P.fold_of_frame) fold_next = __ldg(P.fold_of_frame + t0 + f + 1);
@@ -502,9 +553,11 @@ __global__ void __launch_bounds__(32 * NW, 1) k1_tiled_pw(const __grid_constant_
             }
             // release the stage: this warp has read everything it needs from load G (only the wrap rows are
             // generic-proxy writes inside the TMA box: their writers fence towards the async proxy)
-            if (KS && (w_row[0] >= 0 || w_row[1] >= 0 || w_row[2] >= 0 || w_row[3] >= 0)) fence_proxy_async();
+            if (has_wrap) fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && mbar_arrive_pending(&empty[G % NS]) == 1 && n_ok) issue_load(G % NS, n_i0, n_j0, n_t);
+            if constexpr (WS) {
+                if (lane == 0) mbar_arrive(&empty[G % NS]);
+            } else if (lane == 0 && mbar_arrive_pending(&empty[G % NS]) == 1 && n_ok) issue_load(G % NS, n_i0, n_j0, n_t);
         }
     }
     cp_async_wait<0>();
@@ -560,15 +613,25 @@ bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan) {
     return true;
 }
 
-template <int LIB, int R, int NW> static int launch_pw_g(const CUtensorMap (&map)[2], const PwParams &pp, int grid, cudaStream_t st) {
+// Measured (256 x 2048^2, B200): basic_usage p = 6 2.81 -> 2.69 ms (2.97 -> 2.72 with two folds), KS advection 3.02 -> 2.99,
+// KS p = 3 2.36 -> 2.39 (the march is 95 % of that kernel and it is fp64-issue bound either way), rich p = 9 slower
+// (it needs more than the 224 registers a consumer gets).  Default (-1): the basic_usage dialect and KS advection only.
+#ifndef PG_PW_WS_DEFAULT
+#define PG_PW_WS_DEFAULT -1
+#endif
+template <int LIB, int R, int NW, bool WS = false>
+static int launch_pw_g(const CUtensorMap (&map)[2], const PwParams &pp, int grid, cudaStream_t st) {
     using G_ = GeoPw<R, NW>;
-    PG_CUDA(cudaFuncSetAttribute(k1_tiled_pw<LIB, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
-    k1_tiled_pw<LIB, R, NW><<<grid, G_::THREADS, G_::SMEM, st>>>(map[0], map[1], pp);
+    PG_CUDA(cudaFuncSetAttribute(k1_tiled_pw<LIB, R, NW, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM));
+    k1_tiled_pw<LIB, R, NW, WS><<<grid, G_::THREADS + (WS ? 128 : 0), G_::SMEM, st>>>(map[0], map[1], pp);
     PG_LAUNCHED();
     return PG_OK;
 }
 template <int LIB> static int launch_pw_t(const CUtensorMap (&map)[2], const PwParams &pp, int grid, int geo, cudaStream_t st) {
-    return geo == 1 ? launch_pw_g<LIB, 4, 12>(map, pp, grid, st) : launch_pw_g<LIB, 6, 8>(map, pp, grid, st);
+    if (geo == 1) return launch_pw_g<LIB, 4, 12>(map, pp, grid, st);
+    const int ws = env_int("PG_PW_WS", PG_PW_WS_DEFAULT);
+    if (ws > 0 || (ws < 0 && (LIB == PG_LIB_BASIC || LIB == PG_LIB_KS_TRUE_ADV))) return launch_pw_g<LIB, 6, 8, true>(map, pp, grid, st);
+    return launch_pw_g<LIB, 6, 8>(map, pp, grid, st);
 }
 
 int tiled_pw_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, cudaStream_t st) {
