@@ -684,6 +684,13 @@ def run_ours(args):
     launches = lib.pg_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     k1_ms, k1_best = float(np.mean(k1_all)), float(np.min(k1_all))
+    k1_ranks = None
+    if world > 1:
+        # the step is the max over ranks: every rank's own K1 mean, so that the line shows the skew between the GPUs
+        mine = torch.tensor([k1_ms], dtype=torch.float64, device="cuda")
+        allk = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        k1_ranks = [round(float(x.item()), 3) for x in allk]
     pts_k1 = sum(b - a + 1 for a, b in job.sub) * A * A       # points the K1 launches of one step read
     pts_step = (job.hi - job.lo + 1) * A * A                   # points this rank processes per step
     if args.workload == "c5":
@@ -874,7 +881,7 @@ def run_ours(args):
                      "algorithmic_bytes": 8 * pts_k1, "peak_source": peak_src,
                      # fastest single step of the timed region (see profiles/README.md on the sustained-loop drift)
                      "k1_ms_best": k1_best, "frac_best": 8.0 * pts_k1 / (k1_best * 1e-3) / 1e9 / peak,
-                     "k1_ms_steps": [round(x, 3) for x in k1_all],
+                     "k1_ms_steps": [round(x, 3) for x in k1_all], "k1_ms_ranks": k1_ranks,
                      "frac_of_nominal_8TBps": achieved / 8000.0},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 30 * 3 * 8,

@@ -164,11 +164,15 @@ PG_API int pg_fd_lib_gram_halo(const double *U, int64_t T, int64_t A0, int64_t A
 /*
  * The same with TWO stacks: the library columns come from U, the time derivative from Uy (same shape).  This is the
  * ks2d script's optional denoising with --denoise-space-on features (ks2d:1448-1468, 1510-1511): u_t is taken of the
- * time-smoothed stack, the features of the additionally space-smoothed one.  Generic kernel (reference arithmetic).
+ * time-smoothed stack, the features of the additionally space-smoothed one.  (bt, 8, 8) blocks of the KS dialect run
+ * through the tiled kernel over U: the block mean of the forward difference telescopes to a difference of (8, 8) block
+ * sums of Uy's frames k bt, which a small kernel forms first (it reads 1 / bt of Uy); everything else (pointwise rows,
+ * ragged remainders, other dialects, variant = PG_VARIANT_GENERIC) uses the generic kernel (reference arithmetic).
  */
 PG_API int pg_fd_lib_gram_two(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1,
                        double dt, int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
-                       const int32_t *fold_of_frame, int n_folds, double *stats_out, int64_t *nonfinite_out, void *stream);
+                       const int32_t *fold_of_frame, int n_folds, double *stats_out, int64_t *nonfinite_out, int variant,
+                       void *stream);
 PG_API int pg_fd_gather_rows_two(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1,
                           double dt, int fd_dialect, int library_id, const int64_t *flat_idx, int64_t n, double *X_out,
                           double *y_out, void *stream);

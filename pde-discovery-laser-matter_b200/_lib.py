@@ -60,7 +60,7 @@ _PROTOS = {
     "pg_allreduce_stats": (C.c_int, [_ptr, _ptr, _i32, _ptr]),
     "pg_halo_exchange": (C.c_int, [_ptr, _ptr, _ptr, C.c_size_t, _ptr, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "pg_fd_lib_gram_two": (C.c_int, [_ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr,
-                                     _i32, _ptr, _ptr, _ptr]),
+                                     _i32, _ptr, _ptr, _i32, _ptr]),
     "pg_fd_gather_rows_two": (C.c_int, [_ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _ptr, _i64, _ptr, _ptr, _ptr]),
     "pg_fd_terms": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _ptr, _ptr]),
     "pg_fd_gather_rows": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _i32, _i32, _ptr, _i64, _ptr, _ptr, _ptr]),

@@ -213,10 +213,12 @@ int pg_fd_lib_gram_halo(const double *U, int64_t T, int64_t A0, int64_t A1, doub
 
 int pg_fd_lib_gram_two(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt,
                        int fd_dialect, int library_id, int bt, int b0, int b1, const uint8_t *fold_of_row,
-                       const int32_t *fold_of_frame, int n_folds, double *stats_out, int64_t *nonfinite_out, void *stream) {
+                       const int32_t *fold_of_frame, int n_folds, double *stats_out, int64_t *nonfinite_out, int variant,
+                       void *stream) {
     if (!Uy) PG_FAIL(PG_EINVAL, "Uy is null (use pg_fd_lib_gram)");
+    if (reinterpret_cast<uintptr_t>(Uy) & 15) variant = PG_VARIANT_GENERIC;     // the block-sum kernel reads 16-byte cells
     return fd_lib_gram_impl(U, Uy, T, A0, A1, d0, d1, dt, fd_dialect, library_id, bt, b0, b1, fold_of_row, fold_of_frame, n_folds,
-                            nullptr, nullptr, 0, stats_out, nonfinite_out, PG_VARIANT_GENERIC, stream);
+                            nullptr, nullptr, 0, stats_out, nonfinite_out, variant, stream);
 }
 
 static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_t A0, int64_t A1, double d0, double d1, double dt, int fd_dialect,
@@ -249,7 +251,7 @@ static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_
     const int64_t nBt = (Trows + bt - 1) / bt;
     P.nB0 = (P.R0 + b0 - 1) / b0; P.nB1 = (P.R1 + b1 - 1) / b1;
 
-    if (variant != PG_VARIANT_GENERIC && !halo_flag) {
+    if (variant != PG_VARIANT_GENERIC && !halo_flag && !Uy) {
         rc = two_stage_blocks(P, library_id, nBt, len, stats_out, nonfinite_out, st);
         if (rc <= 0) return rc;
     }
@@ -258,7 +260,9 @@ static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_
     bool tiled = false, pointwise = false;
     if (variant != PG_VARIANT_GENERIC) {
         pointwise = bt == 1 && b0 == 1 && b1 == 1;
-        tiled = pointwise ? tiled_pw_plan(P, library_id, sm_count(), plan) : tiled_plan(P, library_id, nBt, sm_count(), plan);
+        // two stacks: the blockwise kernel takes the time derivative from block sums of Uy; pointwise rows would need
+        // both stacks in shared memory and stay with the generic kernel
+        tiled = pointwise ? (!Uy && tiled_pw_plan(P, library_id, sm_count(), plan)) : tiled_plan(P, library_id, nBt, sm_count(), plan);
         if (!tiled && variant == PG_VARIANT_TILED)
             PG_FAIL(PG_EUNSUPPORTED, "no tiled kernel for dialect %d library %d block (%d,%d,%d) shape (%lld,%lld,%lld)",
                     fd_dialect, library_id, bt, b0, b1, (long long)T, (long long)A0, (long long)A1);
@@ -292,7 +296,9 @@ static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_
         gen_parts += (int64_t)box_ctas[k] * GW_WARPS;
     }
     const int64_t tiled_parts = tiled ? plan.n_parts : 0;
-    const size_t bytes = 64 + sizeof(double) * (size_t)((gen_parts + tiled_parts) * len) + (tiled ? plan.extra_scratch : 0);
+    const size_t b_extra = tiled ? (plan.extra_scratch + 15) / 16 * 16 : 0;
+    const size_t b_ysums = (tiled && Uy) ? sizeof(double) * (size_t)((nBt + 1) * ((A0 + 7) / 8) * (A1 / 8)) : 0;
+    const size_t bytes = 64 + sizeof(double) * (size_t)((gen_parts + tiled_parts) * len) + b_extra + b_ysums;
     void *scr = nullptr;
     rc = scratch_for(st, bytes, &scr);
     if (rc) return rc;
@@ -301,6 +307,12 @@ static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_
     PG_CUDA(cudaMemsetAsync(counters, 0, 64, st));
     P.counters = counters;
     int64_t part_off = 0;
+    if (tiled && Uy) {
+        double *ys = (double *)((char *)(partials + (gen_parts + tiled_parts) * len) + b_extra);
+        rc = launch_frame_block_sums8(Uy, T, A0, A1, bt, nBt, ys, st);
+        if (rc) return rc;
+        P.y_sums = ys;
+    }
     if (tiled) {
         rc = pointwise ? tiled_pw_launch(P, library_id, plan, partials, st)
                        : tiled_launch(P, library_id, plan, partials, (char *)(partials + (gen_parts + tiled_parts) * len), st);

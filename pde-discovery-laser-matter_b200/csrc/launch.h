@@ -44,6 +44,8 @@ struct K1Params {
     // (tiled blockwise kernel only: pg_fd_lib_gram_halo).  counters[3] counts waits that timed out.
     const unsigned int *halo_flag;
     unsigned int halo_epoch;
+    // two-stack path through the tiled blockwise kernel: block sums of Uy's frames min(k bt, T - 1) (launch_frame_block_sums8)
+    const double *y_sums;
 };
 
 struct RowsParams {
@@ -144,5 +146,7 @@ bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &pl
 // rows8 != null: write the block-mean rows [nbt][A0/8][A1/8][p+1] instead of accumulating statistics
 int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, char *extra, cudaStream_t st,
                  double *rows8 = nullptr);
+// out [nbt + 1][ceil(A0 / 8)][A1 / 8]: (8, 8) block sums of frames min(k bt, T - 1) of Uy
+int launch_frame_block_sums8(const double *Uy, int64_t T, int64_t A0, int64_t A1, int bt, int64_t nbt, double *out, cudaStream_t st);
 
 }  // namespace pg

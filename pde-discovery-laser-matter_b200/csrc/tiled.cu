@@ -84,6 +84,11 @@ struct TiledParams {
     // it may be loaded only once *halo_flag has reached halo_epoch (pg_fd_lib_gram_halo)
     const unsigned int *halo_flag;
     unsigned int halo_epoch;
+    // nullable: the time derivative is taken of ANOTHER stack (pg_fd_lib_gram_two).  Over a t-block it telescopes to a
+    // difference of (8, 8) block sums of that stack's frames min(k bt, T - 1), k = 0 .. nbt, which a small kernel has
+    // put here as [nbt + 1][ysum_nb0][A1c / 8]; the block sums of u of THIS stack then only feed the rich library's column.
+    const double *y_sums;
+    int64_t ysum_nb0;
 };
 
 // ----------------------------------------------------------------------------- per-lane block sums
@@ -615,6 +620,10 @@ __global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(con
             // a t-block ends after bt frames, or with the stack (ragged last block: fewer frames, ks2d:384-389)
             if (((fb == 0 && f > 0) || (f == nf && fb != 0)) && band_ok) {
                 double SY = F.SU - su_first;
+                if (P.y_sums) {
+                    const double *ys = P.y_sums + (tbs * P.ysum_nb0 + ib) * (int64_t)(P.A1c >> 3) + jb;
+                    SY = (lane & 8) ? 0.0 : ys[P.ysum_nb0 * (int64_t)(P.A1c >> 3)] - ys[0];
+                }
 #define PG_PAIR(x) x += __shfl_xor_sync(0xffffffffu, x, 8)
                 PG_PAIR(A.SL); PG_PAIR(A.SE1); PG_PAIR(A.SE2); PG_PAIR(A.SGx); PG_PAIR(A.SGy); PG_PAIR(SY);
                 if constexpr (kNeedAdv<LIB>) { PG_PAIR(A.SDx); PG_PAIR(A.SDy); }
@@ -753,6 +762,38 @@ __global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(con
     }
 }
 
+// (8, 8) block sums of the frames min(k bt, T - 1), k = 0 .. nbt, of a stack: the y side of the two-stack path.
+// One thread per block, 16-byte loads (rows are 16-byte aligned: A1 even); a warp reads 2 KB of each of its 8 rows.
+__global__ void frame_block_sums8_kernel(const double *__restrict__ Uy, int64_t T, int64_t A0, int64_t A1, int bt, int64_t nbt,
+                                         int64_t nb0, int64_t nb1, double *__restrict__ out) {
+    const int64_t n = (nbt + 1) * nb0 * nb1;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t jb = idx % nb1, ib = (idx / nb1) % nb0, k = idx / (nb1 * nb0);
+        const int64_t t = min(k * bt, T - 1);
+        double s = 0.0;
+        if (ib * 8 + 8 <= A0) {
+            const double *F = Uy + t * A0 * A1 + ib * 8 * A1 + jb * 8;
+            double r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double2 *q = reinterpret_cast<const double2 *>(F + i * A1);
+                const double2 a = q[0], b = q[1], c = q[2], d = q[3];
+                r[i] = ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
+            }
+            s = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        }
+        out[idx] = s;
+    }
+}
+
+int launch_frame_block_sums8(const double *Uy, int64_t T, int64_t A0, int64_t A1, int bt, int64_t nbt, double *out, cudaStream_t st) {
+    const int64_t nb0 = (A0 + 7) / 8, nb1 = A1 / 8, n = (nbt + 1) * nb0 * nb1;
+    int64_t g = (n + 255) / 256;
+    frame_block_sums8_kernel<<<(unsigned)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g)), 256, 0, st>>>(Uy, T, A0, A1, bt, nbt, nb0, nb1, out);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
 // ----------------------------------------------------------------------------- host side
 // eight consumer warps per CTA (DNW): one 64 x 128 tile, one CTA per SM
 
@@ -889,6 +930,7 @@ int tiled_launch(const K1Params &P, int lib, const TiledPlan &plan, double *part
     tp.rows8 = rows8;
     tp.tail_means = P.tail_means;
     tp.halo_flag = P.halo_flag; tp.halo_epoch = P.halo_epoch;
+    tp.y_sums = P.y_sums; tp.ysum_nb0 = (P.A0 + 7) / 8;
     switch (lib) {
         case PG_LIB_KS_TRUE: return launch_tiled_t<PG_LIB_KS_TRUE>(map, tp, P.n_folds, NW, plan.grid, st);
         case PG_LIB_KS_TRUE_ADV: return launch_tiled_t<PG_LIB_KS_TRUE_ADV>(map, tp, P.n_folds, NW, plan.grid, st);

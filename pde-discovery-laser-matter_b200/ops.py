@@ -63,7 +63,8 @@ def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row
     and end of the tiled blockwise kernel's CTA 0 (effective SM clock of the launch).
 
     ``Uy``: a second stack of U's shape that the time derivative is taken of (the library still comes from U):
-    pg_fd_lib_gram_two, the ks2d script's ``--denoise-space-on features`` (generic kernel).
+    pg_fd_lib_gram_two, the ks2d script's ``--denoise-space-on features``.  (bt, 8, 8) blocks go through the tiled kernel
+    (the block mean of u_t telescopes to block sums of Uy's frames k bt), pointwise rows through the generic kernel.
 
     ``halo`` = (flag_ptr, epoch) from ``slabs.PeerComm.pull_halo``: U[-1] is still being filled by a copy engine; the
     kernel starts at once and reads that frame only after the flag has reached ``epoch`` (pg_fd_lib_gram_halo).
@@ -93,7 +94,7 @@ def fd_lib_gram(U, d0, d1, dt, *, dialect, library, block=(1, 1, 1), fold_of_row
         if Uy.shape != U.shape:
             raise ValueError("Uy must have the shape of U")
         L.check(lib.pg_fd_lib_gram_two(L.ptr(U), L.ptr(Uy), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0,
-                                       b1, L.ptr(fr), L.ptr(ff), n_folds, L.ptr(stats), L.ptr(bad), L.stream_ptr()))
+                                       b1, L.ptr(fr), L.ptr(ff), n_folds, L.ptr(stats), L.ptr(bad), variant, L.stream_ptr()))
     elif halo is not None:
         L.check(lib.pg_fd_lib_gram_halo(L.ptr(U), T, A0, A1, float(d0), float(d1), float(dt), dialect, library, bt, b0,
                                         b1, L.ptr(fr), L.ptr(ff), n_folds, int(halo[0]), int(halo[1]), L.ptr(stats),

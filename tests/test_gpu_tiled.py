@@ -281,3 +281,70 @@ def torch_zeros(ops, n):
     import torch
 
     return torch.zeros(n, dtype=torch.float64, device="cuda")
+
+
+@pytest.mark.parametrize("block,libname,shape", [((3, 8, 8), "LIB_KS_TRUE", (10, 128, 256)),
+                                                 ((3, 8, 8), "LIB_KS_RICH", (9, 72, 144)),      # ragged tile row, shifted column
+                                                 ((3, 16, 16), "LIB_KS_TRUE", (7, 128, 256)),   # EMIT instantiation (two-stage route)
+                                                 ((1, 1, 1), "LIB_KS_TRUE", (6, 96, 256)),      # pointwise kernel
+                                                 ((1, 1, 1), "LIB_KS_TRUE_ADV", (6, 50, 136)),  # pointwise, ragged tile row, shifted column
+                                                 ((1, 1, 1), "LIB_BASIC", (6, 100, 264))])
+def test_producer_warp_and_decoupled_kernels_agree(env, monkeypatch, block, libname, shape):
+    """Both structures of the tiled kernels stay under parity: with the producer warp (warp-specialised, setmaxnreg) and
+    without it (every warp copies its own halo cells, the last arrival re-arms the stage).  The work assignment and the
+    order of every floating-point operation are the same, so the statistics must agree BIT FOR BIT, with time folds, per-row
+    folds and no folds; one of them is also checked against the generic reference-arithmetic kernel."""
+    L, ops = env
+    lib = getattr(L, libname)
+    p = L.LIB_WIDTH[lib]
+    U = field(ops, shape, seed=11)
+    basic = libname == "LIB_BASIC"
+    kw = dict(dialect=L.FD_BASIC_TRIM if basic else L.FD_KS_PERIODIC, library=lib, block=block)
+    fof = (np.arange(shape[0] - 1) >= shape[0] // 2).astype(np.int32)
+    cases = [dict(), dict(fold_of_frame=fof, n_folds=2)]
+    if block == (3, 8, 8):
+        nb = -(-(shape[0] - 1) // 3) * (shape[1] // 8) * (shape[2] // 8)
+        cases.append(dict(fold_of_row=np.random.default_rng(3).integers(0, 2, size=nb).astype(np.uint8), n_folds=2))
+    for extra in cases:
+        out = {}
+        for ws in ("0", "1"):
+            monkeypatch.setenv("PG_TILED_WS", ws)
+            monkeypatch.setenv("PG_PW_WS", ws)
+            out[ws] = ops.fd_lib_gram(U, 0.5, 0.4, 1e-3, variant=L.VARIANT_TILED, **kw, **extra).cpu().numpy()
+        assert np.array_equal(out["0"], out["1"]), (block, libname, sorted(extra))
+        monkeypatch.delenv("PG_TILED_WS")
+        monkeypatch.delenv("PG_PW_WS")
+        gen = ops.fd_lib_gram(U, 0.5, 0.4, 1e-3, variant=L.VARIANT_GENERIC, **kw, **extra).cpu().numpy()
+        for f in range(gen.shape[0]):
+            assert_stats_close(out["1"][f], gen[f], p)
+
+
+@pytest.mark.parametrize("libname", ["LIB_KS_TRUE", "LIB_KS_RICH"])
+@pytest.mark.parametrize("shape,bt", [((10, 128, 256), 3), ((9, 72, 144), 3), ((8, 76, 328), 2), ((12, 192, 128), 5)])
+def test_two_stack_tiled_vs_generic_and_oracle(env, libname, shape, bt):
+    """pg_fd_lib_gram_two (ks2d:1448-1468, --denoise-space-on features): the library from U, the time derivative from a
+    second stack Uy.  (bt, 8, 8) blocks run through the tiled kernel over U with y from (8, 8) block sums of Uy's frames
+    k bt; against the generic kernel on the same two stacks and against the oracle's rows, with and without folds."""
+    from oracle import ks2d as O
+
+    L, ops = env
+    lib = getattr(L, libname)
+    p = L.LIB_WIDTH[lib]
+    U = field(ops, shape, seed=5)
+    Uy = field(ops, shape, seed=6) * 0.7 + 0.3 * U          # a different stack, correlated with U
+    d0, d1, dt = 0.5, 0.4, 1e-3
+    kw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=(bt, 8, 8))
+    fof = (np.arange(shape[0] - 1) >= shape[0] // 2).astype(np.int32)
+    for extra in (dict(), dict(fold_of_frame=fof, n_folds=2)):
+        gen = ops.fd_lib_gram(U, d0, d1, dt, Uy=Uy, variant=L.VARIANT_GENERIC, **kw, **extra).cpu().numpy()
+        til = ops.fd_lib_gram(U, d0, d1, dt, Uy=Uy, variant=L.VARIANT_TILED, **kw, **extra).cpu().numpy()
+        for f in range(gen.shape[0]):
+            assert_stats_close(til[f], gen[f], p)
+    Uh, Uyh = U.cpu().numpy(), Uy.cpu().numpy()
+    names, terms = (O.build_dictionary_true if libname == "LIB_KS_TRUE" else O.build_dictionary)(Uh[:-1], d0, d1)
+    X, y = O.build_blockwise_dataset((Uyh[1:] - Uyh[:-1]) / dt, terms, names, block_t=bt, block_x=8, block_y=8)
+    assert_stats_close(til[0] + til[1], gram.pack_stats(X, y), p)
+    # the same stack twice must reproduce the one-stack statistics
+    one = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_TILED, **kw).cpu().numpy()[0]
+    two = ops.fd_lib_gram(U, d0, d1, dt, Uy=U, variant=L.VARIANT_TILED, **kw).cpu().numpy()[0]
+    assert_stats_close(two, one, p)
