@@ -86,6 +86,7 @@ _PROTOS = {
     "pg_reflect_conv": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _i32, _ptr, _i32, _ptr, _ptr]),
     "pg_time_moving_average": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr]),
     "pg_periodic_conv": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr, _i32, _ptr, _ptr]),
+    "pg_periodic_gaussian_fft": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _ptr]),
     "pg_synth_field": (C.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _u64, _i32, _dbl, _ptr]),
 }
 EXPORTS = tuple(_PROTOS)

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <map>
+#include <vector>
 #include <mutex>
 #include <utility>
 
@@ -700,6 +701,34 @@ int pg_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int ax
     if (axis != 0 && axis != 1) PG_FAIL(PG_EINVAL, "axis must be 0 or 1");
     if (in == out) PG_FAIL(PG_EINVAL, "in-place convolution is not supported");
     return launch_periodic_conv(in, T, A0, A1, axis, offsets, weights, n_taps, out, (cudaStream_t)stream);
+}
+
+int pg_periodic_gaussian_fft(const double *in, int64_t T, int64_t A0, int64_t A1, double sigma_px, double *out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!in || !out) PG_FAIL(PG_EINVAL, "null buffer");
+    if (T < 1 || A0 < 2 || A1 < 2 || A0 > 0x7fffffff || A1 > 0x7fffffff) PG_FAIL(PG_EINVAL, "bad shape");
+    if (!(sigma_px > 0.0)) PG_FAIL(PG_EINVAL, "sigma_px must be > 0");
+    if (in == out) PG_FAIL(PG_EINVAL, "in-place smoothing is not supported");
+    // H(kx, ky) = exp(-sigma^2 (kx^2 + ky^2) / 2) with k = 2 pi fftfreq(n) (ks2d:133-136), split into its two factors
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<double> hx((size_t)A0), hy((size_t)(A1 / 2 + 1));
+    for (int64_t i = 0; i < A0; ++i) {
+        const double f = (double)(i < (A0 + 1) / 2 ? i : i - A0) / (double)A0, k = two_pi * f;
+        hx[(size_t)i] = exp(-0.5 * sigma_px * sigma_px * k * k) / ((double)A0 * (double)A1);
+    }
+    for (int64_t j = 0; j <= A1 / 2; ++j) {
+        const double f = (double)(j < (A1 + 1) / 2 ? j : j - A1) / (double)A1, k = two_pi * f;
+        hy[(size_t)j] = exp(-0.5 * sigma_px * sigma_px * k * k);
+    }
+    int64_t batch = 1;
+    const size_t bytes = periodic_gaussian_fft_scratch(T, A0, A1, &batch);
+    void *scr = nullptr;
+    int rc = scratch_for(st, bytes, &scr);
+    if (rc) return rc;
+    rc = launch_periodic_gaussian_fft(in, T, A0, A1, hx.data(), hy.data(), out, scr, batch, st);
+    if (rc) return rc;
+    PG_CUDA(cudaStreamSynchronize(st));     // hx / hy are host vectors copied asynchronously
+    return PG_OK;
 }
 
 int pg_synth_field(double *U, int64_t T, int64_t A0, int64_t A1, int64_t t_offset, int64_t T_total, uint64_t seed,

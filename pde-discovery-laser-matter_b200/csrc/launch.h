@@ -121,6 +121,11 @@ int launch_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A
 int launch_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int axis, const int32_t *off, const double *w,
                          int n_taps, double *out, cudaStream_t st);
 
+// periodic Gaussian as an FFT product (cuFFT through dlopen): hx [A0] (includes 1 / (A0 A1)), hy [A1 / 2 + 1] on the HOST
+size_t periodic_gaussian_fft_scratch(int64_t T, int64_t A0, int64_t A1, int64_t *batch_out);
+int launch_periodic_gaussian_fft(const double *in, int64_t T, int64_t A0, int64_t A1, const double *hx_host, const double *hy_host,
+                                 double *out, void *scratch, int64_t batch, cudaStream_t st);
+
 int launch_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, int axis, const double *w, int radius,
                         void *out, cudaStream_t st);
 

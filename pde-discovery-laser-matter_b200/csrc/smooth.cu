@@ -7,6 +7,12 @@
 //                                k^2 / 2)), whose taps beyond ~9 sigma are below 1e-17 of the peak: two passes of
 //                                a short periodic stencil (taps computed on the host) reproduce the FFT result
 //                                to rounding without any FFT
+#include <dlfcn.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -39,20 +45,24 @@ __global__ void time_moving_average_kernel(const double *__restrict__ U, int64_t
 }
 
 // out[t][i][j] = sum_k w[k] in[t][wrap(i - off[k])][j]  (axis 0)  or  in[t][i][wrap(j - off[k])]  (axis 1)
+// One thread per output, rows of the stack (t, i) over blockIdx.y / grid-stride, columns over blockIdx.x: no division
+// per point.  Taps are accumulated in the order given (the order of the host's tap list fixes the rounding).
 __global__ void periodic_conv_kernel(const double *__restrict__ in, int64_t T, int64_t A0, int64_t A1, int axis,
                                      const int32_t *__restrict__ off, const double *__restrict__ w, int n_taps,
                                      double *__restrict__ out) {
-    const int64_t frame = A0 * A1, total = T * frame;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t = idx / frame, r = idx % frame, i = r / A1, j = r % A1;
-        const double *F = in + t * frame;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A1) return;
+    for (int64_t row = blockIdx.y; row < T * A0; row += gridDim.y) {
+        const int64_t t = row / A0, i = row - t * A0;       // one division per row of threads
+        const double *F = in + t * A0 * A1;
         double s = 0.0;
         if (axis == 0) {
-            for (int k = 0; k < n_taps; ++k) s = fma(w[k], F[wrap(i - off[k], A0) * A1 + j], s);
+            for (int k = 0; k < n_taps; ++k) s = fma(__ldg(w + k), F[wrap(i - __ldg(off + k), A0) * A1 + j], s);
         } else {
-            for (int k = 0; k < n_taps; ++k) s = fma(w[k], F[i * A1 + wrap(j - off[k], A1)], s);
+            const double *R = F + i * A1;
+            for (int k = 0; k < n_taps; ++k) s = fma(__ldg(w + k), R[wrap(j - __ldg(off + k), A1)], s);
         }
-        out[idx] = s;
+        out[row * A1 + j] = s;
     }
 }
 
@@ -112,8 +122,116 @@ int launch_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_
 
 int launch_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int axis, const int32_t *off, const double *w,
                          int n_taps, double *out, cudaStream_t st) {
-    periodic_conv_kernel<<<grid_of(T * A0 * A1), 256, 0, st>>>(in, T, A0, A1, axis, off, w, n_taps, out);
+    const int64_t rows = T * A0;
+    dim3 grid((unsigned)((A1 + 127) / 128), (unsigned)(rows < 148 * 64 ? rows : 148 * 64));
+    periodic_conv_kernel<<<grid, 128, 0, st>>>(in, T, A0, A1, axis, off, w, n_taps, out);
     PG_LAUNCHED();
+    return PG_OK;
+}
+
+// ----------------------------------------------------------------------------- periodic Gaussian through the FFT
+// gaussian_smooth_periodic_2d IS an FFT product in the reference (ks2d:125-142).  For sigma below ~2.8 px the periodic
+// Gaussian rings and the direct convolution needs ALL n taps per axis (O(n) per point: seconds on a 2048^2 stack), so
+// large frames go the reference's own way: batched real-to-complex 2-D transforms, the product with
+// H = exp(-sigma^2 (kx^2 + ky^2) / 2) / (A0 A1) in one kernel, and the inverse.  cuFFT is a library call like the
+// reference's np.fft (it is resolved with dlopen at first use, so the library has no link-time dependency on it and
+// the entry point fails loudly where it is missing); the product kernel is ours.
+namespace {
+struct Cufft {
+    void *h = nullptr;
+    int (*PlanMany)(int *, int, int *, int *, int, int, int *, int, int, int, int) = nullptr;
+    int (*SetStream)(int, cudaStream_t) = nullptr;
+    int (*ExecD2Z)(int, double *, double2 *) = nullptr;
+    int (*ExecZ2D)(int, double2 *, double *) = nullptr;
+    int (*Destroy)(int) = nullptr;
+    bool ok = false, tried = false;
+};
+Cufft g_cufft;
+std::mutex g_cufft_mu;
+struct PlanKey {
+    int dev;
+    int64_t a0, a1, batch;
+    bool operator<(const PlanKey &o) const {
+        return dev != o.dev ? dev < o.dev : a0 != o.a0 ? a0 < o.a0 : a1 != o.a1 ? a1 < o.a1 : batch < o.batch;
+    }
+};
+std::map<PlanKey, std::pair<int, int>> g_plans;   // (forward D2Z, inverse Z2D)
+
+bool cufft_load() {
+    if (g_cufft.tried) return g_cufft.ok;
+    g_cufft.tried = true;
+    const char *names[] = {"libcufft.so.11", "/usr/local/cuda/lib64/libcufft.so.11", "libcufft.so", "/usr/local/cuda/lib64/libcufft.so"};
+    for (const char *n : names) {
+        g_cufft.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (g_cufft.h) break;
+    }
+    if (!g_cufft.h) return false;
+    g_cufft.PlanMany = (decltype(g_cufft.PlanMany))dlsym(g_cufft.h, "cufftPlanMany");
+    g_cufft.SetStream = (decltype(g_cufft.SetStream))dlsym(g_cufft.h, "cufftSetStream");
+    g_cufft.ExecD2Z = (decltype(g_cufft.ExecD2Z))dlsym(g_cufft.h, "cufftExecD2Z");
+    g_cufft.ExecZ2D = (decltype(g_cufft.ExecZ2D))dlsym(g_cufft.h, "cufftExecZ2D");
+    g_cufft.Destroy = (decltype(g_cufft.Destroy))dlsym(g_cufft.h, "cufftDestroy");
+    g_cufft.ok = g_cufft.PlanMany && g_cufft.SetStream && g_cufft.ExecD2Z && g_cufft.ExecZ2D && g_cufft.Destroy;
+    return g_cufft.ok;
+}
+}  // namespace
+
+// spec[b][i][j] *= hx[i] * hy[j]   (j = 0 .. A1/2; hx carries the 1 / (A0 A1) of the unnormalised inverse)
+__global__ void spectrum_scale_kernel(double2 *__restrict__ spec, int64_t rows, int64_t A0, int64_t nc,
+                                      const double *__restrict__ hx, const double *__restrict__ hy) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nc) return;
+    const double b = hy[j];
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const double a = hx[row % A0] * b;
+        double2 v = spec[row * nc + j];
+        v.x *= a; v.y *= a;
+        spec[row * nc + j] = v;
+    }
+}
+
+size_t periodic_gaussian_fft_scratch(int64_t T, int64_t A0, int64_t A1, int64_t *batch_out) {
+    const int64_t per = A0 * (A1 / 2 + 1) * (int64_t)sizeof(double2);
+    int64_t batch = (int64_t)(512ll << 20) / per;      // spectra of up to 512 MB at a time
+    if (batch < 1) batch = 1;
+    if (batch > T) batch = T;
+    *batch_out = batch;
+    return (size_t)(batch * per) + 2 * 16 + sizeof(double) * (size_t)(A0 + A1 / 2 + 1);
+}
+
+int launch_periodic_gaussian_fft(const double *in, int64_t T, int64_t A0, int64_t A1, const double *hx_host, const double *hy_host,
+                                 double *out, void *scratch, int64_t batch, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_cufft_mu);
+    if (!cufft_load()) PG_FAIL(PG_EUNSUPPORTED, "libcufft.so.11 could not be loaded (dlopen): use pg_periodic_conv");
+    int dev = 0;
+    PG_CUDA(cudaGetDevice(&dev));
+    const int64_t nc = A1 / 2 + 1;
+    double2 *spec = (double2 *)scratch;
+    double *hx = (double *)((char *)scratch + ((batch * A0 * nc * sizeof(double2) + 15) / 16) * 16);
+    double *hy = hx + A0;
+    PG_CUDA(cudaMemcpyAsync(hx, hx_host, sizeof(double) * A0, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(hy, hy_host, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+    for (int64_t t0 = 0; t0 < T; t0 += batch) {
+        const int64_t nb = T - t0 < batch ? T - t0 : batch;
+        auto it = g_plans.find({dev, A0, A1, nb});
+        if (it == g_plans.end()) {
+            int n[2] = {(int)A0, (int)A1}, pf = 0, pi = 0;
+            if (g_cufft.PlanMany(&pf, 2, n, nullptr, 1, 0, nullptr, 1, 0, 0x6a /* CUFFT_D2Z */, (int)nb) != 0 ||
+                g_cufft.PlanMany(&pi, 2, n, nullptr, 1, 0, nullptr, 1, 0, 0x6c /* CUFFT_Z2D */, (int)nb) != 0)
+                PG_FAIL(PG_ECUDA, "cufftPlanMany failed for %lld x %lld x %lld", (long long)nb, (long long)A0, (long long)A1);
+            it = g_plans.emplace(PlanKey{dev, A0, A1, nb}, std::make_pair(pf, pi)).first;
+        }
+        const int pf = it->second.first, pi = it->second.second;
+        if (g_cufft.SetStream(pf, st) != 0 || g_cufft.SetStream(pi, st) != 0) PG_FAIL(PG_ECUDA, "cufftSetStream failed");
+        if (g_cufft.ExecD2Z(pf, const_cast<double *>(in) + t0 * A0 * A1, spec) != 0) PG_FAIL(PG_ECUDA, "cufftExecD2Z failed");
+        PG_LAUNCHED();
+        const int64_t rows = nb * A0;
+        dim3 grid((unsigned)((nc + 127) / 128), (unsigned)(rows < 148 * 64 ? rows : 148 * 64));
+        spectrum_scale_kernel<<<grid, 128, 0, st>>>(spec, rows, A0, nc, hx, hy);
+        PG_LAUNCHED();
+        if (g_cufft.ExecZ2D(pi, spec, out + t0 * A0 * A1) != 0) PG_FAIL(PG_ECUDA, "cufftExecZ2D failed");
+        PG_LAUNCHED();
+    }
     return PG_OK;
 }
 

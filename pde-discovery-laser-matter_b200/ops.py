@@ -521,14 +521,26 @@ def periodic_gaussian_taps(n, sigma_px):
     return off.astype(np.int32), g[off % n].astype(np.float64)
 
 
-def gaussian_smooth_periodic(U, sigma_px):
-    """gaussian_smooth_periodic_2d (ks2d:125-142) for every frame of U: two passes of pg_periodic_conv."""
+def gaussian_smooth_periodic(U, sigma_px, method="auto"):
+    """gaussian_smooth_periodic_2d (ks2d:125-142) for every frame of U.  ``method``: "conv" = two passes of
+    pg_periodic_conv (a direct circular convolution with the taps of the periodic Gaussian: no FFT, but all n taps per
+    axis when sigma < 2.82 px and at least 53 otherwise), "fft" = pg_periodic_gaussian_fft (the reference's own
+    formulation, cuFFT), "auto" = the FFT for frames of 128 x 128 and more (256 x 2048^2, sigma = 3: 29 ms against
+    226 ms; sigma = 1, where the direct route needs all 2048 taps: 29 ms against ~11 s), the direct route below."""
     torch = L.torch_cuda()
     lib = L.load()
     U = field(U)
     T, A0, A1 = U.shape
     if float(sigma_px) <= 0:
         return U.clone()
+    if method not in ("auto", "conv", "fft"):
+        raise ValueError("method must be 'auto', 'conv' or 'fft'")
+    if method == "auto":
+        method = "fft" if (A0 >= 128 and A1 >= 128) else "conv"
+    if method == "fft":
+        out = torch.empty_like(U)
+        L.check(lib.pg_periodic_gaussian_fft(L.ptr(U), T, A0, A1, float(sigma_px), L.ptr(out), L.stream_ptr()))
+        return out
     tmp, out = torch.empty_like(U), torch.empty_like(U)
     for axis, src, dst, n in ((0, U, tmp, A0), (1, tmp, out, A1)):
         off, w = periodic_gaussian_taps(n, sigma_px)

@@ -536,3 +536,24 @@ def test_fit_streamed_from_host_stacks():
         got = slabs.fit_streamed(src, 0.5, 0.5, 1e-3, fold_of_frame=fof, slab_frames=48, **kw).cpu().numpy()
         for f in range(2):
             assert_stats_close(got[f], ref[f], 3, rtol=1e-12)
+
+
+@pytest.mark.parametrize("shape,sigma", [((3, 128, 192), 1.0), ((2, 256, 130), 0.8), ((2, 144, 128), 3.5), ((1, 129, 131), 1.5)])
+def test_periodic_gaussian_fft_route(shape, sigma):
+    """pg_periodic_gaussian_fft (the reference's own formulation of gaussian_smooth_periodic_2d, ks2d:125-142: an FFT
+    product) against the oracle's NumPy FFT and against the direct circular convolution (pg_periodic_conv), on frames
+    with even and odd extents; 1e-13 of the frame's magnitude like the direct route."""
+    from oracle import ks2d as O
+    from pde_b200 import ops
+
+    rng = np.random.default_rng(shape[1])
+    U = rng.standard_normal(shape) + 0.3
+    fft = ops.gaussian_smooth_periodic(U, sigma, method="fft").cpu().numpy()
+    conv = ops.gaussian_smooth_periodic(U, sigma, method="conv").cpu().numpy()
+    auto = ops.gaussian_smooth_periodic(U, sigma).cpu().numpy()
+    for t in range(shape[0]):
+        ref = O.gaussian_smooth_periodic_2d(U[t], sigma)
+        scale = np.abs(ref).max()
+        assert np.abs(fft[t] - ref).max() <= 1e-13 * scale
+        assert np.abs(conv[t] - ref).max() <= 1e-13 * scale
+        assert np.abs(auto[t] - ref).max() <= 1e-13 * scale
