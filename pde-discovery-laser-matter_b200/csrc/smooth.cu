@@ -79,11 +79,13 @@ __device__ __forceinline__ int64_t symmetric_index(int64_t i, int64_t n) {
 template <typename T_>
 __global__ void reflect_conv_kernel(const T_ *__restrict__ in, int64_t T, int64_t A0, int64_t A1, int axis,
                                     const double *__restrict__ w, int radius, T_ *__restrict__ out) {
-    const int64_t frame = A0 * A1, total = T * frame;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t = idx / frame, r = idx % frame, i = r / A1, j = r % A1;
-        const T_ *F = in + t * frame;
-        double acc = __dmul_rn((double)F[r], w[radius]);
+    // columns over blockIdx.x, rows of the stack (t, i) over blockIdx.y / grid-stride: one division per row of threads
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A1) return;
+    for (int64_t row = blockIdx.y; row < T * A0; row += gridDim.y) {
+        const int64_t t = row / A0, i = row - t * A0;
+        const T_ *F = in + t * A0 * A1;
+        double acc = __dmul_rn((double)F[i * A1 + j], __ldg(w + radius));
         for (int jj = -radius; jj < 0; ++jj) {
             double a, b;
             if (axis == 0) {
@@ -93,9 +95,9 @@ __global__ void reflect_conv_kernel(const T_ *__restrict__ in, int64_t T, int64_
                 a = (double)F[i * A1 + symmetric_index(j + jj, A1)];
                 b = (double)F[i * A1 + symmetric_index(j - jj, A1)];
             }
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), w[radius + jj]));
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), __ldg(w + radius + jj)));
         }
-        out[idx] = (T_)acc;
+        out[row * A1 + j] = (T_)acc;
     }
 }
 
@@ -112,10 +114,12 @@ int launch_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A
 
 int launch_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, int axis, const double *w, int radius,
                         void *out, cudaStream_t st) {
+    const int64_t rows = T * A0;
+    dim3 grid((unsigned)((A1 + 127) / 128), (unsigned)(rows < 148 * 64 ? rows : 148 * 64));
     if (dtype == 0)
-        reflect_conv_kernel<float><<<grid_of(T * A0 * A1), 256, 0, st>>>((const float *)in, T, A0, A1, axis, w, radius, (float *)out);
+        reflect_conv_kernel<float><<<grid, 128, 0, st>>>((const float *)in, T, A0, A1, axis, w, radius, (float *)out);
     else
-        reflect_conv_kernel<double><<<grid_of(T * A0 * A1), 256, 0, st>>>((const double *)in, T, A0, A1, axis, w, radius, (double *)out);
+        reflect_conv_kernel<double><<<grid, 128, 0, st>>>((const double *)in, T, A0, A1, axis, w, radius, (double *)out);
     PG_LAUNCHED();
     return PG_OK;
 }
