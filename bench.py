@@ -405,7 +405,7 @@ def run_ours(args):
                 torch.empty((self.Tbuf, A, A), dtype=torch.float64, device="cuda")
             split = int(0.7 * g_rows) // BLOCK[0] * BLOCK[0]
             self.fof = [torch.from_numpy((np.arange(a, b) >= split).astype(np.int32)).cuda() for a, b in sub]
-            self.k1_ev, self.pass_ev = [], []
+            self.k1_ev, self.pass_ev, self.tail_ev = [], [], []
             self.fill(0)
 
         def fill(self, ps, true_halo=False):
@@ -494,19 +494,27 @@ def run_ours(args):
                     self.fill(ps)
                 s = self.k1(ps, library, block, variant, record)
                 stats = s if stats is None else ops.stats_accumulate(stats, s)
+            if record and self.w > 1:
+                e_a = torch.cuda.Event(enable_timing=True)
+                e_a.record()
             stats = self.reduce(stats)
             p = L.LIB_WIDTH[library]
             self.last_stats = stats
-            return ops.stridge_batched(stats[0], p, dialect=L.STRIDGE_KS, flags=L.STRIDGE_RMS_PRESCALE, alphas=alphas,
-                                       thresholds=thrs, max_iter=25, const_cols=[0] if p in (7, 9) else [],
-                                       eval_stats=stats[1])
+            out = ops.stridge_batched(stats[0], p, dialect=L.STRIDGE_KS, flags=L.STRIDGE_RMS_PRESCALE, alphas=alphas,
+                                      thresholds=thrs, max_iter=25, const_cols=[0] if p in (7, 9) else [],
+                                      eval_stats=stats[1])
+            if record and self.w > 1:
+                e_b = torch.cuda.Event(enable_timing=True)
+                e_b.record()
+                self.tail_ev.append((e_a, e_b))
+            return out
 
         def time(self, steps, warmup):
             """(ms per step: device time of the hot path, max over ranks; K1 ms per step list)"""
             for _ in range(warmup):
                 out = self.step()
             barrier() if self.w > 1 else torch.cuda.synchronize()
-            self.k1_ev, self.pass_ev = [], []
+            self.k1_ev, self.pass_ev, self.tail_ev = [], [], []
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(steps):
@@ -519,6 +527,13 @@ def run_ours(args):
                 ms = float(sum(a.elapsed_time(b) for a, b in self.pass_ev))
             ms = max_over_ranks(ms) if self.w > 1 else ms
             k1_all = [sum(a.elapsed_time(b) for a, b in iv) for iv in self.k1_ev]
+            # this rank's mean time from the end of K1 to the end of K3 (all-reduce: waits for the slowest rank) and from
+            # the start of the exchange to the start of K1 (barrier: waits for the slowest rank's previous step)
+            self.phase_ms = None
+            if self.w > 1 and self.tail_ev:
+                tail = float(np.mean([a.elapsed_time(b) for a, b in self.tail_ev]))
+                head = float(np.mean([p[0].elapsed_time(k[0][0]) for p, k in zip(self.pass_ev, self.k1_ev)])) if self.passes == 1 else None
+                self.phase_ms = (head, tail)
             return ms / steps, k1_all, out
 
         def parity(self):
@@ -684,13 +699,20 @@ def run_ours(args):
     launches = lib.pg_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     k1_ms, k1_best = float(np.mean(k1_all)), float(np.min(k1_all))
-    k1_ranks = None
+    k1_ranks, phase_ranks = None, None
     if world > 1:
         # the step is the max over ranks: every rank's own K1 mean, so that the line shows the skew between the GPUs
         mine = torch.tensor([k1_ms], dtype=torch.float64, device="cuda")
         allk = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allk, mine)
         k1_ranks = [round(float(x.item()), 3) for x in allk]
+        ph = getattr(job, "phase_ms", None)
+        if ph is not None:
+            mine = torch.tensor([ph[0] if ph[0] is not None else -1.0, ph[1]], dtype=torch.float64, device="cuda")
+            allp = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allp, mine)
+            phase_ranks = {"exchange_to_k1_start_ms": [round(float(x[0].item()), 3) for x in allp],
+                           "k1_end_to_k3_end_ms": [round(float(x[1].item()), 3) for x in allp]}
     pts_k1 = sum(b - a + 1 for a, b in job.sub) * A * A       # points the K1 launches of one step read
     pts_step = (job.hi - job.lo + 1) * A * A                   # points this rank processes per step
     if args.workload == "c5":
@@ -881,7 +903,7 @@ def run_ours(args):
                      "algorithmic_bytes": 8 * pts_k1, "peak_source": peak_src,
                      # fastest single step of the timed region (see profiles/README.md on the sustained-loop drift)
                      "k1_ms_best": k1_best, "frac_best": 8.0 * pts_k1 / (k1_best * 1e-3) / 1e9 / peak,
-                     "k1_ms_steps": [round(x, 3) for x in k1_all], "k1_ms_ranks": k1_ranks,
+                     "k1_ms_steps": [round(x, 3) for x in k1_all], "k1_ms_ranks": k1_ranks, "phase_ms_ranks": phase_ranks,
                      "frac_of_nominal_8TBps": achieved / 8000.0},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 30 * 3 * 8,
