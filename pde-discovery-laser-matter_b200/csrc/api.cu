@@ -299,7 +299,8 @@ static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_
     const int64_t tiled_parts = tiled ? plan.n_parts : 0;
     const size_t b_extra = tiled ? (plan.extra_scratch + 15) / 16 * 16 : 0;
     const size_t b_ysums = (tiled && Uy) ? sizeof(double) * (size_t)((nBt + 1) * ((A0 + 7) / 8) * (A1 / 8)) : 0;
-    const size_t bytes = 64 + sizeof(double) * (size_t)((gen_parts + tiled_parts) * len) + b_extra + b_ysums;
+    const size_t b_pwext = (tiled && pointwise) ? (tiled_pw_external_scratch(P, library_id) + 15) / 16 * 16 : 0;
+    const size_t bytes = 64 + sizeof(double) * (size_t)((gen_parts + tiled_parts) * len) + b_extra + b_ysums + b_pwext;
     void *scr = nullptr;
     rc = scratch_for(st, bytes, &scr);
     if (rc) return rc;
@@ -330,10 +331,14 @@ static int fd_lib_gram_impl(const double *U, const double *Uy, int64_t T, int64_
         if (rc) return rc;
         part_off += (int64_t)box_ctas[k] * GW_WARPS;
     }
-    if (fallback)
+    if (fallback) {
         rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st, counters + 2, tiled_parts,
                                     (int64_t)box_ctas[0] * GW_WARPS, counters);
-    else
+        if (rc) return rc;
+        if (b_pwext)
+            rc = tiled_pw_external(P, library_id, (double *)((char *)(partials + (gen_parts + tiled_parts) * len) + b_extra + b_ysums),
+                                   counters + 2, stats_out, st);
+    } else
         rc = launch_reduce_partials(partials, part_off, len, stats_out, 0, st, nullptr, 0, 0, counters);
     if (rc) return rc;
     if (nonfinite_out)

@@ -145,6 +145,11 @@ int launch_rollout(int lib, const double *U, int64_t A0, int64_t A1, const FdCon
 // tiled_pw.cu (pointwise rows)
 bool tiled_pw_plan(const K1Params &P, int lib, int n_sm, TiledPlan &plan);
 int tiled_pw_launch(const K1Params &P, int lib, const TiledPlan &plan, double *partials, cudaStream_t st);
+// boundary terms the tiled pointwise kernel leaves out of its accumulators (basic_usage library): scratch bytes, and the
+// launches that add them to the reduced statistics (skipped on the device when *skip_if != 0)
+size_t tiled_pw_external_scratch(const K1Params &P, int lib);
+int tiled_pw_external(const K1Params &P, int lib, double *per_frame, const unsigned long long *skip_if, double *stats_out,
+                      cudaStream_t st);
 
 // tiled.cu ((bt,8,8) block means)
 bool tiled_plan(const K1Params &P, int lib, int64_t nBt, int n_sm, TiledPlan &plan);

@@ -122,7 +122,30 @@ template <int LIB> __host__ __device__ constexpr bool pw_zero(int b) {
     if (LIB == PG_LIB_KS_TRUE_ADV) return b == 2 || b == 3 || b == 5 || b == 6;   // + u_x, u_y
     if (LIB == PG_LIB_KS_RICH) return b >= 4 && b <= 7;                    // u_x, u_y, lap, bih
     if (LIB == PG_LIB_KS_RICH_NOADV) return b == 4 || b == 5;              // lap, bih
+    // basic_usage: not zero, but a BOUNDARY term of the trimmed interior (pw_external below): not accumulated here
+    if (LIB == PG_LIB_BASIC) return b == 3 || b == 4 || b == 5;             // u_x, u_y, lap
     return false;
+}
+
+// basic_usage dialect: the rows are the interior [2:-2, 2:-2] of every frame, and some sums over it telescope to boundary
+// terms (summation by parts; j along a1, i along a0, W = A1, H = A0, sums over the interior of the other axis):
+//   sum (u[j+1] - u[j-1])          = u[W-2] + u[W-3] - u[1] - u[2]                 (u_x; the same along a0 for u_y)
+//   sum (u[j+1] - 2 u[j] + u[j-1]) = (u[W-2] - u[W-3]) - (u[2] - u[1])             (the two halves of lap)
+//   sum u[j] (u[j+1] - u[j-1])     = u[W-3] u[W-2] - u[1] u[2]                      (u u_x; the same for u u_y)
+// So five of the 34 fp64 operations per point (the linear sums of u_x, u_y, lap and the products u u_x, u u_y) are not
+// accumulated by the kernel; basic_boundary_kernel forms them from two rows / columns on each side of every frame (1 %
+// of its bytes) and basic_external_add_kernel adds them to the reduced statistics.  pw_external(a, b): index 0..4 of
+// that quantity for the unique pair (a, b), else -1.
+__host__ __device__ constexpr int pw_external_basic(int a, int b) {
+    if (a == 0 && b == 3) return 0;   // sum u_x
+    if (a == 0 && b == 4) return 1;   // sum u_y
+    if (a == 0 && b == 5) return 2;   // sum lap
+    if (a == 2 && b == 3) return 3;   // sum u u_x
+    if (a == 2 && b == 4) return 4;   // sum u u_y
+    return -1;
+}
+template <int LIB> __host__ __device__ constexpr bool pw_skip_pair(int a, int b) {
+    return LIB == PG_LIB_BASIC && pw_external_basic(a, b) >= 3;
 }
 
 template <int LIB, int NU, int NACC> __device__ __forceinline__ void pw_accumulate(double (&acc)[NACC], const double (&x)[NU - 1]) {
@@ -133,7 +156,10 @@ template <int LIB, int NU, int NACC> __device__ __forceinline__ void pw_accumula
 #pragma unroll
     for (int a = 1; a < NU; ++a)
 #pragma unroll
-        for (int b = a; b < NU; ++b) { acc[k] = fma(x[a - 1], x[b - 1], acc[k]); ++k; }
+        for (int b = a; b < NU; ++b) {
+            if (!pw_skip_pair<LIB>(a, b)) acc[k] = fma(x[a - 1], x[b - 1], acc[k]);
+            ++k;
+        }
 }
 
 // scale of each unique entry (the factor its unscaled accumulation lacks)
@@ -268,7 +294,8 @@ template <int LIB, int E> __device__ __forceinline__ void pw_emit(const double (
     if (lane == (E & 31)) {
         double v;
         if constexpr (pr.a == 0 && pr.b == 0) v = n;
-        else if constexpr (pr.a == 0 && pw_zero<LIB>(pr.b)) v = 0.0;      // periodic sum of a difference stencil
+        else if constexpr (pr.a == 0 && pw_zero<LIB>(pr.b)) v = 0.0;      // periodic sum of a difference stencil / boundary term
+        else if constexpr (pw_skip_pair<LIB>(pr.a, pr.b)) v = 0.0;        // boundary term (basic_usage)
         else if constexpr (pr.a == 0 && pw_dup<LIB>(pr.b).a != 0) {
             constexpr PwPair d = pw_dup<LIB>(pr.b);     // linear sum of a product column: held by the pair's accumulator
             v = acc[pw_slot(X_::NU, d.a, d.b)] * (sc[d.a] * sc[d.b]);
@@ -564,6 +591,91 @@ __global__ void __launch_bounds__(32 * (NW + (WS ? 4 : 0)), 1) k1_tiled_pw(const
     if (cur_fold >= 0) poisoned |= pw_flush<LIB>(acc, cnt, P, lane, slot + cur_fold * S);
     if (bad_fold) atomicAdd(&P.counters[1], bad_fold);
     if (poisoned && lane == 0) atomicAdd(&P.counters[2], 1ull);
+}
+
+// ----------------------------------------------------------------------------- basic_usage boundary terms
+// Per frame t (one CTA): the five unscaled boundary sums of pw_external_basic, reduced in a fixed order.
+__global__ void __launch_bounds__(256) basic_boundary_kernel(const double *__restrict__ U, int64_t A0, int64_t A1, double rho,
+                                                            double *__restrict__ out /* [T-1][5] */) {
+    const double *F = U + (int64_t)blockIdx.x * A0 * A1;
+    double v[5] = {0, 0, 0, 0, 0};
+    // rows i = 2 .. A0-3: columns 1, 2, W-3, W-2
+    for (int64_t i = 2 + threadIdx.x; i < A0 - 2; i += blockDim.x) {
+        const double *R = F + i * A1;
+        const double c1 = R[1], c2 = R[2], c3 = R[A1 - 3], c4 = R[A1 - 2];
+        v[0] += (c4 + c3) - (c1 + c2);
+        v[2] += (c4 - c3) - (c2 - c1);
+        v[3] += c3 * c4 - c1 * c2;
+    }
+    // columns j = 2 .. A1-3: rows 1, 2, H-3, H-2
+    for (int64_t j = 2 + threadIdx.x; j < A1 - 2; j += blockDim.x) {
+        const double r1 = F[A1 + j], r2 = F[2 * A1 + j], r3 = F[(A0 - 3) * A1 + j], r4 = F[(A0 - 2) * A1 + j];
+        v[1] += (r4 + r3) - (r1 + r2);
+        v[2] = fma(rho, (r4 - r3) - (r2 - r1), v[2]);
+        v[4] += r3 * r4 - r1 * r2;
+    }
+    __shared__ double sh[5][256];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sh[k][threadIdx.x] = v[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x < 5) out[(int64_t)blockIdx.x * 5 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// One warp per (fold, quantity): sums the frames of the fold in a fixed order and adds scale * sum to every statistics
+// entry that holds the quantity.  Skipped when the tiled kernel's result is not used (*skip_if != 0: the exact fallback ran).
+struct BasicExternalMap {
+    int n_e[5];
+    int e[5][4];
+    double scale[5];
+};
+__global__ void basic_external_add_kernel(const double *__restrict__ per_frame, int64_t n_frames, const int32_t *__restrict__ fold_of_frame,
+                                          int n_folds, int S, BasicExternalMap map, const unsigned long long *__restrict__ skip_if,
+                                          double *__restrict__ stats) {
+    if (skip_if && *skip_if != 0) return;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= n_folds * 5) return;
+    const int fold = warp / 5, k = warp % 5;
+    double s = 0.0;
+    for (int64_t t = lane; t < n_frames; t += 32)
+        if ((fold_of_frame ? fold_of_frame[t] : 0) == fold) s += per_frame[t * 5 + k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0)
+        for (int q = 0; q < map.n_e[k]; ++q) stats[fold * S + map.e[k][q]] += map.scale[k] * s;
+}
+
+size_t tiled_pw_external_scratch(const K1Params &P, int lib) {
+    return lib == PG_LIB_BASIC ? sizeof(double) * 5 * (size_t)(P.T - 1) : 0;
+}
+
+// after the reduction: add the boundary terms the tiled pointwise kernel leaves out (basic_usage library only)
+int tiled_pw_external(const K1Params &P, int lib, double *per_frame, const unsigned long long *skip_if, double *stats_out,
+                      cudaStream_t st) {
+    if (lib != PG_LIB_BASIC) return PG_OK;
+    const int64_t nrf = P.T - 1;
+    const double rho = P.c.d1sq / P.c.d0sq;
+    basic_boundary_kernel<<<(unsigned)nrf, 256, 0, st>>>(P.U, P.A0, P.A1, rho, per_frame);
+    PG_LAUNCHED();
+    using X_ = Pw<PG_LIB_BASIC>;
+    BasicExternalMap map{};
+    const double h0 = 1.0 / P.c.two_d0, h1 = 1.0 / P.c.two_d1, r1 = 1.0 / P.c.d1sq;
+    const double scale[5] = {h1, h0, r1, h1, h0};      // unique columns: u_x = a1-difference * h1, u_y = a0-difference * h0
+    for (int k = 0; k < 5; ++k) map.scale[k] = scale[k];
+    for (int e = 0; e < X_::S; ++e) {
+        const PwPair pr = pw_entry(e, X_::P, X_::ONE);
+        const int k = pw_external_basic(pr.a, pr.b);
+        if (k >= 0) map.e[k][map.n_e[k]++] = e;
+    }
+    const int warps = P.n_folds * 5;
+    basic_external_add_kernel<<<(warps * 32 + 127) / 128, 128, 0, st>>>(per_frame, nrf, P.fold_of_frame, P.n_folds, X_::S, map, skip_if, stats_out);
+    PG_LAUNCHED();
+    return PG_OK;
 }
 
 // ----------------------------------------------------------------------------- host side
