@@ -348,3 +348,10 @@ def test_two_stack_tiled_vs_generic_and_oracle(env, libname, shape, bt):
     one = ops.fd_lib_gram(U, d0, d1, dt, variant=L.VARIANT_TILED, **kw).cpu().numpy()[0]
     two = ops.fd_lib_gram(U, d0, d1, dt, Uy=U, variant=L.VARIANT_TILED, **kw).cpu().numpy()[0]
     assert_stats_close(two, one, p)
+    # pointwise rows of two stacks have no tiled kernel: the default route is the generic kernel, asking for the tiled one fails loudly
+    pw = dict(dialect=L.FD_KS_PERIODIC, library=lib, block=(1, 1, 1))
+    a = ops.fd_lib_gram(U, d0, d1, dt, Uy=Uy, **pw).cpu().numpy()[0]
+    b = ops.fd_lib_gram(U, d0, d1, dt, Uy=Uy, variant=L.VARIANT_GENERIC, **pw).cpu().numpy()[0]
+    assert np.array_equal(a, b)
+    with pytest.raises(L.PdeGramError):
+        ops.fd_lib_gram(U, d0, d1, dt, Uy=Uy, variant=L.VARIANT_TILED, **pw)
