@@ -180,6 +180,7 @@ int pg_shutdown(void) {
             ++it;
         }
     }
+    fft_plans_release(dev);
     return PG_OK;
 }
 

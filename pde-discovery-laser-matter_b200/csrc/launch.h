@@ -122,6 +122,7 @@ int launch_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, in
                          int n_taps, double *out, cudaStream_t st);
 
 // periodic Gaussian as an FFT product (cuFFT through dlopen): hx [A0] (includes 1 / (A0 A1)), hy [A1 / 2 + 1] on the HOST
+void fft_plans_release(int dev);   // pg_shutdown: destroys the cached cuFFT plans of a device
 size_t periodic_gaussian_fft_scratch(int64_t T, int64_t A0, int64_t A1, int64_t *batch_out);
 int launch_periodic_gaussian_fft(const double *in, int64_t T, int64_t A0, int64_t A1, const double *hx_host, const double *hy_host,
                                  double *out, void *scratch, int64_t batch, cudaStream_t st);

@@ -180,6 +180,18 @@ bool cufft_load() {
 }
 }  // namespace
 
+void fft_plans_release(int dev) {
+    std::lock_guard<std::mutex> lk(g_cufft_mu);
+    for (auto it = g_plans.begin(); it != g_plans.end();) {
+        if (it->first.dev == dev) {
+            if (g_cufft.ok) { g_cufft.Destroy(it->second.first); g_cufft.Destroy(it->second.second); }
+            it = g_plans.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
 // spec[b][i][j] *= hx[i] * hy[j]   (j = 0 .. A1/2; hx carries the 1 / (A0 A1) of the unnormalised inverse)
 __global__ void spectrum_scale_kernel(double2 *__restrict__ spec, int64_t rows, int64_t A0, int64_t nc,
                                       const double *__restrict__ hx, const double *__restrict__ hy) {
