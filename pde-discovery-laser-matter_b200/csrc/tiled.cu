@@ -28,6 +28,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "launch.h"
 #include "tiled_common.cuh"
@@ -556,12 +558,18 @@ __global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(con
         const bool col_ok = (j0 & (TJ - 1)) == 0 || jb >= (int64_t)(P.n_tiles1 - 1) * (TJ / 8);
         int fb = 0;               // f % bt, kept incrementally (no integer division in the frame loop)
         int64_t tbs = tb0 - 1;    // t-block that starts at the latest frame with fb == 0
-        for (int f = 0; f <= nf; ++f, ++G) {
+        // One frame.  FBc carries f % bt as a COMPILE-TIME constant (>= 0) for the frames of whole t-blocks of three, which
+        // the loop below unrolls by three: those frames are never the tail frame, only the first of a block runs the
+        // t-block epilogue and the block-start bookkeeping, and none of that is tested per frame.  FBc < 0: f % bt is the
+        // run-time counter fb (other block lengths, a ragged last t-block, the tail frame).
+        auto frame_step = [&](auto FBc, const int f) {
+            constexpr int FB = decltype(FBc)::value;
+            constexpr bool ST = FB >= 0;
             double *st = stages + cs * STAGE_DOUBLES;
             // where the stage of this frame goes next (known before the frame is even waited for, so the warp
             // that releases it last can re-arm it without any arithmetic in between)
-            int n_i0 = i0, n_j0 = j0, n_t = (int)t0 + f + NSTAGE;
-            bool n_ok = true;
+            [[maybe_unused]] int n_i0 = i0, n_j0 = j0, n_t = (int)t0 + f + NSTAGE;
+            [[maybe_unused]] bool n_ok = true;
             if constexpr (!WS) {
                 if (f + NSTAGE > nf) n_ok = ahead_coords(item, i0, j0, (int)t0, nf, f, NSTAGE, n_i0, n_j0, n_t);
                 if (f + 1 < nf) {
@@ -596,7 +604,7 @@ __global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(con
 
             Sums F;
             if (band_ok) {
-                if (f < nf) march_frame<LIB>(st, lm, P, F);
+                if (ST || f < nf) march_frame<LIB>(st, lm, P, F);
                 else if (P.tail_means && t0 + nf == P.n_row_frames)   // the slab's trailing frame lives on another GPU
                     F.SU = (lane & 8) ? 0.0 : 64.0 * P.tail_means[ib * (int64_t)(P.A1c >> 3) + jb];
                 else F.SU = sum_frame_u(st, lm);
@@ -618,7 +626,7 @@ __global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(con
             if (++cs == NSTAGE) { cs = 0; cph ^= 1; }
 
             // a t-block ends after bt frames, or with the stack (ragged last block: fewer frames, ks2d:384-389)
-            if (((fb == 0 && f > 0) || (f == nf && fb != 0)) && band_ok) {
+            if ((ST ? (FB == 0 && f > 0) : ((fb == 0 && f > 0) || (f == nf && fb != 0))) && band_ok) {
                 double SY = F.SU - su_first;
                 if (P.y_sums) {
                     const double *ys = P.y_sums + (tbs * P.ysum_nb0 + ib) * (int64_t)(P.A1c >> 3) + jb;
@@ -645,7 +653,7 @@ __global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(con
                 }
                 A = Sums();
                 double y_ = y;
-                if (fb != 0) {
+                if (!ST && fb != 0) {
                     // ragged block of fb frames: the common scale assumes bt frames per block
                     const double ratio = (double)P.bt / (double)fb;
                     y_ *= ratio;
@@ -730,8 +738,8 @@ __global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(con
                     }
                 }
             }
-            if (f < nf && band_ok) {
-                if (fb == 0) {
+            if ((ST || f < nf) && band_ok) {
+                if (ST ? FB == 0 : fb == 0) {
                     su_first = F.SU;
                     ++tbs;
                     if constexpr (TIMEFOLD) fold = P.fold_of_frame ? P.fold_of_frame[t0 + f] : 0;
@@ -741,8 +749,20 @@ __global__ void __launch_bounds__(32 * (DNW + (WS ? 4 : 0)), 1) k1_tiled_b88(con
                 if constexpr (kNeedAdv<LIB>) { A.SDx += F.SDx; A.SDy += F.SDy; }
                 if constexpr (kRich<LIB>) { A.SU += F.SU; A.SU2 += F.SU2; A.SUL += F.SUL; }
             }
-            if (++fb == P.bt) fb = 0;
+            if constexpr (!ST)
+                if (++fb == P.bt) fb = 0;
+            ++G;
+        };
+        int f = 0;
+        if constexpr (WS) {
+            if (P.bt == 3)
+                for (; f + 3 <= nf; f += 3) {
+                    frame_step(std::integral_constant<int, 0>{}, f);
+                    frame_step(std::integral_constant<int, 1>{}, f + 1);
+                    frame_step(std::integral_constant<int, 2>{}, f + 2);
+                }
         }
+        for (; f <= nf; ++f) frame_step(std::integral_constant<int, -1>{}, f);
     }
     cp_async_wait<0>();
     if (tid == 0 && blockIdx.x == 0) {
