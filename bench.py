@@ -724,8 +724,13 @@ def run_ours(args):
     coef = out["coef"].cpu().numpy()[0].reshape(-1, len(names))[best]
 
     # ---- end to end through the public API with pinned HOST buffers
-    e2e_value, h2d, ms_e2e, e2e_frames = None, 0, None, 0
+    e2e_value, h2d, ms_e2e, e2e_frames, host_binding = None, 0, None, 0, None
     if not args.skip_e2e:
+        cpus_before = os.sched_getaffinity(0)
+        if not os.environ.get("PG_BENCH_NO_BIND"):
+            # one process per GPU: keep this rank (and the pinned memory it first-touches below) on the GPU's NUMA node
+            from pde_b200 import _xfer
+            host_binding = _xfer.bind_host_to_gpu()
         e2e_frames = min(job.Tbuf, args.e2e_frames if args.e2e_frames > 0 else (job.Tbuf if world == 1 else 256))
         try:
             host = torch.empty((e2e_frames, A, A), dtype=torch.float64).pin_memory()
@@ -754,6 +759,7 @@ def run_ours(args):
         n_slabs = -(-(e2e_frames - 1) // 96)
         h2d = (e2e_frames + n_slabs - 1) * A * A * 8
         del host, bufs
+        os.sched_setaffinity(0, cpus_before)                  # the CPU legs below use every core again
 
     # ---- variants (fewer steps): other libraries / estimators on the same stack
     variants = {}
@@ -910,7 +916,8 @@ def run_ours(args):
                 "h2d_GBps_per_gpu": (h2d * max(2, min(args.steps, 3)) / (ms_e2e * 1e-3) / 1e9) if ms_e2e else None,
                 "sample": f"{e2e_frames} of {job_main_desc['hi'] - job_main_desc['lo'] + 1} frames per GPU streamed from pinned host memory in 96-frame slabs "
                           "(double-buffered), through pde_b200.slabs.fit_streamed + stridge_batched; bound by the host link "
-                          "(PCIe Gen5 x16 per GPU; ranks that share a root complex share it)"},
+                          "(PCIe Gen5 x16 per GPU; ranks that share a root complex share it)",
+                "host_binding": host_binding},
         "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "c5": c5, "variants": variants,
         "patch_ensemble": patch, "reference_configs": ref_cfgs,
     }

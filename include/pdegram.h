@@ -375,6 +375,13 @@ PG_API int pg_rows_metrics_batched(const double *X, const double *y, const doubl
  */
 PG_API int pg_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, int axis, const double *weights,
                     int radius, void *out, void *stream);
+/*
+ * pg_reflect_gauss2d: both axes of the same filter (axis 0, then axis 1, the intermediate rounded to the stack's dtype
+ *   as scipy's is) in one pass over the stack through shared memory: bit-identical to two pg_reflect_conv calls, one
+ *   read and one write of the stack.  radius <= 32 (sigma <= 8 at scipy's truncate = 4).
+ */
+PG_API int pg_reflect_gauss2d(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, const double *weights, int radius,
+                       void *out, void *stream);
 PG_API int pg_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, void *stream);
 PG_API int pg_periodic_conv(const double *in, int64_t T, int64_t A0, int64_t A1, int axis, const int32_t *offsets,
                      const double *weights, int n_taps, double *out, void *stream);

@@ -84,6 +84,7 @@ _PROTOS = {
     "pg_fit_metrics": (C.c_int, [_ptr, _ptr, _i64, _ptr, _ptr]),
     "pg_rows_metrics_batched": (C.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i32, _i64, _ptr, _ptr, _ptr]),
     "pg_reflect_conv": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _i32, _ptr, _i32, _ptr, _ptr]),
+    "pg_reflect_gauss2d": (C.c_int, [_ptr, _i32, _i64, _i64, _i64, _ptr, _i32, _ptr, _ptr]),
     "pg_time_moving_average": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr]),
     "pg_periodic_conv": (C.c_int, [_ptr, _i64, _i64, _i64, _i32, _ptr, _ptr, _i32, _ptr, _ptr]),
     "pg_periodic_gaussian_fft": (C.c_int, [_ptr, _i64, _i64, _i64, _dbl, _ptr, _ptr]),

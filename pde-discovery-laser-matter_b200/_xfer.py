@@ -31,6 +31,45 @@ def _staging(torch):
     return _stage[dev]
 
 
+def bind_host_to_gpu(device=None) -> dict:
+    """Restrict this process to the CPUs NVML names as local to the GPU (its NUMA node), so that the pinned buffers
+    allocated afterwards are first-touched next to the GPU's PCIe root and host -> device copies do not cross the
+    socket interconnect.  One process per GPU calls it once, before allocating pinned memory.  Returns what it did
+    (``{"bound": bool, "cpus": n, "numa_node": k or None, "why": "..."}``); never raises: a box without NVML, without
+    NUMA information (a VM) or with a cpuset that excludes the local CPUs is left as it is."""
+    import os
+    torch = L.torch_cuda()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    info = {"bound": False, "cpus": None, "numa_node": None, "why": ""}
+    try:
+        import pynvml as n
+        n.nvmlInit()
+        pr = torch.cuda.get_device_properties(dev)
+        try:
+            h = n.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:
+            h = n.nvmlDeviceGetHandleByIndex(dev)
+        try:
+            info["numa_node"] = int(n.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        have = os.sched_getaffinity(0)
+        words = n.nvmlDeviceGetCpuAffinity(h, (max(have | {os.cpu_count() or 1}) + 64) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        want = local & have
+        if not want:
+            info["why"] = "the GPU's local CPUs are outside this process's cpuset"
+        elif want == have:
+            info["why"] = "already local (or the box exposes one NUMA node)"
+            info["cpus"] = len(have)
+        else:
+            os.sched_setaffinity(0, want)
+            info.update(bound=True, cpus=len(want))
+    except Exception as e:                                   # noqa: BLE001 - diagnostic only
+        info["why"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 def _as_tensor(torch, a):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", UserWarning)     # read-only arrays: we only read

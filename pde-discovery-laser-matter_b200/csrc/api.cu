@@ -691,6 +691,18 @@ int pg_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1
     return launch_reflect_conv(in, dtype, T, A0, A1, axis, weights, radius, out, (cudaStream_t)stream);
 }
 
+int pg_reflect_gauss2d(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, const double *weights, int radius, void *out,
+                       void *stream) {
+    if (!in || !out || !weights) PG_FAIL(PG_EINVAL, "null buffer");
+    if (dtype != 0 && dtype != 1) PG_FAIL(PG_EINVAL, "dtype must be 0 (float32) or 1 (float64)");
+    if (T < 1 || A0 < 1 || A1 < 1 || radius < 0) PG_FAIL(PG_EINVAL, "bad shape");
+    if (radius > 32) PG_FAIL(PG_EINVAL, "radius > 32: use two pg_reflect_conv passes");
+    if (in == out) PG_FAIL(PG_EINVAL, "in-place filtering is not supported");
+    const int rc = launch_reflect_gauss2d(in, dtype, T, A0, A1, weights, radius, out, (cudaStream_t)stream);
+    if (rc != PG_OK) PG_FAIL(rc, "stack too large for one launch");
+    return rc;
+}
+
 int pg_time_moving_average(const double *U, int64_t T, int64_t A0, int64_t A1, int window, double *out, void *stream) {
     if (!U || !out) PG_FAIL(PG_EINVAL, "null buffer");
     if (T < 1 || A0 < 1 || A1 < 1) PG_FAIL(PG_EINVAL, "bad shape");

@@ -127,6 +127,8 @@ size_t periodic_gaussian_fft_scratch(int64_t T, int64_t A0, int64_t A1, int64_t 
 int launch_periodic_gaussian_fft(const double *in, int64_t T, int64_t A0, int64_t A1, const double *hx_host, const double *hy_host,
                                  double *out, void *scratch, int64_t batch, cudaStream_t st);
 
+int launch_reflect_gauss2d(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, const double *w, int radius, void *out,
+                           cudaStream_t st);
 int launch_reflect_conv(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, int axis, const double *w, int radius,
                         void *out, cudaStream_t st);
 

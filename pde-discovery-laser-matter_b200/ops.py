@@ -470,9 +470,10 @@ def gaussian_taps(sigma, truncate=4.0):
     return r, np.ascontiguousarray(phi[::-1])
 
 
-def gaussian_filter_frames(U, sigma, truncate=4.0):
-    """scipy.ndimage.gaussian_filter(frame, sigma) (mode="reflect") of every frame of a float32 / float64 stack:
-    two pg_reflect_conv passes (rows, then columns, rounding to the stack's dtype in between, as scipy does)."""
+def gaussian_filter_frames(U, sigma, truncate=4.0, two_pass=False):
+    """scipy.ndimage.gaussian_filter(frame, sigma) (mode="reflect") of every frame of a float32 / float64 stack: rows,
+    then columns, rounding to the stack's dtype in between, as scipy does -- one fused pass through shared memory
+    (pg_reflect_gauss2d) for radius <= 32, else (or with ``two_pass``) two pg_reflect_conv passes; same bits."""
     torch = L.torch_cuda()
     lib = L.load()
     if isinstance(U, np.ndarray):
@@ -487,8 +488,12 @@ def gaussian_filter_frames(U, sigma, truncate=4.0):
         return U.clone()
     r, w = gaussian_taps(sigma, truncate)
     w_d = _dev(w)
-    tmp, out = torch.empty_like(U), torch.empty_like(U)
+    out = torch.empty_like(U)
     dt = 0 if U.dtype == torch.float32 else 1
+    if r <= 32 and not two_pass:
+        L.check(lib.pg_reflect_gauss2d(L.ptr(U), dt, T, A0, A1, L.ptr(w_d), r, L.ptr(out), L.stream_ptr()))
+        return out
+    tmp = torch.empty_like(U)
     L.check(lib.pg_reflect_conv(L.ptr(U), dt, T, A0, A1, 0, L.ptr(w_d), r, L.ptr(tmp), L.stream_ptr()))
     L.check(lib.pg_reflect_conv(L.ptr(tmp), dt, T, A0, A1, 1, L.ptr(w_d), r, L.ptr(out), L.stream_ptr()))
     return out

@@ -439,6 +439,21 @@ def test_smoothing_prologue_on_gpu():
     assert np.array_equal(K.gaussian_smooth_periodic_2d(g["frame_a"], 0.0), g["frame_a"])
 
 
+def test_time_moving_average_register_ring_and_plain_kernels():
+    """Windows 3 / 5 / 7 / 9 on frames with an even number of points take the register-ring kernel (one read of the
+    stack), everything else (window 11, odd frames, T < window) the plain one: both bit-identical to the oracle's
+    cumulative-sum formulation (ks2d:145-161)."""
+    from pde_b200 import ks2d as K
+
+    rng = np.random.default_rng(5)
+    for T, A0, A1 in ((23, 6, 10), (23, 5, 7), (4, 6, 10), (9, 8, 8), (10, 3, 4)):
+        U = rng.standard_normal((T, A0, A1))
+        for w in (3, 5, 7, 9, 11):
+            if w // 2 > T - 1:          # np.pad(mode="reflect") needs pad <= T - 1
+                continue
+            assert np.array_equal(K.time_smooth_moving_average(U, w), O.time_smooth_moving_average(U, w)), (T, A0, A1, w)
+
+
 def test_time_holdout_cross_validation():
     """K = 5 time-holdout folds from one K1 pass; K x 30 fits in one K3 launch; every fold's fit and held-out
     score against the oracle on the rows of that fold ("also K = 5")."""
