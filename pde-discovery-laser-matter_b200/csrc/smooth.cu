@@ -239,11 +239,131 @@ static int launch_reflect_gauss2d_t(const T_ *in, int64_t T, int64_t A0, int64_t
     return PG_OK;
 }
 
+// The same for the radii the scripts use (sigma = 1.0, 1.2, 1.5 -> 4, 5, 6; also 2, 3, 8) with the radius a compile-time
+// constant, so that the filter windows live in REGISTERS: along axis 0 a thread marches 18 rows down one column of
+// the window tile (18 + 2 R shared-memory reads for 18 outputs instead of 9 per output), along axis 1 it forms two
+// neighbouring outputs from R + 1 16-byte reads.  Shared memory holds doubles for both dtypes (a float32 stack is
+// widened once per loaded value and the intermediate is rounded through float), so no conversion sits in the inner
+// loops.  Same additions in the same order as the kernels above.  9 warps: 2 x (128 + 2 R) <= 288 column marches,
+// 36 half rows of the 18 x 128 output tile = 4 per warp; the small tile (48 KB of shared memory at R = 4) keeps four
+// CTAs per SM in different phases (measured, 256 x 2048^2 float64, sigma = 1: 36-row tiles 5.8 ms, 18-row tiles 4.5 ms).
+#ifndef PG_RW_TH
+#define PG_RW_TH 18
+#endif
+constexpr int RW_TH = PG_RW_TH, RW_TW = 128, RW_NW = 9, RW_H1 = RW_TH / 2;
+template <typename T_, int R>
+__global__ void __launch_bounds__(32 * RW_NW) reflect_gauss2d_win_kernel(const T_ *__restrict__ in, int64_t A0, int64_t A1, int tiles0,
+                                                                        int tiles1, const double *__restrict__ w, T_ *__restrict__ out) {
+    constexpr int SW = RW_TW + 2 * R, SH = RW_TH + 2 * R, NC = (SW + 31) / 32;
+    extern __shared__ __align__(16) unsigned char rg_smem[];
+    double *tin = reinterpret_cast<double *>(rg_smem);                     // [SH][SW]
+    double *mid = tin + SH * SW;                                           // [RW_TH][SW]
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.x;
+    const int tj = (int)(tile % tiles1), ti = (int)((tile / tiles1) % tiles0);
+    const int64_t t = tile / ((int64_t)tiles1 * tiles0);
+    const int64_t i0 = (int64_t)ti * RW_TH, j0 = (int64_t)tj * RW_TW;
+    const T_ *F = in + t * A0 * A1;
+    double wt[R + 1];                                                      // w[0 .. R]: the taps are symmetric
+#pragma unroll
+    for (int k = 0; k <= R; ++k) wt[k] = __ldg(w + k);
+    {
+        int64_t gj[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) gj[k] = lane + 32 * k < SW ? symmetric_index(j0 - R + lane + 32 * k, A1) : -1;
+#pragma unroll 2
+        for (int a = wid; a < SH; a += RW_NW) {
+            const T_ *Rw = F + symmetric_index(i0 - R + a, A0) * A1;
+            T_ v[NC];
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (gj[k] >= 0) v[k] = Rw[gj[k]];
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (gj[k] >= 0) tin[a * SW + lane + 32 * k] = (double)v[k];
+        }
+    }
+    __syncthreads();
+    // axis 0: thread (seg, c) marches rows seg * RW_H1 .. + RW_H1 - 1 of column c
+    if (threadIdx.x < 2 * SW) {
+        const int seg = threadIdx.x >= SW, c = threadIdx.x - seg * SW;
+        const double *col = tin + seg * RW_H1 * SW + c;
+        double v[RW_H1 + 2 * R];
+#pragma unroll
+        for (int k = 0; k < RW_H1 + 2 * R; ++k) v[k] = col[k * SW];
+#pragma unroll
+        for (int o = 0; o < RW_H1; ++o) {
+            double acc = __dmul_rn(v[o + R], wt[R]);
+#pragma unroll
+            for (int jj = -R; jj < 0; ++jj) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + R + jj], v[o + R - jj]), wt[R + jj]));
+            mid[(seg * RW_H1 + o) * SW + c] = (double)(T_)acc;
+        }
+    }
+    __syncthreads();
+    // axis 1: warp wid takes half rows wid, wid + 9, ..; a lane the outputs 2 lane, 2 lane + 1 of the half row
+    const bool vec = (A1 & 1) == 0;                                        // rows stay aligned for paired stores
+#pragma unroll 2
+    for (int h = wid; h < 2 * RW_TH; h += RW_NW) {
+        const int a = h >> 1, b0 = (h & 1) * 64 + 2 * lane;
+        const double2 *src = reinterpret_cast<const double2 *>(mid + a * SW + b0);
+        double v[2 * R + 2];
+#pragma unroll
+        for (int k = 0; k <= R; ++k) {
+            const double2 x = src[k];
+            v[2 * k] = x.x;
+            v[2 * k + 1] = x.y;
+        }
+        double acc[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            acc[q] = __dmul_rn(v[q + R], wt[R]);
+#pragma unroll
+            for (int jj = -R; jj < 0; ++jj) acc[q] = __dadd_rn(acc[q], __dmul_rn(__dadd_rn(v[q + R + jj], v[q + R - jj]), wt[R + jj]));
+        }
+        const int64_t i = i0 + a, j = j0 + b0;
+        if (i < A0) {
+            T_ *dst = out + (t * A0 + i) * A1 + j;
+            if (vec && j + 1 < A1) {
+                if constexpr (sizeof(T_) == 8) *reinterpret_cast<double2 *>(dst) = make_double2(acc[0], acc[1]);
+                else *reinterpret_cast<float2 *>(dst) = make_float2((float)acc[0], (float)acc[1]);
+            } else {
+                if (j < A1) dst[0] = (T_)acc[0];
+                if (j + 1 < A1) dst[1] = (T_)acc[1];
+            }
+        }
+    }
+}
+
+template <typename T_, int R>
+static int launch_reflect_gauss2d_win(const T_ *in, int64_t T, int64_t A0, int64_t A1, const double *w, T_ *out, cudaStream_t st) {
+    const int64_t tiles0 = (A0 + RW_TH - 1) / RW_TH, tiles1 = (A1 + RW_TW - 1) / RW_TW;
+    if (T * tiles0 * tiles1 > 0x7fffffffLL) return PG_EINVAL;
+    const size_t smem = 8 * (size_t)(RW_TW + 2 * R) * (2 * RW_TH + 2 * R);
+    cudaFuncSetAttribute(reflect_gauss2d_win_kernel<T_, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reflect_gauss2d_win_kernel<T_, R><<<(unsigned)(T * tiles0 * tiles1), 32 * RW_NW, smem, st>>>(in, A0, A1, (int)tiles0, (int)tiles1, w, out);
+    PG_LAUNCHED();
+    return PG_OK;
+}
+
+template <typename T_>
+static int launch_reflect_gauss2d_any(const T_ *in, int64_t T, int64_t A0, int64_t A1, const double *w, int r, T_ *out, cudaStream_t st) {
+    if (((uintptr_t)out % 16) == 0 && !getenv("PG_GAUSS_GENERIC")) switch (r) {
+        case 2: return launch_reflect_gauss2d_win<T_, 2>(in, T, A0, A1, w, out, st);
+        case 3: return launch_reflect_gauss2d_win<T_, 3>(in, T, A0, A1, w, out, st);
+        case 4: return launch_reflect_gauss2d_win<T_, 4>(in, T, A0, A1, w, out, st);
+        case 5: return launch_reflect_gauss2d_win<T_, 5>(in, T, A0, A1, w, out, st);
+        case 6: return launch_reflect_gauss2d_win<T_, 6>(in, T, A0, A1, w, out, st);
+        case 8: return launch_reflect_gauss2d_win<T_, 8>(in, T, A0, A1, w, out, st);
+        default: break;
+    }
+    return launch_reflect_gauss2d_t<T_>(in, T, A0, A1, w, r, out, st);
+}
+
 int launch_reflect_gauss2d(const void *in, int dtype, int64_t T, int64_t A0, int64_t A1, const double *w, int radius, void *out,
                            cudaStream_t st) {
     if (radius > RG_MAX_R) return PG_EINVAL;
-    return dtype == 0 ? launch_reflect_gauss2d_t<float>((const float *)in, T, A0, A1, w, radius, (float *)out, st)
-                      : launch_reflect_gauss2d_t<double>((const double *)in, T, A0, A1, w, radius, (double *)out, st);
+    return dtype == 0 ? launch_reflect_gauss2d_any<float>((const float *)in, T, A0, A1, w, radius, (float *)out, st)
+                      : launch_reflect_gauss2d_any<double>((const double *)in, T, A0, A1, w, radius, (double *)out, st);
 }
 
 static unsigned grid_of(int64_t items) {

@@ -236,7 +236,7 @@ def test_fused_gaussian_filter_equals_two_passes_and_scipy():
     from pde_b200 import ops
 
     rng = np.random.default_rng(11)
-    for shape, sigmas in (((3, 70, 300), (0.5, 1.0, 1.2, 3.0)), ((2, 33, 129), (1.0, 8.0)), ((2, 5, 4), (1.0, 2.0)),
+    for shape, sigmas in (((3, 70, 300), (0.5, 0.75, 1.0, 1.2, 1.5, 2.0, 3.0)), ((2, 33, 129), (1.0, 1.5, 8.0)), ((2, 5, 4), (1.0, 2.0)),
                           ((1, 32, 128), (1.5,)), ((2, 1, 7), (1.0,)), ((1, 64, 257), (9.0,))):
         for dtype in (np.float32, np.float64):
             U = rng.standard_normal(shape).astype(dtype)
