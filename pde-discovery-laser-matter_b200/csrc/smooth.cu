@@ -251,36 +251,39 @@ static int launch_reflect_gauss2d_t(const T_ *in, int64_t T, int64_t A0, int64_t
 #define PG_RW_TH 18
 #endif
 constexpr int RW_TH = PG_RW_TH, RW_TW = 128, RW_NW = 9, RW_H1 = RW_TH / 2;
+__device__ __forceinline__ int symmetric_index32(int i, int n) {
+    while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - i - 1;
+    return i;
+}
+
+// grid (tiles along a1, tiles along a0, frames of this launch); offsets inside a frame are 32-bit (A0 A1 < 2^31)
 template <typename T_, int R>
-__global__ void __launch_bounds__(32 * RW_NW) reflect_gauss2d_win_kernel(const T_ *__restrict__ in, int64_t A0, int64_t A1, int tiles0,
-                                                                        int tiles1, const double *__restrict__ w, T_ *__restrict__ out) {
+__global__ void __launch_bounds__(32 * RW_NW) reflect_gauss2d_win_kernel(const T_ *__restrict__ in, int A0, int A1,
+                                                                        const double *__restrict__ w, T_ *__restrict__ out) {
     constexpr int SW = RW_TW + 2 * R, SH = RW_TH + 2 * R, NC = (SW + 31) / 32;
     extern __shared__ __align__(16) unsigned char rg_smem[];
     double *tin = reinterpret_cast<double *>(rg_smem);                     // [SH][SW]
     double *mid = tin + SH * SW;                                           // [RW_TH][SW]
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile = blockIdx.x;
-    const int tj = (int)(tile % tiles1), ti = (int)((tile / tiles1) % tiles0);
-    const int64_t t = tile / ((int64_t)tiles1 * tiles0);
-    const int64_t i0 = (int64_t)ti * RW_TH, j0 = (int64_t)tj * RW_TW;
-    const T_ *F = in + t * A0 * A1;
+    const int i0 = blockIdx.y * RW_TH, j0 = blockIdx.x * RW_TW;
+    const int64_t fo = (int64_t)blockIdx.z * A0 * A1;
+    const T_ *F = in + fo;
     double wt[R + 1];                                                      // w[0 .. R]: the taps are symmetric
 #pragma unroll
     for (int k = 0; k <= R; ++k) wt[k] = __ldg(w + k);
     {
-        int64_t gj[NC];
+        int gj[NC];                                                        // the lane's window columns, reflections resolved
 #pragma unroll
-        for (int k = 0; k < NC; ++k) gj[k] = lane + 32 * k < SW ? symmetric_index(j0 - R + lane + 32 * k, A1) : -1;
+        for (int k = 0; k < NC; ++k) gj[k] = symmetric_index32(j0 - R + min(lane + 32 * k, SW - 1), A1);
 #pragma unroll 2
         for (int a = wid; a < SH; a += RW_NW) {
-            const T_ *Rw = F + symmetric_index(i0 - R + a, A0) * A1;
+            const T_ *Rw = F + symmetric_index32(i0 - R + a, A0) * A1;
             T_ v[NC];
 #pragma unroll
-            for (int k = 0; k < NC; ++k)
-                if (gj[k] >= 0) v[k] = Rw[gj[k]];
+            for (int k = 0; k < NC; ++k) v[k] = Rw[gj[k]];
 #pragma unroll
             for (int k = 0; k < NC; ++k)
-                if (gj[k] >= 0) tin[a * SW + lane + 32 * k] = (double)v[k];
+                if (32 * (k + 1) <= SW || lane + 32 * k < SW) tin[a * SW + lane + 32 * k] = (double)v[k];
         }
     }
     __syncthreads();
@@ -320,9 +323,9 @@ __global__ void __launch_bounds__(32 * RW_NW) reflect_gauss2d_win_kernel(const T
 #pragma unroll
             for (int jj = -R; jj < 0; ++jj) acc[q] = __dadd_rn(acc[q], __dmul_rn(__dadd_rn(v[q + R + jj], v[q + R - jj]), wt[R + jj]));
         }
-        const int64_t i = i0 + a, j = j0 + b0;
+        const int i = i0 + a, j = j0 + b0;
         if (i < A0) {
-            T_ *dst = out + (t * A0 + i) * A1 + j;
+            T_ *dst = out + fo + (i * A1 + j);
             if (vec && j + 1 < A1) {
                 if constexpr (sizeof(T_) == 8) *reinterpret_cast<double2 *>(dst) = make_double2(acc[0], acc[1]);
                 else *reinterpret_cast<float2 *>(dst) = make_float2((float)acc[0], (float)acc[1]);
@@ -337,17 +340,21 @@ __global__ void __launch_bounds__(32 * RW_NW) reflect_gauss2d_win_kernel(const T
 template <typename T_, int R>
 static int launch_reflect_gauss2d_win(const T_ *in, int64_t T, int64_t A0, int64_t A1, const double *w, T_ *out, cudaStream_t st) {
     const int64_t tiles0 = (A0 + RW_TH - 1) / RW_TH, tiles1 = (A1 + RW_TW - 1) / RW_TW;
-    if (T * tiles0 * tiles1 > 0x7fffffffLL) return PG_EINVAL;
     const size_t smem = 8 * (size_t)(RW_TW + 2 * R) * (2 * RW_TH + 2 * R);
     cudaFuncSetAttribute(reflect_gauss2d_win_kernel<T_, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    reflect_gauss2d_win_kernel<T_, R><<<(unsigned)(T * tiles0 * tiles1), 32 * RW_NW, smem, st>>>(in, A0, A1, (int)tiles0, (int)tiles1, w, out);
+    for (int64_t t0 = 0; t0 < T; t0 += 65535) {                            // gridDim.z <= 65535
+        const int64_t nt = T - t0 < 65535 ? T - t0 : 65535;
+        reflect_gauss2d_win_kernel<T_, R><<<dim3((unsigned)tiles1, (unsigned)tiles0, (unsigned)nt), 32 * RW_NW, smem, st>>>(
+            in + t0 * A0 * A1, (int)A0, (int)A1, w, out + t0 * A0 * A1);
+    }
     PG_LAUNCHED();
     return PG_OK;
 }
 
 template <typename T_>
 static int launch_reflect_gauss2d_any(const T_ *in, int64_t T, int64_t A0, int64_t A1, const double *w, int r, T_ *out, cudaStream_t st) {
-    if (((uintptr_t)out % 16) == 0 && !getenv("PG_GAUSS_GENERIC")) switch (r) {
+    const bool win_ok = ((uintptr_t)out % 16) == 0 && A0 * A1 < 0x7fffffffLL && (A0 + RW_TH - 1) / RW_TH <= 65535;
+    if (win_ok && !getenv("PG_GAUSS_GENERIC")) switch (r) {
         case 2: return launch_reflect_gauss2d_win<T_, 2>(in, T, A0, A1, w, out, st);
         case 3: return launch_reflect_gauss2d_win<T_, 3>(in, T, A0, A1, w, out, st);
         case 4: return launch_reflect_gauss2d_win<T_, 4>(in, T, A0, A1, w, out, st);
