@@ -1004,7 +1004,23 @@ def patch_leg(args, torch, ops, L, alphas, thrs):
     k1.record()
     torch.cuda.synchronize()
     ms_k3 = k0.elapsed_time(k1) / 5
+    # the smoothing the script applies to the stack before the loop (patch:335, 343: gaussian_filter sigma 1.0, then 1.2)
+    def prologue():
+        return ops.gaussian_filter_frames(ops.gaussian_filter_frames(U32, 1.0), 1.2)
+
+    prologue()
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(3):
+        prologue()
+    g1.record()
+    torch.cuda.synchronize()
+    ms_gf = g0.elapsed_time(g1) / 3
     patch = {"workload": f"c3: {Hp}x{Hp}x{Tp} float32 stack, {B} patches x (120 train + 40 test) points, p=8, rt=2 rs=3 deg=3",
+             "prologue": {"what": "gaussian_filter(sigma=1.0) then gaussian_filter(sigma=1.2) of every frame (patch:335,343), "
+                                  "both axes fused per call (pg_reflect_gauss2d)",
+                          "ms": ms_gf, "GBps_read_plus_write": 2 * 2 * 4.0 * Tp * Hp * Hp / (ms_gf * 1e-3) / 1e9},
              "k3_sweep_fits_per_s": B * 30 / (ms_k3 * 1e-3), "k3_sweep_ms": ms_k3,
              "stridge_fits_per_s": B / (ms * 1e-3), "stencil_points_per_s": B * 160 / (ms * 1e-3), "ms_per_pass": ms,
              "launch_mode": mode}
@@ -1027,6 +1043,19 @@ def patch_leg(args, torch, ops, L, alphas, thrs):
         rel = float(np.max(np.abs(Cg[nz] - Co[nz]) / np.abs(Co[nz]))) if nz.any() else 0.0
         patch["parity_vs_port"] = {"patches": n_cpu, "same_support": same, "coef_max_rel": rel, "tolerance": 1e-8}
         assert same and rel <= 1e-8, f"patch ensemble parity gate failed: support {same}, rel {rel}"
+        try:                                   # the prologue against scipy itself on a few frames: time and bits
+            from scipy.ndimage import gaussian_filter as sp_gf
+
+            nf = 4
+            t0c = time.perf_counter()
+            ref_f = np.array([sp_gf(sp_gf(f, sigma=1.0), sigma=1.2) for f in Uh[:nf]])
+            dt_sp = (time.perf_counter() - t0c) / nf
+            got_f = ops.gaussian_filter_frames(ops.gaussian_filter_frames(U32[:nf].contiguous(), 1.0), 1.2).cpu().numpy()
+            patch["prologue"].update(scipy_ms_per_frame=dt_sp * 1e3, scipy_frames=nf, bit_identical_to_scipy=bool(np.array_equal(got_f, ref_f)),
+                                     speedup_vs_scipy_1core=dt_sp * 1e3 * Tp / ms_gf)
+            assert patch["prologue"]["bit_identical_to_scipy"], "gaussian_filter prologue differs from scipy"
+        except ImportError:
+            patch["prologue"]["scipy"] = "not installed"
         if refload.available("patch"):
             pa = refload.load("patch")
             lib8 = pa.Library(names=list(PP.FULL_NAMES))
