@@ -38,10 +38,10 @@ def bind_host_to_gpu(device=None) -> dict:
     (``{"bound": bool, "cpus": n, "numa_node": k or None, "why": "..."}``); never raises: a box without NVML, without
     NUMA information (a VM) or with a cpuset that excludes the local CPUs is left as it is."""
     import os
-    torch = L.torch_cuda()
-    dev = torch.cuda.current_device() if device is None else int(device)
     info = {"bound": False, "cpus": None, "numa_node": None, "why": ""}
     try:
+        torch = L.torch_cuda()
+        dev = torch.cuda.current_device() if device is None else int(device)
         import pynvml as n
         n.nvmlInit()
         pr = torch.cuda.get_device_properties(dev)

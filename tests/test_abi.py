@@ -111,3 +111,19 @@ def test_host_logic_ks_fold_split():
     assert np.array_equal(np.flatnonzero(fold == 0), np.sort(tr)) and np.array_equal(np.flatnonzero(fold == 1), np.sort(te))
     assert K.RICH_NAMES == O.RICH_NAMES and K.TRUE_NAMES == O.TRUE_NAMES
     assert (K.GRID_ALPHAS, K.GRID_THRESHOLDS) == (O.GRID_ALPHAS, O.GRID_THRESHOLDS)
+
+
+def test_host_binding_reports_instead_of_raising():
+    """_xfer.bind_host_to_gpu is a tuning aid of the host-streaming path: where it cannot act (no GPU, no NVML, a cpuset
+    without the GPU's local CPUs) it says why and leaves the process's affinity alone."""
+    import os
+
+    from pde_b200 import _xfer
+
+    before = os.sched_getaffinity(0)
+    info = _xfer.bind_host_to_gpu()
+    assert set(info) == {"bound", "cpus", "numa_node", "why"}
+    import torch
+
+    if not torch.cuda.is_available():
+        assert info["bound"] is False and info["why"] and os.sched_getaffinity(0) == before
